@@ -1,0 +1,61 @@
+"""Builds libcomet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libcomet_b200.so")
+OBJ = os.path.join(HERE, "build")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
+    "-Xptxas", "-v", "-DNDEBUG",
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
+        os.path.join(os.path.dirname(HERE), "include", "comet_b200.h")]
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"nvcc failed for {s}:\n{out}\n")
+        elif verbose:
+            sys.stderr.write(out)
+        with open(os.path.join(OBJ, os.path.basename(s)[:-3] + ".ptxas.log"), "w") as f:
+            f.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    if force or procs or _stale(OUT, objs):
+        cmd = [nvcc, "-shared", "-o", OUT] + objs
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

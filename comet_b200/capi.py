@@ -1,0 +1,231 @@
+"""ctypes binding of include/comet_b200.h.  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcomet_b200.so")
+
+L2, L2SQ, COSINE = 0, 1, 2
+METRICS = {"l2": L2, "l2_squared": L2SQ, "cosine": COSINE}
+PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
+ROUND_SEPARATE, ROUND_FMA = 0, 1
+
+OK, ERR_INVALID_ARG, ERR_DIM_MISMATCH, ERR_ZERO_VECTOR, ERR_NOT_TRAINED, ERR_NOT_FOUND, ERR_CUDA, \
+    ERR_UNSUPPORTED, ERR_TOO_FEW, ERR_BUFFER_TOO_SMALL = range(10)
+
+
+class CometError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("k", C.c_int64), ("threshold", C.c_float), ("nprobes", C.c_int32), ("ef_search", C.c_int32),
+                ("filter_ids", C.POINTER(C.c_uint32)), ("nfilter", C.c_int64), ("path", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class FlatStats(C.Structure):
+    _fields_ = [("path_used", C.c_int32), ("passes", C.c_int32), ("candidates", C.c_int64),
+                ("fallback_queries", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+f32p, u32p, u8p, i32p, i64p, vp = (C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_void_p)
+
+# name -> (restype, argtypes).  Mirrors include/comet_b200.h one to one (tests check that).
+SIGNATURES = {
+    "cm_init": (C.c_int, [i32p, C.c_int]),
+    "cm_shutdown": (None, []),
+    "cm_last_error": (C.c_char_p, []),
+    "cm_device_count": (C.c_int, []),
+    "cm_set_rounding": (C.c_int, [C.c_int]),
+    "cm_get_rounding": (C.c_int, []),
+    "cm_version": (C.c_char_p, []),
+    "cm_kernel_launches": (C.c_int64, []),
+    "cm_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+    "cm_host_free": (C.c_int, [vp]),
+    "cm_distance_pairs": (C.c_int, [C.c_int, f32p, f32p, C.c_int64, C.c_int, f32p]),
+    "cm_preprocess_rows": (C.c_int, [C.c_int, f32p, C.c_int64, C.c_int, i64p]),
+    "cm_flat_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_flat_destroy": (C.c_int, [vp]),
+    "cm_flat_reserve": (C.c_int, [vp, C.c_int64]),
+    "cm_flat_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
+    "cm_flat_add_device": (C.c_int, [vp, u32p, vp, C.c_int64, vp]),
+    "cm_flat_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_flat_flush": (C.c_int, [vp]),
+    "cm_flat_size": (C.c_int64, [vp]),
+    "cm_flat_dim": (C.c_int, [vp]),
+    "cm_flat_metric": (C.c_int, [vp]),
+    "cm_flat_get_vector": (C.c_int, [vp, C.c_uint32, f32p]),
+    "cm_flat_get_rows": (C.c_int, [vp, i64p, C.c_int64, f32p]),
+    "cm_flat_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p,
+                                 i64p, i64p]),
+    "cm_flat_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
+                                        vp, vp, vp]),
+    "cm_flat_last_stats": (C.c_int, [vp, C.POINTER(FlatStats)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libcomet_b200.so (building it in-tree if the sources are newer).  Raises if it cannot be
+    built or loaded -- there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH) or os.environ.get("COMET_B200_REBUILD"):
+        from . import build as _b
+        _b.build()
+    L = C.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)   # AttributeError if the .so is stale: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise CometError(rc, lib().cm_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def make_params(k=10, threshold=0.0, nprobes=0, ef_search=0, filter_ids=None, path=PATH_AUTO):
+    """Returns (params, keepalive)."""
+    f = None
+    p = SearchParams()
+    p.k = int(k)
+    p.threshold = float(threshold)
+    p.nprobes = int(nprobes)
+    p.ef_search = int(ef_search)
+    p.path = int(path)
+    if filter_ids is not None and len(filter_ids) > 0:
+        f = _u32(filter_ids)
+        p.filter_ids = ptr(f, u32p)
+        p.nfilter = len(f)
+    else:
+        p.filter_ids = None
+        p.nfilter = 0
+    return p, f
+
+
+def distance_pairs(metric, a, b):
+    a, b = _f32(a), _f32(b)
+    if a.ndim == 1:
+        a, b = a[None, :], b[None, :]
+    n, d = a.shape
+    out = np.empty(n, np.float32)
+    check(lib().cm_distance_pairs(metric, ptr(a, f32p), ptr(b, f32p), n, d, ptr(out, f32p)))
+    return out
+
+
+def preprocess_rows(metric, rows):
+    """In place on a contiguous float32 array; raises CometError(ERR_ZERO_VECTOR)."""
+    assert rows.dtype == np.float32 and rows.flags.c_contiguous
+    r2 = rows.reshape(-1, rows.shape[-1])
+    bad = C.c_int64(-1)
+    check(lib().cm_preprocess_rows(metric, ptr(r2, f32p), r2.shape[0], r2.shape[1], C.byref(bad)))
+    return rows
+
+
+class FlatIndex:
+    """Thin owner of a cm_flat handle."""
+
+    def __init__(self, dim, metric):
+        self.h = vp()
+        check(lib().cm_flat_create(int(dim), int(metric), C.byref(self.h)))
+        self.dim, self.metric = dim, metric
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cm_flat_destroy(self.h)
+            self.h = None
+
+    def reserve(self, n):
+        check(lib().cm_flat_reserve(self.h, int(n)))
+
+    def add(self, ids, rows, writeback=True):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        check(lib().cm_flat_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
+
+    def add_device(self, ids, rows_dev_ptr, n, stream=0):
+        ids = _u32(ids)
+        check(lib().cm_flat_add_device(self.h, ptr(ids, u32p), vp(rows_dev_ptr), int(n), vp(stream)))
+
+    def remove(self, id_):
+        check(lib().cm_flat_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_flat_flush(self.h))
+
+    def __len__(self):
+        return int(lib().cm_flat_size(self.h))
+
+    def get_vector(self, id_):
+        out = np.empty(self.dim, np.float32)
+        check(lib().cm_flat_get_vector(self.h, int(id_), ptr(out, f32p)))
+        return out
+
+    def get_rows(self, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.int64)
+        out = np.empty((len(pos), self.dim), np.float32)
+        check(lib().cm_flat_get_rows(self.h, ptr(pos, i64p), len(pos), ptr(out, f32p)))
+        return out
+
+    def effective_k(self, k):
+        n = len(self)
+        return n if (k <= 0 or k > n) else k
+
+    def search(self, queries, k=10, threshold=0.0, filter_ids=None, path=PATH_AUTO, with_pos=False):
+        """nq independent searchSingleQuery calls -> (ids[nq,K], scores[nq,K], counts[nq])."""
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        ke = max(self.effective_k(k), 1)
+        ids = np.zeros((nq, ke), np.uint32)
+        sc = np.zeros((nq, ke), np.float32)
+        pos = np.zeros((nq, ke), np.int64) if with_pos else None
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, filter_ids=filter_ids, path=path)
+        check(lib().cm_flat_search(self.h, ptr(q, f32p), nq, d, C.byref(p), ke, ptr(ids, u32p), ptr(sc, f32p),
+                                   ptr(pos, i64p), ptr(cnt, i64p)))
+        if with_pos:
+            return ids, sc, cnt, pos
+        return ids, sc, cnt
+
+    def search_device(self, q_ptr, nq, k, out_ids_ptr, out_scores_ptr, out_counts_ptr, out_stride, stream=0,
+                      threshold=0.0, path=PATH_AUTO, out_pos_ptr=0):
+        p, keep = make_params(k=k, threshold=threshold, path=path)
+        check(lib().cm_flat_search_device(self.h, vp(q_ptr), int(nq), self.dim, C.byref(p), int(out_stride),
+                                          vp(out_ids_ptr), vp(out_scores_ptr), vp(out_pos_ptr) if out_pos_ptr else None,
+                                          vp(out_counts_ptr), vp(stream)))
+
+    def last_stats(self):
+        s = FlatStats()
+        check(lib().cm_flat_last_stats(self.h, C.byref(s)))
+        return {"path_used": s.path_used, "passes": s.passes, "candidates": s.candidates,
+                "fallback_queries": s.fallback_queries, "kernel_launches": s.kernel_launches}

@@ -1,0 +1,175 @@
+// common.cuh -- shared host/device helpers of libcomet_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/comet_b200.h"
+
+namespace cm {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+extern std::atomic<int64_t> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CM_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::cm::fail(CM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                             \
+    } while (0)
+
+#define CM_TRY(call)                 \
+    do {                             \
+        int _rc = (call);            \
+        if (_rc != CM_OK) return _rc; \
+    } while (0)
+
+int ensure_device();            // CM_OK when a CUDA device is usable
+int sm_count();
+int rounding_mode();            // CM_ROUND_*
+size_t max_smem_optin();
+
+// ---------------------------------------------------------------------------------------------
+// reference arithmetic on device (distance.go).  __fmul_rn/__fadd_rn/__fsub_rn are never
+// contracted into FMA by nvcc, so these reproduce gc/amd64's separately rounded `sum += d*d`.
+// ---------------------------------------------------------------------------------------------
+template <bool FMA>
+__device__ __forceinline__ float l2_step(float acc, float a, float b) {
+    float diff = __fsub_rn(a, b);
+    if (FMA) return __fmaf_rn(diff, diff, acc);
+    return __fadd_rn(acc, __fmul_rn(diff, diff));
+}
+template <bool FMA>
+__device__ __forceinline__ float dot_step(float acc, float a, float b) {
+    if (FMA) return __fmaf_rn(a, b, acc);
+    return __fadd_rn(acc, __fmul_rn(a, b));
+}
+// metric-specific accumulate step: L2 / L2SQ accumulate squared differences, cosine the dot product
+template <int METRIC, bool FMA>
+__device__ __forceinline__ float metric_step(float acc, float q, float x) {
+    if (METRIC == CM_COSINE) return dot_step<FMA>(acc, q, x);
+    return l2_step<FMA>(acc, q, x);
+}
+// finish: distance.go:120 float32(math.Sqrt(float64(sum))) == correctly rounded fp32 sqrt;
+// distance.go:208-215 clamp to [-1,1] then 1 - dot.
+template <int METRIC>
+__device__ __forceinline__ float metric_finish(float acc) {
+    if (METRIC == CM_L2) return __fsqrt_rn(acc);
+    if (METRIC == CM_COSINE) {
+        if (acc > 1.0f) acc = 1.0f; else if (acc < -1.0f) acc = -1.0f;
+        return __fsub_rn(1.0f, acc);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordering keys: (score, scan position) ascending == ascending u64.  Scores on this path are
+// never -0.0 (sums of squares, 1 - clamp(dot), sqrt), so the sign-flip transform keeps ties equal.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b; memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t pos) {
+    return ((uint64_t)float_to_ordered(score) << 32) | (uint64_t)pos;
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_float((uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_pos(uint64_t k) { return (uint32_t)k; }
+static constexpr uint64_t KEY_INF = ~0ull;
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA / proxy fences (PTX, sm_90+ forms valid on sm_100a)
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 2-D tiled TMA load: box lands in smem, completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+// 1-D bulk copy global -> smem (bytes multiple of 16, both sides 16-B aligned)
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+#endif
+
+// host: encode a 2-D row-major tensor map (driver entry point fetched at run time, no -lcuda)
+int make_tmap_2d(CUtensorMap *out, CUtensorMapDataType dtype, uint32_t elem_bytes, const void *base,
+                 uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner,
+                 uint32_t box_outer, CUtensorMapSwizzle swizzle);
+
+}  // namespace cm

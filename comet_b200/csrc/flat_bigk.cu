@@ -1,0 +1,101 @@
+// flat_bigk.cu -- flat search when the caller wants (nearly) everything back: WithK(0) or
+// k > 4096 (limiter.go:12-17 turns k <= 0 into "all").  The reference sorts all N results anyway
+// (flat_index_search.go:277); here every row's key goes to HBM and one radix sort per query orders
+// them.  Not a hot path: a result of >4096 rows per query is dominated by returning it.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "flat_index.cuh"
+#include "flat_kernels.cuh"
+
+namespace cm {
+
+template <int METRIC, bool FMA>
+__global__ void all_keys_kernel(const float *__restrict__ rows, int ld, long long n, const float *__restrict__ q,
+                                const uint8_t *__restrict__ skip, float threshold, uint64_t *__restrict__ keys) {
+    extern __shared__ float qs[];
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) qs[j] = q[j];
+    __syncthreads();
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *x = reinterpret_cast<const float4 *>(rows + (size_t)i * ld);
+    float acc = 0.0f;
+    for (int j = 0; j < ld / 4; j++) {
+        float4 v = x[j];
+        acc = metric_step<METRIC, FMA>(acc, qs[4 * j + 0], v.x);
+        acc = metric_step<METRIC, FMA>(acc, qs[4 * j + 1], v.y);
+        acc = metric_step<METRIC, FMA>(acc, qs[4 * j + 2], v.z);
+        acc = metric_step<METRIC, FMA>(acc, qs[4 * j + 3], v.w);
+    }
+    float dist = metric_finish<METRIC>(acc);
+    bool pass = !(skip && skip[i]) && !(threshold > 0.0f && dist > threshold);
+    keys[i] = pass ? make_key(dist, (uint32_t)i) : KEY_INF;
+}
+
+__global__ void emit_sorted_kernel(const uint64_t *__restrict__ keys, long long n, long long k,
+                                   const uint32_t *__restrict__ row_ids, uint32_t *__restrict__ out_ids,
+                                   float *__restrict__ out_scores, long long *__restrict__ out_pos,
+                                   long long *__restrict__ out_count) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i == 0) {
+        // number of valid keys = first index holding KEY_INF (binary search), capped at k
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (keys[mid] == KEY_INF) hi = mid; else lo = mid + 1;
+        }
+        *out_count = lo < k ? lo : k;
+    }
+    if (i >= k || i >= n) return;
+    uint64_t key = keys[i];
+    if (key == KEY_INF) return;
+    uint32_t pos = key_pos(key);
+    out_ids[i] = row_ids[pos];
+    out_scores[i] = key_score(key);
+    if (out_pos) out_pos[i] = pos;
+}
+
+template <int METRIC>
+static void launch_all_keys(bool fma, const float *rows, int ld, int64_t n, const float *q, const uint8_t *skip,
+                            float threshold, uint64_t *keys, cudaStream_t st) {
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (fma) all_keys_kernel<METRIC, true><<<blocks, 128, ld * 4, st>>>(rows, ld, n, q, skip, threshold, keys);
+    else all_keys_kernel<METRIC, false><<<blocks, 128, ld * 4, st>>>(rows, ld, n, q, skip, threshold, keys);
+    count_launch();
+}
+
+int FlatIndex::search_exact_bigk(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
+                                 int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                                 int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+    uint64_t *keys = nullptr, *sorted = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, sorted, (int64_t)n, 0, 64, st);
+    CM_TRY(ws_alloc((void **)&keys, (size_t)n * 8, st));
+    CM_TRY(ws_alloc((void **)&sorted, (size_t)n * 8, st));
+    CM_TRY(ws_alloc(&tmp, tmp_bytes, st));
+    for (int64_t qi = 0; qi < nq; qi++) {
+        const float *q = qp + (size_t)qi * ld;
+        switch (metric) {
+        case CM_L2: launch_all_keys<CM_L2>(fma, rows, ld, n, q, skip, threshold, keys, st); break;
+        case CM_L2SQ: launch_all_keys<CM_L2SQ>(fma, rows, ld, n, q, skip, threshold, keys, st); break;
+        default: launch_all_keys<CM_COSINE>(fma, rows, ld, n, q, skip, threshold, keys, st); break;
+        }
+        CM_CUDA(cudaGetLastError());
+        CM_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, sorted, (int64_t)n, 0, 64, st));
+        count_launch(3);
+        unsigned blocks = (unsigned)((k_eff + 255) / 256);
+        emit_sorted_kernel<<<blocks, 256, 0, st>>>(sorted, n, k_eff, ids, out_ids + (size_t)qi * out_stride,
+                                                  out_scores + (size_t)qi * out_stride,
+                                                  out_pos ? (long long *)out_pos + (size_t)qi * out_stride : nullptr,
+                                                  (long long *)out_counts + qi);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
+    ws_free(keys, st); ws_free(sorted, st); ws_free(tmp, st);
+    stats->path_used = CM_PATH_EXACT;
+    stats->passes = (int)nq;
+    return CM_OK;
+}
+
+}  // namespace cm

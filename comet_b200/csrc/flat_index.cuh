@@ -1,0 +1,65 @@
+// flat_index.cuh -- FlatIndex device object (see flat.cu for the layout).
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <unordered_set>
+#include <vector>
+
+#include "common.cuh"
+
+namespace cm {
+
+int acquire_stream(cudaStream_t *out);
+void release_stream(cudaStream_t s);
+int ws_alloc(void **p, size_t bytes, cudaStream_t s);
+void ws_free(void *p, cudaStream_t s);
+
+struct FlatIndex {
+    int dim = 0, ld = 0, metric = 0, device = 0;
+    int64_t n = 0, cap = 0;
+    float *rows = nullptr;
+    uint32_t *ids = nullptr;
+    uint8_t *deleted = nullptr;
+    CUtensorMap tmap;                       // fp32 rows, box 32 x 128, SWIZZLE_128B
+    std::vector<uint32_t> ids_host_mirror;  // for Remove / lookupNodeVectors (O(N) ID scans stay on the host)
+    std::unordered_set<uint32_t> deleted_ids;
+    int64_t n_deleted_rows = 0;
+
+    // tensor-core candidate pass state (flat_tensor.cu)
+    __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ld] bf16 shadow of rows
+    float *row_sqnorm = nullptr;            // [cap] ||x||^2 (fp32, any order: only used for the bound)
+    int64_t shadow_rows = 0;                // rows [0, shadow_rows) of the shadow are current
+    int64_t shadow_cap = 0;
+    float max_row_norm = 0.0f;
+    CUtensorMap tmap_bf16;
+
+    std::mutex stats_mu;
+    cm_flat_stats last_stats{};
+
+    ~FlatIndex();
+    int reserve(int64_t want);
+    int rebuild_tmap();
+    int add_from_device(const uint32_t *ids_host, const float *src_dev, int64_t n_add, float *writeback_host,
+                        cudaStream_t st);
+    int remove(uint32_t id);
+    int flush();
+    int search_device(const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
+                      uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
+                      bool check_zero_queries);
+    int search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t k_eff, const uint8_t *skip, float threshold,
+                     int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts,
+                     cudaStream_t st, cm_flat_stats *stats);
+    int search_exact_bigk(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
+                          int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                          int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats);
+    // flat_tensor.cu
+    bool tensor_path_eligible(int64_t nq, int64_t k_eff, bool has_skip, float threshold) const;
+    int search_tensor(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
+                      int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                      int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats);
+    void free_shadow();
+};
+
+}  // namespace cm

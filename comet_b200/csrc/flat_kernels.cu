@@ -1,0 +1,411 @@
+// flat_kernels.cu -- exact (reference-order) flat scan for sm_100a, its top-K merge, and the
+// small per-row kernels (preprocess, pair distances, skip mask, gather).
+//
+// flat_scan_kernel replaces the hot loop of flatIndexSearch.searchSingleQuery
+// (flat_index_search.go:254-279): for every stored row, Distance.Calculate in the reference's
+// exact float32 order (distance.go:114-121, 158-165, 201-216), soft-delete / document-filter /
+// threshold tests, then "sort everything, keep k" expressed as a K-smallest selection.
+//
+// Data movement: the row-major [N][ld] fp32 matrix is streamed once from HBM by a dedicated TMA
+// producer warp as 128-row x 32-float boxes (16 KB, SWIZZLE_128B) through an mbarrier ring.  Each
+// of the 128 consumer threads owns one row of the tile and walks it left to right (the order is
+// what makes scores bit-identical to the reference), reading 16-byte pieces whose XOR swizzle makes
+// the 8 threads of every quarter-warp hit 8 distinct bank groups.  Up to QB=8 queries (staged once
+// per CTA with a bulk copy, read as smem broadcasts) share each pass over the rows, which keeps the
+// pass HBM-bound: 3 FP32 ops per element and query against 23 B/clk/SM of HBM.
+#include "flat_kernels.cuh"
+#include "select.cuh"
+
+namespace cm {
+
+// ------------------------------------------------------------------------------------------------
+// exact scan
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, bool FMA, int QB>
+__global__ void __launch_bounds__(SCAN_THREADS) flat_scan_kernel(
+    const __grid_constant__ CUtensorMap tmap, const float *__restrict__ queries, int ld, long long n_rows,
+    int n_tiles, int stages, const uint8_t *__restrict__ skip, float threshold, int K, int C,
+    uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: [stages x 16 KB][q: QB x ld f32][bufs: QB x C u64][cnt QB][tau QB][bars]
+    uint8_t *stage_base = smem;
+    float *q_s = reinterpret_cast<float *>(smem + (size_t)stages * SCAN_STAGE_BYTES);
+    uint64_t *bufs = reinterpret_cast<uint64_t *>(q_s + (size_t)QB * ld);
+    uint64_t *tau = bufs + (size_t)QB * C;
+    uint64_t *full_bar = tau + QB;
+    uint64_t *empty_bar = full_bar + stages;
+    uint64_t *q_bar = empty_bar + stages;
+    int *cnt = reinterpret_cast<int *>(q_bar + 1);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = ld / SCAN_CHUNK;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], SCAN_TILE_ROWS / 32);
+        }
+        mbar_init(q_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < QB) { cnt[tid] = 0; tau[tid] = KEY_INF; }
+    __syncthreads();
+
+    if (warp == SCAN_TILE_ROWS / 32) {
+        // ===== TMA producer warp =====
+        if (lane == 0) {
+            prefetch_tmap(&tmap);
+            mbar_arrive_expect_tx(q_bar, (uint32_t)(QB * ld * sizeof(float)));
+            bulk_load_1d(q_s, queries, (uint32_t)(QB * ld * sizeof(float)), q_bar);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                for (int c = 0; c < n_chunks; c++, it++) {
+                    int s = it % stages;
+                    uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], SCAN_STAGE_BYTES);
+                    tma_load_2d(stage_base + (size_t)s * SCAN_STAGE_BYTES, &tmap, c * SCAN_CHUNK,
+                                t * SCAN_TILE_ROWS, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps: thread r owns row r of every tile =====
+    const NamedBarrier bar{1, SCAN_TILE_ROWS};
+    mbar_wait(q_bar, 0);
+    const int r = tid;
+    const uint32_t row_off = (uint32_t)r * (SCAN_CHUNK * 4);
+    const uint32_t swz = (uint32_t)(r & 7);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        float acc[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; qi++) acc[qi] = 0.0f;
+        for (int c = 0; c < n_chunks; c++, it++) {
+            int s = it % stages;
+            uint32_t ph = (it / stages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            const uint8_t *sp = stage_base + (size_t)s * SCAN_STAGE_BYTES + row_off;
+            float4 xv[SCAN_CHUNK / 4];
+#pragma unroll
+            for (int j = 0; j < SCAN_CHUNK / 4; j++)
+                xv[j] = *reinterpret_cast<const float4 *>(sp + (((uint32_t)j ^ swz) << 4));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);   // row data is in registers: free the slot
+            const float *qc = q_s + c * SCAN_CHUNK;
+#pragma unroll
+            for (int j = 0; j < SCAN_CHUNK / 4; j++) {
+#pragma unroll
+                for (int qi = 0; qi < QB; qi++) {
+                    float4 qv = *reinterpret_cast<const float4 *>(qc + (size_t)qi * ld + j * 4);
+                    float a = acc[qi];
+                    a = metric_step<METRIC, FMA>(a, qv.x, xv[j].x);
+                    a = metric_step<METRIC, FMA>(a, qv.y, xv[j].y);
+                    a = metric_step<METRIC, FMA>(a, qv.z, xv[j].z);
+                    a = metric_step<METRIC, FMA>(a, qv.w, xv[j].w);
+                    acc[qi] = a;
+                }
+            }
+        }
+        // ---- selection for this tile ----
+        long long row = (long long)t * SCAN_TILE_ROWS + r;
+        bool live = row < n_rows;
+        if (live && skip != nullptr) live = skip[row] == 0;
+        bar.sync();   // appends of the previous tile are visible
+        unsigned need = 0;
+#pragma unroll
+        for (int qi = 0; qi < QB; qi++) need |= (cnt[qi] > C - SCAN_TILE_ROWS ? 1u : 0u) << qi;
+        bar.sync();   // everyone has taken the same decision before any count moves again
+#pragma unroll 1
+        for (int qi = 0; qi < QB; qi++) {
+            if (need & (1u << qi))
+                compact_topk(bufs + (size_t)qi * C, C, K, &cnt[qi], &tau[qi], tid, SCAN_TILE_ROWS, bar);
+        }
+#pragma unroll
+        for (int qi = 0; qi < QB; qi++) {
+            float dist = metric_finish<METRIC>(acc[qi]);
+            bool pass = live && !(threshold > 0.0f && dist > threshold);
+            if (pass) {
+                uint64_t key = make_key(dist, (uint32_t)row);
+                if (key < tau[qi]) {
+                    int slot = atomicAdd(&cnt[qi], 1);
+                    bufs[(size_t)qi * C + slot] = key;
+                }
+            }
+        }
+    }
+    // ---- CTA result: K smallest per query ----
+#pragma unroll 1
+    for (int qi = 0; qi < QB; qi++) {
+        compact_topk(bufs + (size_t)qi * C, C, K, &cnt[qi], &tau[qi], tid, SCAN_TILE_ROWS, bar);
+        int m = cnt[qi];
+        uint64_t *dst = part_keys + ((size_t)qi * gridDim.x + blockIdx.x) * K;
+        for (int i = tid; i < m; i += SCAN_TILE_ROWS) dst[i] = bufs[(size_t)qi * C + i];
+        if (tid == 0) part_counts[(size_t)qi * gridDim.x + blockIdx.x] = m;
+    }
+}
+
+static size_t scan_smem_bytes(int qb, int ld, int stages, int C) {
+    return (size_t)stages * SCAN_STAGE_BYTES + (size_t)qb * ld * 4 + (size_t)qb * C * 8 + (size_t)qb * 8 +
+           (size_t)(2 * stages + 1) * 8 + (size_t)qb * 4 + 16;
+}
+
+int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanLaunch *out) {
+    int C = next_pow2(K + 2 * SCAN_TILE_ROWS);
+    if (C < 512) C = 512;
+    size_t cap = max_smem_optin();
+    int qb = nq >= 8 ? 8 : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
+    int stages = 0;
+    for (;; qb >>= 1) {
+        // prefer a deep ring; shrink it, then the query block, until the CTA fits
+        for (stages = 8; stages >= 3; stages--)
+            if (scan_smem_bytes(qb, ld, stages, C) <= cap) break;
+        if (stages >= 3 || qb == 1) break;
+    }
+    if (stages < 3) return fail(CM_ERR_UNSUPPORTED, "k=%d with dim pad %d does not fit the scan kernel's shared memory", K, ld);
+    int64_t n_tiles = (n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    int grid = sm_count();
+    if (grid > n_tiles) grid = (int)(n_tiles > 0 ? n_tiles : 1);
+    out->metric = metric; out->fma = fma; out->qb = qb; out->stages = stages; out->grid = grid;
+    out->K = K; out->C = C; out->smem = scan_smem_bytes(qb, ld, stages, C);
+    return CM_OK;
+}
+
+template <int METRIC, bool FMA, int QB>
+static int launch_scan_t(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
+                         int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *part_keys,
+                         int *part_counts, cudaStream_t stream) {
+    auto kern = flat_scan_kernel<METRIC, FMA, QB>;
+    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    int n_tiles = (int)((n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS);
+    kern<<<L.grid, SCAN_THREADS, L.smem, stream>>>(tmap, queries, ld, (long long)n_rows, n_tiles, L.stages, skip,
+                                                   threshold, L.K, L.C, part_keys, part_counts);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+template <int METRIC, bool FMA>
+static int launch_scan_q(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
+                         int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc,
+                         cudaStream_t st) {
+    switch (L.qb) {
+    case 1: return launch_scan_t<METRIC, FMA, 1>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    case 2: return launch_scan_t<METRIC, FMA, 2>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    case 4: return launch_scan_t<METRIC, FMA, 4>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    case 8: return launch_scan_t<METRIC, FMA, 8>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    }
+    return fail(CM_ERR_INVALID_ARG, "bad query block %d", L.qb);
+}
+
+int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
+                     int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc,
+                     cudaStream_t st) {
+#define CM_SCAN_CASE(M)                                                                                  \
+    case M:                                                                                              \
+        return L.fma ? launch_scan_q<M, true>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st) \
+                     : launch_scan_q<M, false>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    switch (L.metric) {
+        CM_SCAN_CASE(CM_L2)
+        CM_SCAN_CASE(CM_L2SQ)
+        CM_SCAN_CASE(CM_COSINE)
+    }
+#undef CM_SCAN_CASE
+    return fail(CM_ERR_INVALID_ARG, "unknown metric %d", L.metric);
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge of per-CTA partial lists -> final sorted top-K per query
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
+    const uint64_t *__restrict__ part_keys, const int *__restrict__ part_counts, int parts, int Kp, int K, int C,
+    const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
+    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);
+    __shared__ int cnt;
+    __shared__ uint64_t tau;
+    const CtaBarrier bar;
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x;
+    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+    __syncthreads();
+    const uint64_t *pk = part_keys + (size_t)q * parts * Kp;
+    const int *pc = part_counts + (size_t)q * parts;
+    // walk the parts in groups whose worst-case appends fit the free space
+    int p = 0;
+    while (p < parts) {
+        int room = C - cnt;
+        uint64_t t = tau;
+        __syncthreads();   // same decision in every thread before counts move
+        int p_end = p, need = 0;
+        while (p_end < parts && need + pc[p_end] <= room) { need += pc[p_end]; p_end++; }
+        if (p_end == p) {   // no room for the next part: compact first
+            compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
+            continue;
+        }
+        for (int pp = p; pp < p_end; pp++) {
+            int m = pc[pp];
+            for (int i = tid; i < m; i += MERGE_THREADS) {
+                uint64_t key = pk[(size_t)pp * Kp + i];
+                if (key < t) buf[atomicAdd(&cnt, 1)] = key;
+            }
+        }
+        __syncthreads();
+        p = p_end;
+    }
+    compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
+    int m = cnt;
+    for (int i = tid; i < m; i += MERGE_THREADS) {
+        uint64_t key = buf[i];
+        uint32_t pos = key_pos(key);
+        size_t o = (size_t)q * out_stride + i;
+        out_ids[o] = row_ids[pos];
+        out_scores[o] = key_score(key);
+        if (out_pos) out_pos[o] = pos;
+    }
+    if (tid == 0) out_counts[q] = m;
+}
+
+int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int K,
+                      const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream) {
+    int C = next_pow2(K + Kp);
+    if (C < 2048) C = 2048;
+    size_t smem = (size_t)C * 8;
+    if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
+    CM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(part_keys, part_counts, parts, Kp, K, C, row_ids,
+                                                           (long long)out_stride, out_ids, out_scores,
+                                                           (long long *)out_pos, (long long *)out_counts);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-row helpers
+// ------------------------------------------------------------------------------------------------
+// distance.go:244-264 PreprocessInPlace / :269-290 Preprocess.  One thread per row, sequential.
+template <bool FMA>
+__global__ void preprocess_rows_kernel(int metric, const float *__restrict__ src, long long n, int dim, int ld_src,
+                                       float *__restrict__ dst, int ld_dst, int *__restrict__ zero_flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *s = src + (size_t)i * ld_src;
+    float *d = dst + (size_t)i * ld_dst;
+    float scale = 1.0f;
+    int zero = 0;
+    if (metric == CM_COSINE) {
+        float sum = 0.0f;
+        for (int j = 0; j < dim; j++) sum = dot_step<FMA>(sum, s[j], s[j]);
+        float norm = __fsqrt_rn(sum);
+        if (norm == 0.0f) zero = 1;
+        scale = __fdiv_rn(1.0f, norm);
+    }
+    if (zero_flags) zero_flags[i] = zero;
+    if (metric == CM_COSINE && !zero) {
+        for (int j = 0; j < dim; j++) d[j] = __fmul_rn(s[j], scale);
+    } else if (d != s) {
+        for (int j = 0; j < dim; j++) d[j] = s[j];
+    }
+    if (d != s || ld_dst > dim)
+        for (int j = dim; j < ld_dst; j++) d[j] = 0.0f;
+}
+
+int launch_preprocess_rows(int metric, bool fma, const float *src, int64_t n, int dim, int ld_src, float *dst,
+                           int ld_dst, int *zero_flags, cudaStream_t stream) {
+    if (n <= 0) return CM_OK;
+    int threads = 128;
+    long long blocks = (n + threads - 1) / threads;
+    if (fma)
+        preprocess_rows_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(metric, src, n, dim, ld_src, dst, ld_dst, zero_flags);
+    else
+        preprocess_rows_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(metric, src, n, dim, ld_src, dst, ld_dst, zero_flags);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+template <int METRIC, bool FMA>
+__global__ void distance_pairs_kernel(const float *__restrict__ a, const float *__restrict__ b, long long n, int dim,
+                                      float *__restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *x = a + (size_t)i * dim, *y = b + (size_t)i * dim;
+    float acc = 0.0f;
+    for (int j = 0; j < dim; j++) acc = metric_step<METRIC, FMA>(acc, x[j], y[j]);
+    out[i] = metric_finish<METRIC>(acc);
+}
+
+int launch_distance_pairs(int metric, bool fma, const float *a, const float *b, int64_t n, int dim, float *out,
+                          cudaStream_t stream) {
+    if (n <= 0) return CM_OK;
+    int threads = 128;
+    unsigned blocks = (unsigned)((n + threads - 1) / threads);
+#define CM_PAIR_CASE(M)                                                                           \
+    case M:                                                                                       \
+        if (fma) distance_pairs_kernel<M, true><<<blocks, threads, 0, stream>>>(a, b, n, dim, out); \
+        else distance_pairs_kernel<M, false><<<blocks, threads, 0, stream>>>(a, b, n, dim, out);    \
+        break;
+    switch (metric) {
+        CM_PAIR_CASE(CM_L2)
+        CM_PAIR_CASE(CM_L2SQ)
+        CM_PAIR_CASE(CM_COSINE)
+    default: return fail(CM_ERR_INVALID_ARG, "unknown metric %d", metric);
+    }
+#undef CM_PAIR_CASE
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+__global__ void build_skip_kernel(const uint32_t *__restrict__ row_ids, const uint8_t *__restrict__ deleted, long long n,
+                                  const uint32_t *__restrict__ filt, long long nf, uint8_t *__restrict__ skip) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t s = deleted ? deleted[i] : 0;
+    if (!s && nf > 0) {
+        uint32_t id = row_ids[i];
+        long long lo = 0, hi = nf;
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (filt[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        s = !(lo < nf && filt[lo] == id);
+    }
+    skip[i] = s;
+}
+
+int launch_build_skip(const uint32_t *row_ids, const uint8_t *deleted, int64_t n, const uint32_t *filter_sorted,
+                      int64_t nfilter, uint8_t *skip, cudaStream_t stream) {
+    if (n <= 0) return CM_OK;
+    int threads = 256;
+    unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    build_skip_kernel<<<blocks, threads, 0, stream>>>(row_ids, deleted, n, filter_sorted, nfilter, skip);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ rows, int ld, int dim, const long long *__restrict__ pos,
+                                   long long n, float *__restrict__ out) {
+    long long i = blockIdx.x;
+    if (i >= n) return;
+    const float *s = rows + (size_t)pos[i] * ld;
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) out[(size_t)i * dim + j] = s[j];
+}
+
+int launch_gather_rows(const float *rows, int ld, int dim, const int64_t *pos, int64_t n, float *out,
+                       cudaStream_t stream) {
+    if (n <= 0) return CM_OK;
+    gather_rows_kernel<<<(unsigned)n, 128, 0, stream>>>(rows, ld, dim, (const long long *)pos, n, out);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+}  // namespace cm

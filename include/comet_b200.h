@@ -1,0 +1,139 @@
+/*
+ * comet_b200.h -- C ABI of libcomet_b200.so: the B200 (sm_100a) device layer that replaces the
+ * arithmetic loops of wizenheimer/comet's vector search path.  This header is the drop-in
+ * boundary: every entry point below is what a cgo binding in comet's own Go package would call
+ * in place of the reference function it cites (file:line, relative to the reference root).
+ * INTEGRATION.md shows the Go side.
+ *
+ * Conventions
+ *   - every function returns an int status, CM_OK == 0; cm_last_error() returns a thread-local
+ *     message for the last non-zero status on the calling thread;
+ *   - no function keeps a caller pointer after it returns; outputs are caller-allocated;
+ *   - `*_search` entry points are re-entrant (the Go side holds idx.mu.RLock, e.g.
+ *     flat_index_search.go:222); mutators need external exclusion (the Go side holds idx.mu.Lock,
+ *     e.g. flat_index.go:171);
+ *   - host-pointer entry points copy host<->device themselves; `*_device` variants take device
+ *     pointers and a cudaStream_t (as void*) and enqueue without synchronising;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     CM_ERR_CUDA.
+ *
+ * Result order: ascending by (score, scan position) -- the reference's sort.Slice result up to
+ * groups of bit-equal scores (it is an unstable sort; for n <= 12 it is insertion sort and equals
+ * this order exactly).  Scores are bit-identical to the reference's sequential float32 loops.
+ */
+#ifndef COMET_B200_H
+#define COMET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* distance.go:21-38 DistanceKind "l2" | "l2_squared" | "cosine" */
+enum { CM_L2 = 0, CM_L2SQ = 1, CM_COSINE = 2 };
+
+enum {
+    CM_OK = 0,
+    CM_ERR_INVALID_ARG = 1,
+    CM_ERR_DIM_MISMATCH = 2, /* "query dimension mismatch: expected %d, got %d" flat_index_search.go:227 */
+    CM_ERR_ZERO_VECTOR = 3,  /* distance.go:9-12 ErrZeroVector */
+    CM_ERR_NOT_TRAINED = 4,  /* "index must be trained before searching" ivf_index_search.go:223 */
+    CM_ERR_NOT_FOUND = 5,    /* "vector with ID %d not found" flat_index.go:236 */
+    CM_ERR_CUDA = 6,
+    CM_ERR_UNSUPPORTED = 7,
+    CM_ERR_TOO_FEW = 8,      /* "need at least %d training vectors" ivf_index.go:211 */
+    CM_ERR_BUFFER_TOO_SMALL = 9
+};
+
+/* which device pipeline a flat search uses */
+enum {
+    CM_PATH_AUTO = 0,   /* exact scan for small batches, tensor-core candidate pass + exact re-score for large */
+    CM_PATH_EXACT = 1,  /* reference-order fp32 scan of every row */
+    CM_PATH_TENSOR = 2  /* bf16 tcgen05 Q x X^T candidate pass, then reference-order re-score */
+};
+
+/* how `sum += a*b` rounds: separately (gc on amd64, the default) or fused (gc on arm64) */
+enum { CM_ROUND_SEPARATE = 0, CM_ROUND_FMA = 1 };
+
+typedef struct {
+    int64_t k;                  /* WithK: <= 0 or > n means "all" (limiter.go:12-17 sanitizeK) */
+    float threshold;            /* WithThreshold: filters only when > 0 (flat_index_search.go:269) */
+    int32_t nprobes;            /* WithNProbes (IVF, IVFPQ): <= 0 or > nlist means nlist */
+    int32_t ef_search;          /* WithEfSearch (HNSW): <= 0 means the index default */
+    const uint32_t *filter_ids; /* WithDocumentIDs: NULL/0 means every document is eligible */
+    int64_t nfilter;
+    int32_t path;               /* CM_PATH_* (flat only) */
+    int32_t reserved;
+} cm_search_params;
+
+typedef struct cm_flat cm_flat;
+typedef struct cm_ivf cm_ivf;
+typedef struct cm_pq cm_pq;
+typedef struct cm_ivfpq cm_ivfpq;
+typedef struct cm_hnsw cm_hnsw;
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int cm_init(const int *device_ids, int n_devices); /* NULL/0: use the current device */
+void cm_shutdown(void);
+const char *cm_last_error(void);
+int cm_device_count(void);
+int cm_set_rounding(int mode);                     /* CM_ROUND_*; process-wide */
+int cm_get_rounding(void);
+const char *cm_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t cm_kernel_launches(void);
+/* pinned host memory for callers that want async copies (bench.py e2e leg) */
+int cm_host_alloc(void **ptr, size_t bytes);
+int cm_host_free(void *ptr);
+
+/* ---- distance.go --------------------------------------------------------------------------- */
+/* Distance.Calculate for n independent pairs a[i], b[i] (distance.go:114-121, 158-165, 201-216) */
+int cm_distance_pairs(int metric, const float *a, const float *b, int64_t n, int dim, float *out);
+/* Distance.PreprocessInPlace on n rows (distance.go:244-264); first zero vector -> CM_ERR_ZERO_VECTOR
+ * with *bad_row set (rows before it are normalised, like n successive calls) */
+int cm_preprocess_rows(int metric, float *rows, int64_t n, int dim, int64_t *bad_row);
+
+/* ---- flat_index.go / flat_index_search.go -------------------------------------------------- */
+int cm_flat_create(int dim, int metric, cm_flat **out);           /* NewFlatIndex flat_index.go:118 */
+int cm_flat_destroy(cm_flat *h);
+int cm_flat_reserve(cm_flat *h, int64_t n_rows);
+/* n successive FlatIndex.Add calls (flat_index.go:169-189).  `rows` is preprocessed IN PLACE
+ * (cosine normalises the caller's buffer) unless writeback == 0. */
+int cm_flat_add(cm_flat *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
+/* rows already resident on the device (device pointer, row-major n x dim) */
+int cm_flat_add_device(cm_flat *h, const uint32_t *ids_host, const float *rows_dev, int64_t n, void *stream);
+int cm_flat_remove(cm_flat *h, uint32_t id);                      /* flat_index.go:219-250 */
+int cm_flat_flush(cm_flat *h);                                    /* flat_index.go:266-299 */
+int64_t cm_flat_size(const cm_flat *h);                           /* len(idx.vectors), deleted included */
+int cm_flat_dim(const cm_flat *h);
+int cm_flat_metric(const cm_flat *h);
+/* lookupNodeVectors (flat_index_search.go:171-196): stored (preprocessed) vector of a live node */
+int cm_flat_get_vector(const cm_flat *h, uint32_t id, float *out);
+/* stored vectors by scan position (VectorResult.Node.Vector(), index_search.go:84-90) */
+int cm_flat_get_rows(const cm_flat *h, const int64_t *positions, int64_t n, float *out);
+/* nq independent searchSingleQuery calls (flat_index_search.go:221-294) in one device batch.
+ * out_ids/out_scores are nq x out_stride, out_counts[nq]; out_stride >= sanitizeK(k, n).
+ * out_pos (optional, nq x out_stride) receives scan positions. */
+int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                   int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                   int64_t *out_counts);
+int cm_flat_search_device(cm_flat *h, const float *queries_dev, int64_t nq, int dim,
+                          const cm_search_params *p, int64_t out_stride, uint32_t *out_ids_dev,
+                          float *out_scores_dev, int64_t *out_pos_dev, int64_t *out_counts_dev,
+                          void *stream);
+/* statistics of the last search on this handle (for bench.py / profiles): */
+typedef struct {
+    int32_t path_used;          /* CM_PATH_EXACT or CM_PATH_TENSOR */
+    int32_t passes;             /* scan launches over the corpus */
+    int64_t candidates;         /* tensor path: (query,row) pairs re-scored exactly */
+    int64_t fallback_queries;   /* tensor path: queries redone by the exact scan (candidate overflow) */
+    int64_t kernel_launches;
+} cm_flat_stats;
+int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
