@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the comet_b200 flat search path.
+
+Workload (BASELINE.json configs[1]): Flat Cosine, 1M x 768 float32 corpus, K=100, 512 queries per
+GPU per step; synthetic N(0,1) data, random-init (there is no dataset to download).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one device batch: every query of the batch is searched against the whole corpus
+(nq independent searchSingleQuery calls, flat_index_search.go:221-294) and its K best (id, score)
+pairs are produced.  N > 1 (under torchrun): the corpus is row-sharded over the ranks, every rank
+searches the global batch (512 x N queries) against its shard, per-shard top-K lists are
+all-gathered over NCCL and merged -- per-GPU work is constant, so `scaling` is "weak".
+
+`value`  : queries/s with queries already resident in HBM (CUDA events on the launching stream).
+`e2e`    : queries/s through cm_flat_search with HOST buffers (pinned): H2D of the queries and D2H
+           of ids/scores/counts inside the timed region.
+`--impl reference` times the CPU restatement of the reference's Go loops (oracle/, all host threads)
+on a bounded sample of the same workload (the Go toolchain does not exist in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, DIM, K, BATCH = 1_000_000, 768, 100, 512
+SEED = 20261017
+METRIC_NAME = "queries/sec @ recall@K (1Mx768, K=100)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("clock sampler: NVML unavailable:", e)
+            self._nvml = None
+            return self
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        nv = self._nvml
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def gen_rows_device(torch, n, d, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randn((n, d), generator=g, device=device, dtype=torch.float32)
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port), all host threads, bounded sample
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_run(x_host, q_host, k, threads, nq_sample):
+    """Returns (qps, seconds, ids, scores) for nq_sample queries against the full corpus."""
+    from oracle import oracle_py as O
+    O.set_threads(threads)
+    o = O.Flat(x_host.shape[1], O.COSINE)
+    t0 = time.perf_counter()
+    o.add(np.arange(1, x_host.shape[0] + 1, dtype=np.uint32), x_host)   # normalises in place, like Add
+    t_add = time.perf_counter() - t0
+    qs = np.ascontiguousarray(q_host[:nq_sample])
+    t0 = time.perf_counter()
+    ids, sc, cnt = o.search_batch(qs, k)
+    dt = time.perf_counter() - t0
+    return nq_sample / dt, dt, ids, sc, t_add, o
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(SEED)
+    # bounded sample: a 1/8 row sample of the corpus, scaled (the reference's cost is linear in N:
+    # one distance per row plus an N log N sort), so that steps x (cores queries) finish in minutes
+    n_s = N_ROWS // 8
+    x = rng.standard_normal((n_s, DIM), dtype=np.float32)
+    q = rng.standard_normal((max(cores, 1), DIM), dtype=np.float32)
+    from oracle import oracle_py as O
+    O.set_threads(cores)
+    o = O.Flat(DIM, O.COSINE)
+    o.add(np.arange(1, n_s + 1, dtype=np.uint32), x)
+    nq = len(q)
+    for _ in range(args.warmup):
+        o.search_batch(q, K)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.search_batch(q, K)
+    dt = (time.perf_counter() - t0) / args.steps
+    qps = nq / dt * (n_s / N_ROWS)
+    sample = (f"{nq} queries (one per host thread) x {n_s} rows (1/8 row sample of the 1M corpus, QPS scaled by 1/8: "
+              f"reference cost is linear in rows) per step; C restatement of the Go loops incl. the full sort")
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from comet_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    path = {"auto": capi.PATH_AUTO, "exact": capi.PATH_EXACT, "tensor": capi.PATH_TENSOR}[args.path]
+
+    # ---- corpus: rows [rank*shard, (rank+1)*shard) of the 1M x 768 matrix; ids = row + 1 ----
+    shard = N_ROWS // world
+    row0 = rank * shard
+    x = gen_rows_device(torch, shard, DIM, SEED + 1000 * rank, dev)
+    index = capi.FlatIndex(DIM, capi.COSINE)
+    index.add_device(np.arange(row0 + 1, row0 + shard + 1, dtype=np.uint32), x.data_ptr(), shard)
+    torch.cuda.synchronize()
+    x_host = None
+    if rank == 0 and not args.no_cpu_baseline:
+        x_host = x.cpu().numpy()
+    del x
+    torch.cuda.empty_cache()
+
+    nq = BATCH * world                      # global batch; every rank searches all of it on its shard
+    q_dev = gen_rows_device(torch, nq, DIM, SEED + 7, dev)
+    q_host_pinned = torch.empty((nq, DIM), dtype=torch.float32, pin_memory=True)
+    q_host_pinned.copy_(q_dev)
+    torch.cuda.synchronize()
+    q_np = q_host_pinned.numpy()
+
+    out_ids = torch.zeros((nq, K), dtype=torch.int32, device=dev)
+    out_sc = torch.zeros((nq, K), dtype=torch.float32, device=dev)
+    out_cnt = torch.zeros((nq,), dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    if world > 1:
+        g_ids = torch.zeros((world, nq, K), dtype=torch.int32, device=dev)
+        g_sc = torch.zeros((world, nq, K), dtype=torch.float32, device=dev)
+
+    def step_device():
+        index.search_device(q_dev.data_ptr(), nq, K, out_ids.data_ptr(), out_sc.data_ptr(), out_cnt.data_ptr(), K,
+                            stream=stream.cuda_stream, path=path)
+        if world > 1:
+            # the path's one exchange step: all-gather per-shard top-K, then K-way merge on device
+            dist.all_gather_into_tensor(g_ids, out_ids)
+            dist.all_gather_into_tensor(g_sc, out_sc)
+            capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, out_ids.data_ptr(),
+                                     out_sc.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    L.cm_profile_reset()
+    L.cm_profile_enable(1 if args.profile_kernels else 0)
+    launches0 = L.cm_kernel_launches()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.cm_kernel_launches() - launches0
+    L.cm_profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = nq / (ms_per_step * 1e-3)
+    stats = index.last_stats()
+
+    # ---- per-kernel roofline leg (separate short run so event pairs do not perturb `value`) -----
+    roof = None
+    if rank == 0:
+        L.cm_profile_reset(); L.cm_profile_enable(1)
+        for _ in range(max(2, min(args.steps, 5))):
+            step_device()
+        torch.cuda.synchronize()
+        L.cm_profile_enable(0)
+        hbm, tf_burst, tf_sus, which = measured_peaks()
+        scan_ms, scan_n = capi.profile_get(capi.PROF_FLAT_SCAN)
+        gemm_ms, gemm_n = capi.profile_get(capi.PROF_FLAT_GEMM)
+        resc_ms, resc_n = capi.profile_get(capi.PROF_RESCORE)
+        sel_ms, sel_n = capi.profile_get(capi.PROF_SELECT)
+        if gemm_n > 0:
+            per = gemm_ms / gemm_n * 1e-3
+            flops = 2.0 * nq * shard * DIM
+            ach = flops / per / 1e12
+            roof = {"kernel": "flat_gemm_tcgen05", "bound": "tensor", "achieved": ach, "peak": tf_sus,
+                    "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None, "peak_source": which + " (sustained bf16)",
+                    "avg_launch_ms": per * 1e3, "launches_timed": gemm_n}
+        elif scan_n > 0:
+            per = scan_ms / scan_n * 1e-3
+            qb = max(1, nq // max(1, scan_n // max(2, min(args.steps, 5))))
+            abytes = shard * DIM * 4 + qb * DIM * 4
+            ach = abytes / per / 1e9
+            roof = {"kernel": "flat_scan_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                    "frac": ach / hbm, "traffic": None, "peak_source": which, "avg_launch_ms": per * 1e3,
+                    "launches_timed": scan_n, "queries_per_launch": qb}
+        if roof is not None:
+            roof["step_share"] = {"scan_ms": scan_ms, "gemm_ms": gemm_ms, "rescore_ms": resc_ms, "select_ms": sel_ms}
+
+    # ---- e2e: host buffers through the public C ABI call ---------------------------------------
+    h_ids = np.zeros((nq, K), np.uint32)
+    h_sc = np.zeros((nq, K), np.float32)
+    h_cnt = np.zeros(nq, np.int64)
+    import ctypes as C
+    p, keep = capi.make_params(k=K, path=path)
+
+    def step_host():
+        capi.check(L.cm_flat_search(index.h, capi.ptr(q_np, capi.f32p), nq, DIM, C.byref(p), K,
+                                    capi.ptr(h_ids, capi.u32p), capi.ptr(h_sc, capi.f32p), None,
+                                    capi.ptr(h_cnt, capi.i64p)))
+        if world > 1:
+            # host-side callers merge shard results after gathering them; use the device exchange
+            out_ids.copy_(torch.from_numpy(h_ids.view(np.int32)), non_blocking=True)
+            out_sc.copy_(torch.from_numpy(h_sc), non_blocking=True)
+            dist.all_gather_into_tensor(g_ids, out_ids)
+            dist.all_gather_into_tensor(g_sc, out_sc)
+            capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, out_ids.data_ptr(),
+                                     out_sc.data_ptr(), stream.cuda_stream)
+            h_ids[...] = out_ids.cpu().numpy().view(np.uint32)
+            h_sc[...] = out_sc.cpu().numpy()
+
+    for _ in range(min(args.warmup, 3)):
+        step_host()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * DIM * 4),
+           "d2h_bytes_per_step": int(nq * K * 8 + nq * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+
+    # ---- CPU baseline + parity / recall of this very run (rank 0, N=1) -------------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and x_host is not None:
+        cores = os.cpu_count() or 1
+        nq_s = min(nq, max(cores, 8))
+        qps, dt, o_ids, o_sc, t_add, _o = cpu_reference_run(x_host, q_np, K, cores, nq_s)
+        cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{nq_s} of the {nq} queries against the full 1M x 768 corpus, one query per host thread, "
+                         f"{dt:.1f} s; C restatement of the Go loops (scalar, unfused, full N sort per query)"}
+        exact_ids = bool(np.array_equal(h_ids[:nq_s], o_ids[:, :K]))
+        exact_sc = bool(np.array_equal(h_sc[:nq_s].view(np.uint32), o_sc[:, :K].view(np.uint32)))
+        rec = float(np.mean([len(set(h_ids[i].tolist()) & set(o_ids[i, :K].tolist())) / K for i in range(nq_s)]))
+        parity = {"queries_checked": nq_s, "ids_bit_exact": exact_ids, "scores_bit_exact": exact_sc,
+                  "recall_at_k": rec}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K,
+                       "batch_per_gpu": BATCH, "global_batch": nq,
+                       "sharding": "single GPU" if world == 1 else f"rows/{world} per GPU + NCCL all-gather of per-shard top-K + merge",
+                       "path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
+                       "l2_policy": "inputs (3.07 GB corpus) larger than L2; no flush needed",
+                       "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="event-time kernels inside the main timed region too")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -49,6 +49,9 @@ SIGNATURES = {
     "cm_get_rounding": (C.c_int, []),
     "cm_version": (C.c_char_p, []),
     "cm_kernel_launches": (C.c_int64, []),
+    "cm_profile_enable": (C.c_int, [C.c_int]),
+    "cm_profile_reset": (C.c_int, []),
+    "cm_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_double), i64p]),
     "cm_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
     "cm_host_free": (C.c_int, [vp]),
     "cm_distance_pairs": (C.c_int, [C.c_int, f32p, f32p, C.c_int64, C.c_int, f32p]),
@@ -91,6 +94,15 @@ def lib():
         fn.argtypes = args
     _lib = L
     return L
+
+
+PROF_FLAT_SCAN, PROF_FLAT_GEMM, PROF_RESCORE, PROF_SELECT, PROF_IVF_SCAN, PROF_PQ_SCAN, PROF_HNSW, PROF_COARSE = range(8)
+
+
+def profile_get(cls):
+    ms, n = C.c_double(0), C.c_int64(0)
+    check(lib().cm_profile_get(cls, C.byref(ms), C.byref(n)))
+    return ms.value, n.value
 
 
 def check(rc):

@@ -34,6 +34,14 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory
         if (_rc != CM_OK) return _rc; \
     } while (0)
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+// leg).  Disabled by default: a scope costs nothing but a relaxed load.
+struct ProfScope {
+    int cls; cudaStream_t st; void *rec;
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+};
+
 int ensure_device();            // CM_OK when a CUDA device is usable
 int sm_count();
 int rounding_mode();            // CM_ROUND_*

@@ -181,6 +181,7 @@ static int launch_scan_t(const ScanLaunch &L, const CUtensorMap &tmap, const flo
     auto kern = flat_scan_kernel<METRIC, FMA, QB>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     int n_tiles = (int)((n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS);
+    ProfScope prof(CM_PROF_FLAT_SCAN, stream);
     kern<<<L.grid, SCAN_THREADS, L.smem, stream>>>(tmap, queries, ld, (long long)n_rows, n_tiles, L.stages, skip,
                                                    threshold, L.K, L.C, part_keys, part_counts);
     count_launch();
@@ -278,6 +279,7 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
     size_t smem = (size_t)C * 8;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
     CM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(CM_PROF_SELECT, stream);
     merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(part_keys, part_counts, parts, Kp, K, C, row_ids,
                                                            (long long)out_stride, out_ids, out_scores,
                                                            (long long *)out_pos, (long long *)out_counts);

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -70,6 +71,46 @@ int sm_count() { return g_sm_count; }
 size_t max_smem_optin() { return g_smem_optin; }
 int rounding_mode() { return g_rounding.load(); }
 
+// ---- per-kernel-class event timing -----------------------------------------------------------
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec *> g_prof_recs;
+static double g_prof_ms[CM_PROF_CLASSES];
+static int64_t g_prof_n[CM_PROF_CLASSES];
+
+ProfScope::ProfScope(int c, cudaStream_t s) : cls(c), st(s), rec(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec *r = new ProfRec();
+    r->cls = c;
+    cudaEventCreate(&r->e0);
+    cudaEventCreate(&r->e1);
+    cudaEventRecord(r->e0, s);
+    rec = r;
+}
+ProfScope::~ProfScope() {
+    if (!rec) return;
+    ProfRec *r = (ProfRec *)rec;
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+}
+static void prof_drain() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (ProfRec *r : g_prof_recs) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(r->e1) == cudaSuccess && cudaEventElapsedTime(&ms, r->e0, r->e1) == cudaSuccess &&
+            r->cls >= 0 && r->cls < CM_PROF_CLASSES) {
+            g_prof_ms[r->cls] += ms;
+            g_prof_n[r->cls] += 1;
+        }
+        cudaEventDestroy(r->e0);
+        cudaEventDestroy(r->e1);
+        delete r;
+    }
+    g_prof_recs.clear();
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -126,6 +167,25 @@ int cm_set_rounding(int mode) {
 int cm_get_rounding(void) { return cm::g_rounding.load(); }
 const char *cm_version(void) { return "comet_b200 0.1 (sm_100a)"; }
 int64_t cm_kernel_launches(void) { return cm::g_kernel_launches.load(); }
+int cm_profile_enable(int on) {
+    cm::prof_drain();
+    cm::g_prof_on.store(on ? 1 : 0);
+    return CM_OK;
+}
+int cm_profile_reset(void) {
+    cm::prof_drain();
+    std::lock_guard<std::mutex> lk(cm::g_prof_mu);
+    for (int i = 0; i < CM_PROF_CLASSES; i++) { cm::g_prof_ms[i] = 0.0; cm::g_prof_n[i] = 0; }
+    return CM_OK;
+}
+int cm_profile_get(int kernel_class, double *total_ms, int64_t *launches) {
+    if (kernel_class < 0 || kernel_class >= CM_PROF_CLASSES) return cm::fail(CM_ERR_INVALID_ARG, "bad kernel class");
+    cm::prof_drain();
+    std::lock_guard<std::mutex> lk(cm::g_prof_mu);
+    if (total_ms) *total_ms = cm::g_prof_ms[kernel_class];
+    if (launches) *launches = cm::g_prof_n[kernel_class];
+    return CM_OK;
+}
 int cm_host_alloc(void **ptr, size_t bytes) {
     CM_TRY(cm::ensure_device());
     CM_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));

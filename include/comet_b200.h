@@ -84,6 +84,21 @@ int cm_get_rounding(void);
 const char *cm_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t cm_kernel_launches(void);
+/* per-kernel-class device timing (CUDA events on the launching stream); off by default */
+enum {
+    CM_PROF_FLAT_SCAN = 0,   /* exact flat scan (flat_scan_kernel) */
+    CM_PROF_FLAT_GEMM = 1,   /* tcgen05 bf16 candidate pass */
+    CM_PROF_RESCORE = 2,     /* reference-order re-score of candidates */
+    CM_PROF_SELECT = 3,      /* top-K merge / selection */
+    CM_PROF_IVF_SCAN = 4,
+    CM_PROF_PQ_SCAN = 5,
+    CM_PROF_HNSW = 6,
+    CM_PROF_COARSE = 7,
+    CM_PROF_CLASSES = 8
+};
+int cm_profile_enable(int on);
+int cm_profile_reset(void);
+int cm_profile_get(int kernel_class, double *total_ms, int64_t *launches);
 /* pinned host memory for callers that want async copies (bench.py e2e leg) */
 int cm_host_alloc(void **ptr, size_t bytes);
 int cm_host_free(void *ptr);
