@@ -7,6 +7,7 @@
 //   deleted  u8   [cap]       1 when the row's ID is in the soft-delete set (flat_index.go:87);
 //   rows_bf16 / norms         shadow copy for the tensor-core candidate pass (flat_tensor.cu).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -244,7 +245,8 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
 
     // 3. pick the pipeline
     int path = p->path;
-    if (path == CM_PATH_AUTO) path = tensor_path_eligible(nq, k_eff, skip != nullptr, p->threshold) ? CM_PATH_TENSOR : CM_PATH_EXACT;
+    if (path == CM_PATH_AUTO)
+        path = tensor_path_eligible(nq, k_eff, p->filter_ids && p->nfilter > 0, p->threshold) ? CM_PATH_TENSOR : CM_PATH_EXACT;
     int rc = CM_OK;
     if (path == CM_PATH_TENSOR) {
         rc = search_tensor(qp, nq, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
@@ -369,6 +371,7 @@ int cm_flat_create(int dim, int metric, cm_flat **out) {
     h->ix.dim = dim;
     h->ix.ld = (dim + cm::SCAN_CHUNK - 1) / cm::SCAN_CHUNK * cm::SCAN_CHUNK;
     h->ix.metric = metric;
+    if (const char *cg = getenv("COMET_B200_CTA_GROUP")) h->ix.tensor_cta_group = atoi(cg) == 1 ? 1 : 2;
     cudaGetDevice(&h->ix.device);
     *out = h;
     return CM_OK;
@@ -505,7 +508,34 @@ int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const 
     cudaError_t e = cudaStreamSynchronize(st);
     cm::release_stream(st);
     if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "flat_search: %s", cudaGetErrorString(e));
-    return rc;
+    if (rc != CM_OK) return rc;
+    // tensor path: a query whose candidate list overflowed (count -1) is redone by the exact scan
+    std::vector<int64_t> redo;
+    for (int64_t q = 0; q < nq; q++)
+        if (out_counts[q] < 0) redo.push_back(q);
+    if (!redo.empty()) {
+        cm_search_params pe = *p;
+        pe.path = CM_PATH_EXACT;
+        size_t m = redo.size();
+        std::vector<float> rq(m * (size_t)dim);
+        std::vector<uint32_t> rid(m * (size_t)out_stride);
+        std::vector<float> rsc(m * (size_t)out_stride);
+        std::vector<int64_t> rpos(out_pos ? m * (size_t)out_stride : 0), rcnt(m);
+        for (size_t i = 0; i < m; i++) memcpy(&rq[i * dim], queries + (size_t)redo[i] * dim, (size_t)dim * 4);
+        CM_TRY(cm_flat_search(h, rq.data(), (int64_t)m, dim, &pe, out_stride, rid.data(), rsc.data(),
+                              out_pos ? rpos.data() : nullptr, rcnt.data()));
+        for (size_t i = 0; i < m; i++) {
+            size_t o = (size_t)redo[i] * out_stride;
+            memcpy(out_ids + o, &rid[i * out_stride], (size_t)out_stride * 4);
+            memcpy(out_scores + o, &rsc[i * out_stride], (size_t)out_stride * 4);
+            if (out_pos) memcpy(out_pos + o, &rpos[i * out_stride], (size_t)out_stride * 8);
+            out_counts[redo[i]] = rcnt[i];
+        }
+        std::lock_guard<std::mutex> lk(h->ix.stats_mu);
+        h->ix.last_stats.path_used = CM_PATH_TENSOR;
+        h->ix.last_stats.fallback_queries = (int64_t)m;
+    }
+    return CM_OK;
 }
 
 int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out) {

@@ -28,11 +28,14 @@ struct FlatIndex {
     int64_t n_deleted_rows = 0;
 
     // tensor-core candidate pass state (flat_tensor.cu)
-    __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ld] bf16 shadow of rows
-    float *row_sqnorm = nullptr;            // [cap] ||x||^2 (fp32, any order: only used for the bound)
+    __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ldb] bf16 shadow of rows, ldb = dim padded to 64
+    float *row_h = nullptr;                 // [cap] |x|^2 / 2 for L2 / L2^2, 0 for cosine (candidate key offset)
+    unsigned int *max_norm_bits = nullptr;  // device: bits of max_row |x| (rounded up), feeds the error bound
+    int ldb = 0;
     int64_t shadow_rows = 0;                // rows [0, shadow_rows) of the shadow are current
     int64_t shadow_cap = 0;
-    float max_row_norm = 0.0f;
+    int tensor_cta_group = 2;               // 2: CTA pairs (UMMA M=256), 1: single-CTA UMMA M=128
+    std::mutex shadow_mu;
     CUtensorMap tmap_bf16;
 
     std::mutex stats_mu;
@@ -60,6 +63,7 @@ struct FlatIndex {
                       int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                       int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats);
     void free_shadow();
+    int ensure_shadow(cudaStream_t st);
 };
 
 }  // namespace cm

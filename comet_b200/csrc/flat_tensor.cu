@@ -1,19 +1,636 @@
-// flat_tensor.cu -- tensor-core candidate pass (placeholder until the tcgen05 kernel lands).
+// flat_tensor.cu -- batched flat search on the 5th-gen tensor cores: a bf16 tcgen05 Q x X^T
+// candidate pass with a PROVED error bound, then the reference-order fp32 re-score of the few
+// surviving candidates, so results stay bit-identical to flatIndexSearch.searchSingleQuery
+// (flat_index_search.go:221-294) while the corpus is streamed once per batch instead of once per
+// 8 queries.
+//
+// Why the result is exact.  Let s(q,x) be the reference score (distance.go:114-121/158-165/201-216,
+// sequential fp32) and a~(q,x) = h_x - dot_bf16(q,x) the tensor-core key (h_x = |x|^2/2 for L2/L2^2,
+// 0 for cosine; smaller = closer).  bf16 rounding (unit roundoff 2^-8 per operand), fp32 tensor
+// accumulation and the reference's own rounding together move a~ away from the order the reference
+// sorts by by at most
+//     E_q = 1.02 * (0.0078278 * |q| * X + (d + 4) * 2^-22 * (|q| + X)^2),   X = max_row |x|.
+// If tau is the K-th smallest a~ over ANY subset of the rows, every row of the reference's top-K
+// has a~ <= tau + 2 E_q.  The pass therefore runs in up to three phases over disjoint row samples
+// (A: everything is a candidate; B, C: only keys under the bound from the previous phases), a final
+// selection keeps the keys <= tau_final + 2 E_q, and those rows (a few hundred per query on
+// N(0,1) data) are re-scored in reference order and sorted by (score, scan position) -- the same
+// order the exact scan produces.  Candidate-list overflow (adversarial ties) is detected and those
+// queries are redone by the exact scan: never a silent approximation.
+//
+// Kernel shape (flat_gemm_kernel): persistent, warp-specialised, one CTA per SM or one CTA PAIR
+// (cta_group::2, UMMA M=256) per two SMs.  Per CTA: 128 corpus rows x 256 queries per accumulator,
+// two accumulators in TMEM (512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+// operands arrive by TMA (SWIZZLE_128B, 64 bf16 per row) through an mbarrier ring.
+#include <algorithm>
+#include <cmath>
+
 #include "flat_index.cuh"
+#include "flat_kernels.cuh"
+#include "select.cuh"
+#include "tcgen05.cuh"
 
 namespace cm {
 
-bool FlatIndex::tensor_path_eligible(int64_t, int64_t, bool, float) const { return false; }
+static constexpr int GT_ROWS = 128;        // corpus rows per CTA per tile (TMEM lanes)
+static constexpr int GT_QBLK = 256;        // queries per accumulator (UMMA N)
+static constexpr int GT_BK = 64;           // bf16 per k-step: one 128-byte swizzle atom
+static constexpr int GT_THREADS = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
+static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
+static constexpr int CAND_SLOTS = 512;     // candidate slots per (query, CTA) region
+static constexpr int RS_CAP = 2048;        // candidates re-scored per query
 
-int FlatIndex::search_tensor(const float *, int64_t, int64_t, const uint8_t *, float, int64_t, uint32_t *, float *,
-                             int64_t *, int64_t *, cudaStream_t, cm_flat_stats *) {
-    return fail(CM_ERR_UNSUPPORTED, "tensor path not built yet");
+struct GemmPhase {
+    int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
+    int SA, SB;
+    int n_tiles;      // tiles in this class
+};
+
+__device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
+    switch (p.cls) {
+    case 0: return i * p.SA;
+    case 1: { int R = p.SA / p.SB; int j = i + i / (R - 1) + 1; return j * p.SB; }
+    case 2: return i + i / (p.SB - 1) + 1;
+    default: return i;
+    }
 }
 
+template <int CG>
+__global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
+    const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q, GemmPhase phase,
+    int n_qblk, int k_blocks, int stages, long long n_rows, const float *__restrict__ row_h,
+    const uint8_t *__restrict__ skip, const float *__restrict__ g_bound, int nq_pad, int cand_slots,
+    int n_cta_total, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
+    constexpr int B_ROWS = GT_QBLK / CG;                 // query rows this CTA stages per k-step
+    constexpr int B_BYTES = B_ROWS * GT_BK * 2;
+    constexpr int STAGE_BYTES = GT_A_BYTES + B_BYTES;
+    constexpr uint32_t IDESC = tc::make_idesc_bf16(GT_ROWS * CG, GT_QBLK);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *stage_base = smem;
+    float *g_s = reinterpret_cast<float *>(smem + (size_t)stages * STAGE_BYTES);
+    int *cnt_s = reinterpret_cast<int *>(g_s + GT_MAX_NQ);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(cnt_s + GT_MAX_NQ);
+    uint64_t *empty_bar = full_bar + stages;
+    uint64_t *tfull_bar = empty_bar + stages;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t cta_rank = (CG == 2) ? tc::cluster_ctarank() : 0u;
+    const int cluster = (CG == 2) ? (int)tc::cluster_id_x() : (int)blockIdx.x;
+    const int n_clusters = (CG == 2) ? (int)tc::nclusters_x() : (int)gridDim.x;
+    const int n_work = phase.n_tiles * n_qblk;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8 * CG); }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < nq_pad; i += GT_THREADS) {
+        g_s[i] = g_bound[i];
+        cnt_s[i] = cand_cnt[(size_t)blockIdx.x * nq_pad + i];
+    }
+    if (warp == 2) tc::tmem_alloc<CG>(smem_u32(tmem_slot), 512);
+    tc::fence_before_thread_sync();
+    if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            prefetch_tmap(&tmap_x);
+            prefetch_tmap(&tmap_q);
+            uint32_t it = 0;
+            for (int w = cluster; w < n_work; w += n_clusters) {
+                int t = phase_tile(phase, w / n_qblk), nb = w % n_qblk;
+                int row0 = t * (GT_ROWS * CG) + (int)cta_rank * GT_ROWS;
+                int q0 = nb * GT_QBLK + (int)cta_rank * B_ROWS;
+                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                    int s = it % stages;
+                    uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint32_t bar = smem_u32(&full_bar[s]);
+                    if (CG == 2) bar = tc::mapa(bar, 0);
+                    if (cta_rank == 0) tc::mbar_arrive_expect_tx_addr(smem_u32(&full_bar[s]), STAGE_BYTES * CG);
+                    uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+                    tc::tma_load_2d_cg<CG>(sa, &tmap_x, kb * GT_BK, row0, bar);
+                    tc::tma_load_2d_cg<CG>(sa + GT_A_BYTES, &tmap_q, kb * GT_BK, q0, bar);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (one lane of the leader CTA) =====
+        if (cta_rank == 0 && lane == 0) {
+            uint32_t it = 0, wi = 0;
+            for (int w = cluster; w < n_work; w += n_clusters, wi++) {
+                uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                tc::fence_after_thread_sync();
+                uint32_t d_tmem = tmem_base + acc * GT_QBLK;
+                for (int kb = 0; kb < k_blocks; kb++, it++) {
+                    int s = it % stages;
+                    uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc::fence_after_thread_sync();
+                    uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+                    uint64_t adesc = tc::make_smem_desc_sw128(sa);
+                    uint64_t bdesc = tc::make_smem_desc_sw128(sa + GT_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GT_BK / 16; k++) {
+                        // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in 16-byte units
+                        tc::mma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
+                                         (uint32_t)((kb | k) != 0));
+                    }
+                    tc::mma_commit<CG>(smem_u32(&empty_bar[s]));       // frees the smem slot (both CTAs)
+                }
+                tc::mma_commit<CG>(smem_u32(&tfull_bar[acc]));         // accumulator ready (both CTAs)
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps; thread = one corpus row (TMEM lane) x 128 of the 256 query columns =====
+        const int ew = warp & 3, half = (warp - 4) >> 2;
+        uint32_t wi = 0;
+        uint32_t tempty0 = smem_u32(&tempty_bar[0]), tempty1 = smem_u32(&tempty_bar[1]);
+        if (CG == 2) { tempty0 = tc::mapa(tempty0, 0); tempty1 = tc::mapa(tempty1, 0); }
+        uint64_t *my_cand = cand + (size_t)blockIdx.x * cand_slots;   // + q * n_cta_total * cand_slots
+        const size_t q_stride = (size_t)n_cta_total * cand_slots;
+        for (int w = cluster; w < n_work; w += n_clusters, wi++) {
+            uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
+            int t = phase_tile(phase, w / n_qblk), nb = w % n_qblk;
+            long long row = (long long)t * (GT_ROWS * CG) + (long long)cta_rank * GT_ROWS + ew * 32 + lane;
+            bool row_ok = row < n_rows;
+            float hx = row_ok ? row_h[row] : 0.0f;
+            if (row_ok && skip != nullptr) row_ok = skip[row] == 0;
+            const int qbase = nb * GT_QBLK + half * (GT_QBLK / 2);
+            const float *g = g_s + qbase;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc::fence_after_thread_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_QBLK + half * (GT_QBLK / 2);
+            uint32_t v[2][32];
+            tc::tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+            for (int cb = 0; cb < GT_QBLK / 64; cb++) {
+                tc::tmem_ld_wait();
+                if (cb + 1 < GT_QBLK / 64) tc::tmem_ld_32x32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
+                const uint32_t(&vv)[32] = v[cb & 1];
+                float m = -INFINITY;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++) {
+                    float4 gg = *reinterpret_cast<const float4 *>(g + cb * 32 + c4 * 4);
+                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 0]) - gg.x);
+                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 1]) - gg.y);
+                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 2]) - gg.z);
+                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 3]) - gg.w);
+                }
+                if (m >= hx && row_ok) {
+                    // some (row, query) pair of this 32-column strip is a candidate: append it to this
+                    // CTA's private region of the query's list (shared-memory counter, no global atomics)
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        float dot = __uint_as_float(vv[c]);
+                        if (dot - g[cb * 32 + c] >= hx) {
+                            int q = qbase + cb * 32 + c;
+                            int slot = atomicAdd(&cnt_s[q], 1);
+                            if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(hx - dot, (uint32_t)row);
+                        }
+                    }
+                }
+            }
+            tc::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(acc ? tempty1 : tempty0);
+        }
+    }
+
+    // ---- teardown: nobody exits (or frees TMEM) while the peer may still touch this CTA ----
+    tc::fence_before_thread_sync();
+    if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
+    for (int i = tid; i < nq_pad; i += GT_THREADS) cand_cnt[(size_t)blockIdx.x * nq_pad + i] = cnt_s[i];
+    if (warp == 2) {
+        tc::fence_after_thread_sync();
+        tc::tmem_dealloc<CG>(tmem_base, 512);
+    }
+}
+
+static size_t gemm_smem_bytes(int cg, int stages) {
+    size_t stage = GT_A_BYTES + (size_t)(GT_QBLK / cg) * GT_BK * 2;
+    return (size_t)stages * stage + (size_t)GT_MAX_NQ * 8 + (size_t)(2 * stages + 4) * 8 + 16;
+}
+
+template <int CG>
+static int launch_gemm_t(const CUtensorMap &tx, const CUtensorMap &tq, const GemmPhase &ph, int n_qblk, int k_blocks,
+                         int64_t n_rows, const float *row_h, const uint8_t *skip, const float *g_bound, int nq_pad,
+                         uint64_t *cand, int *cand_cnt, cudaStream_t st) {
+    int stages = CG == 2 ? 6 : 4;
+    size_t smem = gemm_smem_bytes(CG, stages);
+    auto kern = flat_gemm_kernel<CG>;
+    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n_work = ph.n_tiles * n_qblk;
+    if (n_work <= 0) return CM_OK;
+    int clusters = std::min(sm_count() / CG, n_work);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(GT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(CM_PROF_FLAT_GEMM, st);
+    CM_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tq, ph, n_qblk, k_blocks, stages, (long long)n_rows, row_h, skip,
+                               g_bound, nq_pad, (int)CAND_SLOTS, sm_count(), cand, cand_cnt));
+    count_launch();
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shadow copies: rows -> bf16 + h_x + max norm; queries -> bf16 + |q|
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&p);
+}
+
+// one warp per row; src [n][ld_src] fp32 (ld_src % 4 == 0), dst [n][ldb] bf16 zero padded
+__global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long n, int dim, int ld_src,
+                                    __nv_bfloat16 *__restrict__ dst, int ldb, float h_scale,
+                                    float *__restrict__ out_h, float *__restrict__ out_norm,
+                                    unsigned int *__restrict__ max_norm_bits) {
+    long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float *s = src + (size_t)row * ld_src;
+    uint2 *d = reinterpret_cast<uint2 *>(dst + (size_t)row * ldb);
+    float sq = 0.0f;
+    for (int j = lane * 4; j < ldb; j += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j + 3 < dim) v = *reinterpret_cast<const float4 *>(s + j);
+        else {
+            if (j < dim) v.x = s[j];
+            if (j + 1 < dim) v.y = s[j + 1];
+            if (j + 2 < dim) v.z = s[j + 2];
+        }
+        sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        d[j >> 2] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) {
+        float nrm = sqrtf(sq) * 1.00001f;
+        if (out_h) out_h[row] = h_scale * sq;
+        if (out_norm) out_norm[row] = nrm;
+        if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));
+    }
+}
+
+static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv_bfloat16 *dst, int ldb, float h_scale,
+                          float *out_h, float *out_norm, unsigned int *max_norm_bits, cudaStream_t st) {
+    if (n <= 0) return CM_OK;
+    int threads = 256;
+    long long blocks = (n * 32 + threads - 1) / threads;
+    to_bf16_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n, dim, ld_src, dst, ldb, h_scale, out_h, out_norm,
+                                                              max_norm_bits);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// candidate selection: K-th smallest key (radix select on the ordered score bits) -> next bound
+// ------------------------------------------------------------------------------------------------
+// block per query.  The query's candidates live in n_cta regions of `slots` keys (one per GEMM CTA).
+// final == 0: g[q] = -(tau_K + 2E) for the next phase.  final == 1: additionally compact the rows
+// with key <= tau_K + 2E into rs[q][*] for the exact re-score.
+__global__ void __launch_bounds__(256) cand_select_kernel(const uint64_t *__restrict__ cand, const int *__restrict__ cand_cnt,
+                                                          int nq_pad, int n_cta, int slots, int K, int dim,
+                                                          const float *__restrict__ q_norm,
+                                                          const unsigned int *__restrict__ max_norm_bits,
+                                                          float *__restrict__ g, int *__restrict__ overflow, int final,
+                                                          uint32_t *__restrict__ rs, int *__restrict__ rs_cnt, int rs_cap) {
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_rank, s_out, s_total, s_ovf;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { s_total = 0; s_ovf = overflow[q]; s_out = 0; }
+    __syncthreads();
+    for (int r = tid; r < n_cta; r += 256) {
+        int c = cand_cnt[(size_t)r * nq_pad + q];
+        if (c > slots) s_ovf = 1;
+        atomicAdd(&s_total, min(c, slots));
+    }
+    __syncthreads();
+    if (s_ovf) {
+        if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; if (final) rs_cnt[q] = 0; }
+        return;
+    }
+    const uint64_t *qcand = cand + (size_t)q * n_cta * slots;
+    // visit every key of this query: warp per region, lanes over the region's keys
+    auto for_each_key = [&](auto &&fn) {
+        for (int r = warp; r < n_cta; r += 8) {
+            int c = cand_cnt[(size_t)r * nq_pad + q];
+            const uint64_t *keys = qcand + (size_t)r * slots;
+            for (int i = lane; i < c; i += 32) fn(keys[i]);
+        }
+    };
+    float bound = INFINITY;
+    if (s_total >= K) {
+        // radix select: 4 passes of 8 bits, most significant first, over the high 32 key bits
+        if (tid == 0) { s_prefix = 0; s_rank = K; }
+        for (int pass = 0; pass < 4; pass++) {
+            int shift = 24 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            uint32_t prefix = s_prefix;
+            uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for_each_key([&](uint64_t key) {
+                uint32_t hi = (uint32_t)(key >> 32);
+                if ((hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255], 1);
+            });
+            __syncthreads();
+            if (tid == 0) {
+                int r = s_rank, b = 0;
+                for (; b < 255; b++) {
+                    if (r <= hist[b]) break;
+                    r -= hist[b];
+                }
+                s_rank = r;
+                s_prefix = prefix | ((uint32_t)b << shift);
+            }
+            __syncthreads();
+        }
+        float tau = ordered_to_float(s_prefix);
+        float nq = q_norm[q], X = __uint_as_float(*max_norm_bits);
+        float E = 1.02f * (0.0078278f * nq * X + (float)(dim + 4) * 2.3841858e-07f * (nq + X) * (nq + X));
+        bound = tau + 2.0f * E;
+        bound = bound + fabsf(bound) * 1e-6f;
+    }
+    if (tid == 0) g[q] = -bound;
+    if (!final) return;
+    for_each_key([&](uint64_t key) {
+        if (key_score(key) <= bound) {
+            int slot = atomicAdd(&s_out, 1);
+            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(key);
+        }
+    });
+    __syncthreads();
+    if (tid == 0) {
+        if (s_out > rs_cap) { overflow[q] = 1; rs_cnt[q] = 0; }
+        else rs_cnt[q] = s_out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact re-score of the candidates in reference order (distance.go loops), 128 candidates per block
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, bool FMA>
+__global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
+                                                      const uint32_t *__restrict__ rs, const int *__restrict__ rs_cnt,
+                                                      int rs_cap, float threshold, uint64_t *__restrict__ out_keys,
+                                                      int *__restrict__ out_cnt) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *q_s = reinterpret_cast<float *>(smem);                    // [ld]
+    uint8_t *stage = smem + (size_t)ld * 4;                          // [2][128 rows][128 B], 16-byte pieces XOR-swizzled
+    __shared__ uint32_t pos_s[128];
+    const int q = blockIdx.y, tid = threadIdx.x;
+    const int cnt = min(rs_cnt[q], rs_cap);
+    const int base = blockIdx.x * 128;
+    if (base >= cnt) return;
+    const int mine = base + tid;
+    const bool live = mine < cnt;
+    const uint32_t pos = rs[(size_t)q * rs_cap + (live ? mine : base)];
+    pos_s[tid] = pos;
+    for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
+    __syncthreads();
+    const int n_chunks = ld / 32;
+    auto issue = [&](int c) {
+        uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            int idx = p * 128 + tid;
+            int r = idx >> 3, piece = idx & 7;
+            const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
+            uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    float acc = 0.0f;
+    for (int c = 0; c < n_chunks; c++) {
+        if (c + 1 < n_chunks) {
+            issue(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
+        const float *qc = q_s + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
+            float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
+            acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+            acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+            acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+            acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+        }
+        __syncthreads();
+    }
+    float dist = metric_finish<METRIC>(acc);
+    if (live && !(threshold > 0.0f && dist > threshold)) {
+        int slot = atomicAdd(&out_cnt[q], 1);
+        out_keys[(size_t)q * rs_cap + slot] = make_key(dist, pos);
+    }
+}
+
+static int launch_rescore(int metric, bool fma, const float *rows, int ld, const float *queries, int nq,
+                          const uint32_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
+                          cudaStream_t st) {
+    dim3 grid(RS_CAP / 128, (unsigned)nq);
+    size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
+    ProfScope prof(CM_PROF_RESCORE, st);
+#define CM_RS_CASE(M)                                                                                                 \
+    case M:                                                                                                           \
+        if (fma) {                                                                                                    \
+            CM_CUDA(cudaFuncSetAttribute(rescore_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            rescore_kernel<M, true><<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt); \
+        } else {                                                                                                      \
+            CM_CUDA(cudaFuncSetAttribute(rescore_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            rescore_kernel<M, false><<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt); \
+        }                                                                                                             \
+        break;
+    switch (metric) {
+        CM_RS_CASE(CM_L2)
+        CM_RS_CASE(CM_L2SQ)
+        CM_RS_CASE(CM_COSINE)
+    default: return fail(CM_ERR_INVALID_ARG, "unknown metric %d", metric);
+    }
+#undef CM_RS_CASE
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+__global__ void init_bounds_kernel(float *__restrict__ g, int nq, int nq_pad) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq_pad) g[q] = q < nq ? -INFINITY : INFINITY;
+}
+
+// queries that overflowed a candidate list get count -1 (the host entry point redoes them exactly)
+__global__ void mark_overflow_kernel(const int *__restrict__ overflow, int nq, long long *__restrict__ out_counts) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && overflow[q]) out_counts[q] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FlatIndex glue
+// ------------------------------------------------------------------------------------------------
 void FlatIndex::free_shadow() {
     cudaFree(rows_bf16);
-    cudaFree(row_sqnorm);
-    rows_bf16 = nullptr; row_sqnorm = nullptr; shadow_rows = shadow_cap = 0;
+    cudaFree(row_h);
+    cudaFree(max_norm_bits);
+    rows_bf16 = nullptr; row_h = nullptr; max_norm_bits = nullptr;
+    shadow_rows = shadow_cap = 0;
+}
+
+int FlatIndex::ensure_shadow(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(shadow_mu);
+    if (rows_bf16 && shadow_rows == n && shadow_cap == cap) return CM_OK;
+    ldb = (dim + GT_BK - 1) / GT_BK * GT_BK;
+    if (!rows_bf16 || shadow_cap != cap) {
+        free_shadow();
+        CM_CUDA(cudaMalloc(&rows_bf16, (size_t)cap * ldb * sizeof(__nv_bfloat16)));
+        CM_CUDA(cudaMalloc(&row_h, (size_t)cap * sizeof(float)));
+        CM_CUDA(cudaMalloc(&max_norm_bits, sizeof(unsigned int)));
+        CM_CUDA(cudaMemsetAsync(max_norm_bits, 0, sizeof(unsigned int), st));
+        shadow_cap = cap;
+        shadow_rows = 0;
+        CM_TRY(make_tmap_2d(&tmap_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_bf16, (uint64_t)ldb, (uint64_t)cap,
+                            (uint64_t)ldb * 2, GT_BK, GT_ROWS, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    if (shadow_rows == 0) CM_CUDA(cudaMemsetAsync(max_norm_bits, 0, sizeof(unsigned int), st));
+    float h_scale = metric == CM_COSINE ? 0.0f : 0.5f;
+    CM_TRY(launch_to_bf16(rows + (size_t)shadow_rows * ld, n - shadow_rows, dim, ld, rows_bf16 + (size_t)shadow_rows * ldb,
+                          ldb, h_scale, row_h + shadow_rows, nullptr, max_norm_bits, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    shadow_rows = n;
+    return CM_OK;
+}
+
+bool FlatIndex::tensor_path_eligible(int64_t nq, int64_t k_eff, bool has_filter, float) const {
+    return nq >= 64 && k_eff <= 256 && n >= 65536 && !has_filter;
+}
+
+int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
+                             int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                             int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
+    if (k_eff > RS_CAP / 2) return fail(CM_ERR_UNSUPPORTED, "tensor path supports k <= %d", RS_CAP / 2);
+    CM_TRY(ensure_shadow(st));
+    const int cg = tensor_cta_group;
+    const int tile_rows = GT_ROWS * cg;
+    const int T = (int)((n + tile_rows - 1) / tile_rows);
+    const int K = (int)k_eff;
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+
+    // ---- phase plan (see the header comment) ----
+    // Phase A gives every cluster at most one tile (its rows all become candidates: <= 128 per
+    // (query, CTA) region); B is sized so that it emits about as many candidates as A did.
+    if (n < 16384) return fail(CM_ERR_UNSUPPORTED, "the tensor path needs at least 16384 rows (have %lld)", (long long)n);
+    const int n_cta = sm_count();
+    const int n_clusters = n_cta / cg;
+    GemmPhase ph[3];
+    int n_ph = 0;
+    {
+        int64_t rows_a = std::min<int64_t>(std::max<int64_t>(32 * (int64_t)K, 2048), 8192);
+        int tA = std::min((int)((rows_a + tile_rows - 1) / tile_rows), std::max(1, n_clusters / 2));
+        rows_a = (int64_t)tA * tile_rows;
+        int64_t rows_b = std::min<int64_t>(rows_a * rows_a / K, n / 4);
+        int tB = (int)(rows_b / tile_rows);
+        int nAB = tA + tB;
+        int SB = T / std::max(1, nAB);
+        if (SB < 2 || tB < tA) {
+            int SA = std::max(2, T / tA);
+            int nA = (T + SA - 1) / SA;
+            ph[n_ph++] = GemmPhase{0, SA, SA, nA};
+            ph[n_ph++] = GemmPhase{2, SA, SA, T - nA};
+        } else {
+            int R = std::max(2, (nAB + tA / 2) / tA);
+            int SA = SB * R;
+            int nA = (T + SA - 1) / SA, nABt = (T + SB - 1) / SB;
+            ph[n_ph++] = GemmPhase{0, SA, SB, nA};
+            ph[n_ph++] = GemmPhase{1, SA, SB, nABt - nA};
+            ph[n_ph++] = GemmPhase{2, SA, SB, T - nABt};
+        }
+    }
+
+    int64_t cand_total = 0;
+    int passes = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
+        int nqc = (int)std::min<int64_t>(GT_MAX_NQ, nq - q0);
+        int nq_pad = (nqc + GT_QBLK - 1) / GT_QBLK * GT_QBLK;
+        int n_qblk = nq_pad / GT_QBLK;
+        // ---- workspace ----
+        __nv_bfloat16 *q16 = nullptr;
+        float *qn = nullptr, *g = nullptr;
+        uint64_t *cand = nullptr, *keys2 = nullptr;
+        int *ccnt = nullptr, *ovf = nullptr, *rcnt = nullptr, *kcnt = nullptr;
+        uint32_t *rs = nullptr;
+        CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
+        CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 4, st));
+        CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
+        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_cta * CAND_SLOTS * 8, st));
+        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_cta + 3) * 4, st));
+        ovf = ccnt + (size_t)nq_pad * n_cta; rcnt = ovf + nq_pad; kcnt = rcnt + nq_pad;
+        CM_TRY(ws_alloc((void **)&rs, (size_t)nq_pad * RS_CAP * 4, st));
+        CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
+        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_cta + 3) * 4, st));
+        CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
+        // g: phase A bound is -inf for real queries (everything is a candidate), +inf for padding
+        init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+        CM_TRY(launch_to_bf16(qp + (size_t)q0 * ld, nqc, dim, ld, q16, ldb, 0.0f, nullptr, qn, nullptr, st));
+        CUtensorMap tq;
+        CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
+                            (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
+        for (int p = 0; p < n_ph; p++) {
+            if (cg == 2)
+                CM_TRY(launch_gemm_t<2>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st));
+            else
+                CM_TRY(launch_gemm_t<1>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st));
+            {
+                ProfScope prof(CM_PROF_SELECT, st);
+                cand_select_kernel<<<nqc, 256, 0, st>>>(cand, ccnt, nq_pad, n_cta, CAND_SLOTS, K, dim, qn, max_norm_bits, g, ovf,
+                                                        p == n_ph - 1 ? 1 : 0, rs, rcnt, RS_CAP);
+                count_launch();
+                CM_CUDA(cudaGetLastError());
+            }
+            passes++;
+        }
+        CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs, rcnt, threshold, keys2, kcnt, st));
+        CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
+                                 out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
+                                 out_counts + q0, st));
+        mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0));
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+        ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
+        ws_free(keys2, st);
+        (void)cand_total;
+    }
+    stats->path_used = CM_PATH_TENSOR;
+    stats->passes = passes;
+    return CM_OK;
 }
 
 }  // namespace cm

@@ -1,0 +1,100 @@
+"""GPU parity tests of the tensor-core flat path (bf16 tcgen05 candidate pass + reference-order
+re-score): results must be BIT-IDENTICAL to the CPU oracle, like the exact scan's."""
+import os
+
+import numpy as np
+import pytest
+
+from comet_b200 import capi
+from oracle import oracle_py as O
+from tests.parity import assert_same_results
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(n, d, metric, seed, cta_group):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    os.environ["COMET_B200_CTA_GROUP"] = str(cta_group)
+    try:
+        g = capi.FlatIndex(d, metric)
+    finally:
+        os.environ.pop("COMET_B200_CTA_GROUP", None)
+    g.add(ids, x.copy())
+    o = O.Flat(d, metric)
+    o.add(ids, x.copy())
+    return g, o, rng
+
+
+def check(g, o, q, k, **kw):
+    ids, sc, cnt = g.search(q, k=k, path=capi.PATH_TENSOR, **kw)
+    st = g.last_stats()
+    assert st["path_used"] == capi.PATH_TENSOR
+    O.set_threads(os.cpu_count() or 1)
+    oi, os_, oc = o.search_batch(q, k, threshold=kw.get("threshold", 0.0))
+    for i in range(q.shape[0]):
+        assert_same_results(ids[i], sc[i], cnt[i], oi[i, :oc[i]], os_[i, :oc[i]], what=f"query {i}")
+    return st
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("metric", [capi.L2SQ, capi.COSINE, capi.L2])
+def test_tensor_path_matches_oracle(metric, cta_group):
+    g, o, rng = make_pair(33_000, 128, metric, 11 + metric, cta_group)
+    q = rng.standard_normal((260, 128)).astype(np.float32)
+    st = check(g, o, q, 10)
+    assert st["fallback_queries"] == 0
+    check(g, o, q[:70], 100)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tensor_path_dim768_k100(cta_group):
+    g, o, rng = make_pair(24_000, 768, capi.COSINE, 5, cta_group)
+    q = rng.standard_normal((300, 768)).astype(np.float32)
+    st = check(g, o, q, 100)
+    assert st["fallback_queries"] == 0
+
+
+def test_tensor_path_odd_dim_and_ragged_tail():
+    # dim not a multiple of 64 (bf16 shadow is zero padded), n not a multiple of the row tile
+    g, o, rng = make_pair(20_000 + 77, 100, capi.L2SQ, 3, 2)
+    q = rng.standard_normal((65, 100)).astype(np.float32)
+    check(g, o, q, 7)
+
+
+def test_tensor_path_with_deletes_and_threshold():
+    g, o, rng = make_pair(30_000, 64, capi.L2, 9, 2)
+    for i in range(1, 2000, 7):
+        g.remove(i)
+        o.remove(i)
+    q = rng.standard_normal((128, 64)).astype(np.float32)
+    check(g, o, q, 20)
+    check(g, o, q, 50, threshold=9.5)
+
+
+def test_tensor_path_ties_fall_back_to_exact():
+    # the reference benchmark data (flat_index_document_filter_test.go:188-200): 100 distinct rows
+    # repeated -> every candidate bound is met by thousands of rows; the overflow must be detected
+    # and those queries answered by the exact scan, still bit-identical to the oracle.
+    n, d = 20_000, 128
+    x = np.repeat((np.arange(n) % 100).astype(np.float32)[:, None], d, axis=1)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    g = capi.FlatIndex(d, capi.L2)
+    g.add(ids, x.copy())
+    o = O.Flat(d, capi.L2)
+    o.add(ids, x.copy())
+    q = np.ones((64, d), np.float32)
+    ids_g, sc_g, cnt_g = g.search(q, k=10, path=capi.PATH_TENSOR)
+    oi, os_, oc = o.search_batch(q, 10)
+    for i in range(len(q)):
+        assert_same_results(ids_g[i], sc_g[i], cnt_g[i], oi[i, :oc[i]], os_[i, :oc[i]], what=f"query {i}")
+
+
+def test_auto_path_picks_tensor_for_large_batches():
+    g, o, rng = make_pair(66_000, 64, capi.COSINE, 21, 2)
+    q = rng.standard_normal((64, 64)).astype(np.float32)
+    g.search(q, k=10)
+    assert g.last_stats()["path_used"] == capi.PATH_TENSOR
+    g.search(q[:8], k=10)
+    assert g.last_stats()["path_used"] == capi.PATH_EXACT
