@@ -30,7 +30,7 @@ struct FlatIndex {
     // tensor-core candidate pass state (flat_tensor.cu)
     __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ldb] bf16 shadow of rows, ldb = dim padded to 64
     float *row_h = nullptr;                 // [cap] |x|^2 / 2 for L2 / L2^2, 0 for cosine (candidate key offset)
-    unsigned int *max_norm_bits = nullptr;  // device: bits of max_row |x| (rounded up), feeds the error bound
+    unsigned int *max_bits = nullptr;       // device [2]: bits of max_row |x| and max_row |x - bf16(x)| (error bound)
     int ldb = 0;
     int64_t shadow_rows = 0;                // rows [0, shadow_rows) of the shadow are current
     int64_t shadow_cap = 0;

@@ -318,9 +318,58 @@ __global__ void preprocess_rows_kernel(int metric, const float *__restrict__ src
         for (int j = dim; j < ld_dst; j++) d[j] = 0.0f;
 }
 
+// Same arithmetic for a SMALL number of rows (a query batch): one warp per row stages the row in
+// shared memory with coalesced loads, lane 0 runs the reference's sequential sum, all lanes scale.
+// (One thread per row is latency-bound there: 768 dependent strided loads per query.)
+template <bool FMA>
+__global__ void preprocess_rows_warp_kernel(int metric, const float *__restrict__ src, long long n, int dim, int ld_src,
+                                            float *__restrict__ dst, int ld_dst, int *__restrict__ zero_flags) {
+    extern __shared__ float prow[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long i = blockIdx.x * (long long)(blockDim.x >> 5) + w;
+    if (i >= n) return;
+    float *r = prow + (size_t)w * dim;
+    const float *s = src + (size_t)i * ld_src;
+    float *d = dst + (size_t)i * ld_dst;
+    for (int j = lane; j < dim; j += 32) r[j] = s[j];
+    __syncwarp();
+    float scale = 1.0f;
+    int zero = 0;
+    if (metric == CM_COSINE) {
+        if (lane == 0) {
+            float sum = 0.0f;
+            for (int j = 0; j < dim; j++) sum = dot_step<FMA>(sum, r[j], r[j]);
+            float norm = __fsqrt_rn(sum);
+            zero = norm == 0.0f;
+            scale = __fdiv_rn(1.0f, norm);
+        }
+        scale = __shfl_sync(0xffffffffu, scale, 0);
+        zero = __shfl_sync(0xffffffffu, zero, 0);
+    }
+    if (zero_flags && lane == 0) zero_flags[i] = zero;
+    bool do_scale = metric == CM_COSINE && !zero;
+    for (int j = lane; j < ld_dst; j += 32) {
+        float v = 0.0f;
+        if (j < dim) v = do_scale ? __fmul_rn(r[j], scale) : r[j];
+        d[j] = v;
+    }
+}
+
 int launch_preprocess_rows(int metric, bool fma, const float *src, int64_t n, int dim, int ld_src, float *dst,
                            int ld_dst, int *zero_flags, cudaStream_t stream) {
     if (n <= 0) return CM_OK;
+    if (n <= 16384 && src != dst && (size_t)dim * 4 * 4 <= 48 * 1024) {
+        int warps = 4;
+        size_t smem = (size_t)warps * dim * 4;
+        unsigned blocks = (unsigned)((n + warps - 1) / warps);
+        if (fma)
+            preprocess_rows_warp_kernel<true><<<blocks, warps * 32, smem, stream>>>(metric, src, n, dim, ld_src, dst, ld_dst, zero_flags);
+        else
+            preprocess_rows_warp_kernel<false><<<blocks, warps * 32, smem, stream>>>(metric, src, n, dim, ld_src, dst, ld_dst, zero_flags);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+        return CM_OK;
+    }
     int threads = 128;
     long long blocks = (n + threads - 1) / threads;
     if (fma)

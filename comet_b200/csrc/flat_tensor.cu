@@ -6,10 +6,13 @@
 //
 // Why the result is exact.  Let s(q,x) be the reference score (distance.go:114-121/158-165/201-216,
 // sequential fp32) and a~(q,x) = h_x - dot_bf16(q,x) the tensor-core key (h_x = |x|^2/2 for L2/L2^2,
-// 0 for cosine; smaller = closer).  bf16 rounding (unit roundoff 2^-8 per operand), fp32 tensor
-// accumulation and the reference's own rounding together move a~ away from the order the reference
-// sorts by by at most
-//     E_q = 1.02 * (0.0078278 * |q| * X + (d + 4) * 2^-22 * (|q| + X)^2),   X = max_row |x|.
+// 0 for cosine; smaller = closer).  Write q = q~ + dq, x = x~ + dx with q~, x~ the bf16 roundings;
+// the residuals are exactly representable in fp32, so |dq| and |dx| are KNOWN, not estimated.  Then
+// |q.x - q~.x~| <= |q~||dx| + |dq||x~| + |dq||dx| (Cauchy-Schwarz), and with the fp32 effects (tensor
+// accumulation, the reference's own sequential rounding, clamp / sqrt plateaus) a~ differs from the
+// quantity the reference orders by by at most
+//     E_q = 1.001 (|q| Dx + |dq| X + |dq| Dx) + 1.01 (d + 8) 2^-23 (|q| X + (|q| + X)^2 / 2),
+// X = max_row |x|, Dx = max_row |dx| (both maintained on the device as rows are added).
 // If tau is the K-th smallest a~ over ANY subset of the rows, every row of the reference's top-K
 // has a~ <= tau + 2 E_q.  The pass therefore runs in up to three phases over disjoint row samples
 // (A: everything is a candidate; B, C: only keys under the bound from the previous phases), a final
@@ -24,6 +27,7 @@
 // operands arrive by TMA (SWIZZLE_128B, 64 bf16 per row) through an mbarrier ring.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
@@ -35,11 +39,15 @@ namespace cm {
 static constexpr int GT_ROWS = 128;        // corpus rows per CTA per tile (TMEM lanes)
 static constexpr int GT_QBLK = 256;        // queries per accumulator (UMMA N)
 static constexpr int GT_BK = 64;           // bf16 per k-step: one 128-byte swizzle atom
-static constexpr int GT_THREADS = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+static constexpr int GT_THREADS = 384;     // warps 0-7 epilogue, 8 TMEM alloc, 9 idle, 10 TMA, 11 MMA.  The issue arbiter
+                                           // favours the highest warp id of a scheduler, so the two single-lane
+                                           // driver warps sit above the (often spinning) epilogue warps.
+static constexpr int GT_WARP_ALLOC = 8, GT_WARP_TMA = 10, GT_WARP_MMA = 11;
 static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
 static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
 static constexpr int CAND_SLOTS = 512;     // candidate slots per (query, CTA) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
+static constexpr int SEL_STAGE_CAP = 24576; // candidate scores staged in smem by the select kernel (96 KB)
 
 struct GemmPhase {
     int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
@@ -92,13 +100,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
         g_s[i] = g_bound[i];
         cnt_s[i] = cand_cnt[(size_t)blockIdx.x * nq_pad + i];
     }
-    if (warp == 2) tc::tmem_alloc<CG>(smem_u32(tmem_slot), 512);
+    if (warp == GT_WARP_ALLOC) tc::tmem_alloc<CG>(smem_u32(tmem_slot), 512);
     tc::fence_before_thread_sync();
     if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == GT_WARP_TMA) {
         // ===== TMA producer (one lane) =====
         if (lane == 0) {
             prefetch_tmap(&tmap_x);
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == GT_WARP_MMA) {
         // ===== MMA issuer (one lane of the leader CTA) =====
         if (cta_rank == 0 && lane == 0) {
             uint32_t it = 0, wi = 0;
@@ -151,33 +159,45 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp < 8) {
         // ===== epilogue: 8 warps; thread = one corpus row (TMEM lane) x 128 of the 256 query columns =====
-        const int ew = warp & 3, half = (warp - 4) >> 2;
+        const int ew = warp & 3, half = warp >> 2;
         uint32_t wi = 0;
         uint32_t tempty0 = smem_u32(&tempty_bar[0]), tempty1 = smem_u32(&tempty_bar[1]);
         if (CG == 2) { tempty0 = tc::mapa(tempty0, 0); tempty1 = tc::mapa(tempty1, 0); }
         uint64_t *my_cand = cand + (size_t)blockIdx.x * cand_slots;   // + q * n_cta_total * cand_slots
         const size_t q_stride = (size_t)n_cta_total * cand_slots;
+        const int row_in_tile = (int)cta_rank * GT_ROWS + ew * 32 + lane;
+        // per-row data of the first item; the next item's is fetched while this one is processed
+        long long row = -1;
+        float hx = 0.0f;
+        bool row_ok = false;
+        auto fetch_row = [&](int w) {
+            if (w < n_work) {
+                row = (long long)phase_tile(phase, w / n_qblk) * (GT_ROWS * CG) + row_in_tile;
+                row_ok = row < n_rows;
+                hx = row_ok ? __ldg(row_h + row) : 0.0f;
+                if (row_ok && skip != nullptr) row_ok = __ldg(skip + row) == 0;
+            }
+        };
+        fetch_row(cluster);
         for (int w = cluster; w < n_work; w += n_clusters, wi++) {
-            uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
-            int t = phase_tile(phase, w / n_qblk), nb = w % n_qblk;
-            long long row = (long long)t * (GT_ROWS * CG) + (long long)cta_rank * GT_ROWS + ew * 32 + lane;
-            bool row_ok = row < n_rows;
-            float hx = row_ok ? row_h[row] : 0.0f;
-            if (row_ok && skip != nullptr) row_ok = skip[row] == 0;
+            const uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
+            const int nb = w % n_qblk;
+            const long long cur_row = row;
+            const float cur_hx = hx;
+            const bool cur_ok = row_ok;
+            fetch_row(w + n_clusters);
             const int qbase = nb * GT_QBLK + half * (GT_QBLK / 2);
             const float *g = g_s + qbase;
-            mbar_wait(&tfull_bar[acc], aph);
+            while (!mbar_try_wait(&tfull_bar[acc], aph)) __nanosleep(128);   // back off: do not steal issue slots
             tc::fence_after_thread_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_QBLK + half * (GT_QBLK / 2);
-            uint32_t v[2][32];
-            tc::tmem_ld_32x32(taddr, v[0]);
-#pragma unroll
+#pragma unroll 1
             for (int cb = 0; cb < GT_QBLK / 64; cb++) {
+                uint32_t vv[32];
+                tc::tmem_ld_32x32(taddr + cb * 32, vv);
                 tc::tmem_ld_wait();
-                if (cb + 1 < GT_QBLK / 64) tc::tmem_ld_32x32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);
-                const uint32_t(&vv)[32] = v[cb & 1];
                 float m = -INFINITY;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {
@@ -187,16 +207,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                     m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 2]) - gg.z);
                     m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 3]) - gg.w);
                 }
-                if (m >= hx && row_ok) {
+                if (m >= cur_hx && cur_ok) {
                     // some (row, query) pair of this 32-column strip is a candidate: append it to this
                     // CTA's private region of the query's list (shared-memory counter, no global atomics)
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
                         float dot = __uint_as_float(vv[c]);
-                        if (dot - g[cb * 32 + c] >= hx) {
+                        if (dot - g[cb * 32 + c] >= cur_hx) {
                             int q = qbase + cb * 32 + c;
                             int slot = atomicAdd(&cnt_s[q], 1);
-                            if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(hx - dot, (uint32_t)row);
+                            if (slot < cand_slots)
+                                my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, (uint32_t)cur_row);
                         }
                     }
                 }
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     tc::fence_before_thread_sync();
     if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
     for (int i = tid; i < nq_pad; i += GT_THREADS) cand_cnt[(size_t)blockIdx.x * nq_pad + i] = cnt_s[i];
-    if (warp == 2) {
+    if (warp == GT_WARP_ALLOC) {
         tc::fence_after_thread_sync();
         tc::tmem_dealloc<CG>(tmem_base, 512);
     }
@@ -260,17 +281,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
-// one warp per row; src [n][ld_src] fp32 (ld_src % 4 == 0), dst [n][ldb] bf16 zero padded
+// one warp per row; src [n][ld_src] fp32 (ld_src % 4 == 0), dst [n][ldb] bf16 zero padded.
+// Besides the bf16 copy it produces what the error bound needs, all rounded UP a little:
+//   |x| and |x - bf16(x)| (the rounding residual is exactly representable in fp32),
+//   per row into out_norms[row] = {|x|, |dx|} (queries) and/or as running maxima in max_bits[0..1] (corpus).
 __global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long n, int dim, int ld_src,
                                     __nv_bfloat16 *__restrict__ dst, int ldb, float h_scale,
-                                    float *__restrict__ out_h, float *__restrict__ out_norm,
-                                    unsigned int *__restrict__ max_norm_bits) {
+                                    float *__restrict__ out_h, float2 *__restrict__ out_norms,
+                                    unsigned int *__restrict__ max_bits) {
     long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n) return;
     const float *s = src + (size_t)row * ld_src;
     uint2 *d = reinterpret_cast<uint2 *>(dst + (size_t)row * ldb);
-    float sq = 0.0f;
+    float sq = 0.0f, rsq = 0.0f;
     for (int j = lane * 4; j < ldb; j += 128) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j + 3 < dim) v = *reinterpret_cast<const float4 *>(s + j);
@@ -279,26 +303,36 @@ __global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long n, 
             if (j + 1 < dim) v.y = s[j + 1];
             if (j + 2 < dim) v.z = s[j + 2];
         }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+        float2 r0 = __bfloat1622float2(p0), r1 = __bfloat1622float2(p1);
+        float ex = v.x - r0.x, ey = v.y - r0.y, ez = v.z - r1.x, ew = v.w - r1.y;
         sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        d[j >> 2] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        rsq += ex * ex + ey * ey + ez * ez + ew * ew;
+        d[j >> 2] = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
+    }
     if (lane == 0) {
-        float nrm = sqrtf(sq) * 1.00001f;
+        float nrm = sqrtf(sq) * 1.0001f, rn = sqrtf(rsq) * 1.0001f;
         if (out_h) out_h[row] = h_scale * sq;
-        if (out_norm) out_norm[row] = nrm;
-        if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));
+        if (out_norms) out_norms[row] = make_float2(nrm, rn);
+        if (max_bits) {
+            atomicMax(&max_bits[0], __float_as_uint(nrm));
+            atomicMax(&max_bits[1], __float_as_uint(rn));
+        }
     }
 }
 
 static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv_bfloat16 *dst, int ldb, float h_scale,
-                          float *out_h, float *out_norm, unsigned int *max_norm_bits, cudaStream_t st) {
+                          float *out_h, float2 *out_norms, unsigned int *max_bits, cudaStream_t st) {
     if (n <= 0) return CM_OK;
     int threads = 256;
     long long blocks = (n * 32 + threads - 1) / threads;
-    to_bf16_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n, dim, ld_src, dst, ldb, h_scale, out_h, out_norm,
-                                                              max_norm_bits);
+    to_bf16_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n, dim, ld_src, dst, ldb, h_scale, out_h, out_norms,
+                                                              max_bits);
     count_launch();
     CM_CUDA(cudaGetLastError());
     return CM_OK;
@@ -308,53 +342,82 @@ static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv
 // candidate selection: K-th smallest key (radix select on the ordered score bits) -> next bound
 // ------------------------------------------------------------------------------------------------
 // block per query.  The query's candidates live in n_cta regions of `slots` keys (one per GEMM CTA).
+// The ordered score bits of all of them are staged once in shared memory (stage_cap entries); the
+// K-th smallest is found there by a 4 x 8-bit radix select.
 // final == 0: g[q] = -(tau_K + 2E) for the next phase.  final == 1: additionally compact the rows
 // with key <= tau_K + 2E into rs[q][*] for the exact re-score.
-__global__ void __launch_bounds__(256) cand_select_kernel(const uint64_t *__restrict__ cand, const int *__restrict__ cand_cnt,
-                                                          int nq_pad, int n_cta, int slots, int K, int dim,
-                                                          const float *__restrict__ q_norm,
-                                                          const unsigned int *__restrict__ max_norm_bits,
-                                                          float *__restrict__ g, int *__restrict__ overflow, int final,
-                                                          uint32_t *__restrict__ rs, int *__restrict__ rs_cnt, int rs_cap) {
+static constexpr int SEL_THREADS = 512;
+__global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
+    const uint64_t *__restrict__ cand, const int *__restrict__ cand_cnt, int nq_pad, int n_cta, int slots, int K, int dim,
+    const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
+    int *__restrict__ overflow, int final, uint32_t *__restrict__ rs, int *__restrict__ rs_cnt, int rs_cap,
+    int stage_cap, float e_scale) {
+    extern __shared__ uint32_t sel_smem[];
+    uint32_t *hi_s = sel_smem;                                         // [stage_cap] ordered score bits
+    int *off_s = reinterpret_cast<int *>(sel_smem + stage_cap);        // [n_cta + 1] region offsets
     __shared__ int hist[256];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_rank, s_out, s_total, s_ovf;
-    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { s_total = 0; s_ovf = overflow[q]; s_out = 0; }
+    __shared__ uint32_t s_prefix, s_lo, s_hi;
+    __shared__ int s_rank, s_out, s_ovf, s_maxc;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_maxc = 0; }
     __syncthreads();
-    for (int r = tid; r < n_cta; r += 256) {
+    for (int r = tid; r < n_cta; r += SEL_THREADS) {
         int c = cand_cnt[(size_t)r * nq_pad + q];
         if (c > slots) s_ovf = 1;
-        atomicAdd(&s_total, min(c, slots));
+        off_s[r + 1] = c;
+        atomicMax(&s_maxc, c);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        off_s[0] = 0;
+        for (int r = 0; r < n_cta; r++) { acc += off_s[r + 1]; off_s[r + 1] = acc; }
+        if (acc > stage_cap) s_ovf = 1;
     }
     __syncthreads();
     if (s_ovf) {
         if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; if (final) rs_cnt[q] = 0; }
         return;
     }
+    const int total = off_s[n_cta], maxc = s_maxc;
     const uint64_t *qcand = cand + (size_t)q * n_cta * slots;
-    // visit every key of this query: warp per region, lanes over the region's keys
-    auto for_each_key = [&](auto &&fn) {
-        for (int r = warp; r < n_cta; r += 8) {
-            int c = cand_cnt[(size_t)r * nq_pad + q];
-            const uint64_t *keys = qcand + (size_t)r * slots;
-            for (int i = lane; i < c; i += 32) fn(keys[i]);
-        }
-    };
+    // one sweep over (region, slot) pairs; independent loads, no dependent chains
+    for (int idx = tid; idx < n_cta * maxc; idx += SEL_THREADS) {
+        int r = idx / maxc, i = idx - r * maxc;
+        int o = off_s[r];
+        if (i < off_s[r + 1] - o) hi_s[o + i] = (uint32_t)(qcand[(size_t)r * slots + i] >> 32);
+    }
+    __syncthreads();
     float bound = INFINITY;
-    if (s_total >= K) {
-        // radix select: 4 passes of 8 bits, most significant first, over the high 32 key bits
+    if (total >= K) {
+        // The scores of one query's candidates share their leading bits (same sign, exponent and top
+        // mantissa bits), which would pile every shared-memory atomic of a plain MSB-first radix pass
+        // onto one bin.  Select on (key - min) instead and start at its highest significant byte.
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (int i = tid; i < total; i += SEL_THREADS) { uint32_t v = hi_s[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (tid == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+        __syncthreads();
+        if ((tid & 31) == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+        __syncthreads();
+        const uint32_t base = s_lo, range = s_hi - s_lo;
+        const int n_pass = range == 0 ? 0 : (32 - __clz(range) + 7) / 8;
         if (tid == 0) { s_prefix = 0; s_rank = K; }
-        for (int pass = 0; pass < 4; pass++) {
-            int shift = 24 - 8 * pass;
-            hist[tid] = 0;
+        __syncthreads();
+        for (int pass = n_pass - 1; pass >= 0; pass--) {
+            int shift = 8 * pass;
+            if (tid < 256) hist[tid] = 0;
             __syncthreads();
             uint32_t prefix = s_prefix;
-            uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-            for_each_key([&](uint64_t key) {
-                uint32_t hi = (uint32_t)(key >> 32);
-                if ((hi & mask) == prefix) atomicAdd(&hist[(hi >> shift) & 255], 1);
-            });
+            uint32_t mask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            for (int i = tid; i < total; i += SEL_THREADS) {
+                uint32_t v = hi_s[i] - base;
+                if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
+            }
             __syncthreads();
             if (tid == 0) {
                 int r = s_rank, b = 0;
@@ -367,20 +430,28 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const uint64_t *__rest
             }
             __syncthreads();
         }
+        if (tid == 0) s_prefix += base;
+        __syncthreads();
         float tau = ordered_to_float(s_prefix);
-        float nq = q_norm[q], X = __uint_as_float(*max_norm_bits);
-        float E = 1.02f * (0.0078278f * nq * X + (float)(dim + 4) * 2.3841858e-07f * (nq + X) * (nq + X));
-        bound = tau + 2.0f * E;
+        // E_q: see the header comment.  X, Dx: max row norm / max bf16 residual norm; nq, dq: the query's.
+        float2 qn = q_norms[q];
+        float nq = qn.x, dq = qn.y, X = __uint_as_float(max_bits[0]), Dx = __uint_as_float(max_bits[1]);
+        float E = 1.001f * (nq * Dx + dq * X + dq * Dx) +
+                  1.01f * (float)(dim + 8) * 1.1920929e-07f * (nq * X + 0.5f * (nq + X) * (nq + X));
+        bound = tau + 2.0f * E * e_scale;
         bound = bound + fabsf(bound) * 1e-6f;
     }
     if (tid == 0) g[q] = -bound;
     if (!final) return;
-    for_each_key([&](uint64_t key) {
-        if (key_score(key) <= bound) {
+    const uint32_t bound_hi = float_to_ordered(bound);
+    for (int idx = tid; idx < n_cta * maxc; idx += SEL_THREADS) {
+        int r = idx / maxc, i = idx - r * maxc;
+        int o = off_s[r];
+        if (i < off_s[r + 1] - o && hi_s[o + i] <= bound_hi) {
             int slot = atomicAdd(&s_out, 1);
-            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(key);
+            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(qcand[(size_t)r * slots + i]);
         }
-    });
+    }
     __syncthreads();
     if (tid == 0) {
         if (s_out > rs_cap) { overflow[q] = 1; rs_cnt[q] = 0; }
@@ -498,8 +569,8 @@ __global__ void mark_overflow_kernel(const int *__restrict__ overflow, int nq, l
 void FlatIndex::free_shadow() {
     cudaFree(rows_bf16);
     cudaFree(row_h);
-    cudaFree(max_norm_bits);
-    rows_bf16 = nullptr; row_h = nullptr; max_norm_bits = nullptr;
+    cudaFree(max_bits);
+    rows_bf16 = nullptr; row_h = nullptr; max_bits = nullptr;
     shadow_rows = shadow_cap = 0;
 }
 
@@ -511,17 +582,17 @@ int FlatIndex::ensure_shadow(cudaStream_t st) {
         free_shadow();
         CM_CUDA(cudaMalloc(&rows_bf16, (size_t)cap * ldb * sizeof(__nv_bfloat16)));
         CM_CUDA(cudaMalloc(&row_h, (size_t)cap * sizeof(float)));
-        CM_CUDA(cudaMalloc(&max_norm_bits, sizeof(unsigned int)));
-        CM_CUDA(cudaMemsetAsync(max_norm_bits, 0, sizeof(unsigned int), st));
+        CM_CUDA(cudaMalloc(&max_bits, 2 * sizeof(unsigned int)));
+        CM_CUDA(cudaMemsetAsync(max_bits, 0, 2 * sizeof(unsigned int), st));
         shadow_cap = cap;
         shadow_rows = 0;
         CM_TRY(make_tmap_2d(&tmap_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_bf16, (uint64_t)ldb, (uint64_t)cap,
                             (uint64_t)ldb * 2, GT_BK, GT_ROWS, CU_TENSOR_MAP_SWIZZLE_128B));
     }
-    if (shadow_rows == 0) CM_CUDA(cudaMemsetAsync(max_norm_bits, 0, sizeof(unsigned int), st));
+    if (shadow_rows == 0) CM_CUDA(cudaMemsetAsync(max_bits, 0, 2 * sizeof(unsigned int), st));
     float h_scale = metric == CM_COSINE ? 0.0f : 0.5f;
     CM_TRY(launch_to_bf16(rows + (size_t)shadow_rows * ld, n - shadow_rows, dim, ld, rows_bf16 + (size_t)shadow_rows * ldb,
-                          ldb, h_scale, row_h + shadow_rows, nullptr, max_norm_bits, st));
+                          ldb, h_scale, row_h + shadow_rows, nullptr, max_bits, st));
     CM_CUDA(cudaStreamSynchronize(st));
     shadow_rows = n;
     return CM_OK;
@@ -573,7 +644,11 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         }
     }
 
-    int64_t cand_total = 0;
+    // debugging aid: widen the candidate band (>= 1 keeps the result exact)
+    float e_scale = 1.0f;
+    if (const char *es = getenv("COMET_B200_E_SCALE")) e_scale = std::max(1.0f, (float)atof(es));
+    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 4 + (size_t)(n_cta + 1) * 4;
+    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     int passes = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
         int nqc = (int)std::min<int64_t>(GT_MAX_NQ, nq - q0);
@@ -581,12 +656,13 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         int n_qblk = nq_pad / GT_QBLK;
         // ---- workspace ----
         __nv_bfloat16 *q16 = nullptr;
-        float *qn = nullptr, *g = nullptr;
+        float2 *qn = nullptr;
+        float *g = nullptr;
         uint64_t *cand = nullptr, *keys2 = nullptr;
         int *ccnt = nullptr, *ovf = nullptr, *rcnt = nullptr, *kcnt = nullptr;
         uint32_t *rs = nullptr;
         CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
-        CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 4, st));
+        CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
         CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_cta * CAND_SLOTS * 8, st));
         CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_cta + 3) * 4, st));
@@ -610,8 +686,9 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
                 CM_TRY(launch_gemm_t<1>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st));
             {
                 ProfScope prof(CM_PROF_SELECT, st);
-                cand_select_kernel<<<nqc, 256, 0, st>>>(cand, ccnt, nq_pad, n_cta, CAND_SLOTS, K, dim, qn, max_norm_bits, g, ovf,
-                                                        p == n_ph - 1 ? 1 : 0, rs, rcnt, RS_CAP);
+                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(cand, ccnt, nq_pad, n_cta, CAND_SLOTS, K, dim, qn,
+                                                                       max_bits, g, ovf, p == n_ph - 1 ? 1 : 0, rs, rcnt,
+                                                                       RS_CAP, SEL_STAGE_CAP, e_scale);
                 count_launch();
                 CM_CUDA(cudaGetLastError());
             }
@@ -626,7 +703,6 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         CM_CUDA(cudaGetLastError());
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);
-        (void)cand_total;
     }
     stats->path_used = CM_PATH_TENSOR;
     stats->passes = passes;

@@ -49,9 +49,12 @@ __device__ __forceinline__ void compact_topk(uint64_t *keys, int C, int K, int *
     bar.sync();
     int n = *count;
     if (n > C) n = C;
-    for (int i = n + tid; i < C; i += nthr) keys[i] = KEY_INF;
+    int Cs = 64;                      // sort only the smallest power of two that holds the n keys
+    while (Cs < n) Cs <<= 1;
+    if (Cs > C) Cs = C;
+    for (int i = n + tid; i < Cs; i += nthr) keys[i] = KEY_INF;
     bar.sync();
-    bitonic_sort_smem(keys, C, tid, nthr, bar);
+    bitonic_sort_smem(keys, Cs, tid, nthr, bar);
     if (tid == 0) {
         int m = n < K ? n : K;
         *count = m;

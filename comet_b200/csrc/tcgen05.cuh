@@ -33,9 +33,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
     return r;
 }
-// arrive (count 1) on an mbarrier given by a shared::cluster address (possibly in the peer CTA)
+// arrive (count 1) on an mbarrier given by a shared::cluster address (possibly in the peer CTA).
+// Relaxed: the only data it orders are TMEM reads, which tcgen05.fence::before_thread_sync covers;
+// a .release here costs a MEMBAR that also waits for every outstanding global store of the warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
