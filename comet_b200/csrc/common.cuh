@@ -145,6 +145,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Wait that parks the warp in hardware until the phase completes (suspend-time hint in ns): it wakes
+// within ~60 cycles of the arrive and, unlike a short-timeout try_wait loop, issues nothing meanwhile.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(10000000u)
+            : "memory");
+    } while (!ok);
+}
 // 2-D tiled TMA load: box lands in smem, completes `bytes` on the mbarrier
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int x, int y,
                                             uint64_t *bar) {

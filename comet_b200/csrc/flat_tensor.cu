@@ -45,7 +45,7 @@ static constexpr int GT_THREADS = 384;     // warps 0-7 epilogue, 8 TMEM alloc, 
 static constexpr int GT_WARP_ALLOC = 8, GT_WARP_TMA = 10, GT_WARP_MMA = 11;
 static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
 static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
-static constexpr int CAND_SLOTS = 512;     // candidate slots per (query, CTA) region
+static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
 static constexpr int SEL_STAGE_CAP = 24576; // candidate scores staged in smem by the select kernel (96 KB)
 
@@ -53,6 +53,7 @@ struct GemmPhase {
     int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
     int SA, SB;
     int n_tiles;      // tiles in this class
+    int dbg;          // debugging aid: 1 = epilogue skips the accumulator scan, 2 = loads TMEM but does not compare
 };
 
 __device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
@@ -64,7 +65,21 @@ __device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
     }
 }
 
-template <int CG>
+// v[c] for a run-time c without spilling the register array: a 32-way switch (taken only on the rare
+// candidate path)
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int c) {
+    switch (c) {
+#define CM_PICK(i) case i: return v[i];
+        CM_PICK(0) CM_PICK(1) CM_PICK(2) CM_PICK(3) CM_PICK(4) CM_PICK(5) CM_PICK(6) CM_PICK(7)
+        CM_PICK(8) CM_PICK(9) CM_PICK(10) CM_PICK(11) CM_PICK(12) CM_PICK(13) CM_PICK(14) CM_PICK(15)
+        CM_PICK(16) CM_PICK(17) CM_PICK(18) CM_PICK(19) CM_PICK(20) CM_PICK(21) CM_PICK(22) CM_PICK(23)
+        CM_PICK(24) CM_PICK(25) CM_PICK(26) CM_PICK(27) CM_PICK(28) CM_PICK(29) CM_PICK(30)
+#undef CM_PICK
+    default: return v[31];
+    }
+}
+
+template <int CG, bool HAS_H>
 __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q, GemmPhase phase,
     int n_qblk, int k_blocks, int stages, long long n_rows, const float *__restrict__ row_h,
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     uint8_t *stage_base = smem;
     float *g_s = reinterpret_cast<float *>(smem + (size_t)stages * STAGE_BYTES);
     int *cnt_s = reinterpret_cast<int *>(g_s + GT_MAX_NQ);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(cnt_s + GT_MAX_NQ);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(cnt_s + 4 * GT_MAX_NQ);
     uint64_t *empty_bar = full_bar + stages;
     uint64_t *tfull_bar = empty_bar + stages;
     uint64_t *tempty_bar = tfull_bar + 2;
@@ -98,7 +113,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     }
     for (int i = tid; i < nq_pad; i += GT_THREADS) {
         g_s[i] = g_bound[i];
-        cnt_s[i] = cand_cnt[(size_t)blockIdx.x * nq_pad + i];
+#pragma unroll
+        for (int e = 0; e < 4; e++) cnt_s[e * GT_MAX_NQ + i] = cand_cnt[((size_t)blockIdx.x * 4 + e) * nq_pad + i];
     }
     if (warp == GT_WARP_ALLOC) tc::tmem_alloc<CG>(smem_u32(tmem_slot), 512);
     tc::fence_before_thread_sync();
@@ -119,7 +135,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                 for (int kb = 0; kb < k_blocks; kb++, it++) {
                     int s = it % stages;
                     uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_wait_parked(&empty_bar[s], ph ^ 1);
                     uint32_t bar = smem_u32(&full_bar[s]);
                     if (CG == 2) bar = tc::mapa(bar, 0);
                     if (cta_rank == 0) tc::mbar_arrive_expect_tx_addr(smem_u32(&full_bar[s]), STAGE_BYTES * CG);
@@ -136,13 +152,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
             uint32_t it = 0, wi = 0;
             for (int w = cluster; w < n_work; w += n_clusters, wi++) {
                 uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                mbar_wait_parked(&tempty_bar[acc], aph ^ 1);
                 tc::fence_after_thread_sync();
                 uint32_t d_tmem = tmem_base + acc * GT_QBLK;
                 for (int kb = 0; kb < k_blocks; kb++, it++) {
                     int s = it % stages;
                     uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait_parked(&full_bar[s], ph);
                     tc::fence_after_thread_sync();
                     uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
                     uint64_t adesc = tc::make_smem_desc_sw128(sa);
@@ -161,12 +177,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
         __syncwarp();
     } else if (warp < 8) {
         // ===== epilogue: 8 warps; thread = one corpus row (TMEM lane) x 128 of the 256 query columns =====
+        // Candidates of query q found by lane quadrant `ew` of this CTA go to the private region
+        // (q, CTA, ew): its fill count is only ever touched by the warps of that quadrant, one query
+        // half each, so a warp ballot hands out the slots -- no atomics, no divergence.
         const int ew = warp & 3, half = warp >> 2;
         uint32_t wi = 0;
         uint32_t tempty0 = smem_u32(&tempty_bar[0]), tempty1 = smem_u32(&tempty_bar[1]);
         if (CG == 2) { tempty0 = tc::mapa(tempty0, 0); tempty1 = tc::mapa(tempty1, 0); }
-        uint64_t *my_cand = cand + (size_t)blockIdx.x * cand_slots;   // + q * n_cta_total * cand_slots
-        const size_t q_stride = (size_t)n_cta_total * cand_slots;
+        uint64_t *my_cand = cand + ((size_t)blockIdx.x * 4 + ew) * cand_slots;   // + q * q_stride
+        const size_t q_stride = (size_t)n_cta_total * 4 * cand_slots;
+        int *cnt_w = cnt_s + ew * GT_MAX_NQ;
+        const uint32_t lt_mask = (1u << lane) - 1u;
         const int row_in_tile = (int)cta_rank * GT_ROWS + ew * 32 + lane;
         // per-row data of the first item; the next item's is fetched while this one is processed
         long long row = -1;
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
             if (w < n_work) {
                 row = (long long)phase_tile(phase, w / n_qblk) * (GT_ROWS * CG) + row_in_tile;
                 row_ok = row < n_rows;
-                hx = row_ok ? __ldg(row_h + row) : 0.0f;
+                hx = (HAS_H && row_ok) ? __ldg(row_h + row) : 0.0f;
                 if (row_ok && skip != nullptr) row_ok = __ldg(skip + row) == 0;
             }
         };
@@ -184,43 +205,49 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
         for (int w = cluster; w < n_work; w += n_clusters, wi++) {
             const uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
             const int nb = w % n_qblk;
-            const long long cur_row = row;
+            const uint32_t cur_row = (uint32_t)row;
             const float cur_hx = hx;
             const bool cur_ok = row_ok;
             fetch_row(w + n_clusters);
             const int qbase = nb * GT_QBLK + half * (GT_QBLK / 2);
             const float *g = g_s + qbase;
-            while (!mbar_try_wait(&tfull_bar[acc], aph)) __nanosleep(128);   // back off: do not steal issue slots
+            if (phase.dbg & 16) { while (!mbar_try_wait(&tfull_bar[acc], aph)) __nanosleep(128); }
+            else if (phase.dbg & 32) mbar_wait(&tfull_bar[acc], aph);
+            else mbar_wait_parked(&tfull_bar[acc], aph);
             tc::fence_after_thread_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * GT_QBLK + half * (GT_QBLK / 2);
 #pragma unroll 1
             for (int cb = 0; cb < GT_QBLK / 64; cb++) {
+                if ((phase.dbg & 15) == 1) break;
                 uint32_t vv[32];
                 tc::tmem_ld_32x32(taddr + cb * 32, vv);
                 tc::tmem_ld_wait();
-                float m = -INFINITY;
+                if ((phase.dbg & 15) == 2) { if ((vv[0] ^ vv[13] ^ vv[31]) == 0x12345678u) cnt_w[0] = 1; continue; }
+                // Scan: t = dot - g_q (- h_x); the sign bit of t is shifted into a per-row hit mask --
+                // 2 (cosine) or 3 (L2) ops per accumulator value and no branches.  The kernel runs at
+                // the board's power cap, so every instruction here costs tensor clocks.
+                uint32_t mask = 0;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {
                     float4 gg = *reinterpret_cast<const float4 *>(g + cb * 32 + c4 * 4);
-                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 0]) - gg.x);
-                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 1]) - gg.y);
-                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 2]) - gg.z);
-                    m = fmaxf(m, __uint_as_float(vv[c4 * 4 + 3]) - gg.w);
+                    float t0 = __uint_as_float(vv[c4 * 4 + 0]) - gg.x, t1 = __uint_as_float(vv[c4 * 4 + 1]) - gg.y;
+                    float t2 = __uint_as_float(vv[c4 * 4 + 2]) - gg.z, t3 = __uint_as_float(vv[c4 * 4 + 3]) - gg.w;
+                    if (HAS_H) { t0 -= cur_hx; t1 -= cur_hx; t2 -= cur_hx; t3 -= cur_hx; }
+                    mask = __funnelshift_l(__float_as_uint(t0), mask, 1);
+                    mask = __funnelshift_l(__float_as_uint(t1), mask, 1);
+                    mask = __funnelshift_l(__float_as_uint(t2), mask, 1);
+                    mask = __funnelshift_l(__float_as_uint(t3), mask, 1);
                 }
-                if (m >= cur_hx && cur_ok) {
-                    // some (row, query) pair of this 32-column strip is a candidate: append it to this
-                    // CTA's private region of the query's list (shared-memory counter, no global atomics)
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        float dot = __uint_as_float(vv[c]);
-                        if (dot - g[cb * 32 + c] >= cur_hx) {
-                            int q = qbase + cb * 32 + c;
-                            int slot = atomicAdd(&cnt_s[q], 1);
-                            if (slot < cand_slots)
-                                my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, (uint32_t)cur_row);
-                        }
-                    }
+                uint32_t hits = cur_ok ? ~mask : 0u;       // bit (31 - c) set <=> column c is a candidate
+                while (hits != 0u) {                        // rare; usually one iteration for one or two lanes
+                    const int c = __clz(hits);
+                    hits &= ~(0x80000000u >> c);
+                    const float dot = __uint_as_float(pick32(vv, c));
+                    const int q = qbase + cb * 32 + c;
+                    const int slot = atomicAdd(&cnt_w[q], 1);   // counter private to this lane quadrant
+                    if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, cur_row);
                 }
+                __syncwarp();
             }
             tc::fence_before_thread_sync();
             __syncwarp();
@@ -231,7 +258,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     // ---- teardown: nobody exits (or frees TMEM) while the peer may still touch this CTA ----
     tc::fence_before_thread_sync();
     if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
-    for (int i = tid; i < nq_pad; i += GT_THREADS) cand_cnt[(size_t)blockIdx.x * nq_pad + i] = cnt_s[i];
+    for (int i = tid; i < nq_pad; i += GT_THREADS) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) cand_cnt[((size_t)blockIdx.x * 4 + e) * nq_pad + i] = cnt_s[e * GT_MAX_NQ + i];
+    }
     if (warp == GT_WARP_ALLOC) {
         tc::fence_after_thread_sync();
         tc::tmem_dealloc<CG>(tmem_base, 512);
@@ -240,16 +270,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
 
 static size_t gemm_smem_bytes(int cg, int stages) {
     size_t stage = GT_A_BYTES + (size_t)(GT_QBLK / cg) * GT_BK * 2;
-    return (size_t)stages * stage + (size_t)GT_MAX_NQ * 8 + (size_t)(2 * stages + 4) * 8 + 16;
+    return (size_t)stages * stage + (size_t)GT_MAX_NQ * 4 * 5 + (size_t)(2 * stages + 4) * 8 + 16;
 }
 
-template <int CG>
+template <int CG, bool HAS_H>
 static int launch_gemm_t(const CUtensorMap &tx, const CUtensorMap &tq, const GemmPhase &ph, int n_qblk, int k_blocks,
                          int64_t n_rows, const float *row_h, const uint8_t *skip, const float *g_bound, int nq_pad,
                          uint64_t *cand, int *cand_cnt, cudaStream_t st) {
     int stages = CG == 2 ? 6 : 4;
     size_t smem = gemm_smem_bytes(CG, stages);
-    auto kern = flat_gemm_kernel<CG>;
+    auto kern = flat_gemm_kernel<CG, HAS_H>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n_work = ph.n_tiles * n_qblk;
     if (n_work <= 0) return CM_OK;
@@ -346,7 +376,7 @@ static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv
 // K-th smallest is found there by a 4 x 8-bit radix select.
 // final == 0: g[q] = -(tau_K + 2E) for the next phase.  final == 1: additionally compact the rows
 // with key <= tau_K + 2E into rs[q][*] for the exact re-score.
-static constexpr int SEL_THREADS = 512;
+static constexpr int SEL_THREADS = 1024;
 __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
     const uint64_t *__restrict__ cand, const int *__restrict__ cand_cnt, int nq_pad, int n_cta, int slots, int K, int dim,
     const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
@@ -354,38 +384,59 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
     int stage_cap, float e_scale) {
     extern __shared__ uint32_t sel_smem[];
     uint32_t *hi_s = sel_smem;                                         // [stage_cap] ordered score bits
-    int *off_s = reinterpret_cast<int *>(sel_smem + stage_cap);        // [n_cta + 1] region offsets
+    int *off_s = reinterpret_cast<int *>(sel_smem + stage_cap);        // [n_cta + 1] region offsets (n_cta <= SEL_THREADS)
     __shared__ int hist[256];
+    __shared__ int warp_tot[SEL_THREADS / 32];
     __shared__ uint32_t s_prefix, s_lo, s_hi;
-    __shared__ int s_rank, s_out, s_ovf, s_maxc;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_maxc = 0; }
+    __shared__ int s_rank, s_out, s_ovf;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; s_prefix = 0; s_rank = K; }
+    // ---- region counts -> exclusive offsets (block scan) ----
+    int c = tid < n_cta ? cand_cnt[(size_t)tid * nq_pad + q] : 0;
     __syncthreads();
-    for (int r = tid; r < n_cta; r += SEL_THREADS) {
-        int c = cand_cnt[(size_t)r * nq_pad + q];
-        if (c > slots) s_ovf = 1;
-        off_s[r + 1] = c;
-        atomicMax(&s_maxc, c);
+    if (c > slots) s_ovf = 1;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        off_s[0] = 0;
-        for (int r = 0; r < n_cta; r++) { acc += off_s[r + 1]; off_s[r + 1] = acc; }
-        if (acc > stage_cap) s_ovf = 1;
-    }
+    int wbase = 0;
+    for (int w2 = 0; w2 < warp; w2++) wbase += warp_tot[w2];
+    if (tid < n_cta) off_s[tid + 1] = wbase + incl;
+    if (tid == 0) off_s[0] = 0;
     __syncthreads();
-    if (s_ovf) {
+    const int total = off_s[n_cta];
+    if (s_ovf || total > stage_cap) {
         if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; if (final) rs_cnt[q] = 0; }
         return;
     }
-    const int total = off_s[n_cta], maxc = s_maxc;
     const uint64_t *qcand = cand + (size_t)q * n_cta * slots;
-    // one sweep over (region, slot) pairs; independent loads, no dependent chains
-    for (int idx = tid; idx < n_cta * maxc; idx += SEL_THREADS) {
-        int r = idx / maxc, i = idx - r * maxc;
-        int o = off_s[r];
-        if (i < off_s[r + 1] - o) hi_s[o + i] = (uint32_t)(qcand[(size_t)r * slots + i] >> 32);
+    // flat candidate index j -> (region, slot): largest r with off_s[r] <= j
+    auto locate = [&](int j) -> size_t {
+        int lo = 0, hi = n_cta;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (off_s[mid] <= j) lo = mid; else hi = mid;
+        }
+        return (size_t)lo * slots + (size_t)(j - off_s[lo]);
+    };
+    // ---- stage the ordered score words (high halves of the keys); loads batched 4 deep ----
+    const uint32_t *qwords = reinterpret_cast<const uint32_t *>(qcand);
+    for (int j0 = 0; j0 < total; j0 += SEL_THREADS * 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int j = j0 + u * SEL_THREADS + tid;
+            v[u] = j < total ? __ldg(qwords + 2 * locate(j) + 1) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int j = j0 + u * SEL_THREADS + tid;
+            if (j < total) hi_s[j] = v[u];
+        }
     }
     __syncthreads();
     float bound = INFINITY;
@@ -400,14 +451,10 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
             lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        if (tid == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
-        __syncthreads();
-        if ((tid & 31) == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
         __syncthreads();
         const uint32_t base = s_lo, range = s_hi - s_lo;
         const int n_pass = range == 0 ? 0 : (32 - __clz(range) + 7) / 8;
-        if (tid == 0) { s_prefix = 0; s_rank = K; }
-        __syncthreads();
         for (int pass = n_pass - 1; pass >= 0; pass--) {
             int shift = 8 * pass;
             if (tid < 256) hist[tid] = 0;
@@ -419,20 +466,32 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
                 if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int r = s_rank, b = 0;
-                for (; b < 255; b++) {
-                    if (r <= hist[b]) break;
-                    r -= hist[b];
+            if (warp == 0) {
+                // bin holding rank s_rank: warp scan over 8 bins per lane
+                int h[8], sum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) { h[u] = hist[lane * 8 + u]; sum += h[u]; }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
                 }
-                s_rank = r;
-                s_prefix = prefix | ((uint32_t)b << shift);
+                int r = s_rank, before = inc - sum;
+                bool mine = r > before && r <= inc;
+                if (mine) {
+                    int rr = r - before, b = 0;
+                    for (; b < 7; b++) {
+                        if (rr <= h[b]) break;
+                        rr -= h[b];
+                    }
+                    s_rank = rr;
+                    s_prefix = prefix | ((uint32_t)(lane * 8 + b) << shift);
+                }
             }
             __syncthreads();
         }
-        if (tid == 0) s_prefix += base;
-        __syncthreads();
-        float tau = ordered_to_float(s_prefix);
+        float tau = ordered_to_float(s_prefix + base);
         // E_q: see the header comment.  X, Dx: max row norm / max bf16 residual norm; nq, dq: the query's.
         float2 qn = q_norms[q];
         float nq = qn.x, dq = qn.y, X = __uint_as_float(max_bits[0]), Dx = __uint_as_float(max_bits[1]);
@@ -444,12 +503,10 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
     if (tid == 0) g[q] = -bound;
     if (!final) return;
     const uint32_t bound_hi = float_to_ordered(bound);
-    for (int idx = tid; idx < n_cta * maxc; idx += SEL_THREADS) {
-        int r = idx / maxc, i = idx - r * maxc;
-        int o = off_s[r];
-        if (i < off_s[r + 1] - o && hi_s[o + i] <= bound_hi) {
+    for (int j = tid; j < total; j += SEL_THREADS) {
+        if (hi_s[j] <= bound_hi) {
             int slot = atomicAdd(&s_out, 1);
-            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(qcand[(size_t)r * slots + i]);
+            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(qcand[locate(j)]);
         }
     }
     __syncthreads();
@@ -632,24 +689,27 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         if (SB < 2 || tB < tA) {
             int SA = std::max(2, T / tA);
             int nA = (T + SA - 1) / SA;
-            ph[n_ph++] = GemmPhase{0, SA, SA, nA};
-            ph[n_ph++] = GemmPhase{2, SA, SA, T - nA};
+            ph[n_ph++] = GemmPhase{0, SA, SA, nA, 0};
+            ph[n_ph++] = GemmPhase{2, SA, SA, T - nA, 0};
         } else {
             int R = std::max(2, (nAB + tA / 2) / tA);
             int SA = SB * R;
             int nA = (T + SA - 1) / SA, nABt = (T + SB - 1) / SB;
-            ph[n_ph++] = GemmPhase{0, SA, SB, nA};
-            ph[n_ph++] = GemmPhase{1, SA, SB, nABt - nA};
-            ph[n_ph++] = GemmPhase{2, SA, SB, T - nABt};
+            ph[n_ph++] = GemmPhase{0, SA, SB, nA, 0};
+            ph[n_ph++] = GemmPhase{1, SA, SB, nABt - nA, 0};
+            ph[n_ph++] = GemmPhase{2, SA, SB, T - nABt, 0};
         }
     }
 
     // debugging aid: widen the candidate band (>= 1 keeps the result exact)
     float e_scale = 1.0f;
     if (const char *es = getenv("COMET_B200_E_SCALE")) e_scale = std::max(1.0f, (float)atof(es));
-    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 4 + (size_t)(n_cta + 1) * 4;
+    const int n_reg = n_cta * 4;   // candidate regions per query: (CTA, lane quadrant)
+    if (n_reg > SEL_THREADS) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
+    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 4 + (size_t)(n_reg + 1) * 4;
     CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     int passes = 0;
+    if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
     for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
         int nqc = (int)std::min<int64_t>(GT_MAX_NQ, nq - q0);
         int nq_pad = (nqc + GT_QBLK - 1) / GT_QBLK * GT_QBLK;
@@ -664,12 +724,12 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
         CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
-        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_cta * CAND_SLOTS * 8, st));
-        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_cta + 3) * 4, st));
-        ovf = ccnt + (size_t)nq_pad * n_cta; rcnt = ovf + nq_pad; kcnt = rcnt + nq_pad;
+        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * CAND_SLOTS * 8, st));
+        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 3) * 4, st));
+        ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + nq_pad;
         CM_TRY(ws_alloc((void **)&rs, (size_t)nq_pad * RS_CAP * 4, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
-        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_cta + 3) * 4, st));
+        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 3) * 4, st));
         CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
         // g: phase A bound is -inf for real queries (everything is a candidate), +inf for padding
         init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad);
@@ -680,13 +740,18 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
                             (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
         for (int p = 0; p < n_ph; p++) {
-            if (cg == 2)
-                CM_TRY(launch_gemm_t<2>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st));
+            const bool has_h = metric != CM_COSINE;   // cosine keys are -dot: no per-row offset
+            if (cg == 2 && has_h)
+                CM_TRY((launch_gemm_t<2, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
+            else if (cg == 2)
+                CM_TRY((launch_gemm_t<2, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
+            else if (has_h)
+                CM_TRY((launch_gemm_t<1, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else
-                CM_TRY(launch_gemm_t<1>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st));
+                CM_TRY((launch_gemm_t<1, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             {
                 ProfScope prof(CM_PROF_SELECT, st);
-                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(cand, ccnt, nq_pad, n_cta, CAND_SLOTS, K, dim, qn,
+                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn,
                                                                        max_bits, g, ovf, p == n_ph - 1 ? 1 : 0, rs, rcnt,
                                                                        RS_CAP, SEL_STAGE_CAP, e_scale);
                 count_launch();

@@ -23,6 +23,7 @@ def run(tag, reps=5):
     torch.cuda.synchronize(); L.cm_profile_enable(0)
     gm, gn = capi.profile_get(capi.PROF_FLAT_GEMM); sm, sn = capi.profile_get(capi.PROF_SELECT); rm, rn = capi.profile_get(capi.PROF_RESCORE)
     print(f"{tag}: gemm {gm/reps:.3f} ms/step ({gn//reps} launches)  select {sm/reps:.3f}  rescore {rm/reps:.3f}  min cnt {int(oc.min())}", flush=True)
-for es in sys.argv[1:]:
-    os.environ["COMET_B200_E_SCALE"] = es
-    run("E_SCALE=" + es)
+for kv in sys.argv[1:]:
+    k, v = kv.split("=")
+    os.environ[k] = v
+    run(kv)
