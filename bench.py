@@ -217,16 +217,28 @@ def run_ours(args):
     if world > 1:
         g_ids = torch.zeros((world, nq, K), dtype=torch.int32, device=dev)
         g_sc = torch.zeros((world, nq, K), dtype=torch.float32, device=dev)
+        g_cnt = torch.zeros((world, nq), dtype=torch.int64, device=dev)
+        m_ids = torch.zeros((nq, K), dtype=torch.int32, device=dev)
+        m_sc = torch.zeros((nq, K), dtype=torch.float32, device=dev)
+        m_cnt = torch.zeros((nq,), dtype=torch.int64, device=dev)
 
-    def step_device():
+    def exchange():
+        # the path's one exchange step: all-gather per-shard top-K over NCCL, then the device merge
+        dist.all_gather_into_tensor(g_ids.view(world * nq, K), out_ids)
+        dist.all_gather_into_tensor(g_sc.view(world * nq, K), out_sc)
+        dist.all_gather_into_tensor(g_cnt.view(world * nq), out_cnt)
+        capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(), world, nq, K, K,
+                                 m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), out_stride=K,
+                                 stream=stream.cuda_stream)
+
+    def step_local():
         index.search_device(q_dev.data_ptr(), nq, K, out_ids.data_ptr(), out_sc.data_ptr(), out_cnt.data_ptr(), K,
                             stream=stream.cuda_stream, path=path)
+
+    def step_device():
+        step_local()
         if world > 1:
-            # the path's one exchange step: all-gather per-shard top-K, then K-way merge on device
-            dist.all_gather_into_tensor(g_ids, out_ids)
-            dist.all_gather_into_tensor(g_sc, out_sc)
-            capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, out_ids.data_ptr(),
-                                     out_sc.data_ptr(), stream.cuda_stream)
+            exchange()
 
     def barrier():
         if world > 1:
@@ -266,7 +278,7 @@ def run_ours(args):
         L.cm_profile_reset(); L.cm_profile_enable(1)
         n_prof = max(2, min(args.steps, 5))
         for _ in range(n_prof):
-            step_device()
+            step_local()          # rank-local kernels only: no collective on this leg
         torch.cuda.synchronize()
         L.cm_profile_enable(0)
         hbm, tf_burst, tf_sus, which = measured_peaks()
@@ -311,15 +323,14 @@ def run_ours(args):
                                     capi.ptr(h_ids, capi.u32p), capi.ptr(h_sc, capi.f32p), None,
                                     capi.ptr(h_cnt, capi.i64p)))
         if world > 1:
-            # host-side callers merge shard results after gathering them; use the device exchange
+            # shard results go back to the device for the exchange step; the merged list returns to the host
             out_ids.copy_(torch.from_numpy(h_ids.view(np.int32)), non_blocking=True)
             out_sc.copy_(torch.from_numpy(h_sc), non_blocking=True)
-            dist.all_gather_into_tensor(g_ids, out_ids)
-            dist.all_gather_into_tensor(g_sc, out_sc)
-            capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), world, nq, K, out_ids.data_ptr(),
-                                     out_sc.data_ptr(), stream.cuda_stream)
-            h_ids[...] = out_ids.cpu().numpy().view(np.uint32)
-            h_sc[...] = out_sc.cpu().numpy()
+            out_cnt.copy_(torch.from_numpy(h_cnt), non_blocking=True)
+            exchange()
+            h_ids[...] = m_ids.cpu().numpy().view(np.uint32)
+            h_sc[...] = m_sc.cpu().numpy()
+            h_cnt[...] = m_cnt.cpu().numpy()
 
     for _ in range(min(args.warmup, 3)):
         step_host()

@@ -73,6 +73,7 @@ SIGNATURES = {
     "cm_flat_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                         vp, vp, vp]),
     "cm_flat_last_stats": (C.c_int, [vp, C.POINTER(FlatStats)]),
+    "cm_merge_shards_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp]),
 }
 
 _lib = None
@@ -139,6 +140,14 @@ def make_params(k=10, threshold=0.0, nprobes=0, ef_search=0, filter_ids=None, pa
         p.filter_ids = None
         p.nfilter = 0
     return p, f
+
+
+def merge_shards_device(ids_ptr, scores_ptr, counts_ptr, world, nq, in_stride, k, out_ids_ptr, out_scores_ptr,
+                        out_counts_ptr=0, out_stride=None, stream=0):
+    """All arguments are device pointers: gathered [world][nq][in_stride] lists -> global top-k."""
+    check(lib().cm_merge_shards_device(vp(ids_ptr), vp(scores_ptr), vp(counts_ptr) if counts_ptr else None, int(world),
+                                       int(nq), int(in_stride), int(k), int(out_stride or k), vp(out_ids_ptr),
+                                       vp(out_scores_ptr), vp(out_counts_ptr) if out_counts_ptr else None, vp(stream)))
 
 
 def distance_pairs(metric, a, b):

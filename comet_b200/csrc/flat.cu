@@ -538,6 +538,18 @@ int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const 
     return CM_OK;
 }
 
+int cm_merge_shards_device(const uint32_t *ids_dev, const float *scores_dev, const int64_t *counts_dev, int world,
+                           int64_t nq, int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids_dev,
+                           float *out_scores_dev, int64_t *out_counts_dev, void *stream) {
+    CM_TRY(cm::ensure_device());
+    if (!ids_dev || !scores_dev || !out_ids_dev || !out_scores_dev || world <= 0 || in_stride <= 0)
+        return cm::fail(CM_ERR_INVALID_ARG, "bad argument");
+    if (k <= 0 || k > (int64_t)world * in_stride) k = (int64_t)world * in_stride;
+    if (out_stride < k) return cm::fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < k %lld", (long long)out_stride, (long long)k);
+    return cm::launch_merge_shards(ids_dev, scores_dev, counts_dev, world, nq, in_stride, (int)k, out_stride, out_ids_dev,
+                                   out_scores_dev, out_counts_dev, (cudaStream_t)stream);
+}
+
 int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out) {
     if (!h || !out) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(const_cast<cm_flat *>(h)->ix.stats_mu);

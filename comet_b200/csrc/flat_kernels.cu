@@ -289,6 +289,61 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
 }
 
 // ------------------------------------------------------------------------------------------------
+// merge of per-SHARD results (multi-GPU): shard r holds rows [r*shard, (r+1)*shard) of the corpus and
+// returns its own sorted top-K; the global order (score, scan position) is (score, shard, rank in
+// the shard's list), so the merge needs nothing but the gathered lists.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
+    const uint32_t *__restrict__ ids, const float *__restrict__ scores, const long long *__restrict__ counts, int world,
+    long long nq, long long in_stride, int K, int C, long long out_stride, uint32_t *__restrict__ out_ids,
+    float *__restrict__ out_scores, long long *__restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);
+    __shared__ int cnt;
+    __shared__ uint64_t tau;
+    const CtaBarrier bar;
+    const int tid = threadIdx.x;
+    const long long q = blockIdx.x;
+    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+    __syncthreads();
+    for (int r = 0; r < world; r++) {
+        long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
+        if (c > in_stride) c = in_stride;
+        const float *sc = scores + ((size_t)r * nq + q) * in_stride;
+        for (int j = tid; j < c; j += MERGE_THREADS) buf[atomicAdd(&cnt, 1)] = make_key(sc[j], (uint32_t)(r * in_stride + j));
+    }
+    compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
+    int m = cnt;
+    for (int i = tid; i < m; i += MERGE_THREADS) {
+        uint64_t key = buf[i];
+        uint32_t src = key_pos(key);
+        uint32_t r = src / (uint32_t)in_stride, j = src % (uint32_t)in_stride;
+        out_ids[(size_t)q * out_stride + i] = ids[((size_t)r * nq + q) * in_stride + j];
+        out_scores[(size_t)q * out_stride + i] = key_score(key);
+    }
+    if (tid == 0 && out_counts) out_counts[q] = m;
+}
+
+int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
+                        int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                        int64_t *out_counts, cudaStream_t stream) {
+    if (nq <= 0) return CM_OK;
+    int C = next_pow2((int)(world * in_stride));
+    if (C < 512) C = 512;
+    size_t smem = (size_t)C * 8;
+    if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "%d shards x k=%lld too large for the shard merge", world, (long long)in_stride);
+    CM_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(CM_PROF_SELECT, stream);
+    merge_shards_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>(ids, scores, (const long long *)counts, world,
+                                                                      (long long)nq, (long long)in_stride, K, C,
+                                                                      (long long)out_stride, out_ids, out_scores,
+                                                                      (long long *)out_counts);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-row helpers
 // ------------------------------------------------------------------------------------------------
 // distance.go:244-264 PreprocessInPlace / :269-290 Preprocess.  One thread per row, sequential.

@@ -37,6 +37,12 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
                       const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                       int64_t *out_pos, int64_t *out_counts, cudaStream_t stream);
 
+// Merge `world` per-shard sorted result lists per query ([world][nq][in_stride], counts [world][nq] or
+// NULL = full) into the global top-K ordered by (score, shard, rank within the shard).
+int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
+                        int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                        int64_t *out_counts, cudaStream_t stream);
+
 // Distance.Preprocess / PreprocessInPlace on n rows (one thread per row, reference order).
 // dst rows have leading dimension ld_dst (zero padded beyond dim); flags[i] = 1 for a zero vector.
 int launch_preprocess_rows(int metric, bool fma, const float *src, int64_t n, int dim, int ld_src, float *dst,

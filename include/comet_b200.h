@@ -138,6 +138,15 @@ int cm_flat_search_device(cm_flat *h, const float *queries_dev, int64_t nq, int 
                           const cm_search_params *p, int64_t out_stride, uint32_t *out_ids_dev,
                           float *out_scores_dev, int64_t *out_pos_dev, int64_t *out_counts_dev,
                           void *stream);
+/* Multi-GPU flat search: the corpus is row-sharded, shard r (rank r) holding rows [r*n/W, (r+1)*n/W) in
+ * scan order.  Every rank searches its shard, the [nq][in_stride] result lists are all-gathered
+ * (NCCL) into [W][nq][in_stride] device buffers, and this merges them into the global result in the
+ * reference's order (score, scan position) == (score, shard, rank within the shard's list).
+ * counts_dev: [W][nq] valid entries per list, or NULL when every list is full.  Replaces nothing in
+ * the single-process reference; it is the path's one exchange step. */
+int cm_merge_shards_device(const uint32_t *ids_dev, const float *scores_dev, const int64_t *counts_dev, int world,
+                           int64_t nq, int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids_dev,
+                           float *out_scores_dev, int64_t *out_counts_dev, void *stream);
 /* statistics of the last search on this handle (for bench.py / profiles): */
 typedef struct {
     int32_t path_used;          /* CM_PATH_EXACT or CM_PATH_TENSOR */

@@ -232,3 +232,38 @@ def test_full_size_1m_x_768_exact_path():
     o.add(np.arange(1, n + 1, dtype=np.uint32), xh)
     oi, os_ = o.search(q[0], k=100)
     assert_same_results(ids[0], sc[0], cnt[0], oi, os_, "1M x 768")
+
+
+def test_merge_shards_device_matches_single_index():
+    # multi-GPU exchange step on one GPU: two row shards searched separately, lists stacked as an
+    # all-gather would, merged by cm_merge_shards_device; must equal the oracle on the whole corpus
+    import torch
+    rng = np.random.default_rng(77)
+    n, d, k, nq = 5000, 48, 17, 9
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[10] = x[4000]                                   # a tie across the shard boundary
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q[0] = x[10]
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    half = n // 2
+    parts = []
+    for r0, r1 in [(0, half), (half, n)]:
+        g = capi.FlatIndex(d, capi.L2SQ)
+        g.add(ids[r0:r1], x[r0:r1].copy())
+        parts.append(g.search(q, k=k))
+    g_ids = torch.from_numpy(np.stack([p[0] for p in parts]).view(np.int32)).cuda()
+    g_sc = torch.from_numpy(np.stack([p[1] for p in parts])).cuda()
+    g_cnt = torch.from_numpy(np.stack([p[2] for p in parts])).cuda()
+    o_ids = torch.zeros((nq, k), dtype=torch.int32, device="cuda")
+    o_sc = torch.zeros((nq, k), dtype=torch.float32, device="cuda")
+    o_cnt = torch.zeros((nq,), dtype=torch.int64, device="cuda")
+    capi.merge_shards_device(g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(), 2, nq, k, k, o_ids.data_ptr(),
+                             o_sc.data_ptr(), o_cnt.data_ptr(), out_stride=k,
+                             stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    o = O.Flat(d, capi.L2SQ)
+    o.add(ids, x.copy())
+    for i in range(nq):
+        oi, os_ = o.search(q[i], k=k)
+        assert_same_results(o_ids[i].cpu().numpy().view(np.uint32), o_sc[i].cpu().numpy(), int(o_cnt[i]), oi, os_,
+                            what=f"query {i}")
