@@ -73,6 +73,20 @@ SIGNATURES = {
     "cm_flat_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                         vp, vp, vp]),
     "cm_flat_last_stats": (C.c_int, [vp, C.POINTER(FlatStats)]),
+    "cm_ivf_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_ivf_destroy": (C.c_int, [vp]),
+    "cm_ivf_set_centroids": (C.c_int, [vp, f32p]),
+    "cm_ivf_trained": (C.c_int, [vp]),
+    "cm_ivf_size": (C.c_int64, [vp]),
+    "cm_ivf_default_nprobes": (C.c_int, [vp]),
+    "cm_ivf_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
+    "cm_ivf_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_ivf_flush": (C.c_int, [vp]),
+    "cm_ivf_get_rows": (C.c_int, [vp, i64p, C.c_int64, f32p]),
+    "cm_ivf_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p,
+                                i64p, i64p]),
+    "cm_ivf_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
+                                       vp, vp, vp]),
     "cm_merge_shards_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp]),
 }
 
@@ -178,7 +192,7 @@ class FlatIndex:
         self.dim, self.metric = dim, metric
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().cm_flat_destroy(self.h)
             self.h = None
 
@@ -250,3 +264,60 @@ class FlatIndex:
         check(lib().cm_flat_last_stats(self.h, C.byref(s)))
         return {"path_used": s.path_used, "passes": s.passes, "candidates": s.candidates,
                 "fallback_queries": s.fallback_queries, "kernel_launches": s.kernel_launches}
+
+
+class IVFIndex:
+    """Thin owner of a cm_ivf handle."""
+
+    def __init__(self, dim, nlist, metric):
+        self.h = vp()
+        check(lib().cm_ivf_create(int(dim), int(nlist), int(metric), C.byref(self.h)))
+        self.dim, self.nlist, self.metric = dim, nlist, metric
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().cm_ivf_destroy(self.h)
+            self.h = None
+
+    def set_centroids(self, c):
+        c = _f32(c).reshape(self.nlist, self.dim)
+        check(lib().cm_ivf_set_centroids(self.h, ptr(c, f32p)))
+
+    def add(self, ids, rows, writeback=True):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        lists = np.zeros(len(ids), np.int32)
+        check(lib().cm_ivf_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0,
+                               ptr(lists, i32p)))
+        return lists
+
+    def remove(self, id_):
+        check(lib().cm_ivf_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_ivf_flush(self.h))
+
+    def __len__(self):
+        return int(lib().cm_ivf_size(self.h))
+
+    def default_nprobes(self):
+        return int(lib().cm_ivf_default_nprobes(self.h))
+
+    def search(self, queries, k=10, nprobes=None, threshold=0.0, filter_ids=None, out_stride=None):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        if nprobes is None:
+            nprobes = self.default_nprobes()
+        n = len(self)
+        stride = out_stride or max(1, n if (k <= 0 or k > n) else k)
+        ids = np.zeros((nq, stride), np.uint32)
+        sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, nprobes=nprobes, filter_ids=filter_ids)
+        check(lib().cm_ivf_search(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p), ptr(sc, f32p), None,
+                                  ptr(cnt, i64p)))
+        return ids, sc, cnt

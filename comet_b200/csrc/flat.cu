@@ -102,9 +102,10 @@ int FlatIndex::add_from_device(const uint32_t *ids_host, const float *src_dev, i
     bool fma = rounding_mode() == CM_ROUND_FMA;
     int *flags = nullptr;
     CM_TRY(ws_alloc((void **)&flags, (size_t)n_add * sizeof(int), st));
-    CM_TRY(launch_preprocess_rows(metric, fma, src_dev, n_add, dim, dim, rows + (size_t)n * ld, ld, flags, st));
+    const int pre_metric = raw_rows ? CM_L2 : metric;
+    CM_TRY(launch_preprocess_rows(pre_metric, fma, src_dev, n_add, dim, dim, rows + (size_t)n * ld, ld, flags, st));
     int64_t good = n_add;
-    if (metric == CM_COSINE) {
+    if (pre_metric == CM_COSINE) {
         std::vector<int> hflags((size_t)n_add);
         CM_CUDA(cudaMemcpyAsync(hflags.data(), flags, (size_t)n_add * sizeof(int), cudaMemcpyDeviceToHost, st));
         CM_CUDA(cudaStreamSynchronize(st));
@@ -121,7 +122,7 @@ int FlatIndex::add_from_device(const uint32_t *ids_host, const float *src_dev, i
         CM_CUDA(cudaMemcpyAsync(ids + n, ids_host, (size_t)good * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         if (any_del) CM_CUDA(cudaMemcpyAsync(deleted + n, del.data(), (size_t)good, cudaMemcpyHostToDevice, st));
         else CM_CUDA(cudaMemsetAsync(deleted + n, 0, (size_t)good, st));
-        if (writeback_host && metric == CM_COSINE)
+        if (writeback_host && pre_metric == CM_COSINE)
             CM_CUDA(cudaMemcpy2DAsync(writeback_host, (size_t)dim * 4, rows + (size_t)n * ld, (size_t)ld * 4,
                                       (size_t)dim * 4, (size_t)good, cudaMemcpyDeviceToHost, st));
         CM_CUDA(cudaStreamSynchronize(st));

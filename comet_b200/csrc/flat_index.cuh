@@ -26,6 +26,7 @@ struct FlatIndex {
     std::vector<uint32_t> ids_host_mirror;  // for Remove / lookupNodeVectors (O(N) ID scans stay on the host)
     std::unordered_set<uint32_t> deleted_ids;
     int64_t n_deleted_rows = 0;
+    bool raw_rows = false;                  // true: Add stores rows as given (k-means centroids are never normalised)
 
     // tensor-core candidate pass state (flat_tensor.cu)
     __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ldb] bf16 shadow of rows, ldb = dim padded to 64

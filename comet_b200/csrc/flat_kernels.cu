@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
         uint64_t key = buf[i];
         uint32_t pos = key_pos(key);
         size_t o = (size_t)q * out_stride + i;
-        out_ids[o] = row_ids[pos];
+        out_ids[o] = row_ids ? row_ids[pos] : pos;
         out_scores[o] = key_score(key);
         if (out_pos) out_pos[o] = pos;
     }

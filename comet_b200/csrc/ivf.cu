@@ -1,0 +1,590 @@
+// ivf.cu -- IVFIndex device state, search and the cm_ivf_* entry points of the C ABI.
+//
+// Replaces ivfIndexSearch.searchSingleQuery (ivf_index_search.go:217-322): coarse scan of the nlist
+// centroids + full sort (K5), exact scan of the vectors of the nprobes nearest lists (K6), full sort
+// of the candidates, top k -- with scores, ranks and ids bit-identical to the reference.
+//
+// Device layout (replaces lists [][]VectorNode, ivf_index.go:82-119):
+//   coarse   FlatIndex of the nlist centroids, rows stored RAW (k-means output is never normalised,
+//            clustering.go:213-239), scan position == list index;
+//   store    FlatIndex of every added vector in ARRIVAL order (preprocessed like IVFIndex.Add,
+//            ivf_index.go:269-277), with ids and the soft-delete mask;
+//   members  u32 [n]        store positions grouped by list, insertion order inside a list (CSR);
+//   list_off i64 [nlist+1]
+// A search never moves rows: list scans gather 3 KB rows by position with 16-byte cp.async pieces.
+//
+// Pipeline per batch of queries: preprocess -> exact coarse scan (flat_scan_kernel, k = nprobes) ->
+// ivf_offsets_kernel (per query prefix sums of the probed list lengths = the candidate numbering of
+// the reference's append loop) -> ivf_scan_kernel (128 candidates per CTA, reference-order distance,
+// delete / document filter / threshold) -> merge_topk_kernel ordered by (score, candidate number) ->
+// ivf_emit_kernel (candidate number -> store position -> id).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+#include "flat_index.cuh"
+#include "flat_kernels.cuh"
+#include "select.cuh"
+
+namespace cm {
+
+struct IVFIndex {
+    int dim = 0, nlist = 0, metric = 0, device = 0;
+    bool trained = false;
+    FlatIndex coarse, store;
+    std::vector<std::vector<uint32_t>> lists;   // store positions per list, insertion order
+    std::vector<int32_t> list_of;               // list of every store position
+    uint32_t *members = nullptr;
+    long long *list_off = nullptr;
+    int64_t members_cap = 0;
+    bool csr_dirty = true;
+    std::vector<int64_t> sizes_desc;            // list lengths, descending (bound on candidates per query)
+    std::mutex csr_mu;
+
+    ~IVFIndex() { cudaFree(members); cudaFree(list_off); }
+    int sync_csr(cudaStream_t st);
+    int64_t candidate_bound(int nprobes) const;
+};
+
+int IVFIndex::sync_csr(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(csr_mu);
+    if (!csr_dirty) return CM_OK;
+    int64_t n = store.n;
+    if (n > members_cap || !members) {
+        cudaFree(members);
+        members_cap = std::max<int64_t>(n + n / 2, 1024);
+        CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
+    }
+    if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
+    std::vector<uint32_t> flat;
+    flat.reserve((size_t)n);
+    std::vector<long long> off((size_t)nlist + 1, 0);
+    sizes_desc.assign((size_t)nlist, 0);
+    for (int l = 0; l < nlist; l++) {
+        off[(size_t)l] = (long long)flat.size();
+        flat.insert(flat.end(), lists[(size_t)l].begin(), lists[(size_t)l].end());
+        sizes_desc[(size_t)l] = (int64_t)lists[(size_t)l].size();
+    }
+    off[(size_t)nlist] = (long long)flat.size();
+    std::sort(sizes_desc.begin(), sizes_desc.end(), std::greater<int64_t>());
+    if (!flat.empty()) CM_CUDA(cudaMemcpyAsync(members, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(list_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    csr_dirty = false;
+    return CM_OK;
+}
+
+int64_t IVFIndex::candidate_bound(int nprobes) const {
+    int64_t b = 0;
+    for (int i = 0; i < nprobes && i < (int)sizes_desc.size(); i++) b += sizes_desc[(size_t)i];
+    return b;
+}
+
+// per query: q_off[q][p] = number of candidates contributed by probes 0..p-1 (p = 0..nprobes)
+__global__ void ivf_offsets_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ probe_cnt,
+                                   const long long *__restrict__ list_off, int nprobes, long long *__restrict__ q_off) {
+    const int q = blockIdx.x;
+    __shared__ long long carry;
+    __shared__ long long wsum[8];
+    if (threadIdx.x == 0) { carry = 0; q_off[(size_t)q * (nprobes + 1)] = 0; }
+    __syncthreads();
+    const int np = (int)min((long long)nprobes, probe_cnt[q]);
+    for (int p0 = 0; p0 < nprobes; p0 += 256) {
+        int p = p0 + threadIdx.x;
+        long long len = 0;
+        if (p < np) {
+            long long l = probe_list[(size_t)q * nprobes + p];
+            len = list_off[l + 1] - list_off[l];
+        }
+        long long inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        long long base = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += wsum[w];
+        if (p < nprobes) q_off[(size_t)q * (nprobes + 1) + p + 1] = base + inc;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = base + inc;
+        __syncthreads();
+    }
+}
+
+// candidate number c of query q -> store position (largest p with q_off[p] <= c)
+__device__ __forceinline__ uint32_t ivf_locate(const long long *__restrict__ qo, int nprobes,
+                                               const long long *__restrict__ probe_list,
+                                               const long long *__restrict__ list_off,
+                                               const uint32_t *__restrict__ members, long long c) {
+    int lo = 0, hi = nprobes;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (qo[mid] <= c) lo = mid; else hi = mid;
+    }
+    long long l = probe_list[lo];
+    return members[list_off[l] + (c - qo[lo])];
+}
+
+// 128 candidates of one query per CTA: gather rows, reference-order distance, filters, keys out
+template <int METRIC, bool FMA>
+__global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
+                                                       const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
+                                                       const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
+                                                       int nprobes, const uint8_t *__restrict__ skip, float threshold,
+                                                       long long cap_c, int n_chunks, uint64_t *__restrict__ out_keys,
+                                                       int *__restrict__ out_cnt) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *q_s = reinterpret_cast<float *>(smem);
+    uint8_t *stage = smem + (size_t)ld * 4;
+    __shared__ uint32_t pos_s[128];
+    __shared__ int s_cnt;
+    const int q = blockIdx.y, tid = threadIdx.x;
+    const long long *qo = q_off + (size_t)q * (nprobes + 1);
+    const long long cq = qo[nprobes];
+    const long long base = (long long)blockIdx.x * 128;
+    if (base >= cq) return;
+    const long long mine = base + tid;
+    const bool live = mine < cq;
+    const uint32_t pos = ivf_locate(qo, nprobes, probe_list + (size_t)q * nprobes, list_off, members, live ? mine : base);
+    pos_s[tid] = pos;
+    if (tid == 0) s_cnt = 0;
+    for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
+    __syncthreads();
+    const int n_ch = ld / 32;
+    auto issue = [&](int c) {
+        uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            int idx = p * 128 + tid;
+            int r = idx >> 3, piece = idx & 7;
+            const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
+            uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    float acc = 0.0f;
+    for (int c = 0; c < n_ch; c++) {
+        if (c + 1 < n_ch) {
+            issue(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
+        const float *qc = q_s + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
+            float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
+            acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+            acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+            acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+            acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+        }
+        __syncthreads();
+    }
+    float dist = metric_finish<METRIC>(acc);
+    bool pass = live && !(skip != nullptr && skip[pos]) && !(threshold > 0.0f && dist > threshold);
+    if (pass) {
+        int slot = atomicAdd(&s_cnt, 1);
+        out_keys[(size_t)q * cap_c + base + slot] = make_key(dist, (uint32_t)mine);
+    }
+    __syncthreads();
+    if (tid == 0) out_cnt[(size_t)q * n_chunks + blockIdx.x] = s_cnt;
+}
+
+// candidate numbers of the final lists -> store positions and ids
+__global__ void ivf_emit_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
+                                const long long *__restrict__ list_off, const uint32_t *__restrict__ members, int nprobes,
+                                const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
+                                long long *__restrict__ out_pos, const long long *__restrict__ out_counts) {
+    const int q = blockIdx.x;
+    const long long m = out_counts[q];
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+        size_t o = (size_t)q * out_stride + i;
+        uint32_t pos = ivf_locate(q_off + (size_t)q * (nprobes + 1), nprobes, probe_list + (size_t)q * nprobes, list_off,
+                                  members, (long long)out_ids[o]);
+        out_ids[o] = row_ids[pos];
+        if (out_pos) out_pos[o] = pos;
+    }
+}
+
+template <int METRIC>
+static int launch_ivf_scan_m(bool fma, dim3 grid, size_t smem, cudaStream_t st, const float *rows, int ld, const float *queries,
+                             const long long *probe_list, const long long *q_off, const long long *list_off,
+                             const uint32_t *members, int nprobes, const uint8_t *skip, float threshold, long long cap_c,
+                             int n_chunks, uint64_t *out_keys, int *out_cnt) {
+    if (fma) {
+        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ivf_scan_kernel<METRIC, true><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes,
+                                                               skip, threshold, cap_c, n_chunks, out_keys, out_cnt);
+    } else {
+        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ivf_scan_kernel<METRIC, false><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes,
+                                                                skip, threshold, cap_c, n_chunks, out_keys, out_cnt);
+    }
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// nq independent searchSingleQuery calls; q_dev raw queries [nq][dim] on the device
+static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
+                             uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
+                             bool check_zero_queries) {
+    if (nq <= 0) return CM_OK;
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");   // ivf_index_search.go:223
+    int nprobes = p->nprobes;
+    if (nprobes <= 0 || nprobes > ix.nlist) nprobes = ix.nlist;                                    // :233-236
+    CM_TRY(ix.sync_csr(st));
+    FlatIndex &S = ix.store;
+    const int ld = S.ld;
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+    const int64_t bound_c = ix.candidate_bound(nprobes);
+    int64_t k_eff = p->k;
+    if (k_eff <= 0 || k_eff > bound_c) k_eff = bound_c;    // sanitizeK against the most candidates any query can have
+    if (out_stride < k_eff)
+        return fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)k_eff);
+    if (k_eff > 16000) return fail(CM_ERR_UNSUPPORTED, "ivf search supports k <= 16000 (got %lld)", (long long)k_eff);
+
+    // 1. Distance.Preprocess on the queries (ivf_index_search.go:239), zero-padded block for the scans
+    int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+    float *qp = nullptr;
+    int *qflags = nullptr;
+    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
+    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
+    if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
+    CM_TRY(launch_preprocess_rows(ix.metric, fma, q_dev, nq, ix.dim, ix.dim, qp, ld, qflags, st));
+    if (check_zero_queries && ix.metric == CM_COSINE) {
+        std::vector<int> hf((size_t)nq);
+        CM_CUDA(cudaMemcpyAsync(hf.data(), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < nq; i++)
+            if (hf[(size_t)i]) {
+                ws_free(qp, st); ws_free(qflags, st);
+                return fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)i);
+            }
+    }
+    if (bound_c == 0 || k_eff == 0) {
+        CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
+        ws_free(qp, st); ws_free(qflags, st);
+        return CM_OK;
+    }
+
+    // 2. coarse quantiser: exact scan of the centroids, the nprobes nearest by (distance, list index)
+    uint32_t *c_ids = nullptr;
+    float *c_sc = nullptr;
+    long long *probe_list = nullptr, *probe_cnt = nullptr, *q_off = nullptr;
+    CM_TRY(ws_alloc((void **)&c_ids, (size_t)nq * nprobes * 4, st));
+    CM_TRY(ws_alloc((void **)&c_sc, (size_t)nq * nprobes * 4, st));
+    CM_TRY(ws_alloc((void **)&probe_list, (size_t)nq * nprobes * 8, st));
+    CM_TRY(ws_alloc((void **)&probe_cnt, (size_t)nq * 8, st));
+    CM_TRY(ws_alloc((void **)&q_off, (size_t)nq * (nprobes + 1) * 8, st));
+    cm_flat_stats cst{};
+    CM_TRY(ix.coarse.search_exact(qp, nq, nq_pad, nprobes, nullptr, 0.0f, nprobes, c_ids, c_sc, (int64_t *)probe_list,
+                                  (int64_t *)probe_cnt, st, &cst));
+
+    // 3. candidate numbering
+    ivf_offsets_kernel<<<(unsigned)nq, 256, 0, st>>>(probe_list, probe_cnt, ix.list_off, nprobes, q_off);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+
+    // 4. soft deletes + document filter -> skip mask over store positions
+    const uint8_t *skip = nullptr;
+    uint8_t *skip_buf = nullptr;
+    uint32_t *filt_dev = nullptr;
+    if (p->filter_ids && p->nfilter > 0) {
+        std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
+        std::sort(f.begin(), f.end());
+        f.erase(std::unique(f.begin(), f.end()), f.end());
+        CM_TRY(ws_alloc((void **)&filt_dev, f.size() * 4, st));
+        CM_TRY(ws_alloc((void **)&skip_buf, (size_t)S.n, st));
+        CM_CUDA(cudaMemcpyAsync(filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
+        CM_TRY(launch_build_skip(S.ids, S.deleted, S.n, filt_dev, (int64_t)f.size(), skip_buf, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        skip = skip_buf;
+    } else if (S.n_deleted_rows > 0) {
+        skip = S.deleted;
+    }
+
+    // 5. list scans, in query groups so that the key workspace stays bounded (<= 1 GiB)
+    const int n_chunks = (int)((bound_c + 127) / 128);
+    const long long cap_c = (long long)n_chunks * 128;
+    int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (cap_c * 8)));
+    uint64_t *keys = nullptr;
+    int *kcnt = nullptr;
+    CM_TRY(ws_alloc((void **)&keys, (size_t)qgroup * cap_c * 8, st));
+    CM_TRY(ws_alloc((void **)&kcnt, (size_t)qgroup * n_chunks * 4, st));
+    size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
+    for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
+        int64_t m = std::min(qgroup, nq - q0);
+        CM_CUDA(cudaMemsetAsync(kcnt, 0, (size_t)m * n_chunks * 4, st));
+        dim3 grid((unsigned)n_chunks, (unsigned)m);
+        const float *qq = qp + (size_t)q0 * ld;
+        const long long *pl = probe_list + (size_t)q0 * nprobes, *qo = q_off + (size_t)q0 * (nprobes + 1);
+        ProfScope prof(CM_PROF_IVF_SCAN, st);
+        switch (ix.metric) {
+        case CM_L2: CM_TRY(launch_ivf_scan_m<CM_L2>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
+        case CM_L2SQ: CM_TRY(launch_ivf_scan_m<CM_L2SQ>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
+        default: CM_TRY(launch_ivf_scan_m<CM_COSINE>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
+        }
+        CM_TRY(launch_merge_topk(keys, kcnt, (int)m, n_chunks, 128, (int)k_eff, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
+                                 out_scores + (size_t)q0 * out_stride, nullptr, out_counts + q0, st));
+        ivf_emit_kernel<<<(unsigned)m, 128, 0, st>>>(pl, qo, ix.list_off, ix.members, nprobes, S.ids, (long long)out_stride,
+                                                     out_ids + (size_t)q0 * out_stride,
+                                                     out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,
+                                                     (const long long *)(out_counts + q0));
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
+    ws_free(qp, st); ws_free(qflags, st); ws_free(c_ids, st); ws_free(c_sc, st); ws_free(probe_list, st); ws_free(probe_cnt, st);
+    ws_free(q_off, st); ws_free(skip_buf, st); ws_free(filt_dev, st); ws_free(keys, st); ws_free(kcnt, st);
+    return CM_OK;
+}
+
+}  // namespace cm
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+struct cm_ivf {
+    cm::IVFIndex ix;
+};
+
+extern "C" {
+
+int cm_ivf_create(int dim, int nlist, int metric, cm_ivf **out) {
+    if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return cm::fail(CM_ERR_INVALID_ARG, "dimension must be positive");             // ivf_index.go:149
+    if (nlist <= 0) return cm::fail(CM_ERR_INVALID_ARG, "nlist must be positive");               // ivf_index.go:152
+    if (metric < 0 || metric > 2) return cm::fail(CM_ERR_INVALID_ARG, "unknown distance kind");
+    CM_TRY(cm::ensure_device());
+    cm_ivf *h = new cm_ivf();
+    h->ix.dim = dim; h->ix.nlist = nlist; h->ix.metric = metric;
+    cudaGetDevice(&h->ix.device);
+    for (cm::FlatIndex *f : {&h->ix.coarse, &h->ix.store}) {
+        f->dim = dim;
+        f->ld = (dim + cm::SCAN_CHUNK - 1) / cm::SCAN_CHUNK * cm::SCAN_CHUNK;
+        f->metric = metric;
+        f->device = h->ix.device;
+    }
+    h->ix.coarse.raw_rows = true;
+    h->ix.lists.resize((size_t)nlist);
+    *out = h;
+    return CM_OK;
+}
+int cm_ivf_destroy(cm_ivf *h) {
+    delete h;
+    return CM_OK;
+}
+
+// Load trained centroids (nlist x dim, row-major) -- the result of IVFIndex.Train (ivf_index.go:205-246).
+int cm_ivf_set_centroids(cm_ivf *h, const float *centroids) {
+    if (!h || !centroids) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    if (h->ix.store.n > 0) return cm::fail(CM_ERR_INVALID_ARG, "cannot replace centroids of a non-empty index");
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    cm::FlatIndex &c = h->ix.coarse;
+    c.n = 0; c.ids_host_mirror.clear();
+    float *stage = nullptr;
+    size_t bytes = (size_t)h->ix.nlist * h->ix.dim * 4;
+    int rc = cm::ws_alloc((void **)&stage, bytes, st);
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(stage, centroids, bytes, cudaMemcpyHostToDevice, st);
+        std::vector<uint32_t> ids((size_t)h->ix.nlist);
+        std::iota(ids.begin(), ids.end(), 0u);
+        rc = c.add_from_device(ids.data(), stage, h->ix.nlist, nullptr, st);
+    }
+    cm::ws_free(stage, st);
+    cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    if (rc == CM_OK) h->ix.trained = true;
+    return rc;
+}
+int cm_ivf_trained(const cm_ivf *h) { return h && h->ix.trained ? 1 : 0; }
+int64_t cm_ivf_size(const cm_ivf *h) { return h ? h->ix.store.n : 0; }
+int cm_ivf_default_nprobes(const cm_ivf *h) {   // ivf_index.go:410 int(sqrt(nlist))
+    if (!h) return 0;
+    int r = (int)std::sqrt((double)h->ix.nlist);
+    while ((long long)(r + 1) * (r + 1) <= h->ix.nlist) r++;
+    while ((long long)r * r > h->ix.nlist) r--;
+    return r;
+}
+
+// n successive IVFIndex.Add calls (ivf_index.go:258-283): PreprocessInPlace, nearest centroid
+// (FindNearestCentroidIndex, clustering.go:252-272: first minimum wins), append to that list.
+int cm_ivf_add(cm_ivf *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists) {
+    if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before adding vectors");   // ivf_index.go:264
+    if (n <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cm::IVFIndex &ix = h->ix;
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    int rc = CM_OK;
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(128u << 20) / ((int64_t)ix.dim * 4));
+    float *stage = nullptr;
+    uint32_t *a_ids = nullptr;
+    float *a_sc = nullptr;
+    long long *a_pos = nullptr, *a_cnt = nullptr;
+    int64_t sl = std::min(slab, n);
+    rc = cm::ws_alloc((void **)&stage, (size_t)sl * ix.dim * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&a_ids, (size_t)sl * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&a_sc, (size_t)sl * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&a_pos, (size_t)sl * 8, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&a_cnt, (size_t)sl * 8, st);
+    std::vector<long long> hpos((size_t)sl);
+    for (int64_t i0 = 0; rc == CM_OK && i0 < n; i0 += slab) {
+        int64_t m = std::min(slab, n - i0);
+        int64_t n_before = ix.store.n;
+        cudaMemcpyAsync(stage, rows + (size_t)i0 * ix.dim, (size_t)m * ix.dim * 4, cudaMemcpyHostToDevice, st);
+        int rc_add = ix.store.add_from_device(ids + i0, stage, m, writeback ? rows + (size_t)i0 * ix.dim : nullptr, st);
+        int64_t good = ix.store.n - n_before;          // rows before a zero vector were added, like n successive Add()s
+        if (good > 0) {
+            // assignment: the stored (preprocessed) rows are the queries of a k = 1 exact scan of the centroids
+            int64_t gpad = (good + cm::SCAN_MAX_QB - 1) / cm::SCAN_MAX_QB * cm::SCAN_MAX_QB;
+            rc = ix.store.reserve(n_before + gpad);     // the scan reads query blocks of 8 rows: keep the tail in bounds
+            cm_flat_stats cst{};
+            if (rc == CM_OK)
+                rc = ix.coarse.search_exact(ix.store.rows + (size_t)n_before * ix.store.ld, good, gpad, 1, nullptr, 0.0f, 1, a_ids,
+                                            a_sc, (int64_t *)a_pos, (int64_t *)a_cnt, st, &cst);
+            if (rc == CM_OK) {
+                cudaMemcpyAsync(hpos.data(), a_pos, (size_t)good * 8, cudaMemcpyDeviceToHost, st);
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "ivf_add: %s", cudaGetErrorString(e));
+            }
+            if (rc == CM_OK) {
+                for (int64_t i = 0; i < good; i++) {
+                    int32_t l = (int32_t)hpos[(size_t)i];
+                    ix.lists[(size_t)l].push_back((uint32_t)(n_before + i));
+                    ix.list_of.push_back(l);
+                    if (out_lists) out_lists[i0 + i] = l;
+                }
+                ix.csr_dirty = true;
+            }
+        }
+        if (rc == CM_OK) rc = rc_add;
+    }
+    cm::ws_free(stage, st); cm::ws_free(a_ids, st); cm::ws_free(a_sc, st); cm::ws_free(a_pos, st); cm::ws_free(a_cnt, st);
+    cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    return rc;
+}
+
+int cm_ivf_remove(cm_ivf *h, uint32_t id) {     // ivf_index.go:296-330 soft delete
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return h->ix.store.remove(id);
+}
+
+int cm_ivf_flush(cm_ivf *h) {                   // ivf_index.go:342-390: drop deleted vectors from every list
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cm::IVFIndex &ix = h->ix;
+    if (ix.store.deleted_ids.empty()) return CM_OK;
+    int64_t n_old = ix.store.n;
+    std::vector<int64_t> new_pos((size_t)n_old, -1);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n_old; i++)
+        if (!ix.store.deleted_ids.count(ix.store.ids_host_mirror[(size_t)i])) new_pos[(size_t)i] = m++;
+    CM_TRY(ix.store.flush());
+    std::vector<int32_t> nlo((size_t)m);
+    for (auto &l : ix.lists) {
+        size_t w = 0;
+        for (uint32_t pos : l)
+            if (new_pos[pos] >= 0) l[w++] = (uint32_t)new_pos[pos];
+        l.resize(w);
+    }
+    for (int64_t i = 0; i < n_old; i++)
+        if (new_pos[(size_t)i] >= 0) nlo[(size_t)new_pos[(size_t)i]] = ix.list_of[(size_t)i];
+    ix.list_of.swap(nlo);
+    ix.csr_dirty = true;
+    return CM_OK;
+}
+
+int cm_ivf_get_rows(const cm_ivf *h, const int64_t *positions, int64_t n, float *out) {
+    if (!h || (n > 0 && (!positions || !out))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (n <= 0) return CM_OK;
+    const cm::FlatIndex &S = h->ix.store;
+    for (int64_t i = 0; i < n; i++)
+        if (positions[i] < 0 || positions[i] >= S.n) return cm::fail(CM_ERR_NOT_FOUND, "position %lld out of range", (long long)positions[i]);
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    int64_t *dpos = nullptr;
+    float *dout = nullptr;
+    int rc = cm::ws_alloc((void **)&dpos, (size_t)n * 8, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&dout, (size_t)n * S.dim * 4, st);
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(dpos, positions, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+        rc = cm::launch_gather_rows(S.rows, S.ld, S.dim, dpos, n, dout, st);
+        cudaMemcpyAsync(out, dout, (size_t)n * S.dim * 4, cudaMemcpyDeviceToHost, st);
+    }
+    cm::ws_free(dpos, st); cm::ws_free(dout, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "ivf_get_rows: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int cm_ivf_search_device(cm_ivf *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                         int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
+                         int64_t *out_counts_dev, void *stream) {
+    if (!h || !p || (nq > 0 && (!queries_dev || !out_ids_dev || !out_scores_dev || !out_counts_dev)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
+    if (dim != h->ix.dim)
+        return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ix.dim, dim);
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::ivf_search_device(h->ix, queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_pos_dev,
+                                 out_counts_dev, (cudaStream_t)stream, false);
+}
+
+int cm_ivf_search(cm_ivf *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                  uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
+    if (!h || !p || (nq > 0 && (!queries || !out_ids || !out_scores || !out_counts)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
+    if (dim != h->ix.dim)
+        return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ix.dim, dim);
+    if (nq <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    float *dq = nullptr, *dsc = nullptr;
+    uint32_t *dids = nullptr;
+    int64_t *dpos = nullptr, *dcnt = nullptr;
+    size_t no = (size_t)nq * (size_t)(out_stride > 0 ? out_stride : 1);
+    int rc = cm::ws_alloc((void **)&dq, (size_t)nq * dim * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&dids, no * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&dsc, no * 4, st);
+    if (rc == CM_OK && out_pos) rc = cm::ws_alloc((void **)&dpos, no * 8, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&dcnt, (size_t)nq * 8, st);
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(dq, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st);
+        rc = cm::ivf_search_device(h->ix, dq, nq, p, out_stride, dids, dsc, dpos, dcnt, st, true);
+    }
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(out_ids, dids, no * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_scores, dsc, no * 4, cudaMemcpyDeviceToHost, st);
+        if (out_pos) cudaMemcpyAsync(out_pos, dpos, no * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_counts, dcnt, (size_t)nq * 8, cudaMemcpyDeviceToHost, st);
+    }
+    cm::ws_free(dq, st); cm::ws_free(dids, st); cm::ws_free(dsc, st); cm::ws_free(dpos, st); cm::ws_free(dcnt, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "ivf_search: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+}  // extern "C"

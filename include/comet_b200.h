@@ -157,6 +157,30 @@ typedef struct {
 } cm_flat_stats;
 int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out);
 
+/* ---- ivf_index.go / ivf_index_search.go ----------------------------------------------------- */
+int cm_ivf_create(int dim, int nlist, int metric, cm_ivf **out);     /* NewIVFIndex ivf_index.go:147 */
+int cm_ivf_destroy(cm_ivf *h);
+/* the result of IVFIndex.Train (ivf_index.go:205-246): nlist x dim centroids, stored as given */
+int cm_ivf_set_centroids(cm_ivf *h, const float *centroids);
+int cm_ivf_trained(const cm_ivf *h);
+int64_t cm_ivf_size(const cm_ivf *h);
+int cm_ivf_default_nprobes(const cm_ivf *h);                        /* ivf_index.go:410 int(sqrt(nlist)) */
+/* n successive IVFIndex.Add calls (ivf_index.go:258-283): PreprocessInPlace (rows written back unless
+ * writeback == 0), FindNearestCentroidIndex (clustering.go:252-272), append to the list.
+ * out_lists (optional, n entries) receives the list each row went to. */
+int cm_ivf_add(cm_ivf *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
+int cm_ivf_remove(cm_ivf *h, uint32_t id);                          /* ivf_index.go:296-330 */
+int cm_ivf_flush(cm_ivf *h);                                        /* ivf_index.go:342-390 */
+int cm_ivf_get_rows(const cm_ivf *h, const int64_t *positions, int64_t n, float *out);
+/* nq independent searchSingleQuery calls (ivf_index_search.go:217-322); p->nprobes as WithNProbes.
+ * out_stride >= min(k, B) where B = the most candidates nprobes lists can hold (k <= 0: B itself). */
+int cm_ivf_search(cm_ivf *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                  int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                  int64_t *out_counts);
+int cm_ivf_search_device(cm_ivf *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                         int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
+                         int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
