@@ -87,6 +87,29 @@ SIGNATURES = {
                                 i64p, i64p]),
     "cm_ivf_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                        vp, vp, vp]),
+    "cm_pq_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_pq_destroy": (C.c_int, [vp]),
+    "cm_pq_set_codebooks": (C.c_int, [vp, f32p]),
+    "cm_pq_trained": (C.c_int, [vp]),
+    "cm_pq_size": (C.c_int64, [vp]),
+    "cm_pq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
+    "cm_pq_get_codes": (C.c_int, [vp, C.c_int64, C.c_int64, u8p]),
+    "cm_pq_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_pq_flush": (C.c_int, [vp]),
+    "cm_pq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
+    "cm_pq_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp, vp]),
+    "cm_ivfpq_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_ivfpq_destroy": (C.c_int, [vp]),
+    "cm_ivfpq_set_trained": (C.c_int, [vp, f32p, f32p]),
+    "cm_ivfpq_trained": (C.c_int, [vp]),
+    "cm_ivfpq_size": (C.c_int64, [vp]),
+    "cm_ivfpq_default_nprobes": (C.c_int, [vp]),
+    "cm_ivfpq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
+    "cm_ivfpq_get_codes": (C.c_int, [vp, C.c_int64, C.c_int64, u8p]),
+    "cm_ivfpq_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_ivfpq_flush": (C.c_int, [vp]),
+    "cm_ivfpq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
+    "cm_ivfpq_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp, vp]),
     "cm_merge_shards_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp]),
 }
 
@@ -321,3 +344,98 @@ class IVFIndex:
         check(lib().cm_ivf_search(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p), ptr(sc, f32p), None,
                                   ptr(cnt, i64p)))
         return ids, sc, cnt
+
+
+class _ADCIndex:
+    """Shared ctypes plumbing of the PQ and IVFPQ handles."""
+    _p = ""
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            getattr(lib(), self._p + "_destroy")(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(getattr(lib(), self._p + "_size")(self.h))
+
+    def remove(self, id_):
+        check(getattr(lib(), self._p + "_remove")(self.h, int(id_)))
+
+    def flush(self):
+        check(getattr(lib(), self._p + "_flush")(self.h))
+
+    def codes(self):
+        n = len(self)
+        out = np.zeros((n, self.M), np.uint8)
+        if n:
+            check(getattr(lib(), self._p + "_get_codes")(self.h, 0, n, ptr(out, u8p)))
+        return out
+
+    def _rows(self, ids, rows):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        return ids, rows.reshape(len(ids), self.dim)
+
+    def _search(self, queries, k, threshold, nprobes, filter_ids, out_stride):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        n = len(self)
+        stride = out_stride or max(1, n if (k <= 0 or k > n) else k)
+        ids = np.zeros((nq, stride), np.uint32)
+        sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, nprobes=nprobes, filter_ids=filter_ids)
+        check(getattr(lib(), self._p + "_search")(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p),
+                                                  ptr(sc, f32p), None, ptr(cnt, i64p)))
+        return ids, sc, cnt
+
+
+class PQIndex(_ADCIndex):
+    _p = "cm_pq"
+
+    def __init__(self, dim, metric, M, nbits):
+        self.h = vp()
+        check(lib().cm_pq_create(int(dim), int(metric), int(M), int(nbits), C.byref(self.h)))
+        self.dim, self.metric, self.M, self.nbits = dim, metric, M, nbits
+
+    def set_codebooks(self, cb):
+        cb = _f32(cb)
+        check(lib().cm_pq_set_codebooks(self.h, ptr(cb, f32p)))
+
+    def add(self, ids, rows, writeback=True):
+        ids, rows2 = self._rows(ids, rows)
+        check(lib().cm_pq_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
+
+    def search(self, queries, k=10, threshold=0.0, filter_ids=None, out_stride=None):
+        return self._search(queries, k, threshold, 0, filter_ids, out_stride)
+
+
+class IVFPQIndex(_ADCIndex):
+    _p = "cm_ivfpq"
+
+    def __init__(self, dim, metric, nlist, M, nbits):
+        self.h = vp()
+        check(lib().cm_ivfpq_create(int(dim), int(metric), int(nlist), int(M), int(nbits), C.byref(self.h)))
+        self.dim, self.metric, self.nlist, self.M, self.nbits = dim, metric, nlist, M, nbits
+
+    def set_trained(self, centroids, codebooks):
+        c, cb = _f32(centroids), _f32(codebooks)
+        check(lib().cm_ivfpq_set_trained(self.h, ptr(c, f32p), ptr(cb, f32p)))
+
+    def default_nprobes(self):
+        return int(lib().cm_ivfpq_default_nprobes(self.h))
+
+    def add(self, ids, rows, writeback=True):
+        ids, rows2 = self._rows(ids, rows)
+        lists = np.zeros(len(ids), np.int32)
+        check(lib().cm_ivfpq_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0,
+                                 ptr(lists, i32p)))
+        return lists
+
+    def search(self, queries, k=10, nprobes=None, threshold=0.0, filter_ids=None, out_stride=None):
+        if nprobes is None:
+            nprobes = self.default_nprobes()
+        return self._search(queries, k, threshold, nprobes, filter_ids, out_stride)

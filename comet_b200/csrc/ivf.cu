@@ -116,6 +116,14 @@ __global__ void ivf_offsets_kernel(const long long *__restrict__ probe_list, con
     }
 }
 
+int launch_ivf_offsets(const long long *probe_list, const long long *probe_cnt, const long long *list_off, int nprobes,
+                       int64_t nq, long long *q_off, cudaStream_t st) {
+    ivf_offsets_kernel<<<(unsigned)nq, 256, 0, st>>>(probe_list, probe_cnt, list_off, nprobes, q_off);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
 // candidate number c of query q -> store position (largest p with q_off[p] <= c)
 __device__ __forceinline__ uint32_t ivf_locate(const long long *__restrict__ qo, int nprobes,
                                                const long long *__restrict__ probe_list,
@@ -293,9 +301,7 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
                                   (int64_t *)probe_cnt, st, &cst));
 
     // 3. candidate numbering
-    ivf_offsets_kernel<<<(unsigned)nq, 256, 0, st>>>(probe_list, probe_cnt, ix.list_off, nprobes, q_off);
-    count_launch();
-    CM_CUDA(cudaGetLastError());
+    CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, st));
 
     // 4. soft deletes + document filter -> skip mask over store positions
     const uint8_t *skip = nullptr;

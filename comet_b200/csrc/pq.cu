@@ -1,0 +1,788 @@
+// pq.cu -- PQIndex and IVFPQIndex device state, search and the cm_pq_* / cm_ivfpq_* entry points.
+//
+// Replaces pqIndexSearch.searchSingleQuery (pq_index_search.go:218-325) and
+// ivfpqIndexSearch.searchSingleQuery / computeDistanceTables / asymmetricDistance
+// (ivfpq_index_search.go:231-390): per-query (PQ) or per-probe residual (IVFPQ) lookup tables
+//   LUT[m][c] = sum_j (r[m*dsub+j] - codebook[m][c*dsub+j])^2     sequential fp32 (K7, K9)
+// and the ADC scan  dist = float32(sqrt(float64(sum_m LUT[m][code[m]])))  sequential over m (K8),
+// delete / document filter / threshold, full sort of the candidates, top k -- bit-identical.
+//
+// Device layout (replaces codes [][]uint8 / lists [][]CompressedVector of heap slices):
+//   codebooks f32 [M][Ksub][dsub]
+//   codes     u8  [cap][M]      arrival order;  ids u32 [cap];  deleted u8 [cap]
+//   IVFPQ adds: coarse FlatIndex of the nlist centroids (raw), members u32 [n] (store positions
+//   grouped by list, CSR) and list_off i64 [nlist+1].
+// One kernel, adc_scan_kernel, serves both: a CTA owns one (query, probe) pair and up to ADC_CHUNK
+// of its codes; it builds the pair's LUT in shared memory straight from the codebooks (only the
+// 256 entries per sub-quantiser a uint8 code can address, pq_index.go:469), scans, and keeps its
+// K best keys (score, candidate number).  merge_topk_kernel + adc_emit_kernel finish the query.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <unordered_set>
+#include <vector>
+
+#include "flat_index.cuh"
+#include "flat_kernels.cuh"
+#include "select.cuh"
+
+namespace cm {
+
+static constexpr int ADC_THREADS = 256;
+static constexpr int ADC_CHUNK = 4096;      // codes per CTA
+
+struct CodeStore {
+    int M = 0;
+    int64_t n = 0, cap = 0;
+    uint8_t *codes = nullptr;
+    uint32_t *ids = nullptr;
+    uint8_t *deleted = nullptr;
+    std::vector<uint32_t> ids_host;
+    std::unordered_set<uint32_t> deleted_ids;
+    int64_t n_deleted_rows = 0;
+
+    ~CodeStore() { cudaFree(codes); cudaFree(ids); cudaFree(deleted); }
+    int reserve(int64_t want) {
+        if (want <= cap) return CM_OK;
+        int64_t ncap = cap ? cap : 4096;
+        while (ncap < want) ncap = ncap + ncap / 2 + 4096;
+        uint8_t *nc = nullptr, *nd = nullptr;
+        uint32_t *ni = nullptr;
+        CM_CUDA(cudaMalloc(&nc, (size_t)ncap * M));
+        CM_CUDA(cudaMalloc(&ni, (size_t)ncap * 4));
+        CM_CUDA(cudaMalloc(&nd, (size_t)ncap));
+        CM_CUDA(cudaMemset(nd, 0, (size_t)ncap));
+        if (n > 0) {
+            CM_CUDA(cudaMemcpy(nc, codes, (size_t)n * M, cudaMemcpyDeviceToDevice));
+            CM_CUDA(cudaMemcpy(ni, ids, (size_t)n * 4, cudaMemcpyDeviceToDevice));
+            CM_CUDA(cudaMemcpy(nd, deleted, (size_t)n, cudaMemcpyDeviceToDevice));
+        }
+        cudaFree(codes); cudaFree(ids); cudaFree(deleted);
+        codes = nc; ids = ni; deleted = nd; cap = ncap;
+        return CM_OK;
+    }
+    // bookkeeping after `m` codes were written at [n, n+m) by an encode kernel
+    int commit(const uint32_t *ids_h, int64_t m, cudaStream_t st) {
+        std::vector<uint8_t> del((size_t)m, 0);
+        bool any = false;
+        for (int64_t i = 0; i < m; i++)
+            if (!deleted_ids.empty() && deleted_ids.count(ids_h[i])) { del[(size_t)i] = 1; any = true; n_deleted_rows++; }
+        CM_CUDA(cudaMemcpyAsync(ids + n, ids_h, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        if (any) CM_CUDA(cudaMemcpyAsync(deleted + n, del.data(), (size_t)m, cudaMemcpyHostToDevice, st));
+        else CM_CUDA(cudaMemsetAsync(deleted + n, 0, (size_t)m, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        ids_host.insert(ids_host.end(), ids_h, ids_h + m);
+        n += m;
+        return CM_OK;
+    }
+    int remove(uint32_t id) {      // pq_index.go:299-330 / ivfpq_index.go:330-360: soft delete
+        std::vector<int64_t> hits;
+        for (int64_t i = 0; i < n; i++)
+            if (ids_host[(size_t)i] == id) hits.push_back(i);
+        if (hits.empty()) return fail(CM_ERR_NOT_FOUND, "vector with ID %u not found", id);
+        if (deleted_ids.count(id)) return fail(CM_ERR_NOT_FOUND, "vector with ID %u already deleted", id);
+        deleted_ids.insert(id);
+        uint8_t one = 1;
+        for (int64_t i : hits) CM_CUDA(cudaMemcpy(deleted + i, &one, 1, cudaMemcpyHostToDevice));
+        n_deleted_rows += (int64_t)hits.size();
+        return CM_OK;
+    }
+    // drop deleted rows keeping order; new_pos[i] = new position or -1
+    int flush(std::vector<int64_t> *new_pos_out) {
+        std::vector<int64_t> new_pos((size_t)n, -1);
+        std::vector<int64_t> keep;
+        for (int64_t i = 0; i < n; i++)
+            if (!deleted_ids.count(ids_host[(size_t)i])) { new_pos[(size_t)i] = (int64_t)keep.size(); keep.push_back(i); }
+        int64_t m = (int64_t)keep.size();
+        if (m < n) {
+            std::vector<uint8_t> hc((size_t)n * M), nc((size_t)std::max<int64_t>(m, 1) * M);
+            CM_CUDA(cudaMemcpy(hc.data(), codes, (size_t)n * M, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> ni((size_t)m);
+            for (int64_t i = 0; i < m; i++) {
+                memcpy(&nc[(size_t)i * M], &hc[(size_t)keep[(size_t)i] * M], (size_t)M);
+                ni[(size_t)i] = ids_host[(size_t)keep[(size_t)i]];
+            }
+            if (m > 0) {
+                CM_CUDA(cudaMemcpy(codes, nc.data(), (size_t)m * M, cudaMemcpyHostToDevice));
+                CM_CUDA(cudaMemcpy(ids, ni.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+            }
+            CM_CUDA(cudaMemset(deleted, 0, (size_t)cap));
+            ids_host.swap(ni);
+            n = m;
+        }
+        n_deleted_rows = 0;
+        deleted_ids.clear();
+        if (new_pos_out) new_pos_out->swap(new_pos);
+        return CM_OK;
+    }
+};
+
+struct PQCore {
+    int dim = 0, metric = 0, M = 0, nbits = 0, Ksub = 0, dsub = 0, device = 0, ld = 0;
+    bool trained = false;
+    float *codebooks = nullptr;     // [M][Ksub][dsub]
+    CodeStore store;
+    // IVFPQ only
+    int nlist = 0;
+    FlatIndex coarse;
+    std::vector<std::vector<uint32_t>> lists;
+    std::vector<int32_t> list_of;
+    uint32_t *members = nullptr;
+    long long *list_off = nullptr;
+    int64_t members_cap = 0;
+    bool csr_dirty = true;
+    std::vector<int64_t> sizes_desc;
+    std::mutex csr_mu;
+
+    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); }
+    int lut_entries() const { return Ksub < 256 ? Ksub : 256; }
+    int sync_csr(cudaStream_t st);
+};
+
+int PQCore::sync_csr(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(csr_mu);
+    if (!csr_dirty || nlist == 0) return CM_OK;
+    int64_t n = store.n;
+    if (n > members_cap || !members) {
+        cudaFree(members);
+        members_cap = std::max<int64_t>(n + n / 2, 1024);
+        CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
+    }
+    if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
+    std::vector<uint32_t> flat;
+    flat.reserve((size_t)n);
+    std::vector<long long> off((size_t)nlist + 1, 0);
+    sizes_desc.assign((size_t)nlist, 0);
+    for (int l = 0; l < nlist; l++) {
+        off[(size_t)l] = (long long)flat.size();
+        flat.insert(flat.end(), lists[(size_t)l].begin(), lists[(size_t)l].end());
+        sizes_desc[(size_t)l] = (int64_t)lists[(size_t)l].size();
+    }
+    off[(size_t)nlist] = (long long)flat.size();
+    std::sort(sizes_desc.begin(), sizes_desc.end(), std::greater<int64_t>());
+    if (!flat.empty()) CM_CUDA(cudaMemcpyAsync(members, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(list_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    csr_dirty = false;
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode: PQIndex.encode (pq_index.go:439-473) / IVFPQIndex.encodeResidual (ivfpq_index.go:467-500)
+// one thread per (row, sub-quantiser): first minimum over ALL Ksub centroids, then uint8(minIdx)
+// ------------------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void pq_encode_kernel(const float *__restrict__ rows, int ld, long long n, int M, int Ksub, int dsub,
+                                 const float *__restrict__ codebooks, const float *__restrict__ centroids, int cld,
+                                 const long long *__restrict__ row_list, uint8_t *__restrict__ codes) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * M) return;
+    long long row = t / M;
+    int m = (int)(t - row * M);
+    const float *v = rows + (size_t)row * ld + (size_t)m * dsub;
+    const float *cen = centroids ? centroids + (size_t)row_list[row] * cld + (size_t)m * dsub : nullptr;
+    const float *cb = codebooks + (size_t)m * Ksub * dsub;
+    float best = INFINITY;
+    int best_i = 0;
+    for (int c = 0; c < Ksub; c++) {
+        float dist = 0.0f;
+        for (int j = 0; j < dsub; j++) {
+            float r = cen ? __fsub_rn(v[j], cen[j]) : v[j];
+            dist = l2_step<FMA>(dist, r, cb[(size_t)c * dsub + j]);
+        }
+        if (dist < best) { best = dist; best_i = c; }
+    }
+    codes[(size_t)row * M + m] = (uint8_t)best_i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ADC scan.  blockIdx.y = pair = query * nprobes + probe, blockIdx.x = chunk of the pair's codes.
+//   members == nullptr (PQ): the pair's codes are store positions [0, n), candidate number = position
+//   else (IVFPQ): list l = probe_list[pair]; codes at members[list_off[l] + j]; candidate number =
+//   q_off[query][probe] + j (the order of the reference's append loop)
+// ------------------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void __launch_bounds__(ADC_THREADS) adc_scan_kernel(
+    const float *__restrict__ queries, int ld, int dim, int M, int Ksub, int dsub, int lut_n,
+    const float *__restrict__ codebooks, const uint8_t *__restrict__ codes, long long n_store,
+    const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
+    const long long *__restrict__ q_off, const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
+    int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C, int n_chunks,
+    uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *lut = reinterpret_cast<float *>(smem);                       // [M][lut_n]
+    float *res = lut + (size_t)M * lut_n;                               // [dim] query (residual)
+    uint64_t *buf = reinterpret_cast<uint64_t *>(res + ((dim + 3) & ~3));   // [C]
+    __shared__ int cnt;
+    __shared__ uint64_t tau;
+    const CtaBarrier bar;
+    const int tid = threadIdx.x;
+    const long long pair = blockIdx.y;
+    const int q = (int)(pair / nprobes), pr = (int)(pair % nprobes);
+    long long len, order0;
+    const uint32_t *mem = nullptr;
+    long long list = -1;
+    if (members) {
+        list = probe_list[pair];
+        len = list_off[list + 1] - list_off[list];
+        mem = members + list_off[list];
+        order0 = q_off[(size_t)q * (nprobes + 1) + pr];
+    } else {
+        len = n_store;
+        order0 = 0;
+    }
+    const long long c0 = (long long)blockIdx.x * ADC_CHUNK;
+    const size_t part = (size_t)pair * n_chunks + blockIdx.x;
+    if (c0 >= len) return;                                              // part_counts was zeroed by the host
+    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+    // query residual (ivfpq_index_search.go:285-296) or the query itself
+    for (int j = tid; j < dim; j += ADC_THREADS) {
+        float v = queries[(size_t)q * ld + j];
+        res[j] = centroids ? __fsub_rn(v, centroids[(size_t)list * cld + j]) : v;
+    }
+    __syncthreads();
+    // lookup table in the reference's summation order
+    for (int e = tid; e < M * lut_n; e += ADC_THREADS) {
+        int m = e / lut_n, c = e - m * lut_n;
+        const float *cb = codebooks + ((size_t)m * Ksub + c) * dsub;
+        const float *r = res + (size_t)m * dsub;
+        float dist = 0.0f;
+        for (int j = 0; j < dsub; j++) dist = l2_step<FMA>(dist, r[j], cb[j]);
+        lut[e] = dist;
+    }
+    __syncthreads();
+    const long long c1 = min(len, c0 + ADC_CHUNK);
+    for (long long cbase = c0; cbase < c1; cbase += ADC_THREADS) {
+        long long j = cbase + tid;
+        bool live = j < c1;
+        uint32_t pos = 0;
+        float dist = 0.0f;
+        if (live) {
+            pos = mem ? mem[j] : (uint32_t)j;
+            const uint8_t *code = codes + (size_t)pos * M;
+            float sum = 0.0f;
+            for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+            dist = __fsqrt_rn(sum);
+            if (skip != nullptr && skip[pos]) live = false;
+            if (threshold > 0.0f && dist > threshold) live = false;
+        }
+        // selection: append below the running bound, compact when the buffer may overflow
+        bar.sync();
+        bool need = cnt > C - ADC_THREADS;
+        bar.sync();
+        if (need) compact_topk(buf, C, K, &cnt, &tau, tid, ADC_THREADS, bar);
+        if (live) {
+            uint64_t key = make_key(dist, (uint32_t)(order0 + j));
+            if (key < tau) buf[atomicAdd(&cnt, 1)] = key;
+        }
+    }
+    compact_topk(buf, C, K, &cnt, &tau, tid, ADC_THREADS, bar);
+    int mcount = cnt;
+    uint64_t *dst = part_keys + part * K;
+    for (int i = tid; i < mcount; i += ADC_THREADS) dst[i] = buf[i];
+    if (tid == 0) part_counts[part] = mcount;
+}
+
+// candidate numbers of the final lists -> store positions and ids
+__global__ void adc_emit_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
+                                const long long *__restrict__ list_off, const uint32_t *__restrict__ members, int nprobes,
+                                const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
+                                long long *__restrict__ out_pos, const long long *__restrict__ out_counts) {
+    const int q = blockIdx.x;
+    const long long m = out_counts[q];
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+        size_t o = (size_t)q * out_stride + i;
+        long long c = out_ids[o];
+        uint32_t pos;
+        if (members) {
+            const long long *qo = q_off + (size_t)q * (nprobes + 1);
+            int lo = 0, hi = nprobes;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (qo[mid] <= c) lo = mid; else hi = mid;
+            }
+            long long l = probe_list[(size_t)q * nprobes + lo];
+            pos = members[list_off[l] + (c - qo[lo])];
+        } else {
+            pos = (uint32_t)c;
+        }
+        out_ids[o] = row_ids[pos];
+        if (out_pos) out_pos[o] = pos;
+    }
+}
+
+// ivf.cu: per query prefix sums of the probed list lengths (the reference's candidate numbering)
+int launch_ivf_offsets(const long long *probe_list, const long long *probe_cnt, const long long *list_off, int nprobes,
+                       int64_t nq, long long *q_off, cudaStream_t st);
+
+static int prepare_queries(int metric, int dim, int ld, const float *q_dev, int64_t nq, bool check_zero, float **qp_out,
+                           cudaStream_t st) {
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+    int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+    float *qp = nullptr;
+    int *qflags = nullptr;
+    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
+    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
+    if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
+    CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp, ld, qflags, st));
+    if (check_zero && metric == CM_COSINE) {
+        std::vector<int> hf((size_t)nq);
+        CM_CUDA(cudaMemcpyAsync(hf.data(), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < nq; i++)
+            if (hf[(size_t)i]) {
+                ws_free(qp, st); ws_free(qflags, st);
+                return fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)i);
+            }
+    }
+    ws_free(qflags, st);
+    *qp_out = qp;
+    return CM_OK;
+}
+
+static int build_skip(CodeStore &S, const cm_search_params *p, const uint8_t **skip, uint8_t **skip_buf, uint32_t **filt_dev,
+                      cudaStream_t st) {
+    *skip = nullptr; *skip_buf = nullptr; *filt_dev = nullptr;
+    if (p->filter_ids && p->nfilter > 0) {
+        std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
+        std::sort(f.begin(), f.end());
+        f.erase(std::unique(f.begin(), f.end()), f.end());
+        CM_TRY(ws_alloc((void **)filt_dev, f.size() * 4, st));
+        CM_TRY(ws_alloc((void **)skip_buf, (size_t)S.n, st));
+        CM_CUDA(cudaMemcpyAsync(*filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
+        CM_TRY(launch_build_skip(S.ids, S.deleted, S.n, *filt_dev, (int64_t)f.size(), *skip_buf, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        *skip = *skip_buf;
+    } else if (S.n_deleted_rows > 0) {
+        *skip = S.deleted;
+    }
+    return CM_OK;
+}
+
+// nq independent searchSingleQuery calls (PQ when ix.nlist == 0, else IVFPQ)
+static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
+                             uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
+                             bool check_zero) {
+    if (nq <= 0) return CM_OK;
+    const bool ivf = ix.nlist > 0;
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ivf ? "index must be trained before searching" : "index not trained");
+    CodeStore &S = ix.store;
+    int nprobes = 1;
+    if (ivf) {
+        nprobes = p->nprobes;
+        if (nprobes <= 0 || nprobes > ix.nlist) nprobes = ix.nlist;
+        CM_TRY(ix.sync_csr(st));
+    }
+    int64_t bound_c = S.n, max_len = S.n;
+    if (ivf) {
+        bound_c = 0;
+        for (int i = 0; i < nprobes && i < (int)ix.sizes_desc.size(); i++) bound_c += ix.sizes_desc[(size_t)i];
+        max_len = ix.sizes_desc.empty() ? 0 : ix.sizes_desc[0];
+    }
+    int64_t k_eff = p->k;
+    if (k_eff <= 0 || k_eff > bound_c) k_eff = bound_c;
+    if (out_stride < k_eff)
+        return fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)k_eff);
+    if (k_eff > 8192) return fail(CM_ERR_UNSUPPORTED, "pq / ivfpq search supports k <= 8192 (got %lld)", (long long)k_eff);
+    float *qp = nullptr;
+    if (!ivf && S.n == 0) {      // pq_index_search.go:232: an empty index answers before Preprocess
+        CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
+        return CM_OK;
+    }
+    CM_TRY(prepare_queries(ix.metric, ix.dim, ix.ld, q_dev, nq, check_zero, &qp, st));
+    if (bound_c == 0 || k_eff == 0) {
+        CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
+        ws_free(qp, st);
+        return CM_OK;
+    }
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+    int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+
+    long long *probe_list = nullptr, *probe_cnt = nullptr, *q_off = nullptr;
+    uint32_t *c_ids = nullptr;
+    float *c_sc = nullptr;
+    if (ivf) {
+        CM_TRY(ws_alloc((void **)&c_ids, (size_t)nq * nprobes * 4, st));
+        CM_TRY(ws_alloc((void **)&c_sc, (size_t)nq * nprobes * 4, st));
+        CM_TRY(ws_alloc((void **)&probe_list, (size_t)nq * nprobes * 8, st));
+        CM_TRY(ws_alloc((void **)&probe_cnt, (size_t)nq * 8, st));
+        CM_TRY(ws_alloc((void **)&q_off, (size_t)nq * (nprobes + 1) * 8, st));
+        cm_flat_stats cst{};
+        CM_TRY(ix.coarse.search_exact(qp, nq, nq_pad, nprobes, nullptr, 0.0f, nprobes, c_ids, c_sc, (int64_t *)probe_list,
+                                      (int64_t *)probe_cnt, st, &cst));
+        CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, st));
+    }
+    const uint8_t *skip = nullptr;
+    uint8_t *skip_buf = nullptr;
+    uint32_t *filt_dev = nullptr;
+    CM_TRY(build_skip(S, p, &skip, &skip_buf, &filt_dev, st));
+
+    const int K = (int)k_eff;
+    int C = next_pow2(K + 2 * ADC_THREADS);
+    if (C < 1024) C = 1024;
+    const int lut_n = ix.lut_entries();
+    size_t smem = (size_t)ix.M * lut_n * 4 + (size_t)((ix.dim + 3) & ~3) * 4 + (size_t)C * 8;
+    if (smem > max_smem_optin())
+        return fail(CM_ERR_UNSUPPORTED, "M=%d x %d table entries + k=%d do not fit shared memory", ix.M, lut_n, K);
+    const int n_chunks = (int)std::max<int64_t>(1, (max_len + ADC_CHUNK - 1) / ADC_CHUNK);
+    const int64_t parts = (int64_t)nprobes * n_chunks;              // per query
+    int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 29) / (parts * K * 8)));
+    if (qgroup * nprobes > 65535) qgroup = std::max<int64_t>(1, 65535 / nprobes);   // grid.y limit
+    uint64_t *pk = nullptr;
+    int *pc = nullptr;
+    CM_TRY(ws_alloc((void **)&pk, (size_t)qgroup * parts * K * 8, st));
+    CM_TRY(ws_alloc((void **)&pc, (size_t)qgroup * parts * 4, st));
+    auto kern = fma ? adc_scan_kernel<true> : adc_scan_kernel<false>;
+    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
+        int64_t m = std::min(qgroup, nq - q0);
+        CM_CUDA(cudaMemsetAsync(pc, 0, (size_t)m * parts * 4, st));
+        dim3 grid((unsigned)n_chunks, (unsigned)(m * nprobes));
+        {
+            ProfScope prof(CM_PROF_PQ_SCAN, st);
+            kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
+                                                  ix.codebooks, S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
+                                                  ix.coarse.ld, ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
+                                                  ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
+                                                  ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, n_chunks, pk, pc);
+            count_launch();
+            CM_CUDA(cudaGetLastError());
+        }
+        CM_TRY(launch_merge_topk(pk, pc, (int)m, (int)parts, K, K, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
+                                 out_scores + (size_t)q0 * out_stride, nullptr, out_counts + q0, st));
+        adc_emit_kernel<<<(unsigned)m, 128, 0, st>>>(ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
+                                                     ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
+                                                     ivf ? ix.members : nullptr, nprobes, S.ids, (long long)out_stride,
+                                                     out_ids + (size_t)q0 * out_stride,
+                                                     out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,
+                                                     (const long long *)(out_counts + q0));
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
+    ws_free(qp, st); ws_free(c_ids, st); ws_free(c_sc, st); ws_free(probe_list, st); ws_free(probe_cnt, st); ws_free(q_off, st);
+    ws_free(skip_buf, st); ws_free(filt_dev, st); ws_free(pk, st); ws_free(pc, st);
+    return CM_OK;
+}
+
+// n successive Add calls: PreprocessInPlace, [nearest centroid, residual], encode, append
+static int adc_add(PQCore &ix, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists) {
+    const bool ivf = ix.nlist > 0;
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ivf ? "index must be trained before adding" : "index must be trained before adding vectors");
+    if (n <= 0) return CM_OK;
+    bool fma = rounding_mode() == CM_ROUND_FMA;
+    cudaStream_t st;
+    CM_TRY(acquire_stream(&st));
+    const int64_t slab = std::max<int64_t>(8, (int64_t)(64u << 20) / ((int64_t)ix.ld * 4));
+    int64_t sl = std::min(slab, n);
+    int64_t sl_pad = (sl + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+    float *raw = nullptr, *pre = nullptr, *a_sc = nullptr;
+    int *flags = nullptr;
+    uint32_t *a_ids = nullptr;
+    long long *a_pos = nullptr, *a_cnt = nullptr;
+    int rc = ws_alloc((void **)&raw, (size_t)sl * ix.dim * 4, st);
+    if (rc == CM_OK) rc = ws_alloc((void **)&pre, (size_t)sl_pad * ix.ld * 4, st);
+    if (rc == CM_OK) rc = ws_alloc((void **)&flags, (size_t)sl * 4, st);
+    if (rc == CM_OK && ivf) {
+        rc = ws_alloc((void **)&a_ids, (size_t)sl * 4, st);
+        if (rc == CM_OK) rc = ws_alloc((void **)&a_sc, (size_t)sl * 4, st);
+        if (rc == CM_OK) rc = ws_alloc((void **)&a_pos, (size_t)sl * 8, st);
+        if (rc == CM_OK) rc = ws_alloc((void **)&a_cnt, (size_t)sl * 8, st);
+    }
+    std::vector<int> hflags((size_t)sl);
+    std::vector<long long> hpos((size_t)sl);
+    int rc_zero = CM_OK;
+    for (int64_t i0 = 0; rc == CM_OK && rc_zero == CM_OK && i0 < n; i0 += slab) {
+        int64_t m = std::min(slab, n - i0);
+        cudaMemcpyAsync(raw, rows + (size_t)i0 * ix.dim, (size_t)m * ix.dim * 4, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(pre, 0, (size_t)sl_pad * ix.ld * 4, st);
+        rc = launch_preprocess_rows(ix.metric, fma, raw, m, ix.dim, ix.dim, pre, ix.ld, flags, st);
+        if (rc != CM_OK) break;
+        int64_t good = m;
+        if (ix.metric == CM_COSINE) {
+            cudaMemcpyAsync(hflags.data(), flags, (size_t)m * 4, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            for (int64_t i = 0; i < m; i++)
+                if (hflags[(size_t)i]) { good = i; break; }
+            if (writeback && good > 0)
+                cudaMemcpy2DAsync(rows + (size_t)i0 * ix.dim, (size_t)ix.dim * 4, pre, (size_t)ix.ld * 4, (size_t)ix.dim * 4,
+                                  (size_t)good, cudaMemcpyDeviceToHost, st);
+        }
+        if (good < m) rc_zero = fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (row %lld of this Add batch)", (long long)(i0 + good));
+        if (good == 0) break;
+        if (ivf) {
+            int64_t gpad = (good + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+            cm_flat_stats cst{};
+            rc = ix.coarse.search_exact(pre, good, gpad, 1, nullptr, 0.0f, 1, a_ids, a_sc, (int64_t *)a_pos, (int64_t *)a_cnt, st, &cst);
+            if (rc != CM_OK) break;
+        }
+        rc = ix.store.reserve(ix.store.n + good);
+        if (rc != CM_OK) break;
+        long long threads = good * ix.M;
+        unsigned blocks = (unsigned)((threads + 127) / 128);
+        if (fma)
+            pq_encode_kernel<true><<<blocks, 128, 0, st>>>(pre, ix.ld, good, ix.M, ix.Ksub, ix.dsub, ix.codebooks,
+                                                          ivf ? ix.coarse.rows : nullptr, ix.coarse.ld, a_pos,
+                                                          ix.store.codes + (size_t)ix.store.n * ix.M);
+        else
+            pq_encode_kernel<false><<<blocks, 128, 0, st>>>(pre, ix.ld, good, ix.M, ix.Ksub, ix.dsub, ix.codebooks,
+                                                           ivf ? ix.coarse.rows : nullptr, ix.coarse.ld, a_pos,
+                                                           ix.store.codes + (size_t)ix.store.n * ix.M);
+        count_launch();
+        if (ivf) cudaMemcpyAsync(hpos.data(), a_pos, (size_t)good * 8, cudaMemcpyDeviceToHost, st);
+        int64_t n_before = ix.store.n;
+        rc = ix.store.commit(ids + i0, good, st);      // synchronises the stream
+        if (rc != CM_OK) break;
+        if (ivf) {
+            for (int64_t i = 0; i < good; i++) {
+                int32_t l = (int32_t)hpos[(size_t)i];
+                ix.lists[(size_t)l].push_back((uint32_t)(n_before + i));
+                ix.list_of.push_back(l);
+                if (out_lists) out_lists[i0 + i] = l;
+            }
+            ix.csr_dirty = true;
+        }
+    }
+    ws_free(raw, st); ws_free(pre, st); ws_free(flags, st); ws_free(a_ids, st); ws_free(a_sc, st); ws_free(a_pos, st); ws_free(a_cnt, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) return fail(CM_ERR_CUDA, "add: %s", cudaGetErrorString(e));
+    return rc != CM_OK ? rc : rc_zero;
+}
+
+static int adc_flush(PQCore &ix) {
+    if (ix.store.deleted_ids.empty()) return CM_OK;
+    std::vector<int64_t> new_pos;
+    int64_t n_old = ix.store.n;
+    CM_TRY(ix.store.flush(&new_pos));
+    if (ix.nlist > 0) {
+        std::vector<int32_t> nlo((size_t)ix.store.n);
+        for (auto &l : ix.lists) {
+            size_t w = 0;
+            for (uint32_t pos : l)
+                if (new_pos[pos] >= 0) l[w++] = (uint32_t)new_pos[pos];
+            l.resize(w);
+        }
+        for (int64_t i = 0; i < n_old; i++)
+            if (new_pos[(size_t)i] >= 0) nlo[(size_t)new_pos[(size_t)i]] = ix.list_of[(size_t)i];
+        ix.list_of.swap(nlo);
+        ix.csr_dirty = true;
+    }
+    return CM_OK;
+}
+
+static int core_create(int dim, int metric, int nlist, int M, int nbits, bool ivf, PQCore *ix) {
+    // pq_index.go:135-170 / ivfpq_index.go:114-160 constructor checks
+    if (dim <= 0) return fail(CM_ERR_INVALID_ARG, "dimension must be positive");
+    if (ivf && nlist <= 0) return fail(CM_ERR_INVALID_ARG, "nlist must be positive");
+    if (M <= 0) return fail(CM_ERR_INVALID_ARG, "M must be positive");
+    if (dim % M != 0) return fail(CM_ERR_INVALID_ARG, "dimension %d must be divisible by M %d", dim, M);
+    if (nbits <= 0 || nbits > 16) return fail(CM_ERR_INVALID_ARG, "Nbits must be between 1 and 16");
+    if (metric < 0 || metric > 2) return fail(CM_ERR_INVALID_ARG, "unknown distance kind");
+    CM_TRY(ensure_device());
+    ix->dim = dim; ix->metric = metric; ix->M = M; ix->nbits = nbits; ix->Ksub = 1 << nbits; ix->dsub = dim / M;
+    ix->ld = (dim + SCAN_CHUNK - 1) / SCAN_CHUNK * SCAN_CHUNK;
+    ix->nlist = ivf ? nlist : 0;
+    ix->store.M = M;
+    cudaGetDevice(&ix->device);
+    if (ivf) {
+        ix->coarse.dim = dim; ix->coarse.ld = ix->ld; ix->coarse.metric = metric; ix->coarse.device = ix->device;
+        ix->coarse.raw_rows = true;
+        ix->lists.resize((size_t)nlist);
+    }
+    return CM_OK;
+}
+
+static int core_set_trained(PQCore &ix, const float *centroids, const float *codebooks) {
+    if (ix.store.n > 0) return fail(CM_ERR_INVALID_ARG, "cannot replace the trained state of a non-empty index");
+    size_t cb_bytes = (size_t)ix.M * ix.Ksub * ix.dsub * 4;
+    if (!ix.codebooks) CM_CUDA(cudaMalloc(&ix.codebooks, cb_bytes));
+    CM_CUDA(cudaMemcpy(ix.codebooks, codebooks, cb_bytes, cudaMemcpyHostToDevice));
+    if (ix.nlist > 0) {
+        cudaStream_t st;
+        CM_TRY(acquire_stream(&st));
+        ix.coarse.n = 0; ix.coarse.ids_host_mirror.clear();
+        float *stage = nullptr;
+        size_t bytes = (size_t)ix.nlist * ix.dim * 4;
+        int rc = ws_alloc((void **)&stage, bytes, st);
+        if (rc == CM_OK) {
+            cudaMemcpyAsync(stage, centroids, bytes, cudaMemcpyHostToDevice, st);
+            std::vector<uint32_t> ids((size_t)ix.nlist);
+            std::iota(ids.begin(), ids.end(), 0u);
+            rc = ix.coarse.add_from_device(ids.data(), stage, ix.nlist, nullptr, st);
+        }
+        ws_free(stage, st);
+        cudaStreamSynchronize(st);
+        release_stream(st);
+        CM_TRY(rc);
+    }
+    ix.trained = true;
+    return CM_OK;
+}
+
+static int core_search_host(PQCore &ix, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                            uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ix.nlist > 0 ? "index must be trained before searching" : "index not trained");
+    if (dim != ix.dim) return fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", ix.dim, dim);
+    if (nq <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(ix.device));
+    cudaStream_t st;
+    CM_TRY(acquire_stream(&st));
+    float *dq = nullptr, *dsc = nullptr;
+    uint32_t *dids = nullptr;
+    int64_t *dpos = nullptr, *dcnt = nullptr;
+    size_t no = (size_t)nq * (size_t)(out_stride > 0 ? out_stride : 1);
+    int rc = ws_alloc((void **)&dq, (size_t)nq * dim * 4, st);
+    if (rc == CM_OK) rc = ws_alloc((void **)&dids, no * 4, st);
+    if (rc == CM_OK) rc = ws_alloc((void **)&dsc, no * 4, st);
+    if (rc == CM_OK && out_pos) rc = ws_alloc((void **)&dpos, no * 8, st);
+    if (rc == CM_OK) rc = ws_alloc((void **)&dcnt, (size_t)nq * 8, st);
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(dq, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st);
+        rc = adc_search_device(ix, dq, nq, p, out_stride, dids, dsc, dpos, dcnt, st, true);
+    }
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(out_ids, dids, no * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_scores, dsc, no * 4, cudaMemcpyDeviceToHost, st);
+        if (out_pos) cudaMemcpyAsync(out_pos, dpos, no * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_counts, dcnt, (size_t)nq * 8, cudaMemcpyDeviceToHost, st);
+    }
+    ws_free(dq, st); ws_free(dids, st); ws_free(dsc, st); ws_free(dpos, st); ws_free(dcnt, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) return fail(CM_ERR_CUDA, "search: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+}  // namespace cm
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+struct cm_pq { cm::PQCore ix; };
+struct cm_ivfpq { cm::PQCore ix; };
+
+extern "C" {
+
+int cm_pq_create(int dim, int metric, int M, int nbits, cm_pq **out) {
+    if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    cm_pq *h = new cm_pq();
+    int rc = cm::core_create(dim, metric, 0, M, nbits, false, &h->ix);
+    if (rc != CM_OK) { delete h; return rc; }
+    *out = h;
+    return CM_OK;
+}
+int cm_pq_destroy(cm_pq *h) { delete h; return CM_OK; }
+int cm_pq_set_codebooks(cm_pq *h, const float *codebooks) {
+    if (!h || !codebooks) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_set_trained(h->ix, nullptr, codebooks);
+}
+int cm_pq_trained(const cm_pq *h) { return h && h->ix.trained ? 1 : 0; }
+int64_t cm_pq_size(const cm_pq *h) { return h ? h->ix.store.n : 0; }
+int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeback) {
+    if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_add(h->ix, ids, rows, n, writeback, nullptr);
+}
+int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out) {
+    if (!h || !out || first < 0 || first + n > h->ix.store.n) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    CM_CUDA(cudaMemcpy(out, h->ix.store.codes + (size_t)first * h->ix.M, (size_t)n * h->ix.M, cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+int cm_pq_remove(cm_pq *h, uint32_t id) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return h->ix.store.remove(id);
+}
+int cm_pq_flush(cm_pq *h) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_flush(h->ix);
+}
+int cm_pq_search(cm_pq *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                 uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
+    if (!h || !p || (nq > 0 && (!queries || !out_ids || !out_scores || !out_counts)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    return cm::core_search_host(h->ix, queries, nq, dim, p, out_stride, out_ids, out_scores, out_pos, out_counts);
+}
+int cm_pq_search_device(cm_pq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                        int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
+                        int64_t *out_counts_dev, void *stream) {
+    if (!h || !p || (nq > 0 && (!queries_dev || !out_ids_dev || !out_scores_dev || !out_counts_dev)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (dim != h->ix.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ix.dim, dim);
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_search_device(h->ix, queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_pos_dev,
+                                 out_counts_dev, (cudaStream_t)stream, false);
+}
+
+int cm_ivfpq_create(int dim, int metric, int nlist, int M, int nbits, cm_ivfpq **out) {
+    if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    cm_ivfpq *h = new cm_ivfpq();
+    int rc = cm::core_create(dim, metric, nlist, M, nbits, true, &h->ix);
+    if (rc != CM_OK) { delete h; return rc; }
+    *out = h;
+    return CM_OK;
+}
+int cm_ivfpq_destroy(cm_ivfpq *h) { delete h; return CM_OK; }
+int cm_ivfpq_set_trained(cm_ivfpq *h, const float *centroids, const float *codebooks) {
+    if (!h || !centroids || !codebooks) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_set_trained(h->ix, centroids, codebooks);
+}
+int cm_ivfpq_trained(const cm_ivfpq *h) { return h && h->ix.trained ? 1 : 0; }
+int64_t cm_ivfpq_size(const cm_ivfpq *h) { return h ? h->ix.store.n : 0; }
+int cm_ivfpq_default_nprobes(const cm_ivfpq *h) {   // ivfpq_index.go:446 int(sqrt(nlist))
+    if (!h) return 0;
+    int r = (int)std::sqrt((double)h->ix.nlist);
+    while ((long long)(r + 1) * (r + 1) <= h->ix.nlist) r++;
+    while ((long long)r * r > h->ix.nlist) r--;
+    return r;
+}
+int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists) {
+    if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_add(h->ix, ids, rows, n, writeback, out_lists);
+}
+int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out) {
+    if (!h || !out || first < 0 || first + n > h->ix.store.n) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    CM_CUDA(cudaMemcpy(out, h->ix.store.codes + (size_t)first * h->ix.M, (size_t)n * h->ix.M, cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return h->ix.store.remove(id);
+}
+int cm_ivfpq_flush(cm_ivfpq *h) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_flush(h->ix);
+}
+int cm_ivfpq_search(cm_ivfpq *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                    uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
+    if (!h || !p || (nq > 0 && (!queries || !out_ids || !out_scores || !out_counts)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    return cm::core_search_host(h->ix, queries, nq, dim, p, out_stride, out_ids, out_scores, out_pos, out_counts);
+}
+int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                           int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
+                           int64_t *out_counts_dev, void *stream) {
+    if (!h || !p || (nq > 0 && (!queries_dev || !out_ids_dev || !out_scores_dev || !out_counts_dev)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
+    if (dim != h->ix.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ix.dim, dim);
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_search_device(h->ix, queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_pos_dev,
+                                 out_counts_dev, (cudaStream_t)stream, false);
+}
+
+}  // extern "C"

@@ -181,6 +181,46 @@ int cm_ivf_search_device(cm_ivf *h, const float *queries_dev, int64_t nq, int di
                          int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
                          int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
 
+/* ---- pq_index.go / pq_index_search.go ------------------------------------------------------- */
+int cm_pq_create(int dim, int metric, int M, int nbits, cm_pq **out);   /* NewPQIndex pq_index.go:135 */
+int cm_pq_destroy(cm_pq *h);
+/* the result of PQIndex.Train (pq_index.go:193-247): M x Ksub x dsub codebook floats */
+int cm_pq_set_codebooks(cm_pq *h, const float *codebooks);
+int cm_pq_trained(const cm_pq *h);
+int64_t cm_pq_size(const cm_pq *h);
+/* n successive PQIndex.Add calls (pq_index.go:262-292): PreprocessInPlace + encode (pq_index.go:439-473) */
+int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
+int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out);   /* idx.codes[first:first+n] */
+int cm_pq_remove(cm_pq *h, uint32_t id);
+int cm_pq_flush(cm_pq *h);
+/* nq independent searchSingleQuery calls (pq_index_search.go:218-325) */
+int cm_pq_search(cm_pq *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                 uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts);
+int cm_pq_search_device(cm_pq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                        int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
+                        int64_t *out_counts_dev, void *stream);
+
+/* ---- ivfpq_index.go / ivfpq_index_search.go ------------------------------------------------- */
+int cm_ivfpq_create(int dim, int metric, int nlist, int M, int nbits, cm_ivfpq **out);   /* NewIVFPQIndex ivfpq_index.go:114 */
+int cm_ivfpq_destroy(cm_ivfpq *h);
+/* the result of IVFPQIndex.Train (ivfpq_index.go:180-259): nlist x dim centroids + residual codebooks */
+int cm_ivfpq_set_trained(cm_ivfpq *h, const float *centroids, const float *codebooks);
+int cm_ivfpq_trained(const cm_ivfpq *h);
+int64_t cm_ivfpq_size(const cm_ivfpq *h);
+int cm_ivfpq_default_nprobes(const cm_ivfpq *h);                        /* ivfpq_index.go:446 */
+/* n successive IVFPQIndex.Add calls (ivfpq_index.go:279-319): preprocess, nearest centroid, residual, encode */
+int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
+int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out);   /* codes in arrival order */
+int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id);
+int cm_ivfpq_flush(cm_ivfpq *h);
+/* nq independent searchSingleQuery calls (ivfpq_index_search.go:231-390) */
+int cm_ivfpq_search(cm_ivfpq *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                    int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                    int64_t *out_counts);
+int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                           int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
+                           int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

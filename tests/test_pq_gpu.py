@@ -1,0 +1,129 @@
+"""GPU parity tests of the PQ and IVFPQ paths against the CPU oracle on a SHARED trained index (the oracle
+trains codebooks / centroids with the reference's deterministic k-means; the device loads them): codes,
+list assignment, ids, ranks and score bits must be identical.  Ties are frequent in ADC scores (few
+distinct table sums) -- both sides order them by candidate number."""
+import numpy as np
+import pytest
+
+from comet_b200 import capi
+from oracle import oracle_py as O
+from tests.parity import assert_same_results
+
+pytestmark = pytest.mark.gpu
+
+
+def data(n, d, seed, shift=0.0):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((n, d)).astype(np.float32) + np.float32(shift)), rng
+
+
+def pq_pair(n, d, metric, M, nbits, seed):
+    x, rng = data(n, d, seed, 0.2 if metric == capi.COSINE else 0.0)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    o = O.PQ(d, metric, M, nbits)
+    o.train(x[:max(1 << nbits, 600)].copy())
+    g = capi.PQIndex(d, metric, M, nbits)
+    g.set_codebooks(o.codebooks())
+    o.add(ids, x.copy())
+    g.add(ids, x.copy())
+    return g, o, rng
+
+
+def check_pq(g, o, q, k, **kw):
+    ids, sc, cnt = g.search(q, k=k, **kw)
+    for i in range(q.shape[0]):
+        oi, os_ = o.search(q[i], k=k, **kw)
+        assert_same_results(ids[i], sc[i], cnt[i], oi, os_, what=f"query {i}")
+
+
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_pq_codes_and_search_match_oracle(metric):
+    g, o, rng = pq_pair(9000, 32, metric, 8, 6, 40 + metric)
+    assert np.array_equal(g.codes(), o.codes())
+    q = rng.standard_normal((13, 32)).astype(np.float32)
+    check_pq(g, o, q, 10)
+    check_pq(g, o, q[:4], 300)
+    check_pq(g, o, q[:3], 25, threshold=4.0 if metric == capi.L2 else 0.9)
+    check_pq(g, o, q[:3], 25, filter_ids=np.arange(5, 9000, 7, dtype=np.uint32))
+
+
+def test_pq_m96_nbits8_dim768():
+    g, o, rng = pq_pair(3000, 768, capi.L2SQ, 96, 8, 5)
+    assert np.array_equal(g.codes(), o.codes())
+    q = rng.standard_normal((6, 768)).astype(np.float32)
+    check_pq(g, o, q, 100)
+
+
+def test_pq_delete_flush_and_errors():
+    g, o, rng = pq_pair(5000, 16, capi.L2, 4, 4, 77)
+    q = rng.standard_normal((5, 16)).astype(np.float32)
+    for i in range(3, 1500, 4):
+        g.remove(i)
+        o.remove(i)
+    check_pq(g, o, q, 20)
+    g.flush()
+    o.flush()
+    assert len(g) == len(o)
+    assert np.array_equal(g.codes(), o.codes())
+    check_pq(g, o, q, 20)
+    h = capi.PQIndex(16, capi.L2, 4, 4)
+    with pytest.raises(capi.CometError) as e:
+        h.search(q, k=1)
+    assert e.value.code == capi.ERR_NOT_TRAINED and "index not trained" in e.value.msg
+    with pytest.raises(capi.CometError):
+        capi.PQIndex(10, capi.L2, 4, 8)            # dim not divisible by M (pq_index.go:146)
+    with pytest.raises(capi.CometError):
+        capi.PQIndex(16, capi.L2, 4, 256)          # the reference's own benchmark argument: rejected (pq_index.go:152)
+    h.set_codebooks(o.codebooks())
+    assert h.search(q, k=3)[2].tolist() == [0] * 5   # trained, empty
+
+
+def ivfpq_pair(n, d, metric, nlist, M, nbits, seed):
+    x, rng = data(n, d, seed, 0.2 if metric == capi.COSINE else 0.0)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    o = O.IVFPQ(d, metric, nlist, M, nbits)
+    o.train(x[:max(nlist * 10, (1 << nbits) * 2, 800)].copy())
+    g = capi.IVFPQIndex(d, metric, nlist, M, nbits)
+    g.set_trained(o.centroids(), o.codebooks())
+    o.add(ids, x.copy())
+    lists = g.add(ids, x.copy())
+    return g, o, rng, lists
+
+
+def check_ivfpq(g, o, q, k, nprobes, **kw):
+    ids, sc, cnt = g.search(q, k=k, nprobes=nprobes, **kw)
+    for i in range(q.shape[0]):
+        oi, os_ = o.search(q[i], k=k, nprobes=nprobes, **kw)
+        assert_same_results(ids[i], sc[i], cnt[i], oi, os_, what=f"query {i}")
+
+
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_ivfpq_lists_codes_and_search_match_oracle(metric):
+    g, o, rng, lists = ivfpq_pair(8000, 32, metric, 20, 8, 5, 60 + metric)
+    ol = o.lists()
+    codes = g.codes()
+    for l in range(20):
+        mine = np.nonzero(lists == l)[0]
+        assert np.array_equal((mine + 1).astype(np.uint32), ol[l][0]), f"list {l} membership"
+        assert np.array_equal(codes[mine], ol[l][1]), f"list {l} residual codes"
+    q = rng.standard_normal((11, 32)).astype(np.float32)
+    for nprobes in (1, 4, 20):
+        check_ivfpq(g, o, q, 10, nprobes)
+    check_ivfpq(g, o, q[:3], 0, 2)
+    check_ivfpq(g, o, q[:3], 50, 4, threshold=5.0 if metric == capi.L2 else 1.1)
+    check_ivfpq(g, o, q[:3], 50, 4, filter_ids=np.arange(2, 8000, 5, dtype=np.uint32))
+
+
+def test_ivfpq_m96_dim768_and_delete_flush():
+    g, o, rng, _ = ivfpq_pair(4000, 768, capi.L2SQ, 16, 96, 8, 9)
+    assert g.default_nprobes() == o.default_nprobes() == 4
+    q = rng.standard_normal((5, 768)).astype(np.float32)
+    check_ivfpq(g, o, q, 100, 4)
+    for i in range(1, 800, 3):
+        g.remove(i)
+        o.remove(i)
+    check_ivfpq(g, o, q, 100, 4)
+    g.flush()
+    o.flush()
+    assert len(g) == o.total()
+    check_ivfpq(g, o, q, 100, 16)
