@@ -110,6 +110,16 @@ SIGNATURES = {
     "cm_ivfpq_flush": (C.c_int, [vp]),
     "cm_ivfpq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
     "cm_ivfpq_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp, vp]),
+    "cm_hnsw_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_hnsw_destroy": (C.c_int, [vp]),
+    "cm_hnsw_size": (C.c_int64, [vp]),
+    "cm_hnsw_ef_search": (C.c_int, [vp]),
+    "cm_hnsw_load_graph": (C.c_int, [vp, C.c_int64, u32p, f32p, i32p, i64p, u32p, C.c_uint32, C.c_int]),
+    "cm_hnsw_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_hnsw_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p,
+                                 i64p, i64p, i64p]),
+    "cm_hnsw_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
+                                        vp, vp, vp, vp]),
     "cm_merge_shards_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp]),
 }
 
@@ -439,3 +449,63 @@ class IVFPQIndex(_ADCIndex):
         if nprobes is None:
             nprobes = self.default_nprobes()
         return self._search(queries, k, threshold, nprobes, filter_ids, out_stride)
+
+
+class HNSWIndex:
+    """Thin owner of a cm_hnsw handle (search on device; the graph is uploaded)."""
+
+    def __init__(self, dim, metric, m=16, ef_construction=200, ef_search=200):
+        self.h = vp()
+        check(lib().cm_hnsw_create(int(dim), int(metric), int(m), int(ef_construction), int(ef_search), C.byref(self.h)))
+        self.dim, self.metric = dim, metric
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().cm_hnsw_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(lib().cm_hnsw_size(self.h))
+
+    def ef_search(self):
+        return int(lib().cm_hnsw_ef_search(self.h))
+
+    def load_graph(self, ids, rows, levels, layers, entry_id, max_level):
+        """layers: per layer (offsets[n+1], neighbour ids) as exported by the builder."""
+        ids = _u32(ids)
+        rows = _f32(rows).reshape(len(ids), self.dim)
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        n = len(ids)
+        offs = [0]
+        chunks = []
+        for s in range(n):
+            for layer in range(int(levels[s]) + 1):
+                lo, nb = layers[layer]
+                seg = nb[lo[s]:lo[s + 1]]
+                chunks.append(seg)
+                offs.append(offs[-1] + len(seg))
+        edge_off = np.asarray(offs, dtype=np.int64)
+        edge_ids = _u32(np.concatenate(chunks)) if chunks and offs[-1] > 0 else np.zeros(1, np.uint32)
+        check(lib().cm_hnsw_load_graph(self.h, n, ptr(ids, u32p), ptr(rows, f32p), ptr(levels, i32p),
+                                       ptr(edge_off, i64p), ptr(edge_ids, u32p), int(entry_id), int(max_level)))
+
+    def remove(self, id_):
+        check(lib().cm_hnsw_remove(self.h, int(id_)))
+
+    def search(self, queries, k=10, ef_search=0, threshold=0.0, filter_ids=None, with_work=False):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        ef = ef_search if ef_search > 0 else self.ef_search()
+        stride = max(1, ef if (k <= 0 or k > ef) else k)
+        ids = np.zeros((nq, stride), np.uint32)
+        sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        work = np.zeros((nq, 2), np.int64)
+        p, keep = make_params(k=k, threshold=threshold, ef_search=ef_search, filter_ids=filter_ids)
+        check(lib().cm_hnsw_search(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p), ptr(sc, f32p), None,
+                                   ptr(cnt, i64p), ptr(work, i64p)))
+        if with_work:
+            return ids, sc, cnt, work
+        return ids, sc, cnt

@@ -221,6 +221,26 @@ int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, in
                            int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
                            int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
 
+/* ---- hnsw_index.go / hnsw_index_search.go --------------------------------------------------- */
+int cm_hnsw_create(int dim, int metric, int m, int ef_construction, int ef_search, cm_hnsw **out);   /* NewHNSWIndex hnsw_index.go:172 */
+int cm_hnsw_destroy(cm_hnsw *h);
+int64_t cm_hnsw_size(const cm_hnsw *h);
+int cm_hnsw_ef_search(const cm_hnsw *h);
+/* Upload a graph built by HNSWIndex.Add / insertNode (hnsw_index.go:228-288, 493-552).  rows are the STORED
+ * (already preprocessed) vectors, n x dim; slots = insertion order; edge_off has sum(levels[i]+1)+1 entries,
+ * pairs ordered by (slot, layer 0..level); edge_ids are neighbour node IDs in the reference's edge order. */
+int cm_hnsw_load_graph(cm_hnsw *h, int64_t n, const uint32_t *ids, const float *rows, const int32_t *levels,
+                       const int64_t *edge_off, const uint32_t *edge_ids, uint32_t entry_id, int max_level);
+int cm_hnsw_remove(cm_hnsw *h, uint32_t id);                         /* soft delete, hnsw_index.go:300-330 */
+/* nq independent searchSingleQuery calls (hnsw_index_search.go:248-354 + searchLayer hnsw_index.go:565-629);
+ * p->ef_search as WithEfSearch.  out_stride >= min(k, ef, n).  out_work (optional, nq x 2): distance
+ * evaluations and node expansions per query (the algorithmic-bytes figure of the roofline). */
+int cm_hnsw_search(cm_hnsw *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                   uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, int64_t *out_work);
+int cm_hnsw_search_device(cm_hnsw *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                          int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
+                          int64_t *out_counts_dev, int64_t *work_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
