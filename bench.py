@@ -107,6 +107,15 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def measured_traffic(key):
+    """DRAM bytes of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 def gen_rows_device(torch, n, d, seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -294,7 +303,10 @@ def run_ours(args):
             ach = flops / per / 1e12
             roof = {"kernel": "flat_gemm_kernel (tcgen05 bf16, %d launches per step)" % (gemm_n // n_prof),
                     "bound": "tensor", "achieved": ach, "peak": tf_sus,
-                    "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None, "peak_source": which + " (sustained bf16)",
+                    "unit": "TFLOP/s", "frac": ach / tf_sus,
+                    "traffic": measured_traffic("flat_gemm_kernel_per_step_bytes") if world == 1 else None,
+                    "traffic_note": "DRAM bytes of the 3 launches of one step, ncu capture in profiles/r01_tensor_path.md; algorithmic = %d (bf16 shadow once)" % (shard * DIM * 2),
+                    "peak_source": which + " (sustained bf16)",
                     "gemm_ms_per_step": per * 1e3, "launches_timed": gemm_n,
                     "hbm_equiv": {"note": "algorithmic bytes of one fp32 corpus pass / GEMM time, vs measured HBM peak",
                                   "achieved_gbs": (shard * DIM * 4 + nq * DIM * 4 + nq * K * 8) / per / 1e9,
@@ -305,7 +317,8 @@ def run_ours(args):
             abytes = shard * DIM * 4 + qb * DIM * 4
             ach = abytes / per / 1e9
             roof = {"kernel": "flat_scan_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                    "frac": ach / hbm, "traffic": None, "peak_source": which, "avg_launch_ms": per * 1e3,
+                    "frac": ach / hbm, "traffic": measured_traffic("flat_scan_kernel_per_launch_bytes") if world == 1 else None,
+                    "peak_source": which, "avg_launch_ms": per * 1e3,
                     "launches_timed": scan_n, "queries_per_launch": qb}
         if roof is not None:
             roof["step_share"] = {"steps": n_prof, "scan_ms": scan_ms, "gemm_ms": gemm_ms, "rescore_ms": resc_ms,
