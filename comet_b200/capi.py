@@ -76,6 +76,8 @@ SIGNATURES = {
     "cm_ivf_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_ivf_destroy": (C.c_int, [vp]),
     "cm_ivf_set_centroids": (C.c_int, [vp, f32p]),
+    "cm_ivf_train": (C.c_int, [vp, f32p, C.c_int64]),
+    "cm_ivf_get_centroids": (C.c_int, [vp, f32p]),
     "cm_ivf_trained": (C.c_int, [vp]),
     "cm_ivf_size": (C.c_int64, [vp]),
     "cm_ivf_default_nprobes": (C.c_int, [vp]),
@@ -90,6 +92,8 @@ SIGNATURES = {
     "cm_pq_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_pq_destroy": (C.c_int, [vp]),
     "cm_pq_set_codebooks": (C.c_int, [vp, f32p]),
+    "cm_pq_train": (C.c_int, [vp, f32p, C.c_int64]),
+    "cm_pq_get_codebooks": (C.c_int, [vp, f32p]),
     "cm_pq_trained": (C.c_int, [vp]),
     "cm_pq_size": (C.c_int64, [vp]),
     "cm_pq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
@@ -101,6 +105,8 @@ SIGNATURES = {
     "cm_ivfpq_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_ivfpq_destroy": (C.c_int, [vp]),
     "cm_ivfpq_set_trained": (C.c_int, [vp, f32p, f32p]),
+    "cm_ivfpq_train": (C.c_int, [vp, f32p, C.c_int64]),
+    "cm_ivfpq_get_trained": (C.c_int, [vp, f32p, f32p]),
     "cm_ivfpq_trained": (C.c_int, [vp]),
     "cm_ivfpq_size": (C.c_int64, [vp]),
     "cm_ivfpq_default_nprobes": (C.c_int, [vp]),
@@ -316,6 +322,15 @@ class IVFIndex:
         c = _f32(c).reshape(self.nlist, self.dim)
         check(lib().cm_ivf_set_centroids(self.h, ptr(c, f32p)))
 
+    def train(self, rows):
+        r = _f32(rows).reshape(-1, self.dim)
+        check(lib().cm_ivf_train(self.h, ptr(r, f32p), r.shape[0]))
+
+    def centroids(self):
+        out = np.zeros((self.nlist, self.dim), np.float32)
+        check(lib().cm_ivf_get_centroids(self.h, ptr(out, f32p)))
+        return out
+
     def add(self, ids, rows, writeback=True):
         ids = _u32(np.atleast_1d(ids))
         if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
@@ -415,6 +430,16 @@ class PQIndex(_ADCIndex):
         cb = _f32(cb)
         check(lib().cm_pq_set_codebooks(self.h, ptr(cb, f32p)))
 
+    def train(self, rows):
+        r = _f32(rows).reshape(-1, self.dim)
+        check(lib().cm_pq_train(self.h, ptr(r, f32p), r.shape[0]))
+
+    def codebooks(self):
+        ksub = 1 << self.nbits
+        out = np.zeros((self.M, ksub, self.dim // self.M), np.float32)
+        check(lib().cm_pq_get_codebooks(self.h, ptr(out, f32p)))
+        return out
+
     def add(self, ids, rows, writeback=True):
         ids, rows2 = self._rows(ids, rows)
         check(lib().cm_pq_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
@@ -437,6 +462,17 @@ class IVFPQIndex(_ADCIndex):
 
     def default_nprobes(self):
         return int(lib().cm_ivfpq_default_nprobes(self.h))
+
+    def train(self, rows):
+        r = _f32(rows).reshape(-1, self.dim)
+        check(lib().cm_ivfpq_train(self.h, ptr(r, f32p), r.shape[0]))
+
+    def trained_state(self):
+        ksub = 1 << self.nbits
+        c = np.zeros((self.nlist, self.dim), np.float32)
+        cb = np.zeros((self.M, ksub, self.dim // self.M), np.float32)
+        check(lib().cm_ivfpq_get_trained(self.h, ptr(c, f32p), ptr(cb, f32p)))
+        return c, cb
 
     def add(self, ids, rows, writeback=True):
         ids, rows2 = self._rows(ids, rows)

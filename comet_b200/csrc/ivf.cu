@@ -27,6 +27,7 @@
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+#include "kmeans.cuh"
 #include "select.cuh"
 
 namespace cm {
@@ -416,6 +417,34 @@ int cm_ivf_set_centroids(cm_ivf *h, const float *centroids) {
     cm::release_stream(st);
     if (rc == CM_OK) h->ix.trained = true;
     return rc;
+}
+// IVFIndex.Train (ivf_index.go:205-246): KMeans(raw vectors, nlist, index distance, 20) on the device
+int cm_ivf_train(cm_ivf *h, const float *rows, int64_t n) {
+    if (!h || (n > 0 && !rows)) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (n < h->ix.nlist)
+        return cm::fail(CM_ERR_TOO_FEW, "need at least %d training vectors for %d clusters (got %lld)", h->ix.nlist, h->ix.nlist, (long long)n);
+    if (h->ix.store.n > 0) return cm::fail(CM_ERR_UNSUPPORTED, "retraining a non-empty index is not supported");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    float *d = nullptr;
+    int rc = cm::upload_training_rows(rows, n, h->ix.dim, h->ix.coarse.ld, &d, st);
+    if (rc == CM_OK) rc = cm::kmeans_full(h->ix.coarse, d, n, h->ix.nlist, 20, nullptr, st);
+    cm::ws_free(d, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "ivf_train: %s", cudaGetErrorString(e));
+    if (rc == CM_OK) h->ix.trained = true;
+    return rc;
+}
+// trained centroids back to the host (nlist x dim), e.g. for IVFIndex.WriteTo
+int cm_ivf_get_centroids(const cm_ivf *h, float *out) {
+    if (!h || !out) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    CM_CUDA(cudaMemcpy2D(out, (size_t)h->ix.dim * 4, h->ix.coarse.rows, (size_t)h->ix.coarse.ld * 4, (size_t)h->ix.dim * 4,
+                         (size_t)h->ix.nlist, cudaMemcpyDeviceToHost));
+    return CM_OK;
 }
 int cm_ivf_trained(const cm_ivf *h) { return h && h->ix.trained ? 1 : 0; }
 int64_t cm_ivf_size(const cm_ivf *h) { return h ? h->ix.store.n : 0; }

@@ -26,6 +26,7 @@
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+#include "kmeans.cuh"
 #include "select.cuh"
 
 namespace cm {
@@ -621,6 +622,49 @@ static int core_set_trained(PQCore &ix, const float *centroids, const float *cod
     return CM_OK;
 }
 
+// PQIndex.Train (pq_index.go:193-247) / IVFPQIndex.Train (ivfpq_index.go:180-259) on the device
+static int core_train(PQCore &ix, const float *rows, int64_t n) {
+    const bool ivf = ix.nlist > 0;
+    if (ivf && n < (int64_t)ix.nlist * 10) return fail(CM_ERR_TOO_FEW, "need at least %d vectors for training", ix.nlist * 10);
+    if (!ivf && n < ix.Ksub) return fail(CM_ERR_TOO_FEW, "need at least %d vectors for training", ix.Ksub);
+    if (ix.store.n > 0) return fail(CM_ERR_UNSUPPORTED, "retraining a non-empty index is not supported");
+    cudaStream_t st;
+    CM_TRY(acquire_stream(&st));
+    float *x = nullptr, *res = nullptr;
+    long long *assign = nullptr;
+    size_t cb_bytes = (size_t)ix.M * ix.Ksub * ix.dsub * 4;
+    int rc = upload_training_rows(rows, n, ix.dim, ix.ld, &x, st);
+    if (rc == CM_OK && !ix.codebooks) {
+        cudaError_t e = cudaMalloc(&ix.codebooks, cb_bytes);
+        if (e != cudaSuccess) rc = fail(CM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    const float *sub_src = x;
+    if (rc == CM_OK && ivf) {
+        rc = ws_alloc((void **)&assign, (size_t)n * 8, st);
+        if (rc == CM_OK) rc = ws_alloc((void **)&res, (size_t)n * ix.ld * 4, st);
+        if (rc == CM_OK) rc = kmeans_full(ix.coarse, x, n, ix.nlist, 20, assign, st);
+        if (rc == CM_OK) rc = launch_residuals(x, n, ix.dim, ix.ld, ix.coarse.rows, assign, res, st);
+        sub_src = res;
+    }
+    for (int m = 0; rc == CM_OK && m < ix.M; m++)
+        rc = kmeans_subspace(sub_src, n, ix.ld, m * ix.dsub, ix.dsub, ix.Ksub, 20, ix.codebooks + (size_t)m * ix.Ksub * ix.dsub, st);
+    ws_free(x, st); ws_free(res, st); ws_free(assign, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    release_stream(st);
+    if (rc == CM_OK && e != cudaSuccess) rc = fail(CM_ERR_CUDA, "train: %s", cudaGetErrorString(e));
+    if (rc == CM_OK) ix.trained = true;
+    return rc;
+}
+
+static int core_get_trained(const PQCore &ix, float *centroids, float *codebooks) {
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, "index must be trained");
+    if (codebooks) CM_CUDA(cudaMemcpy(codebooks, ix.codebooks, (size_t)ix.M * ix.Ksub * ix.dsub * 4, cudaMemcpyDeviceToHost));
+    if (centroids && ix.nlist > 0)
+        CM_CUDA(cudaMemcpy2D(centroids, (size_t)ix.dim * 4, ix.coarse.rows, (size_t)ix.coarse.ld * 4, (size_t)ix.dim * 4, (size_t)ix.nlist,
+                             cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+
 static int core_search_host(PQCore &ix, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
                             uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
     if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ix.nlist > 0 ? "index must be trained before searching" : "index not trained");
@@ -680,6 +724,16 @@ int cm_pq_set_codebooks(cm_pq *h, const float *codebooks) {
     CM_CUDA(cudaSetDevice(h->ix.device));
     return cm::core_set_trained(h->ix, nullptr, codebooks);
 }
+int cm_pq_train(cm_pq *h, const float *rows, int64_t n) {
+    if (!h || (n > 0 && !rows)) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_train(h->ix, rows, n);
+}
+int cm_pq_get_codebooks(const cm_pq *h, float *out) {
+    if (!h || !out) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_get_trained(h->ix, nullptr, out);
+}
 int cm_pq_trained(const cm_pq *h) { return h && h->ix.trained ? 1 : 0; }
 int64_t cm_pq_size(const cm_pq *h) { return h ? h->ix.store.n : 0; }
 int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeback) {
@@ -735,6 +789,16 @@ int cm_ivfpq_set_trained(cm_ivfpq *h, const float *centroids, const float *codeb
     if (!h || !centroids || !codebooks) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     CM_CUDA(cudaSetDevice(h->ix.device));
     return cm::core_set_trained(h->ix, centroids, codebooks);
+}
+int cm_ivfpq_train(cm_ivfpq *h, const float *rows, int64_t n) {
+    if (!h || (n > 0 && !rows)) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_train(h->ix, rows, n);
+}
+int cm_ivfpq_get_trained(const cm_ivfpq *h, float *centroids, float *codebooks) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::core_get_trained(h->ix, centroids, codebooks);
 }
 int cm_ivfpq_trained(const cm_ivfpq *h) { return h && h->ix.trained ? 1 : 0; }
 int64_t cm_ivfpq_size(const cm_ivfpq *h) { return h ? h->ix.store.n : 0; }

@@ -162,6 +162,9 @@ int cm_ivf_create(int dim, int nlist, int metric, cm_ivf **out);     /* NewIVFIn
 int cm_ivf_destroy(cm_ivf *h);
 /* the result of IVFIndex.Train (ivf_index.go:205-246): nlist x dim centroids, stored as given */
 int cm_ivf_set_centroids(cm_ivf *h, const float *centroids);
+/* IVFIndex.Train on the device: the reference's deterministic KMeans (clustering.go:119-239), bit for bit */
+int cm_ivf_train(cm_ivf *h, const float *rows, int64_t n);
+int cm_ivf_get_centroids(const cm_ivf *h, float *out);                /* nlist x dim */
 int cm_ivf_trained(const cm_ivf *h);
 int64_t cm_ivf_size(const cm_ivf *h);
 int cm_ivf_default_nprobes(const cm_ivf *h);                        /* ivf_index.go:410 int(sqrt(nlist)) */
@@ -186,6 +189,9 @@ int cm_pq_create(int dim, int metric, int M, int nbits, cm_pq **out);   /* NewPQ
 int cm_pq_destroy(cm_pq *h);
 /* the result of PQIndex.Train (pq_index.go:193-247): M x Ksub x dsub codebook floats */
 int cm_pq_set_codebooks(cm_pq *h, const float *codebooks);
+/* PQIndex.Train on the device: per sub-space KMeansSubspace on the RAW vectors (pq_index.go:210-243) */
+int cm_pq_train(cm_pq *h, const float *rows, int64_t n);
+int cm_pq_get_codebooks(const cm_pq *h, float *out);
 int cm_pq_trained(const cm_pq *h);
 int64_t cm_pq_size(const cm_pq *h);
 /* n successive PQIndex.Add calls (pq_index.go:262-292): PreprocessInPlace + encode (pq_index.go:439-473) */
@@ -205,6 +211,9 @@ int cm_ivfpq_create(int dim, int metric, int nlist, int M, int nbits, cm_ivfpq *
 int cm_ivfpq_destroy(cm_ivfpq *h);
 /* the result of IVFPQIndex.Train (ivfpq_index.go:180-259): nlist x dim centroids + residual codebooks */
 int cm_ivfpq_set_trained(cm_ivfpq *h, const float *centroids, const float *codebooks);
+/* IVFPQIndex.Train on the device: KMeans, assignment, residuals, per sub-space KMeansSubspace */
+int cm_ivfpq_train(cm_ivfpq *h, const float *rows, int64_t n);
+int cm_ivfpq_get_trained(const cm_ivfpq *h, float *centroids, float *codebooks);   /* either may be NULL */
 int cm_ivfpq_trained(const cm_ivfpq *h);
 int64_t cm_ivfpq_size(const cm_ivfpq *h);
 int cm_ivfpq_default_nprobes(const cm_ivfpq *h);                        /* ivfpq_index.go:446 */
