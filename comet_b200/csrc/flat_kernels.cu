@@ -158,16 +158,23 @@ int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanL
     if (C < 512) C = 512;
     size_t cap = max_smem_optin();
     int qb = nq >= 8 ? 8 : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
-    int stages = 0;
-    for (;; qb >>= 1) {
-        // prefer a deep ring; shrink it, then the query block, until the CTA fits
-        for (stages = 8; stages >= 3; stages--)
-            if (scan_smem_bytes(qb, ld, stages, C) <= cap) break;
-        if (stages >= 3 || qb == 1) break;
+    int stages = 0, ctas_per_sm = 1;
+    // Each consumer thread walks one row sequentially, so a CTA issues from only 4 warps: the scan is
+    // latency bound unless two CTAs share an SM.  Prefer a footprint of half the SM (ring of 3-4 stages);
+    // fall back to one CTA per SM with a deep ring, then to a smaller query block.
+    const size_t half = (cap + 1024) / 2 - 2048;      // two CTAs + the per-CTA reserved kilobyte
+    for (int s = 4; s >= 3; s--)
+        if (scan_smem_bytes(qb, ld, s, C) <= half) { stages = s; ctas_per_sm = 2; break; }
+    if (stages == 0) {
+        for (;; qb >>= 1) {
+            for (stages = 8; stages >= 3; stages--)
+                if (scan_smem_bytes(qb, ld, stages, C) <= cap) break;
+            if (stages >= 3 || qb == 1) break;
+        }
     }
     if (stages < 3) return fail(CM_ERR_UNSUPPORTED, "k=%d with dim pad %d does not fit the scan kernel's shared memory", K, ld);
     int64_t n_tiles = (n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
-    int grid = sm_count();
+    int grid = sm_count() * ctas_per_sm;
     if (grid > n_tiles) grid = (int)(n_tiles > 0 ? n_tiles : 1);
     out->metric = metric; out->fma = fma; out->qb = qb; out->stages = stages; out->grid = grid;
     out->K = K; out->C = C; out->smem = scan_smem_bytes(qb, ld, stages, C);

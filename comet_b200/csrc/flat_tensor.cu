@@ -423,19 +423,25 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
         }
         return (size_t)lo * slots + (size_t)(j - off_s[lo]);
     };
-    // ---- stage the ordered score words (high halves of the keys); loads batched 4 deep ----
+    // ---- stage the ordered score words (high halves of the keys): a warp takes 4 regions at a time,
+    // lanes run over their entries, the 4 loads of a lane are issued before any is used ----
     const uint32_t *qwords = reinterpret_cast<const uint32_t *>(qcand);
-    for (int j0 = 0; j0 < total; j0 += SEL_THREADS * 4) {
-        uint32_t v[4];
+    for (int r0 = warp * 4; r0 < n_cta; r0 += (SEL_THREADS / 32) * 4) {
+        int o[4], c[4], mc = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            int j = j0 + u * SEL_THREADS + tid;
-            v[u] = j < total ? __ldg(qwords + 2 * locate(j) + 1) : 0u;
+            int r = r0 + u;
+            o[u] = r < n_cta ? off_s[r] : 0;
+            c[u] = r < n_cta ? off_s[r + 1] - o[u] : 0;
+            mc = max(mc, c[u]);
         }
+        for (int i = lane; i < mc; i += 32) {
+            uint32_t v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int j = j0 + u * SEL_THREADS + tid;
-            if (j < total) hi_s[j] = v[u];
+            for (int u = 0; u < 4; u++) v[u] = i < c[u] ? __ldg(qwords + 2 * ((size_t)(r0 + u) * slots + i) + 1) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i < c[u]) hi_s[o[u] + i] = v[u];
         }
     }
     __syncthreads();
