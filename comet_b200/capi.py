@@ -82,6 +82,7 @@ SIGNATURES = {
     "cm_ivf_size": (C.c_int64, [vp]),
     "cm_ivf_default_nprobes": (C.c_int, [vp]),
     "cm_ivf_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
+    "cm_ivf_last_scanned": (C.c_int64, [vp]),
     "cm_ivf_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_ivf_flush": (C.c_int, [vp]),
     "cm_ivf_get_rows": (C.c_int, [vp, i64p, C.c_int64, f32p]),
@@ -112,6 +113,7 @@ SIGNATURES = {
     "cm_ivfpq_default_nprobes": (C.c_int, [vp]),
     "cm_ivfpq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
     "cm_ivfpq_get_codes": (C.c_int, [vp, C.c_int64, C.c_int64, u8p]),
+    "cm_ivfpq_last_scanned": (C.c_int64, [vp]),
     "cm_ivfpq_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_ivfpq_flush": (C.c_int, [vp]),
     "cm_ivfpq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),

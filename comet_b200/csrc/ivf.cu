@@ -44,8 +44,9 @@ struct IVFIndex {
     bool csr_dirty = true;
     std::vector<int64_t> sizes_desc;            // list lengths, descending (bound on candidates per query)
     std::mutex csr_mu;
+    unsigned long long *scanned_total = nullptr;   // device: candidates scanned by the last search (all queries)
 
-    ~IVFIndex() { cudaFree(members); cudaFree(list_off); }
+    ~IVFIndex() { cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); }
     int sync_csr(cudaStream_t st);
     int64_t candidate_bound(int nprobes) const;
 };
@@ -86,7 +87,8 @@ int64_t IVFIndex::candidate_bound(int nprobes) const {
 
 // per query: q_off[q][p] = number of candidates contributed by probes 0..p-1 (p = 0..nprobes)
 __global__ void ivf_offsets_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ probe_cnt,
-                                   const long long *__restrict__ list_off, int nprobes, long long *__restrict__ q_off) {
+                                   const long long *__restrict__ list_off, int nprobes, long long *__restrict__ q_off,
+                                   unsigned long long *__restrict__ total) {
     const int q = blockIdx.x;
     __shared__ long long carry;
     __shared__ long long wsum[8];
@@ -115,11 +117,12 @@ __global__ void ivf_offsets_kernel(const long long *__restrict__ probe_list, con
         if (threadIdx.x == 255) carry = base + inc;
         __syncthreads();
     }
+    if (threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)carry);
 }
 
 int launch_ivf_offsets(const long long *probe_list, const long long *probe_cnt, const long long *list_off, int nprobes,
-                       int64_t nq, long long *q_off, cudaStream_t st) {
-    ivf_offsets_kernel<<<(unsigned)nq, 256, 0, st>>>(probe_list, probe_cnt, list_off, nprobes, q_off);
+                       int64_t nq, long long *q_off, unsigned long long *total, cudaStream_t st) {
+    ivf_offsets_kernel<<<(unsigned)nq, 256, 0, st>>>(probe_list, probe_cnt, list_off, nprobes, q_off, total);
     count_launch();
     CM_CUDA(cudaGetLastError());
     return CM_OK;
@@ -302,7 +305,9 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
                                   (int64_t *)probe_cnt, st, &cst));
 
     // 3. candidate numbering
-    CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, st));
+    if (!ix.scanned_total) CM_CUDA(cudaMalloc(&ix.scanned_total, 8));
+    CM_CUDA(cudaMemsetAsync(ix.scanned_total, 0, 8, st));
+    CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, ix.scanned_total, st));
 
     // 4. soft deletes + document filter -> skip mask over store positions
     const uint8_t *skip = nullptr;
@@ -514,6 +519,16 @@ int cm_ivf_add(cm_ivf *h, const uint32_t *ids, float *rows, int64_t n, int write
     cudaStreamSynchronize(st);
     cm::release_stream(st);
     return rc;
+}
+
+// candidates (vectors of probed lists) scanned by the last search on this handle, all queries together:
+// the measured factor of the scan's algorithmic bytes
+int64_t cm_ivf_last_scanned(const cm_ivf *h) {
+    if (!h || !h->ix.scanned_total) return 0;
+    unsigned long long v = 0;
+    cudaSetDevice(h->ix.device);
+    if (cudaMemcpy(&v, h->ix.scanned_total, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
 }
 
 int cm_ivf_remove(cm_ivf *h, uint32_t id) {     // ivf_index.go:296-330 soft delete

@@ -136,8 +136,9 @@ struct PQCore {
     bool csr_dirty = true;
     std::vector<int64_t> sizes_desc;
     std::mutex csr_mu;
+    unsigned long long *scanned_total = nullptr;   // device: codes scanned by the last IVFPQ search (all queries)
 
-    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); }
+    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); }
     int lut_entries() const { return Ksub < 256 ? Ksub : 256; }
     int sync_csr(cudaStream_t st);
 };
@@ -250,7 +251,18 @@ __global__ void __launch_bounds__(ADC_THREADS) adc_scan_kernel(
         const float *cb = codebooks + ((size_t)m * Ksub + c) * dsub;
         const float *r = res + (size_t)m * dsub;
         float dist = 0.0f;
-        for (int j = 0; j < dsub; j++) dist = l2_step<FMA>(dist, r[j], cb[j]);
+        if ((dsub & 3) == 0) {                       // 16-byte codebook loads; same summation order
+            const float4 *cb4 = reinterpret_cast<const float4 *>(cb);
+            for (int j = 0; j < dsub / 4; j++) {
+                float4 v = __ldg(cb4 + j);
+                dist = l2_step<FMA>(dist, r[4 * j + 0], v.x);
+                dist = l2_step<FMA>(dist, r[4 * j + 1], v.y);
+                dist = l2_step<FMA>(dist, r[4 * j + 2], v.z);
+                dist = l2_step<FMA>(dist, r[4 * j + 3], v.w);
+            }
+        } else {
+            for (int j = 0; j < dsub; j++) dist = l2_step<FMA>(dist, r[j], cb[j]);
+        }
         lut[e] = dist;
     }
     __syncthreads();
@@ -264,7 +276,24 @@ __global__ void __launch_bounds__(ADC_THREADS) adc_scan_kernel(
             pos = mem ? mem[j] : (uint32_t)j;
             const uint8_t *code = codes + (size_t)pos * M;
             float sum = 0.0f;
-            for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+            if ((M & 15) == 0) {                     // 16 codes per load; table sums stay in sub-quantiser order
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(code);
+                const float *lp = lut;
+                for (int w = 0; w < M / 16; w++) {
+                    uint4 v = __ldg(c4 + w);
+                    uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            sum = __fadd_rn(sum, lp[(wd[t] >> (8 * b)) & 0xffu]);
+                            lp += lut_n;
+                        }
+                    }
+                }
+            } else {
+                for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+            }
             dist = __fsqrt_rn(sum);
             if (skip != nullptr && skip[pos]) live = false;
             if (threshold > 0.0f && dist > threshold) live = false;
@@ -316,7 +345,7 @@ __global__ void adc_emit_kernel(const long long *__restrict__ probe_list, const 
 
 // ivf.cu: per query prefix sums of the probed list lengths (the reference's candidate numbering)
 int launch_ivf_offsets(const long long *probe_list, const long long *probe_cnt, const long long *list_off, int nprobes,
-                       int64_t nq, long long *q_off, cudaStream_t st);
+                       int64_t nq, long long *q_off, unsigned long long *total, cudaStream_t st);
 
 static int prepare_queries(int metric, int dim, int ld, const float *q_dev, int64_t nq, bool check_zero, float **qp_out,
                            cudaStream_t st) {
@@ -413,7 +442,9 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         cm_flat_stats cst{};
         CM_TRY(ix.coarse.search_exact(qp, nq, nq_pad, nprobes, nullptr, 0.0f, nprobes, c_ids, c_sc, (int64_t *)probe_list,
                                       (int64_t *)probe_cnt, st, &cst));
-        CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, st));
+        if (!ix.scanned_total) CM_CUDA(cudaMalloc(&ix.scanned_total, 8));
+        CM_CUDA(cudaMemsetAsync(ix.scanned_total, 0, 8, st));
+        CM_TRY(launch_ivf_offsets(probe_list, probe_cnt, ix.list_off, nprobes, nq, q_off, ix.scanned_total, st));
     }
     const uint8_t *skip = nullptr;
     uint8_t *skip_buf = nullptr;
@@ -820,6 +851,13 @@ int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out
     CM_CUDA(cudaSetDevice(h->ix.device));
     CM_CUDA(cudaMemcpy(out, h->ix.store.codes + (size_t)first * h->ix.M, (size_t)n * h->ix.M, cudaMemcpyDeviceToHost));
     return CM_OK;
+}
+int64_t cm_ivfpq_last_scanned(const cm_ivfpq *h) {
+    if (!h || !h->ix.scanned_total) return 0;
+    unsigned long long v = 0;
+    cudaSetDevice(h->ix.device);
+    if (cudaMemcpy(&v, h->ix.scanned_total, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
 }
 int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id) {
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");

@@ -172,6 +172,9 @@ int cm_ivf_default_nprobes(const cm_ivf *h);                        /* ivf_index
  * writeback == 0), FindNearestCentroidIndex (clustering.go:252-272), append to the list.
  * out_lists (optional, n entries) receives the list each row went to. */
 int cm_ivf_add(cm_ivf *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
+/* vectors of probed lists scanned by the last search on this handle (all queries): the measured
+ * factor of the scan's algorithmic bytes */
+int64_t cm_ivf_last_scanned(const cm_ivf *h);
 int cm_ivf_remove(cm_ivf *h, uint32_t id);                          /* ivf_index.go:296-330 */
 int cm_ivf_flush(cm_ivf *h);                                        /* ivf_index.go:342-390 */
 int cm_ivf_get_rows(const cm_ivf *h, const int64_t *positions, int64_t n, float *out);
@@ -220,6 +223,7 @@ int cm_ivfpq_default_nprobes(const cm_ivfpq *h);                        /* ivfpq
 /* n successive IVFPQIndex.Add calls (ivfpq_index.go:279-319): preprocess, nearest centroid, residual, encode */
 int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
 int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out);   /* codes in arrival order */
+int64_t cm_ivfpq_last_scanned(const cm_ivfpq *h);                    /* codes scanned by the last search */
 int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id);
 int cm_ivfpq_flush(cm_ivfpq *h);
 /* nq independent searchSingleQuery calls (ivfpq_index_search.go:231-390) */

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Throughput of the IVF / PQ / IVFPQ / HNSW device search paths at moderate sizes (the BASELINE.json
+configs[2..3] are parity-test cases; this script characterises their kernels for DESIGN.md / profiles/).
+Indexes are trained and filled through the C ABI on the GPU; the HNSW graph comes from a host builder
+(the CPU checker under oracle/, used here only as a graph BUILDER for measurement input, never on the
+timed path)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from comet_b200 import capi  # noqa: E402
+
+
+def timed(fn, reps=5):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=500_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--nq", type=int, default=512)
+    ap.add_argument("--hnsw-n", type=int, default=20_000)
+    args = ap.parse_args()
+    rng = np.random.default_rng(1)
+    n, d, nq = args.n, args.dim, args.nq
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    out = {}
+
+    nlist, nprobe = 1024, 32
+    ivf = capi.IVFIndex(d, nlist, capi.L2)
+    t0 = time.perf_counter(); ivf.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
+    t0 = time.perf_counter(); ivf.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+    dt = timed(lambda: ivf.search(q, k=100, nprobes=nprobe))
+    scanned = n * nprobe / nlist
+    out["ivf"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "k": 100, "train_s": t_train, "add_s": t_add,
+                  "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3,
+                  "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9}
+    del ivf
+
+    M = 96
+    pq = capi.PQIndex(d, capi.L2, M, 8)
+    t0 = time.perf_counter(); pq.train(x[:20000].copy()); t_train = time.perf_counter() - t0
+    t0 = time.perf_counter(); pq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+    dt = timed(lambda: pq.search(q[:128], k=100), reps=3)
+    out["pq"] = {"n": n, "dim": d, "M": M, "nbits": 8, "k": 100, "train_s": t_train, "add_s": t_add, "qps_host_api": 128 / dt,
+                 "ms_per_batch_128q": dt * 1e3, "lookups_per_s": 128 * n * M / dt, "code_GBps": 128 * n * M / dt / 1e9}
+    del pq
+
+    ivfpq = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
+    t0 = time.perf_counter(); ivfpq.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
+    t0 = time.perf_counter(); ivfpq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+    dt = timed(lambda: ivfpq.search(q, k=100, nprobes=nprobe))
+    out["ivfpq"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "train_s": t_train,
+                    "add_s": t_add, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3,
+                    "lookups_per_s": nq * scanned * M / dt, "lut_builds_per_s": nq * nprobe / dt}
+    del ivfpq
+
+    # HNSW: graph from the host builder, search on the device
+    from oracle import oracle_py as O
+    hn = args.hnsw_n
+    lv = O.hnsw_random_levels(hn, 16, 3)
+    lv[0] = 0
+    o = O.HNSW(d, capi.L2, 16, 100, 128)
+    t0 = time.perf_counter(); o.add(ids[:hn], x[:hn].copy(), lv); t_build = time.perf_counter() - t0
+    eids, elev, erows, layers = o.export()
+    g = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
+    g.load_graph(eids, erows, elev, layers, o.entry_point, o.max_level)
+    res = {}
+    def run():
+        res["r"] = g.search(q, k=10, ef_search=128, with_work=True)
+    dt = timed(run)
+    work = res["r"][3]
+    evals = float(work[:, 0].mean())
+    out["hnsw"] = {"n": hn, "dim": d, "M": 16, "ef": 128, "k": 10, "host_build_s": t_build, "qps_host_api": nq / dt,
+                   "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
+                   "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
