@@ -276,10 +276,16 @@ int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t
     int *pc = nullptr;
     CM_TRY(ws_alloc((void **)&pk, (size_t)nq_run * L.grid * L.K * 8, st));
     CM_TRY(ws_alloc((void **)&pc, (size_t)nq_run * L.grid * sizeof(int), st));
+    // big corpus: one pass (launch) per query group streams all rows; small table (fewer tiles than the
+    // persistent grid): many query groups share one launch, otherwise most SMs would idle
+    const int64_t n_tiles = (n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    const int64_t n_groups = nq_run / L.qb;
+    const int64_t per_launch = n_tiles >= 2 * (int64_t)sm_count() ? 1 : std::min<int64_t>(n_groups, 32768);
     int passes = 0;
-    for (int64_t q0 = 0; q0 < nq_run; q0 += L.qb, passes++) {
-        CM_TRY(launch_flat_scan(L, tmap, qp + (size_t)q0 * ld, ld, n, skip, threshold,
-                                pk + (size_t)q0 * L.grid * L.K, pc + (size_t)q0 * L.grid, st));
+    for (int64_t g0 = 0; g0 < n_groups; g0 += per_launch, passes++) {
+        int64_t q0 = g0 * L.qb;
+        CM_TRY(launch_flat_scan(L, tmap, qp + (size_t)q0 * ld, ld, n, skip, threshold, pk + (size_t)q0 * L.grid * L.K,
+                                pc + (size_t)q0 * L.grid, (int)std::min(per_launch, n_groups - g0), st));
     }
     CM_TRY(launch_merge_topk(pk, pc, (int)nq, L.grid, L.K, (int)k_eff, ids, out_stride, out_ids, out_scores, out_pos,
                              out_counts, st));

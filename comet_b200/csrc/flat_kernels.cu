@@ -40,6 +40,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) flat_scan_kernel(
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int n_chunks = ld / SCAN_CHUNK;
+    // blockIdx.y = query group (QB queries each): small tables are scanned for many groups in one launch
+    queries += (size_t)blockIdx.y * QB * ld;
+    part_keys += (size_t)blockIdx.y * QB * gridDim.x * K;
+    part_counts += (size_t)blockIdx.y * QB * gridDim.x;
 
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
@@ -184,12 +188,12 @@ int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanL
 template <int METRIC, bool FMA, int QB>
 static int launch_scan_t(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
                          int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *part_keys,
-                         int *part_counts, cudaStream_t stream) {
+                         int *part_counts, int n_groups, cudaStream_t stream) {
     auto kern = flat_scan_kernel<METRIC, FMA, QB>;
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     int n_tiles = (int)((n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS);
     ProfScope prof(CM_PROF_FLAT_SCAN, stream);
-    kern<<<L.grid, SCAN_THREADS, L.smem, stream>>>(tmap, queries, ld, (long long)n_rows, n_tiles, L.stages, skip,
+    kern<<<dim3((unsigned)L.grid, (unsigned)n_groups), SCAN_THREADS, L.smem, stream>>>(tmap, queries, ld, (long long)n_rows, n_tiles, L.stages, skip,
                                                    threshold, L.K, L.C, part_keys, part_counts);
     count_launch();
     CM_CUDA(cudaGetLastError());
@@ -198,24 +202,24 @@ static int launch_scan_t(const ScanLaunch &L, const CUtensorMap &tmap, const flo
 
 template <int METRIC, bool FMA>
 static int launch_scan_q(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
-                         int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc,
+                         int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc, int n_groups,
                          cudaStream_t st) {
     switch (L.qb) {
-    case 1: return launch_scan_t<METRIC, FMA, 1>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
-    case 2: return launch_scan_t<METRIC, FMA, 2>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
-    case 4: return launch_scan_t<METRIC, FMA, 4>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
-    case 8: return launch_scan_t<METRIC, FMA, 8>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+    case 1: return launch_scan_t<METRIC, FMA, 1>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st);
+    case 2: return launch_scan_t<METRIC, FMA, 2>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st);
+    case 4: return launch_scan_t<METRIC, FMA, 4>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st);
+    case 8: return launch_scan_t<METRIC, FMA, 8>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st);
     }
     return fail(CM_ERR_INVALID_ARG, "bad query block %d", L.qb);
 }
 
 int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
-                     int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc,
+                     int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *pk, int *pc, int n_groups,
                      cudaStream_t st) {
 #define CM_SCAN_CASE(M)                                                                                  \
     case M:                                                                                              \
-        return L.fma ? launch_scan_q<M, true>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st) \
-                     : launch_scan_q<M, false>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, st);
+        return L.fma ? launch_scan_q<M, true>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st) \
+                     : launch_scan_q<M, false>(L, tmap, queries, ld, n_rows, skip, threshold, pk, pc, n_groups, st);
     switch (L.metric) {
         CM_SCAN_CASE(CM_L2)
         CM_SCAN_CASE(CM_L2SQ)

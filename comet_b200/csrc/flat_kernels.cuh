@@ -25,11 +25,11 @@ struct ScanLaunch {
 // Pick QB / stages / grid for a scan of `n_rows` rows with leading dimension ld floats.
 int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanLaunch *out);
 
-// One pass: QB queries (device, [qb][ld], preprocessed, zero padded) against all rows.
-// part_keys: [qb][grid][K], part_counts: [qb][grid].
+// One launch: n_groups groups of QB queries (device, [n_groups * qb][ld], preprocessed, zero padded)
+// against all rows (blockIdx.y = group).  part_keys: [n_groups * qb][grid][K], part_counts likewise.
 int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *queries, int ld,
                      int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *part_keys,
-                     int *part_counts, cudaStream_t stream);
+                     int *part_counts, int n_groups, cudaStream_t stream);
 
 // Merge `parts` partial lists per query into the final sorted top-K and materialise outputs.
 // part_keys: [nq][parts][Kp]; outputs are [nq][out_stride].
