@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ROWS, DIM, K, BATCH = 1_000_000, 768, 100, 512
+N_ROWS, DIM, K, BATCH = 1_000_000, 768, 100, 512   # --rows overrides N_ROWS (e.g. 12_500_000 = one shard of configs[4])
 SEED = 20261017
 METRIC_NAME = "queries/sec @ recall@K (1Mx768, K=100)"
 
@@ -125,11 +125,11 @@ def gen_rows_device(torch, n, d, seed, device):
 # -------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm (oracle port), all host threads, bounded sample
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_run(x_host, q_host, k, threads, nq_sample):
+def cpu_reference_run(x_host, q_host, k, threads, nq_sample, metric=2):
     """Returns (qps, seconds, ids, scores) for nq_sample queries against the full corpus."""
     from oracle import oracle_py as O
     O.set_threads(threads)
-    o = O.Flat(x_host.shape[1], O.COSINE)
+    o = O.Flat(x_host.shape[1], metric)
     t0 = time.perf_counter()
     o.add(np.arange(1, x_host.shape[0] + 1, dtype=np.uint32), x_host)   # normalises in place, like Add
     t_add = time.perf_counter() - t0
@@ -201,14 +201,19 @@ def run_ours(args):
     # ---- corpus: rows [rank*shard, (rank+1)*shard) of the 1M x 768 matrix; ids = row + 1 ----
     shard = N_ROWS // world
     row0 = rank * shard
-    x = gen_rows_device(torch, shard, DIM, SEED + 1000 * rank, dev)
-    index = capi.FlatIndex(DIM, capi.COSINE)
-    index.add_device(np.arange(row0 + 1, row0 + shard + 1, dtype=np.uint32), x.data_ptr(), shard)
-    torch.cuda.synchronize()
+    metric_code = capi.METRICS[args.metric_kind]
+    index = capi.FlatIndex(DIM, metric_code)
+    index.reserve(shard)
     x_host = None
-    if rank == 0 and not args.no_cpu_baseline:
-        x_host = x.cpu().numpy()
-    del x
+    slab = 2_000_000                                  # generate + add in slabs: a 12.5M-row shard is 38 GB
+    for s0 in range(0, shard, slab):
+        m = min(slab, shard - s0)
+        x = gen_rows_device(torch, m, DIM, SEED + 1000 * rank + 7919 * (s0 // slab), dev)
+        index.add_device(np.arange(row0 + s0 + 1, row0 + s0 + m + 1, dtype=np.uint32), x.data_ptr(), m)
+        torch.cuda.synchronize()
+        if rank == 0 and not args.no_cpu_baseline and shard <= slab:
+            x_host = x.cpu().numpy()
+        del x
     torch.cuda.empty_cache()
 
     nq = BATCH * world                      # global batch; every rank searches all of it on its shard
@@ -280,6 +285,11 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = nq / (ms_per_step * 1e-3)
     stats = index.last_stats()
+    # a query whose candidate lists overflowed comes back with count -1 from the device entry point
+    # (the host entry point redoes it with the exact scan): such a run would not have done the work
+    unanswered = int((out_cnt < 0).sum().item())
+    if unanswered:
+        raise RuntimeError(f"{unanswered} queries were not answered by the device path (candidate overflow): number invalid")
 
     # ---- per-kernel roofline leg (separate short run so event pairs do not perturb `value`) -----
     roof = None
@@ -304,7 +314,7 @@ def run_ours(args):
             roof = {"kernel": "flat_gemm_kernel (tcgen05 bf16, %d launches per step)" % (gemm_n // n_prof),
                     "bound": "tensor", "achieved": ach, "peak": tf_sus,
                     "unit": "TFLOP/s", "frac": ach / tf_sus,
-                    "traffic": measured_traffic("flat_gemm_kernel_per_step_bytes") if world == 1 else None,
+                    "traffic": measured_traffic("flat_gemm_kernel_per_step_bytes") if (world == 1 and N_ROWS == 1_000_000) else None,
                     "traffic_note": "DRAM bytes of the 3 launches of one step, ncu capture in profiles/r01_tensor_path.md; algorithmic = %d (bf16 shadow once)" % (shard * DIM * 2),
                     "peak_source": which + " (sustained bf16)",
                     "gemm_ms_per_step": per * 1e3, "launches_timed": gemm_n,
@@ -367,7 +377,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and x_host is not None:
         cores = os.cpu_count() or 1
         nq_s = min(nq, max(cores, 8))
-        qps, dt, o_ids, o_sc, t_add, _o = cpu_reference_run(x_host, q_np, K, cores, nq_s)
+        qps, dt, o_ids, o_sc, t_add, _o = cpu_reference_run(x_host, q_np, K, cores, nq_s, metric_code)
         cpu = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": f"{nq_s} of the {nq} queries against the full 1M x 768 corpus, one query per host thread, "
                          f"{dt:.1f} s; C restatement of the Go loops (scalar, unfused, full N sort per query)"}
@@ -382,11 +392,12 @@ def run_ours(args):
             "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K,
+            "config": {"workload": "flat_%s_%dx768_k100_b512" % (args.metric_kind, N_ROWS) if (N_ROWS != 1_000_000 or args.metric_kind != "cosine") else "flat_cosine_1Mx768_k100_b512",
+                       "rows": N_ROWS, "dim": DIM, "k": K,
                        "batch_per_gpu": BATCH, "global_batch": nq,
                        "sharding": "single GPU" if world == 1 else f"rows/{world} per GPU + NCCL all-gather of per-shard top-K + merge",
                        "path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
-                       "l2_policy": "inputs (3.07 GB corpus) larger than L2; no flush needed",
+                       "l2_policy": "inputs (%.2f GB fp32 corpus + bf16 shadow per GPU) larger than the 126 MB L2; no flush needed" % (shard * DIM * 4 / 1e9),
                        "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,
@@ -406,7 +417,12 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="event-time kernels inside the main timed region too")
+    ap.add_argument("--rows", type=int, default=0, help="corpus rows (default 1M = BASELINE configs[1]); 12500000 = one 1/8 shard of the 100M x 768 config")
+    ap.add_argument("--metric-kind", default="cosine", choices=["cosine", "l2", "l2_squared"])
     args = ap.parse_args()
+    if args.rows > 0:
+        global N_ROWS
+        N_ROWS = args.rows
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

@@ -59,6 +59,26 @@ void ws_free(void *p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
 }
 
+// per-thread pinned staging for the zero-vector flags of the query batch in flight
+static thread_local int *tl_zero_flags = nullptr;
+static thread_local int64_t tl_zero_cap = 0, tl_zero_n = 0;
+int *zero_flags_host(int64_t nq) {
+    if (nq > tl_zero_cap) {
+        if (tl_zero_flags) cudaFreeHost(tl_zero_flags);
+        tl_zero_cap = std::max<int64_t>(nq, 4096);
+        if (cudaHostAlloc((void **)&tl_zero_flags, (size_t)tl_zero_cap * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+            tl_zero_flags = nullptr; tl_zero_cap = 0;
+        }
+    }
+    tl_zero_n = nq;
+    return tl_zero_flags;
+}
+static int64_t first_zero_query() {
+    for (int64_t i = 0; i < tl_zero_n; i++)
+        if (tl_zero_flags[i]) return i;
+    return -1;
+}
+
 int FlatIndex::rebuild_tmap() {
     if (!rows) return CM_OK;
     return make_tmap_2d(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, (uint64_t)ld, (uint64_t)cap,
@@ -216,14 +236,9 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
     if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
     CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp, ld, qflags, st));
     if (check_zero_queries && metric == CM_COSINE) {
-        std::vector<int> hf((size_t)nq);
-        CM_CUDA(cudaMemcpyAsync(hf.data(), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CM_CUDA(cudaStreamSynchronize(st));
-        for (int64_t i = 0; i < nq; i++)
-            if (hf[(size_t)i]) {
-                ws_free(qp, st); ws_free(qflags, st);
-                return fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)i);
-            }
+        // the host entry point reads these flags after its final synchronise: a zero query is reported
+        // then (its row of results is garbage by then, and discarded) without stalling the pipeline here
+        CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
 
     // 2. soft deletes + document filter -> per-row skip mask (flat_index_search.go:255-263)
@@ -490,6 +505,7 @@ int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const 
         return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ix.dim, dim);
     if (nq <= 0) return CM_OK;
     CM_CUDA(cudaSetDevice(h->ix.device));
+    cm::tl_zero_n = 0;
     cudaStream_t st;
     CM_TRY(cm::acquire_stream(&st));
     float *dq = nullptr, *dsc = nullptr;
@@ -516,6 +532,11 @@ int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const 
     cm::release_stream(st);
     if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "flat_search: %s", cudaGetErrorString(e));
     if (rc != CM_OK) return rc;
+    if (h->ix.metric == CM_COSINE && h->ix.n > 0) {           // distance.go:269-290: Preprocess fails on a zero query
+        int64_t z = cm::first_zero_query();
+        cm::tl_zero_n = 0;
+        if (z >= 0) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)z);
+    }
     // tensor path: a query whose candidate list overflowed (count -1) is redone by the exact scan
     std::vector<int64_t> redo;
     for (int64_t q = 0; q < nq; q++)

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
@@ -682,29 +683,38 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     if (n < 16384) return fail(CM_ERR_UNSUPPORTED, "the tensor path needs at least 16384 rows (have %lld)", (long long)n);
     const int n_cta = sm_count();
     const int n_clusters = n_cta / cg;
-    GemmPhase ph[3];
+    // Geometric phases: A ~ 50 K rows (at most one tile per cluster, so its all-candidate rows fit the
+    // per-CTA regions), every later phase ~ 10x the rows seen so far, the last one takes the rest once
+    // it is within 25x of the rows already seen.  A phase then emits ~ 2 K x (its rows / rows seen
+    // before) keys per query whatever n is (sweep on 1M and 12.5M x 768: profiles/r01_tensor_path.md).
+    // Tile t belongs to the first level whose stride divides t (strides nest: S_0 | S_1 | ... ).
+    constexpr int MAX_PH = 6;
+    GemmPhase ph[MAX_PH];
     int n_ph = 0;
     {
-        int64_t rows_a = std::min<int64_t>(std::max<int64_t>(32 * (int64_t)K, 2048), 8192);
+        int64_t rows_a = std::min<int64_t>(std::max<int64_t>(50 * (int64_t)K, 2048), 8192);
+        if (const char *e = getenv("COMET_B200_ROWS_A")) rows_a = atoll(e);
         int tA = std::min((int)((rows_a + tile_rows - 1) / tile_rows), std::max(1, n_clusters / 2));
-        rows_a = (int64_t)tA * tile_rows;
-        int64_t rows_b = std::min<int64_t>(rows_a * rows_a / K, n / 4);
-        int tB = (int)(rows_b / tile_rows);
-        int nAB = tA + tB;
-        int SB = T / std::max(1, nAB);
-        if (SB < 2 || tB < tA) {
-            int SA = std::max(2, T / tA);
-            int nA = (T + SA - 1) / SA;
-            ph[n_ph++] = GemmPhase{0, SA, SA, nA, 0};
-            ph[n_ph++] = GemmPhase{2, SA, SA, T - nA, 0};
-        } else {
-            int R = std::max(2, (nAB + tA / 2) / tA);
-            int SA = SB * R;
-            int nA = (T + SA - 1) / SA, nABt = (T + SB - 1) / SB;
-            ph[n_ph++] = GemmPhase{0, SA, SB, nA, 0};
-            ph[n_ph++] = GemmPhase{1, SA, SB, nABt - nA, 0};
-            ph[n_ph++] = GemmPhase{2, SA, SB, T - nABt, 0};
+        int64_t growth = 10;
+        if (const char *e = getenv("COMET_B200_PHASE_GROWTH")) growth = std::max<int64_t>(2, atoll(e));
+        // cumulative tile targets of the sampled levels
+        std::vector<int64_t> cum;
+        cum.push_back(tA);
+        while ((int)cum.size() < MAX_PH - 1 && (T - cum.back()) > 25 * cum.back()) cum.push_back(cum.back() * (growth + 1));
+        // strides from the finest level up, each a multiple of the next
+        int L = (int)cum.size();
+        std::vector<int> S((size_t)L);
+        S[(size_t)L - 1] = (int)std::max<int64_t>(2, T / cum[(size_t)L - 1]);
+        for (int i = L - 2; i >= 0; i--) {
+            int R = (int)std::max<int64_t>(2, (cum[(size_t)i + 1] + cum[(size_t)i] / 2) / cum[(size_t)i]);
+            S[(size_t)i] = S[(size_t)i + 1] * R;
         }
+        auto mult = [&](int stride) { return (int)((T + stride - 1) / stride); };   // multiples of stride in [0, T)
+        ph[n_ph++] = GemmPhase{0, S[0], S[0], mult(S[0]), 0};
+        for (int i = 1; i < L; i++) ph[n_ph++] = GemmPhase{1, S[(size_t)i - 1], S[(size_t)i], mult(S[(size_t)i]) - mult(S[(size_t)i - 1]), 0};
+        ph[n_ph++] = GemmPhase{2, S[(size_t)L - 1], S[(size_t)L - 1], T - mult(S[(size_t)L - 1]), 0};
+        if (ph[0].n_tiles > n_clusters)
+            return fail(CM_ERR_UNSUPPORTED, "phase plan: %d first-phase tiles for %d clusters", ph[0].n_tiles, n_clusters);
     }
 
     // debugging aid: widen the candidate band (>= 1 keeps the result exact)
