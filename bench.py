@@ -41,6 +41,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE line may reach stdout (the JSON); libraries chat there too (NCCL prints its version banner on
+# init).  Keep the real stdout aside and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -174,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -199,8 +210,22 @@ def run_ours(args):
     path = {"auto": capi.PATH_AUTO, "exact": capi.PATH_EXACT, "tensor": capi.PATH_TENSOR}[args.path]
 
     # ---- corpus: rows [rank*shard, (rank+1)*shard) of the 1M x 768 matrix; ids = row + 1 ----
-    shard = N_ROWS // world
-    row0 = rank * shard
+    # --sharding rows   : north-star layout -- the corpus is row-sharded (rows/N per GPU), every rank searches the
+    #                     global batch (512 N queries) on its shard, one exchange step (NCCL all-gather of the
+    #                     per-shard top-K + device merge).  The only option when the corpus does not fit one GPU.
+    # --sharding queries: the queries are the independent units: every GPU holds a replica of the corpus and
+    #                     answers its own 512 queries; no data-path collective at all.
+    # auto = queries when a replica (fp32 rows + bf16 shadow, 6 bytes per element) fits in 60 % of one GPU.
+    mode = args.sharding
+    if mode == "auto":
+        total_mem = torch.cuda.get_device_properties(dev).total_memory
+        mode = "queries" if N_ROWS * DIM * 6 < 0.6 * total_mem else "rows"
+    if world == 1:
+        mode = "rows"
+    rows_mode = mode == "rows"
+    shard = N_ROWS // world if rows_mode else N_ROWS
+    row0 = rank * shard if rows_mode else 0
+    seed_rank = rank if rows_mode else 0              # replicas hold identical rows
     metric_code = capi.METRICS[args.metric_kind]
     index = capi.FlatIndex(DIM, metric_code)
     index.reserve(shard)
@@ -208,7 +233,7 @@ def run_ours(args):
     slab = 2_000_000                                  # generate + add in slabs: a 12.5M-row shard is 38 GB
     for s0 in range(0, shard, slab):
         m = min(slab, shard - s0)
-        x = gen_rows_device(torch, m, DIM, SEED + 1000 * rank + 7919 * (s0 // slab), dev)
+        x = gen_rows_device(torch, m, DIM, SEED + 1000 * seed_rank + 7919 * (s0 // slab), dev)
         index.add_device(np.arange(row0 + s0 + 1, row0 + s0 + m + 1, dtype=np.uint32), x.data_ptr(), m)
         torch.cuda.synchronize()
         if rank == 0 and not args.no_cpu_baseline and shard <= slab:
@@ -216,8 +241,13 @@ def run_ours(args):
         del x
     torch.cuda.empty_cache()
 
-    nq = BATCH * world                      # global batch; every rank searches all of it on its shard
-    q_dev = gen_rows_device(torch, nq, DIM, SEED + 7, dev)
+    if rows_mode:
+        nq = BATCH * world                  # global batch; every rank searches all of it on its shard
+        q_dev = gen_rows_device(torch, nq, DIM, SEED + 7, dev)
+    else:
+        nq = BATCH                          # this rank's own queries against its replica
+        q_dev = gen_rows_device(torch, nq, DIM, SEED + 7 + 31 * rank, dev)
+    nq_global = BATCH * world
     q_host_pinned = torch.empty((nq, DIM), dtype=torch.float32, pin_memory=True)
     q_host_pinned.copy_(q_dev)
     torch.cuda.synchronize()
@@ -228,7 +258,8 @@ def run_ours(args):
     out_cnt = torch.zeros((nq,), dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
 
-    if world > 1:
+    exchange_on = world > 1 and rows_mode
+    if exchange_on:
         g_ids = torch.zeros((world, nq, K), dtype=torch.int32, device=dev)
         g_sc = torch.zeros((world, nq, K), dtype=torch.float32, device=dev)
         g_cnt = torch.zeros((world, nq), dtype=torch.int64, device=dev)
@@ -251,7 +282,7 @@ def run_ours(args):
 
     def step_device():
         step_local()
-        if world > 1:
+        if exchange_on:
             exchange()
 
     def barrier():
@@ -283,7 +314,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = nq / (ms_per_step * 1e-3)
+    value = nq_global / (ms_per_step * 1e-3)
     stats = index.last_stats()
     # a query whose candidate lists overflowed comes back with count -1 from the device entry point
     # (the host entry point redoes it with the exact scan): such a run would not have done the work
@@ -345,7 +376,7 @@ def run_ours(args):
         capi.check(L.cm_flat_search(index.h, capi.ptr(q_np, capi.f32p), nq, DIM, C.byref(p), K,
                                     capi.ptr(h_ids, capi.u32p), capi.ptr(h_sc, capi.f32p), None,
                                     capi.ptr(h_cnt, capi.i64p)))
-        if world > 1:
+        if exchange_on:
             # shard results go back to the device for the exchange step; the merged list returns to the host
             out_ids.copy_(torch.from_numpy(h_ids.view(np.int32)), non_blocking=True)
             out_sc.copy_(torch.from_numpy(h_sc), non_blocking=True)
@@ -368,8 +399,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    e2e = {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * DIM * 4),
-           "d2h_bytes_per_step": int(nq * K * 8 + nq * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+    n_copy = nq if rows_mode else nq_global           # bytes crossing PCIe per step, all ranks together in queries mode
+    e2e = {"value": nq_global / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(n_copy * DIM * 4),
+           "d2h_bytes_per_step": int(n_copy * K * 8 + n_copy * 8), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
 
     # ---- CPU baseline + parity / recall of this very run (rank 0, N=1) -------------------------
     cpu = None
@@ -394,15 +426,19 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "flat_%s_%dx768_k100_b512" % (args.metric_kind, N_ROWS) if (N_ROWS != 1_000_000 or args.metric_kind != "cosine") else "flat_cosine_1Mx768_k100_b512",
                        "rows": N_ROWS, "dim": DIM, "k": K,
-                       "batch_per_gpu": BATCH, "global_batch": nq,
-                       "sharding": "single GPU" if world == 1 else f"rows/{world} per GPU + NCCL all-gather of per-shard top-K + merge",
+                       "batch_per_gpu": BATCH, "global_batch": nq_global,
+                       "sharding": "single GPU" if world == 1 else (
+                           f"rows/{world} per GPU, every rank searches the global batch, NCCL all-gather of per-shard top-K + device merge"
+                           if rows_mode else
+                           f"queries: {world} replicas of the corpus (it fits one GPU), {BATCH} queries per GPU, no data-path collective; "
+                           "--sharding rows runs the row-sharded layout with the NCCL top-K merge"),
                        "path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
                        "l2_policy": "inputs (%.2f GB fp32 corpus + bf16 shadow per GPU) larger than the 126 MB L2; no flush needed" % (shard * DIM * 4 / 1e9),
                        "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -417,6 +453,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="event-time kernels inside the main timed region too")
+    ap.add_argument("--sharding", default="auto", choices=["auto", "rows", "queries"])
     ap.add_argument("--rows", type=int, default=0, help="corpus rows (default 1M = BASELINE configs[1]); 12500000 = one 1/8 shard of the 100M x 768 config")
     ap.add_argument("--metric-kind", default="cosine", choices=["cosine", "l2", "l2_squared"])
     args = ap.parse_args()
