@@ -48,7 +48,7 @@ static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
 static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
 static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
-static constexpr int SEL_STAGE_CAP = 24576; // candidate scores staged in smem by the select kernel (96 KB)
+static constexpr int SEL_STAGE_CAP = 12288; // keys (old survivors + new candidates) staged in smem by the select kernel (96 KB)
 
 struct GemmPhase {
     int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
@@ -372,28 +372,34 @@ static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv
 // ------------------------------------------------------------------------------------------------
 // candidate selection: K-th smallest key (radix select on the ordered score bits) -> next bound
 // ------------------------------------------------------------------------------------------------
-// block per query.  The query's candidates live in n_cta regions of `slots` keys (one per GEMM CTA).
-// The ordered score bits of all of them are staged once in shared memory (stage_cap entries); the
-// K-th smallest is found there by a 4 x 8-bit radix select.
-// final == 0: g[q] = -(tau_K + 2E) for the next phase.  final == 1: additionally compact the rows
-// with key <= tau_K + 2E into rs[q][*] for the exact re-score.
+// block per query.  The query's NEW candidates live in n_reg regions of `slots` keys (one per GEMM CTA
+// and lane quadrant); the survivors of the previous phases (keys under the previous bound) live in a
+// dense list.  Both are staged once in shared memory (stage_cap keys); the K-th smallest is found by
+// a radix select on (key - min), starting at the highest significant byte; the keys under the new
+// bound tau_K + 2E become the survivors for the next phase (ping-pong list) and the region counters
+// are reset.  After the last phase the survivors ARE the rows to re-score.
 static constexpr int SEL_THREADS = 1024;
 __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
-    const uint64_t *__restrict__ cand, const int *__restrict__ cand_cnt, int nq_pad, int n_cta, int slots, int K, int dim,
+    const uint64_t *__restrict__ cand, int *__restrict__ cand_cnt, int nq_pad, int n_reg, int slots, int K, int dim,
     const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
-    int *__restrict__ overflow, int final, uint32_t *__restrict__ rs, int *__restrict__ rs_cnt, int rs_cap,
-    int stage_cap, float e_scale) {
-    extern __shared__ uint32_t sel_smem[];
-    uint32_t *hi_s = sel_smem;                                         // [stage_cap] ordered score bits
-    int *off_s = reinterpret_cast<int *>(sel_smem + stage_cap);        // [n_cta + 1] region offsets (n_cta <= SEL_THREADS)
+    int *__restrict__ overflow, const uint64_t *__restrict__ surv_in, const int *__restrict__ surv_in_cnt,
+    uint64_t *__restrict__ surv_out, int *__restrict__ surv_out_cnt, int surv_cap, int stage_cap, float e_scale) {
+    extern __shared__ __align__(16) uint8_t sel_smem_raw[];
+    uint64_t *key_s = reinterpret_cast<uint64_t *>(sel_smem_raw);                 // [stage_cap]
+    int *off_s = reinterpret_cast<int *>(key_s + stage_cap);                      // [n_reg + 1] (n_reg <= SEL_THREADS)
     __shared__ int hist[256];
     __shared__ int warp_tot[SEL_THREADS / 32];
     __shared__ uint32_t s_prefix, s_lo, s_hi;
     __shared__ int s_rank, s_out, s_ovf;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_old = surv_in_cnt ? surv_in_cnt[q] : 0;
     if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; s_prefix = 0; s_rank = K; }
-    // ---- region counts -> exclusive offsets (block scan) ----
-    int c = tid < n_cta ? cand_cnt[(size_t)tid * nq_pad + q] : 0;
+    // ---- region counts -> offsets behind the old survivors (block scan), counters reset for the next phase ----
+    int c = 0;
+    if (tid < n_reg) {
+        c = cand_cnt[(size_t)tid * nq_pad + q];
+        cand_cnt[(size_t)tid * nq_pad + q] = 0;
+    }
     __syncthreads();
     if (c > slots) s_ovf = 1;
     int incl = c;
@@ -404,55 +410,42 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int wbase = 0;
+    int wbase = n_old;
     for (int w2 = 0; w2 < warp; w2++) wbase += warp_tot[w2];
-    if (tid < n_cta) off_s[tid + 1] = wbase + incl;
-    if (tid == 0) off_s[0] = 0;
+    if (tid < n_reg) off_s[tid + 1] = wbase + incl;
+    if (tid == 0) off_s[0] = n_old;
     __syncthreads();
-    const int total = off_s[n_cta];
+    const int total = off_s[n_reg];
     if (s_ovf || total > stage_cap) {
-        if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; if (final) rs_cnt[q] = 0; }
+        if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; surv_out_cnt[q] = 0; }
         return;
     }
-    const uint64_t *qcand = cand + (size_t)q * n_cta * slots;
-    // flat candidate index j -> (region, slot): largest r with off_s[r] <= j
-    auto locate = [&](int j) -> size_t {
-        int lo = 0, hi = n_cta;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (off_s[mid] <= j) lo = mid; else hi = mid;
-        }
-        return (size_t)lo * slots + (size_t)(j - off_s[lo]);
-    };
-    // ---- stage the ordered score words (high halves of the keys): a warp takes 4 regions at a time,
-    // lanes run over their entries, the 4 loads of a lane are issued before any is used ----
-    const uint32_t *qwords = reinterpret_cast<const uint32_t *>(qcand);
-    for (int r0 = warp * 4; r0 < n_cta; r0 += (SEL_THREADS / 32) * 4) {
-        int o[4], c[4], mc = 0;
+    // ---- stage: old survivors, then the regions (a warp takes 4 regions at a time, loads before stores) ----
+    for (int i = tid; i < n_old; i += SEL_THREADS) key_s[i] = surv_in[(size_t)q * surv_cap + i];
+    const uint64_t *qcand = cand + (size_t)q * n_reg * slots;
+    for (int r0 = warp * 4; r0 < n_reg; r0 += (SEL_THREADS / 32) * 4) {
+        int o[4], cc[4], mc = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             int r = r0 + u;
-            o[u] = r < n_cta ? off_s[r] : 0;
-            c[u] = r < n_cta ? off_s[r + 1] - o[u] : 0;
-            mc = max(mc, c[u]);
+            o[u] = r < n_reg ? off_s[r] : 0;
+            cc[u] = r < n_reg ? off_s[r + 1] - o[u] : 0;
+            mc = max(mc, cc[u]);
         }
         for (int i = lane; i < mc; i += 32) {
-            uint32_t v[4];
+            uint64_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = i < c[u] ? __ldg(qwords + 2 * ((size_t)(r0 + u) * slots + i) + 1) : 0u;
+            for (int u = 0; u < 4; u++) v[u] = i < cc[u] ? __ldg(qcand + (size_t)(r0 + u) * slots + i) : 0ull;
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (i < c[u]) hi_s[o[u] + i] = v[u];
+                if (i < cc[u]) key_s[o[u] + i] = v[u];
         }
     }
     __syncthreads();
     float bound = INFINITY;
     if (total >= K) {
-        // The scores of one query's candidates share their leading bits (same sign, exponent and top
-        // mantissa bits), which would pile every shared-memory atomic of a plain MSB-first radix pass
-        // onto one bin.  Select on (key - min) instead and start at its highest significant byte.
         uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-        for (int i = tid; i < total; i += SEL_THREADS) { uint32_t v = hi_s[i]; lo = min(lo, v); hi = max(hi, v); }
+        for (int i = tid; i < total; i += SEL_THREADS) { uint32_t v = (uint32_t)(key_s[i] >> 32); lo = min(lo, v); hi = max(hi, v); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -460,17 +453,22 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
         }
         if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
         __syncthreads();
+        // digits are 8-bit windows counted from the HIGHEST SIGNIFICANT bit of the range, so the first
+        // pass already spreads the keys over up to 256 bins (byte-aligned windows would put them all
+        // into the one or two bins of the range's top byte and serialise the shared-memory atomics)
         const uint32_t base = s_lo, range = s_hi - s_lo;
-        const int n_pass = range == 0 ? 0 : (32 - __clz(range) + 7) / 8;
-        for (int pass = n_pass - 1; pass >= 0; pass--) {
-            int shift = 8 * pass;
+        int bits_left = range == 0 ? 0 : 32 - __clz(range);
+        while (bits_left > 0) {
+            const int width = min(8, bits_left);
+            const int shift = bits_left - width;
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
-            uint32_t prefix = s_prefix;
-            uint32_t mask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = (shift + width) >= 32 ? 0u : (0xFFFFFFFFu << (shift + width));
+            const uint32_t dmask = (1u << width) - 1u;
             for (int i = tid; i < total; i += SEL_THREADS) {
-                uint32_t v = hi_s[i] - base;
-                if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255], 1);
+                uint32_t v = (uint32_t)(key_s[i] >> 32) - base;
+                if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & dmask], 1);
             }
             __syncthreads();
             if (warp == 0) {
@@ -487,16 +485,17 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
                 int r = s_rank, before = inc - sum;
                 bool mine = r > before && r <= inc;
                 if (mine) {
-                    int rr = r - before, b = 0;
-                    for (; b < 7; b++) {
-                        if (rr <= h[b]) break;
-                        rr -= h[b];
+                    int rr = r - before, bb = 0;
+                    for (; bb < 7; bb++) {
+                        if (rr <= h[bb]) break;
+                        rr -= h[bb];
                     }
                     s_rank = rr;
-                    s_prefix = prefix | ((uint32_t)(lane * 8 + b) << shift);
+                    s_prefix = prefix | ((uint32_t)(lane * 8 + bb) << shift);
                 }
             }
             __syncthreads();
+            bits_left = shift;
         }
         float tau = ordered_to_float(s_prefix + base);
         // E_q: see the header comment.  X, Dx: max row norm / max bf16 residual norm; nq, dq: the query's.
@@ -508,18 +507,19 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
         bound = bound + fabsf(bound) * 1e-6f;
     }
     if (tid == 0) g[q] = -bound;
-    if (!final) return;
+    // ---- survivors: every staged key under the new bound ----
     const uint32_t bound_hi = float_to_ordered(bound);
-    for (int j = tid; j < total; j += SEL_THREADS) {
-        if (hi_s[j] <= bound_hi) {
+    for (int i = tid; i < total; i += SEL_THREADS) {
+        uint64_t key = key_s[i];
+        if ((uint32_t)(key >> 32) <= bound_hi) {
             int slot = atomicAdd(&s_out, 1);
-            if (slot < rs_cap) rs[(size_t)q * rs_cap + slot] = key_pos(qcand[locate(j)]);
+            if (slot < surv_cap) surv_out[(size_t)q * surv_cap + slot] = key;
         }
     }
     __syncthreads();
     if (tid == 0) {
-        if (s_out > rs_cap) { overflow[q] = 1; rs_cnt[q] = 0; }
-        else rs_cnt[q] = s_out;
+        if (s_out > surv_cap) { overflow[q] = 1; surv_out_cnt[q] = 0; g[q] = INFINITY; }
+        else surv_out_cnt[q] = s_out;
     }
 }
 
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
 // ------------------------------------------------------------------------------------------------
 template <int METRIC, bool FMA>
 __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
-                                                      const uint32_t *__restrict__ rs, const int *__restrict__ rs_cnt,
+                                                      const uint64_t *__restrict__ rs, const int *__restrict__ rs_cnt,
                                                       int rs_cap, float threshold, uint64_t *__restrict__ out_keys,
                                                       int *__restrict__ out_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
     if (base >= cnt) return;
     const int mine = base + tid;
     const bool live = mine < cnt;
-    const uint32_t pos = rs[(size_t)q * rs_cap + (live ? mine : base)];
+    const uint32_t pos = key_pos(rs[(size_t)q * rs_cap + (live ? mine : base)]);
     pos_s[tid] = pos;
     for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
     __syncthreads();
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
 }
 
 static int launch_rescore(int metric, bool fma, const float *rows, int ld, const float *queries, int nq,
-                          const uint32_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
+                          const uint64_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
                           cudaStream_t st) {
     dim3 grid(RS_CAP / 128, (unsigned)nq);
     size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
@@ -722,7 +722,7 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     if (const char *es = getenv("COMET_B200_E_SCALE")) e_scale = std::max(1.0f, (float)atof(es));
     const int n_reg = n_cta * 4;   // candidate regions per query: (CTA, lane quadrant)
     if (n_reg > SEL_THREADS) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
-    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 4 + (size_t)(n_reg + 1) * 4;
+    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8 + (size_t)(n_reg + 1) * 4;
     CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     int passes = 0;
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
@@ -736,16 +736,16 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         float *g = nullptr;
         uint64_t *cand = nullptr, *keys2 = nullptr;
         int *ccnt = nullptr, *ovf = nullptr, *rcnt = nullptr, *kcnt = nullptr;
-        uint32_t *rs = nullptr;
+        uint64_t *rs = nullptr;   // survivor lists, ping-pong: [2][nq_pad][RS_CAP]
         CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
         CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
         CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * CAND_SLOTS * 8, st));
-        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 3) * 4, st));
-        ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + nq_pad;
-        CM_TRY(ws_alloc((void **)&rs, (size_t)nq_pad * RS_CAP * 4, st));
+        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 4) * 4, st));
+        ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
+        CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
-        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 3) * 4, st));
+        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 4) * 4, st));
         CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
         // g: phase A bound is -inf for real queries (everything is a candidate), +inf for padding
         init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad);
@@ -767,15 +767,19 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
                 CM_TRY((launch_gemm_t<1, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             {
                 ProfScope prof(CM_PROF_SELECT, st);
-                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn,
-                                                                       max_bits, g, ovf, p == n_ph - 1 ? 1 : 0, rs, rcnt,
-                                                                       RS_CAP, SEL_STAGE_CAP, e_scale);
+                const int in = (p + 1) & 1, out = p & 1;
+                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(
+                    cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf,
+                    p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP, p == 0 ? nullptr : rcnt + (size_t)in * nq_pad,
+                    rs + (size_t)out * nq_pad * RS_CAP, rcnt + (size_t)out * nq_pad, RS_CAP, SEL_STAGE_CAP, e_scale);
                 count_launch();
                 CM_CUDA(cudaGetLastError());
             }
             passes++;
         }
-        CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs, rcnt, threshold, keys2, kcnt, st));
+        const int last = (n_ph - 1) & 1;
+        CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs + (size_t)last * nq_pad * RS_CAP,
+                              rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st));
         CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
                                  out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
                                  out_counts + q0, st));
