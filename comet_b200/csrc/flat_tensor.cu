@@ -457,8 +457,11 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
         // pass already spreads the keys over up to 256 bins (byte-aligned windows would put them all
         // into the one or two bins of the range's top byte and serialise the shared-memory atomics)
         const uint32_t base = s_lo, range = s_hi - s_lo;
+        // Two windows (16 significant bits) are enough: the bound only has to be >= the K-th smallest key,
+        // so the undecided low bits are rounded UP (all ones) -- at most 2^-16 of the key range looser.
         int bits_left = range == 0 ? 0 : 32 - __clz(range);
-        while (bits_left > 0) {
+        const int stop_at = max(0, bits_left - 16);
+        while (bits_left > stop_at) {
             const int width = min(8, bits_left);
             const int shift = bits_left - width;
             if (tid < 256) hist[tid] = 0;
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
             __syncthreads();
             bits_left = shift;
         }
-        float tau = ordered_to_float(s_prefix + base);
+        float tau = ordered_to_float(s_prefix + ((1u << bits_left) - 1u) + base);
         // E_q: see the header comment.  X, Dx: max row norm / max bf16 residual norm; nq, dq: the query's.
         float2 qn = q_norms[q];
         float nq = qn.x, dq = qn.y, X = __uint_as_float(max_bits[0]), Dx = __uint_as_float(max_bits[1]);
