@@ -267,3 +267,36 @@ def test_merge_shards_device_matches_single_index():
         oi, os_ = o.search(q[i], k=k)
         assert_same_results(o_ids[i].cpu().numpy().view(np.uint32), o_sc[i].cpu().numpy(), int(o_cnt[i]), oi, os_,
                             what=f"query {i}")
+
+
+def test_concurrent_searches_are_reentrant():
+    # flat_index_search_test.go:392-465: goroutines searching the same index concurrently (RLock holders).
+    # ctypes drops the GIL during the C call, so these threads really overlap inside the library.
+    import threading
+    rng = np.random.default_rng(4)
+    n, d, k = 30000, 64, 10
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    g = capi.FlatIndex(d, capi.L2SQ)
+    g.add(ids, x.copy())
+    o = O.Flat(d, capi.L2SQ)
+    o.add(ids, x.copy())
+    qs = [rng.standard_normal((m, d)).astype(np.float32) for m in (3, 70, 9, 130, 1, 64)]   # exact and tensor paths mixed
+    want = [o.search_batch(q, k) for q in qs]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(5):
+                gi, gs, gc = g.search(qs[i], k=k)
+                oi, os_, oc = want[i]
+                assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(bits(gs), bits(os_))
+        except Exception as e:      # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(qs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

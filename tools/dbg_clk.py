@@ -1,6 +1,6 @@
 import os, sys, time, subprocess, threading
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from comet_b200 import capi
 import pynvml
 pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
