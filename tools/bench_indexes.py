@@ -31,7 +31,9 @@ def main():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--nq", type=int, default=512)
     ap.add_argument("--hnsw-n", type=int, default=20_000)
+    ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw")
     args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else {"ivf", "pq", "ivfpq", "hnsw"}
     rng = np.random.default_rng(1)
     n, d, nq = args.n, args.dim, args.nq
     # clustered corpus (2048 Gaussian blobs): i.i.d. N(0,1) rows have no cluster structure in 768-d, k-means
@@ -42,55 +44,97 @@ def main():
     ids = np.arange(1, n + 1, dtype=np.uint32)
     out = {}
 
-    nlist, nprobe = 1024, 32
-    ivf = capi.IVFIndex(d, nlist, capi.L2)
-    t0 = time.perf_counter(); ivf.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
-    t0 = time.perf_counter(); ivf.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
-    dt = timed(lambda: ivf.search(q, k=100, nprobes=nprobe))
-    scanned = capi.lib().cm_ivf_last_scanned(ivf.h) / nq       # measured: vectors of probed lists per query
-    out["ivf"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "k": 100, "train_s": t_train, "add_s": t_add,
-                  "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
-                  "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9}
-    del ivf
+    nlist, nprobe, M = 1024, 32, 96
+    if "ivf" in only:
+        ivf = capi.IVFIndex(d, nlist, capi.L2)
+        t0 = time.perf_counter(); ivf.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
+        t0 = time.perf_counter(); ivf.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+        dt = timed(lambda: ivf.search(q, k=100, nprobes=nprobe))
+        scanned = capi.lib().cm_ivf_last_scanned(ivf.h) / nq       # measured: vectors of probed lists per query
+        out["ivf"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "k": 100, "train_s": t_train, "add_s": t_add,
+                      "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
+                      "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9}
+        del ivf
+    if "pq" in only:
+        pq = capi.PQIndex(d, capi.L2, M, 8)
+        t0 = time.perf_counter(); pq.train(x[:20000].copy()); t_train = time.perf_counter() - t0
+        t0 = time.perf_counter(); pq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+        dt = timed(lambda: pq.search(q[:128], k=100), reps=3)
+        out["pq"] = {"n": n, "dim": d, "M": M, "nbits": 8, "k": 100, "train_s": t_train, "add_s": t_add, "qps_host_api": 128 / dt,
+                     "ms_per_batch_128q": dt * 1e3, "lookups_per_s": 128 * n * M / dt, "code_GBps": 128 * n * M / dt / 1e9}
+        del pq
+    if "ivfpq" in only:
+        ivfpq = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
+        t0 = time.perf_counter(); ivfpq.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
+        t0 = time.perf_counter(); ivfpq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+        dt = timed(lambda: ivfpq.search(q, k=100, nprobes=nprobe))
+        scanned = capi.lib().cm_ivfpq_last_scanned(ivfpq.h) / nq
+        out["ivfpq"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "train_s": t_train,
+                        "add_s": t_add, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
+                        "lookups_per_s": nq * scanned * M / dt, "lut_builds_per_s": nq * nprobe / dt}
+        del ivfpq
+    if "hnswknn" in only:
+        # A HEALTHY layer-0 graph (exact 32-nearest-neighbour graph built with the flat index on the GPU) to show
+        # what the traversal kernel does when the search really explores: graphs built by the reference's own
+        # insertNode collapse to a 2M+1 clique around the entry point (see "hnsw" below and DESIGN.md).
+        hn = min(n, 200_000)
+        # rows on a 24-dimensional manifold (one connected cloud; the blob corpus above gives one component per blob)
+        Wk = rng.standard_normal((24, d), dtype=np.float32)
+        xk = (rng.standard_normal((hn, 24), dtype=np.float32) @ Wk).astype(np.float32)
+        qk = (rng.standard_normal((nq, 24), dtype=np.float32) @ Wk).astype(np.float32)
+        flat = capi.FlatIndex(d, capi.L2)
+        flat.add(ids[:hn], xk.copy())
+        nbr = np.zeros((hn, 32), np.uint32)
+        for s0 in range(0, hn, 4096):
+            gi, _, _ = flat.search(xk[s0:s0 + 4096], k=33)
+            nbr[s0:s0 + 4096] = gi[:, 1:33]
+        del flat
+        levels = np.zeros(hn, np.int32)
+        off = np.arange(hn + 1, dtype=np.int64) * 32
+        g = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
+        g.load_graph(ids[:hn], xk, levels, [(off, nbr.ravel())], 1, 0)
+        res = {}
 
-    M = 96
-    pq = capi.PQIndex(d, capi.L2, M, 8)
-    t0 = time.perf_counter(); pq.train(x[:20000].copy()); t_train = time.perf_counter() - t0
-    t0 = time.perf_counter(); pq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
-    dt = timed(lambda: pq.search(q[:128], k=100), reps=3)
-    out["pq"] = {"n": n, "dim": d, "M": M, "nbits": 8, "k": 100, "train_s": t_train, "add_s": t_add, "qps_host_api": 128 / dt,
-                 "ms_per_batch_128q": dt * 1e3, "lookups_per_s": 128 * n * M / dt, "code_GBps": 128 * n * M / dt / 1e9}
-    del pq
+        def run_knn():
+            res["r"] = g.search(qk, k=10, ef_search=128, with_work=True)
+        dt = timed(run_knn)
+        work = res["r"][3]
+        evals = float(work[:, 0].mean())
+        flat2 = capi.FlatIndex(d, capi.L2)
+        flat2.add(ids[:hn], xk.copy())
+        ti, _, _ = flat2.search(qk, k=10)
+        rec = float(np.mean([len(set(res["r"][0][i, :10].tolist()) & set(ti[i].tolist())) / 10 for i in range(nq)]))
+        out["hnsw_knn_graph"] = {"n": hn, "dim": d, "degree": 32, "ef": 128, "k": 10, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3,
+                                 "dist_evals_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
+                                 "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9, "recall_at_10_vs_flat": rec}
+        del g, flat2
+    if "hnsw" in only:
+        # HNSW: graph from the host builder, search on the device.  Rows on a 24-dimensional manifold: with i.i.d.
+        # 768-d Gaussian rows all pairwise distances coincide and the reference's build (entry point never promoted,
+        # plain "M nearest" selection) leaves only a few dozen nodes reachable from the entry point.
+        from oracle import oracle_py as O
+        hn = args.hnsw_n
+        z = rng.standard_normal((hn, 24), dtype=np.float32)
+        W = rng.standard_normal((24, d), dtype=np.float32)
+        xh = (z @ W + 0.05 * rng.standard_normal((hn, d), dtype=np.float32)).astype(np.float32)
+        qh = (rng.standard_normal((nq, 24), dtype=np.float32) @ W).astype(np.float32)
+        lv = O.hnsw_random_levels(hn, 16, 3)
+        lv[0] = 0
+        o = O.HNSW(d, capi.L2, 16, 100, 128)
+        t0 = time.perf_counter(); o.add(ids[:hn], xh.copy(), lv); t_build = time.perf_counter() - t0
+        eids, elev, erows, layers = o.export()
+        g = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
+        g.load_graph(eids, erows, elev, layers, o.entry_point, o.max_level)
+        res = {}
 
-    ivfpq = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
-    t0 = time.perf_counter(); ivfpq.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
-    t0 = time.perf_counter(); ivfpq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
-    dt = timed(lambda: ivfpq.search(q, k=100, nprobes=nprobe))
-    scanned = capi.lib().cm_ivfpq_last_scanned(ivfpq.h) / nq
-    out["ivfpq"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "train_s": t_train,
-                    "add_s": t_add, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
-                    "lookups_per_s": nq * scanned * M / dt, "lut_builds_per_s": nq * nprobe / dt}
-    del ivfpq
-
-    # HNSW: graph from the host builder, search on the device
-    from oracle import oracle_py as O
-    hn = args.hnsw_n
-    lv = O.hnsw_random_levels(hn, 16, 3)
-    lv[0] = 0
-    o = O.HNSW(d, capi.L2, 16, 100, 128)
-    t0 = time.perf_counter(); o.add(ids[:hn], x[:hn].copy(), lv); t_build = time.perf_counter() - t0
-    eids, elev, erows, layers = o.export()
-    g = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
-    g.load_graph(eids, erows, elev, layers, o.entry_point, o.max_level)
-    res = {}
-    def run():
-        res["r"] = g.search(q, k=10, ef_search=128, with_work=True)
-    dt = timed(run)
-    work = res["r"][3]
-    evals = float(work[:, 0].mean())
-    out["hnsw"] = {"n": hn, "dim": d, "M": 16, "ef": 128, "k": 10, "host_build_s": t_build, "qps_host_api": nq / dt,
-                   "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
-                   "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9}
+        def run():
+            res["r"] = g.search(qh, k=10, ef_search=128, with_work=True)
+        dt = timed(run)
+        work = res["r"][3]
+        evals = float(work[:, 0].mean())
+        out["hnsw"] = {"n": hn, "dim": d, "M": 16, "ef": 128, "k": 10, "host_build_s": t_build, "qps_host_api": nq / dt,
+                       "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
+                       "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9}
     print(json.dumps(out, indent=1))
 
 
