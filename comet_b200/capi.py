@@ -60,6 +60,7 @@ SIGNATURES = {
     "cm_flat_destroy": (C.c_int, [vp]),
     "cm_flat_reserve": (C.c_int, [vp, C.c_int64]),
     "cm_flat_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
+    "cm_flat_load_rows": (C.c_int, [vp, u32p, f32p, C.c_int64]),
     "cm_flat_add_device": (C.c_int, [vp, u32p, vp, C.c_int64, vp]),
     "cm_flat_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_flat_flush": (C.c_int, [vp]),
@@ -72,6 +73,10 @@ SIGNATURES = {
                                  i64p, i64p]),
     "cm_flat_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                         vp, vp, vp]),
+    "cm_flat_batcher_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cm_flat_batcher_destroy": (C.c_int, [vp]),
+    "cm_flat_batcher_search": (C.c_int, [vp, f32p, C.c_int, C.c_int64, C.c_float, C.c_int64, u32p, f32p, i64p]),
+    "cm_flat_batcher_stats": (C.c_int, [vp, i64p, i64p]),
     "cm_flat_last_stats": (C.c_int, [vp, C.POINTER(FlatStats)]),
     "cm_ivf_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_ivf_destroy": (C.c_int, [vp]),
@@ -82,6 +87,7 @@ SIGNATURES = {
     "cm_ivf_size": (C.c_int64, [vp]),
     "cm_ivf_default_nprobes": (C.c_int, [vp]),
     "cm_ivf_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
+    "cm_ivf_load_lists": (C.c_int, [vp, u32p, f32p, i32p, C.c_int64]),
     "cm_ivf_last_scanned": (C.c_int64, [vp]),
     "cm_ivf_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_ivf_flush": (C.c_int, [vp]),
@@ -99,6 +105,7 @@ SIGNATURES = {
     "cm_pq_size": (C.c_int64, [vp]),
     "cm_pq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
     "cm_pq_get_codes": (C.c_int, [vp, C.c_int64, C.c_int64, u8p]),
+    "cm_pq_load_codes": (C.c_int, [vp, u32p, u8p, C.c_int64]),
     "cm_pq_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_pq_flush": (C.c_int, [vp]),
     "cm_pq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
@@ -113,6 +120,7 @@ SIGNATURES = {
     "cm_ivfpq_default_nprobes": (C.c_int, [vp]),
     "cm_ivfpq_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
     "cm_ivfpq_get_codes": (C.c_int, [vp, C.c_int64, C.c_int64, u8p]),
+    "cm_ivfpq_load_codes": (C.c_int, [vp, u32p, u8p, i32p, C.c_int64]),
     "cm_ivfpq_last_scanned": (C.c_int64, [vp]),
     "cm_ivfpq_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_ivfpq_flush": (C.c_int, [vp]),
@@ -247,6 +255,12 @@ class FlatIndex:
         rows2 = rows.reshape(len(ids), self.dim)
         check(lib().cm_flat_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
 
+    def load_rows(self, ids, rows):
+        """Restore stored (already preprocessed) rows as they are (FlatIndex.ReadFrom)."""
+        ids = _u32(np.atleast_1d(ids))
+        rows2 = _f32(rows).reshape(len(ids), self.dim)
+        check(lib().cm_flat_load_rows(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids)))
+
     def add_device(self, ids, rows_dev_ptr, n, stream=0):
         ids = _u32(ids)
         check(lib().cm_flat_add_device(self.h, ptr(ids, u32p), vp(rows_dev_ptr), int(n), vp(stream)))
@@ -342,6 +356,18 @@ class IVFIndex:
         check(lib().cm_ivf_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0,
                                ptr(lists, i32p)))
         return lists
+
+    def load_lists(self, ids, rows, list_of):
+        ids = _u32(np.atleast_1d(ids))
+        rows2 = _f32(rows).reshape(len(ids), self.dim)
+        lo = np.ascontiguousarray(list_of, dtype=np.int32)
+        check(lib().cm_ivf_load_lists(self.h, ptr(ids, u32p), ptr(rows2, f32p), ptr(lo, i32p), len(ids)))
+
+    def get_rows(self, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.int64)
+        out = np.empty((len(pos), self.dim), np.float32)
+        check(lib().cm_ivf_get_rows(self.h, ptr(pos, i64p), len(pos), ptr(out, f32p)))
+        return out
 
     def remove(self, id_):
         check(lib().cm_ivf_remove(self.h, int(id_)))
@@ -446,6 +472,11 @@ class PQIndex(_ADCIndex):
         ids, rows2 = self._rows(ids, rows)
         check(lib().cm_pq_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
 
+    def load_codes(self, ids, codes):
+        ids = _u32(np.atleast_1d(ids))
+        c = np.ascontiguousarray(codes, dtype=np.uint8).reshape(len(ids), self.M)
+        check(lib().cm_pq_load_codes(self.h, ptr(ids, u32p), ptr(c, u8p), len(ids)))
+
     def search(self, queries, k=10, threshold=0.0, filter_ids=None, out_stride=None):
         return self._search(queries, k, threshold, 0, filter_ids, out_stride)
 
@@ -482,6 +513,12 @@ class IVFPQIndex(_ADCIndex):
         check(lib().cm_ivfpq_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0,
                                  ptr(lists, i32p)))
         return lists
+
+    def load_codes(self, ids, codes, list_of):
+        ids = _u32(np.atleast_1d(ids))
+        c = np.ascontiguousarray(codes, dtype=np.uint8).reshape(len(ids), self.M)
+        lo = np.ascontiguousarray(list_of, dtype=np.int32)
+        check(lib().cm_ivfpq_load_codes(self.h, ptr(ids, u32p), ptr(c, u8p), ptr(lo, i32p), len(ids)))
 
     def search(self, queries, k=10, nprobes=None, threshold=0.0, filter_ids=None, out_stride=None):
         if nprobes is None:
@@ -547,3 +584,34 @@ class HNSWIndex:
         if with_work:
             return ids, sc, cnt, work
         return ids, sc, cnt
+
+
+class FlatBatcher:
+    """Coalesces concurrent single-query searches on a FlatIndex into device batches (cm_flat_batcher_*)."""
+
+    def __init__(self, index, max_batch=512, max_wait_us=200):
+        self.index = index          # keeps the index alive
+        self.h = vp()
+        check(lib().cm_flat_batcher_create(index.h, int(max_batch), int(max_wait_us), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cm_flat_batcher_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def search(self, query, k=10, threshold=0.0):
+        q = _f32(query).reshape(-1)
+        ke = max(self.index.effective_k(k), 1)
+        ids = np.zeros(ke, np.uint32)
+        sc = np.zeros(ke, np.float32)
+        cnt = C.c_int64(0)
+        check(lib().cm_flat_batcher_search(self.h, ptr(q, f32p), len(q), int(k), float(threshold), ke, ptr(ids, u32p),
+                                           ptr(sc, f32p), C.byref(cnt)))
+        return ids[:cnt.value], sc[:cnt.value]
+
+    def stats(self):
+        b, r = C.c_int64(0), C.c_int64(0)
+        check(lib().cm_flat_batcher_stats(self.h, C.byref(b), C.byref(r)))
+        return b.value, r.value

@@ -430,6 +430,32 @@ int cm_flat_add(cm_flat *h, const uint32_t *ids, float *rows, int64_t n, int wri
     cm::release_stream(st);
     return rc;
 }
+// FlatIndex.ReadFrom (flat_index.go:488-614) restores vectors that were preprocessed when they were first
+// added: they are stored as they are (normalising a unit vector again could move its last bit).
+int cm_flat_load_rows(cm_flat *h, const uint32_t *ids, const float *rows, int64_t n) {
+    if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (n <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)h->ix.dim * 4));
+    float *stage = nullptr;
+    int rc = cm::ws_alloc((void **)&stage, (size_t)std::min(slab, n) * h->ix.dim * 4, st);
+    if (rc == CM_OK) rc = h->ix.reserve(h->ix.n + n);
+    const bool was_raw = h->ix.raw_rows;
+    h->ix.raw_rows = true;
+    for (int64_t i0 = 0; rc == CM_OK && i0 < n; i0 += slab) {
+        int64_t m = std::min(slab, n - i0);
+        cudaError_t e = cudaMemcpyAsync(stage, rows + (size_t)i0 * h->ix.dim, (size_t)m * h->ix.dim * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = cm::fail(CM_ERR_CUDA, "load_rows: %s", cudaGetErrorString(e)); break; }
+        rc = h->ix.add_from_device(ids + i0, stage, m, nullptr, st);
+    }
+    h->ix.raw_rows = was_raw;
+    cm::ws_free(stage, st);
+    cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    return rc;
+}
 int cm_flat_add_device(cm_flat *h, const uint32_t *ids_host, const float *rows_dev, int64_t n, void *stream) {
     if (!h || (n > 0 && (!ids_host || !rows_dev))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     CM_CUDA(cudaSetDevice(h->ix.device));

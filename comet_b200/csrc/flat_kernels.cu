@@ -164,11 +164,14 @@ int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanL
     int qb = nq >= 8 ? 8 : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
     int stages = 0, ctas_per_sm = 1;
     // Each consumer thread walks one row sequentially, so a CTA issues from only 4 warps: the scan is
-    // latency bound unless two CTAs share an SM.  Prefer a footprint of half the SM (ring of 3-4 stages);
-    // fall back to one CTA per SM with a deep ring, then to a smaller query block.
-    const size_t half = (cap + 1024) / 2 - 2048;      // two CTAs + the per-CTA reserved kilobyte
-    for (int s = 4; s >= 3; s--)
-        if (scan_smem_bytes(qb, ld, s, C) <= half) { stages = s; ctas_per_sm = 2; break; }
+    // latency bound unless several CTAs share an SM.  Prefer the largest CTA count per SM whose footprint
+    // (ring of 3-4 stages) fits; fall back to one CTA per SM with a deep ring, then to a smaller query block
+    // (small query blocks leave room for three or four).
+    for (int ctas = 4; ctas >= 2 && stages == 0; ctas--) {
+        const size_t share = (cap + 1024) / ctas - 2048;      // per-CTA budget incl. the reserved kilobyte
+        for (int s = 4; s >= 3; s--)
+            if (scan_smem_bytes(qb, ld, s, C) <= share) { stages = s; ctas_per_sm = ctas; break; }
+    }
     if (stages == 0) {
         for (;; qb >>= 1) {
             for (stages = 8; stages >= 3; stages--)

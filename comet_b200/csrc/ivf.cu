@@ -531,6 +531,43 @@ int64_t cm_ivf_last_scanned(const cm_ivf *h) {
     return (int64_t)v;
 }
 
+// IVFIndex.ReadFrom (ivf_index.go:611-785): restore stored vectors with the list each one belongs to,
+// in the order given (the order inside a list is the order of appearance here).  Nothing is re-derived.
+int cm_ivf_load_lists(cm_ivf *h, const uint32_t *ids, const float *rows, const int32_t *list_of, int64_t n) {
+    if (!h || (n > 0 && (!ids || !rows || !list_of))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!h->ix.trained) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained (centroids loaded) before vectors are restored");
+    if (n <= 0) return CM_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (list_of[i] < 0 || list_of[i] >= h->ix.nlist) return cm::fail(CM_ERR_INVALID_ARG, "row %lld: list %d out of range", (long long)i, list_of[i]);
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cm::IVFIndex &ix = h->ix;
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(128u << 20) / ((int64_t)ix.dim * 4));
+    float *stage = nullptr;
+    int rc = cm::ws_alloc((void **)&stage, (size_t)std::min(slab, n) * ix.dim * 4, st);
+    const bool was_raw = ix.store.raw_rows;
+    ix.store.raw_rows = true;
+    for (int64_t i0 = 0; rc == CM_OK && i0 < n; i0 += slab) {
+        int64_t m = std::min(slab, n - i0);
+        int64_t n_before = ix.store.n;
+        cudaMemcpyAsync(stage, rows + (size_t)i0 * ix.dim, (size_t)m * ix.dim * 4, cudaMemcpyHostToDevice, st);
+        rc = ix.store.add_from_device(ids + i0, stage, m, nullptr, st);
+        if (rc != CM_OK) break;
+        for (int64_t i = 0; i < m; i++) {
+            int32_t l = list_of[i0 + i];
+            ix.lists[(size_t)l].push_back((uint32_t)(n_before + i));
+            ix.list_of.push_back(l);
+        }
+        ix.csr_dirty = true;
+    }
+    ix.store.raw_rows = was_raw;
+    cm::ws_free(stage, st);
+    cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    return rc;
+}
+
 int cm_ivf_remove(cm_ivf *h, uint32_t id) {     // ivf_index.go:296-330 soft delete
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
     CM_CUDA(cudaSetDevice(h->ix.device));

@@ -583,6 +583,37 @@ static int adc_add(PQCore &ix, const uint32_t *ids, float *rows, int64_t n, int 
     return rc != CM_OK ? rc : rc_zero;
 }
 
+// PQIndex.ReadFrom (pq_index.go:652-846) / IVFPQIndex.ReadFrom: restore codes (and list membership) as stored
+static int adc_load_codes(PQCore &ix, const uint32_t *ids, const uint8_t *codes, const int32_t *list_of, int64_t n) {
+    const bool ivf = ix.nlist > 0;
+    if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, "index must be trained (codebooks loaded) before codes are restored");
+    if (n <= 0) return CM_OK;
+    if (ivf) {
+        if (!list_of) return fail(CM_ERR_INVALID_ARG, "list_of is required for an IVFPQ index");
+        for (int64_t i = 0; i < n; i++)
+            if (list_of[i] < 0 || list_of[i] >= ix.nlist) return fail(CM_ERR_INVALID_ARG, "row %lld: list %d out of range", (long long)i, list_of[i]);
+    }
+    cudaStream_t st;
+    CM_TRY(acquire_stream(&st));
+    int rc = ix.store.reserve(ix.store.n + n);
+    int64_t n_before = ix.store.n;
+    if (rc == CM_OK) {
+        cudaError_t e = cudaMemcpyAsync(ix.store.codes + (size_t)n_before * ix.M, codes, (size_t)n * ix.M, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = fail(CM_ERR_CUDA, "load_codes: %s", cudaGetErrorString(e));
+    }
+    if (rc == CM_OK) rc = ix.store.commit(ids, n, st);
+    if (rc == CM_OK && ivf) {
+        for (int64_t i = 0; i < n; i++) {
+            ix.lists[(size_t)list_of[i]].push_back((uint32_t)(n_before + i));
+            ix.list_of.push_back(list_of[i]);
+        }
+        ix.csr_dirty = true;
+    }
+    cudaStreamSynchronize(st);
+    release_stream(st);
+    return rc;
+}
+
 static int adc_flush(PQCore &ix) {
     if (ix.store.deleted_ids.empty()) return CM_OK;
     std::vector<int64_t> new_pos;
@@ -772,6 +803,11 @@ int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeba
     CM_CUDA(cudaSetDevice(h->ix.device));
     return cm::adc_add(h->ix, ids, rows, n, writeback, nullptr);
 }
+int cm_pq_load_codes(cm_pq *h, const uint32_t *ids, const uint8_t *codes, int64_t n) {
+    if (!h || (n > 0 && (!ids || !codes))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_load_codes(h->ix, ids, codes, nullptr, n);
+}
 int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out) {
     if (!h || !out || first < 0 || first + n > h->ix.store.n) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
     if (n <= 0) return CM_OK;
@@ -844,6 +880,11 @@ int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int w
     if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     CM_CUDA(cudaSetDevice(h->ix.device));
     return cm::adc_add(h->ix, ids, rows, n, writeback, out_lists);
+}
+int cm_ivfpq_load_codes(cm_ivfpq *h, const uint32_t *ids, const uint8_t *codes, const int32_t *list_of, int64_t n) {
+    if (!h || (n > 0 && (!ids || !codes || !list_of))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::adc_load_codes(h->ix, ids, codes, list_of, n);
 }
 int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out) {
     if (!h || !out || first < 0 || first + n > h->ix.store.n) return cm::fail(CM_ERR_INVALID_ARG, "bad range");

@@ -73,6 +73,7 @@ typedef struct cm_ivf cm_ivf;
 typedef struct cm_pq cm_pq;
 typedef struct cm_ivfpq cm_ivfpq;
 typedef struct cm_hnsw cm_hnsw;
+typedef struct cm_flat_batcher cm_flat_batcher;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 int cm_init(const int *device_ids, int n_devices); /* NULL/0: use the current device */
@@ -117,6 +118,10 @@ int cm_flat_reserve(cm_flat *h, int64_t n_rows);
 /* n successive FlatIndex.Add calls (flat_index.go:169-189).  `rows` is preprocessed IN PLACE
  * (cosine normalises the caller's buffer) unless writeback == 0. */
 int cm_flat_add(cm_flat *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
+/* FlatIndex.ReadFrom (flat_index.go:488-614): restore STORED (already preprocessed) vectors as they are.  The
+ * byte formats (FLAT / IVFX / PQIX / IVPQ / HNSW, magic + version 1) stay host code: the Go package's WriteTo /
+ * ReadFrom keep working on its host mirror, and ReadFrom pushes the decoded state through the cm_*_load_* calls. */
+int cm_flat_load_rows(cm_flat *h, const uint32_t *ids, const float *rows, int64_t n);
 /* rows already resident on the device (device pointer, row-major n x dim) */
 int cm_flat_add_device(cm_flat *h, const uint32_t *ids_host, const float *rows_dev, int64_t n, void *stream);
 int cm_flat_remove(cm_flat *h, uint32_t id);                      /* flat_index.go:219-250 */
@@ -147,6 +152,16 @@ int cm_flat_search_device(cm_flat *h, const float *queries_dev, int64_t nq, int 
 int cm_merge_shards_device(const uint32_t *ids_dev, const float *scores_dev, const int64_t *counts_dev, int world,
                            int64_t nq, int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids_dev,
                            float *out_scores_dev, int64_t *out_counts_dev, void *stream);
+/* Cross-call dynamic batching.  The reference's callers issue one query per Execute()
+ * (flat_index_search.go:109-165), often from many goroutines; cm_flat_batcher_search blocks its caller while a
+ * worker coalesces the concurrent requests that share (k, threshold) into ONE device batch (at most max_batch
+ * requests, the oldest waits at most max_wait_us) and hands each caller its own result.  Same results as a direct
+ * cm_flat_search.  The batcher must be destroyed before the index. */
+int cm_flat_batcher_create(cm_flat *index, int max_batch, int max_wait_us, cm_flat_batcher **out);
+int cm_flat_batcher_destroy(cm_flat_batcher *b);
+int cm_flat_batcher_search(cm_flat_batcher *b, const float *query, int dim, int64_t k, float threshold, int64_t out_stride,
+                           uint32_t *out_ids, float *out_scores, int64_t *out_count);
+int cm_flat_batcher_stats(cm_flat_batcher *b, int64_t *batches, int64_t *requests);
 /* statistics of the last search on this handle (for bench.py / profiles): */
 typedef struct {
     int32_t path_used;          /* CM_PATH_EXACT or CM_PATH_TENSOR */
@@ -175,6 +190,8 @@ int cm_ivf_add(cm_ivf *h, const uint32_t *ids, float *rows, int64_t n, int write
 /* vectors of probed lists scanned by the last search on this handle (all queries): the measured
  * factor of the scan's algorithmic bytes */
 int64_t cm_ivf_last_scanned(const cm_ivf *h);
+/* IVFIndex.ReadFrom (ivf_index.go:611-785): stored vectors + the list of each, in list-append order */
+int cm_ivf_load_lists(cm_ivf *h, const uint32_t *ids, const float *rows, const int32_t *list_of, int64_t n);
 int cm_ivf_remove(cm_ivf *h, uint32_t id);                          /* ivf_index.go:296-330 */
 int cm_ivf_flush(cm_ivf *h);                                        /* ivf_index.go:342-390 */
 int cm_ivf_get_rows(const cm_ivf *h, const int64_t *positions, int64_t n, float *out);
@@ -200,6 +217,7 @@ int64_t cm_pq_size(const cm_pq *h);
 /* n successive PQIndex.Add calls (pq_index.go:262-292): PreprocessInPlace + encode (pq_index.go:439-473) */
 int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
 int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out);   /* idx.codes[first:first+n] */
+int cm_pq_load_codes(cm_pq *h, const uint32_t *ids, const uint8_t *codes, int64_t n);   /* PQIndex.ReadFrom pq_index.go:652-846 */
 int cm_pq_remove(cm_pq *h, uint32_t id);
 int cm_pq_flush(cm_pq *h);
 /* nq independent searchSingleQuery calls (pq_index_search.go:218-325) */
@@ -223,6 +241,7 @@ int cm_ivfpq_default_nprobes(const cm_ivfpq *h);                        /* ivfpq
 /* n successive IVFPQIndex.Add calls (ivfpq_index.go:279-319): preprocess, nearest centroid, residual, encode */
 int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
 int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out);   /* codes in arrival order */
+int cm_ivfpq_load_codes(cm_ivfpq *h, const uint32_t *ids, const uint8_t *codes, const int32_t *list_of, int64_t n);
 int64_t cm_ivfpq_last_scanned(const cm_ivfpq *h);                    /* codes scanned by the last search */
 int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id);
 int cm_ivfpq_flush(cm_ivfpq *h);

@@ -300,3 +300,49 @@ def test_concurrent_searches_are_reentrant():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_dynamic_batcher_coalesces_concurrent_single_queries():
+    # many threads, one query per call (the reference's usage) -> few device batches, same answers
+    import threading
+    import time
+    rng = np.random.default_rng(8)
+    n, d, k = 70000, 64, 10
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    g = capi.FlatIndex(d, capi.COSINE)
+    g.add(ids, x.copy())
+    n_threads, per = 64, 6
+    qs = rng.standard_normal((n_threads, per, d)).astype(np.float32)
+    want_i, want_s, want_c = g.search(qs.reshape(-1, d), k=k, path=capi.PATH_EXACT)
+    b = capi.FlatBatcher(g, max_batch=256, max_wait_us=2000)
+    got = {}
+    errors = []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                got[(t, j)] = b.search(qs[t, j], k=k)
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    dt = time.perf_counter() - t0
+    assert not errors, errors
+    for t in range(n_threads):
+        for j in range(per):
+            gi, gs = got[(t, j)]
+            r = t * per + j
+            assert np.array_equal(gi, want_i[r, :want_c[r]]) and np.array_equal(bits(gs), bits(want_s[r, :want_c[r]]))
+    batches, requests = b.stats()
+    assert requests == n_threads * per and batches < requests / 4, (batches, requests)
+    with pytest.raises(capi.CometError) as e:
+        b.search(np.zeros(d, np.float32), k=k)          # zero query under cosine: the batch reports ErrZeroVector
+    assert e.value.code == capi.ERR_ZERO_VECTOR
+    b.close()
+    print(f"batcher: {requests} single-query calls in {batches} device batches, {requests / dt:.0f} q/s")
