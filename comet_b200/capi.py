@@ -131,6 +131,10 @@ SIGNATURES = {
     "cm_hnsw_size": (C.c_int64, [vp]),
     "cm_hnsw_ef_search": (C.c_int, [vp]),
     "cm_hnsw_load_graph": (C.c_int, [vp, C.c_int64, u32p, f32p, i32p, i64p, u32p, C.c_uint32, C.c_int]),
+    "cm_hnsw_add": (C.c_int, [vp, u32p, f32p, i32p, C.c_int64, C.c_int]),
+    "cm_hnsw_max_level": (C.c_int, [vp]),
+    "cm_hnsw_edge_count": (C.c_int64, [vp]),
+    "cm_hnsw_export_graph": (C.c_int, [vp, i32p, i64p, u32p, u32p, i32p]),
     "cm_hnsw_remove": (C.c_int, [vp, C.c_uint32]),
     "cm_hnsw_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p,
                                  i64p, i64p, i64p]),
@@ -563,6 +567,32 @@ class HNSWIndex:
         edge_ids = _u32(np.concatenate(chunks)) if chunks and offs[-1] > 0 else np.zeros(1, np.uint32)
         check(lib().cm_hnsw_load_graph(self.h, n, ptr(ids, u32p), ptr(rows, f32p), ptr(levels, i32p),
                                        ptr(edge_off, i64p), ptr(edge_ids, u32p), int(entry_id), int(max_level)))
+
+    def add(self, ids, rows, levels, writeback=True):
+        """n successive HNSWIndex.Add calls on the device with the caller's level draws."""
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        lv = np.ascontiguousarray(np.atleast_1d(levels), dtype=np.int32)
+        check(lib().cm_hnsw_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), ptr(lv, i32p), len(ids), 1 if writeback else 0))
+
+    def max_level(self):
+        return int(lib().cm_hnsw_max_level(self.h))
+
+    def export_graph(self):
+        """-> levels[n], edge_off[pairs+1], edge_ids, entry_id, max_level (pairs ordered by (slot, layer))."""
+        n = len(self)
+        ne = int(lib().cm_hnsw_edge_count(self.h))
+        levels = np.zeros(max(n, 1), np.int32)
+        # first call with a generous offsets buffer: at most 17 layers per node
+        edge_off = np.zeros(n * 17 + 1, np.int64)
+        edge_ids = np.zeros(max(ne, 1), np.uint32)
+        entry, ml = C.c_uint32(0), C.c_int(0)
+        check(lib().cm_hnsw_export_graph(self.h, ptr(levels, i32p), ptr(edge_off, i64p), ptr(edge_ids, u32p), C.byref(entry),
+                                         C.byref(ml)))
+        pairs = int((levels[:n] + 1).sum())
+        return levels[:n], edge_off[:pairs + 1], edge_ids[:ne], entry.value, ml.value
 
     def remove(self, id_):
         check(lib().cm_hnsw_remove(self.h, int(id_)))

@@ -1,20 +1,29 @@
-// hnsw.cu -- HNSWIndex device state, warp-per-query graph search and the cm_hnsw_* entry points.
+// hnsw.cu -- HNSWIndex device state, warp-per-query graph search, device-side insertion and the
+// cm_hnsw_* entry points.
 //
-// Replaces hnswIndexSearch.searchSingleQuery (hnsw_index_search.go:248-354) and HNSWIndex.searchLayer
-// (hnsw_index.go:565-629): greedy descent through the upper layers (K10), beam search on layer 0 with
-// Go's container/heap semantics (K11: Push = append + sift-up, Pop = swap(0, n-1) + sift-down, strict
-// comparisons -- the order of equal keys decides which node is expanded next, so the heaps are
-// reproduced operation by operation), document filter and threshold applied after the traversal.
-// Results are bit-identical to a sequential CPU replay of the reference on the SAME graph.  (The reference draws node levels
-// from an unseeded global RNG, hnsw_index.go:474-484, so two reference builds never agree with each
-// other either; parity is defined on a shared graph.)
+// Replaces hnswIndexSearch.searchSingleQuery (hnsw_index_search.go:248-354), HNSWIndex.searchLayer
+// (hnsw_index.go:565-629) and HNSWIndex.Add / insertNode / selectNeighbors / pruneConnections
+// (hnsw_index.go:228-288, 493-552, 637-694): greedy descent through the upper layers (K10), beam
+// search with Go's container/heap semantics (K11: Push = append + sift-up, Pop = swap(0, n-1) +
+// sift-down, strict comparisons -- the order of equal keys decides which node is expanded next, so
+// the heaps are reproduced operation by operation), document filter and threshold applied after the
+// traversal.  Results AND graphs are bit-identical to a sequential CPU replay of the reference given
+// the same level draws (the reference draws levels from an unseeded global RNG, hnsw_index.go:474-484,
+// so the caller supplies them).
 //
-// Device layout (replaces map[uint32]*hnswNode, hnsw_index.go:50-61, 111-155):
-//   rows fp32 [n][ld], ids u32 [n], deleted u8 [n], levels i32 [n]   -- by slot (insertion order)
-//   node_base i64 [n+1]  : first (node, layer) pair of a slot;  edge_off i64 [pairs+1];  edges u32 (slots)
-// One warp per query: the 32 lanes evaluate up to 32 neighbour distances at once -- each lane walks
-// its own row in the reference's sequential order -- and lane 0 replays the heap operations in edge
-// order.  The visited set is one bit per node per in-flight query (global memory, atomicOr).
+// Two reference behaviours are reproduced on purpose (SURVEY 2.1, quirks b and the prune below):
+//   * the entry point is the first node ever inserted and is never promoted (hnsw_index.go:273-278);
+//   * while a node is being inserted it is not yet in idx.nodes, so pruneConnections of a neighbour
+//     whose list overflowed skips -- i.e. drops -- the very back-edge that was just appended
+//     (hnsw_index.go:540-545, 668-671).
+//
+// Device layout (replaces map[uint32]*hnswNode, hnsw_index.go:50-61, 111-155), by slot = insertion order:
+//   rows fp32 [cap][ld], ids u32 [cap], deleted u8 [cap], levels i32 [cap]
+//   adj0 u32 [cap][E0] + deg0 i32 [cap]            layer 0, E0 >= 2M + 1 (one slot for append-then-prune)
+//   up_of i32 [cap] -> upper block or -1;  adjU u32 [cap_up][16][EU] + degU i32 [cap_up][16], EU >= M + 1
+// One warp per query (or per insertion): the 32 lanes evaluate up to 32 neighbour distances at once --
+// each lane walks its own row in the reference's sequential order -- and lane 0 replays the heap
+// operations in edge order.  Visited set: one bit per node (global memory, atomicOr).
 #include <algorithm>
 #include <cstring>
 #include <unordered_map>
@@ -27,29 +36,85 @@
 namespace cm {
 
 static constexpr int HNSW_WARPS = 4;
+static constexpr int HNSW_MAX_LEVELS = 17;      // levels 0..16 (hnsw_index.go:474-484 caps the draw at 16)
+
+struct HCand { float d; uint32_t slot; };
+
+// what the kernels see of the graph
+struct GraphView {
+    const float *rows; int ld;
+    const uint32_t *ids; const uint8_t *deleted; const int *levels;
+    uint32_t *adj0; int *deg0; int E0;
+    const int *up_of; uint32_t *adjU; int *degU; int EU;
+
+    __device__ __forceinline__ uint32_t *edges(long long slot, int layer, int **deg_out) const {
+        if (layer == 0) { *deg_out = deg0 + slot; return adj0 + (size_t)slot * E0; }
+        int u = up_of[slot];
+        *deg_out = degU + (size_t)u * HNSW_MAX_LEVELS + layer;
+        return adjU + ((size_t)u * HNSW_MAX_LEVELS + layer) * EU;
+    }
+};
 
 struct HNSWIndex {
     int dim = 0, ld = 0, metric = 0, m = 0, efc = 0, efs = 0, device = 0;
-    int64_t n = 0;
+    int64_t n = 0, cap = 0, n_up = 0, cap_up = 0;
+    int E0 = 0, EU = 0;
     float *rows = nullptr;
     uint32_t *ids = nullptr;
     uint8_t *deleted = nullptr;
-    int *levels = nullptr;
-    long long *node_base = nullptr, *edge_off = nullptr;
-    uint32_t *edges = nullptr;
+    int *levels = nullptr, *deg0 = nullptr, *up_of = nullptr, *degU = nullptr;
+    uint32_t *adj0 = nullptr, *adjU = nullptr;
     long long entry_slot = -1;
     int max_level = -1;
     std::unordered_map<uint32_t, int64_t> slot_of;
     std::unordered_set<uint32_t> deleted_ids;
+    std::vector<int> levels_host;
 
     void free_dev() {
-        cudaFree(rows); cudaFree(ids); cudaFree(deleted); cudaFree(levels); cudaFree(node_base); cudaFree(edge_off); cudaFree(edges);
-        rows = nullptr; ids = nullptr; deleted = nullptr; levels = nullptr; node_base = nullptr; edge_off = nullptr; edges = nullptr;
+        cudaFree(rows); cudaFree(ids); cudaFree(deleted); cudaFree(levels); cudaFree(deg0); cudaFree(up_of); cudaFree(degU);
+        cudaFree(adj0); cudaFree(adjU);
+        rows = nullptr; ids = nullptr; deleted = nullptr; levels = nullptr; deg0 = nullptr; up_of = nullptr; degU = nullptr;
+        adj0 = nullptr; adjU = nullptr;
+        cap = cap_up = 0;
     }
     ~HNSWIndex() { free_dev(); }
+    GraphView view() const { return GraphView{rows, ld, ids, deleted, levels, adj0, deg0, E0, up_of, adjU, degU, EU}; }
+    int reserve(int64_t want, int64_t want_up);
 };
 
-struct HCand { float d; uint32_t slot; };
+template <typename T>
+static int grow(T **p, int64_t old_n, int64_t new_cap, size_t per, bool zero) {
+    T *np = nullptr;
+    CM_CUDA(cudaMalloc(&np, (size_t)new_cap * per * sizeof(T)));
+    if (zero) CM_CUDA(cudaMemset(np, 0, (size_t)new_cap * per * sizeof(T)));
+    if (old_n > 0 && *p) CM_CUDA(cudaMemcpy(np, *p, (size_t)old_n * per * sizeof(T), cudaMemcpyDeviceToDevice));
+    cudaFree(*p);
+    *p = np;
+    return CM_OK;
+}
+
+int HNSWIndex::reserve(int64_t want, int64_t want_up) {
+    if (want > cap) {
+        int64_t nc = cap ? cap : 1024;
+        while (nc < want) nc = nc + nc / 2 + 1024;
+        CM_TRY(grow(&rows, n, nc, (size_t)ld, true));
+        CM_TRY(grow(&ids, n, nc, 1, true));
+        CM_TRY(grow(&deleted, n, nc, 1, true));
+        CM_TRY(grow(&levels, n, nc, 1, true));
+        CM_TRY(grow(&deg0, n, nc, 1, true));
+        CM_TRY(grow(&up_of, n, nc, 1, true));
+        CM_TRY(grow(&adj0, n, nc, (size_t)E0, true));
+        cap = nc;
+    }
+    if (want_up > cap_up) {
+        int64_t nc = cap_up ? cap_up : 256;
+        while (nc < want_up) nc = nc + nc / 2 + 256;
+        CM_TRY(grow(&degU, n_up, nc, HNSW_MAX_LEVELS, true));
+        CM_TRY(grow(&adjU, n_up, nc, (size_t)HNSW_MAX_LEVELS * EU, true));
+        cap_up = nc;
+    }
+    return CM_OK;
+}
 
 // ---- Go container/heap on (distance, slot) pairs; IS_MAX: less(i, j) = d[i] > d[j], else d[i] < d[j] ----
 template <bool IS_MAX>
@@ -85,7 +150,7 @@ __device__ __forceinline__ HCand h_pop(HCand *a, int &n) {
     return a[last];
 }
 
-// Distance.Calculate(query, row) by ONE lane in the reference's order (distance.go loops)
+// Distance.Calculate(a = vector in shared memory, b = row) by ONE lane in the reference's order
 template <int METRIC, bool FMA>
 __device__ __forceinline__ float row_distance(const float *__restrict__ row, const float *__restrict__ q_s, int ld) {
     const float4 *x = reinterpret_cast<const float4 *>(row);
@@ -101,59 +166,67 @@ __device__ __forceinline__ float row_distance(const float *__restrict__ row, con
     }
     return metric_finish<METRIC>(acc);
 }
-
+// same for rows that were written earlier in the SAME kernel (insertion): no read-only path
 template <int METRIC, bool FMA>
-__global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
-    const float *__restrict__ rows, int ld, const uint32_t *__restrict__ ids, const uint8_t *__restrict__ deleted,
-    const int *__restrict__ levels, const long long *__restrict__ node_base, const long long *__restrict__ edge_off,
-    const uint32_t *__restrict__ edges, long long entry_slot, int max_level, const float *__restrict__ queries, int nq, int ef,
-    long long k_req, float threshold, const uint8_t *__restrict__ doc_skip, uint32_t *__restrict__ visited, long long vis_words,
-    HCand *__restrict__ cand_heaps, int cand_cap, long long out_stride, uint32_t *__restrict__ out_ids,
-    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts,
-    long long *__restrict__ work /* [nq][2]: distance evaluations, expansions */) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * HNSW_WARPS + warp;
-    if (q >= nq) return;
-    const size_t per_warp = (size_t)ld * 4 + (size_t)(ef + 1) * sizeof(HCand) + 32 * 12;
-    uint8_t *base = smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
-    float *q_s = reinterpret_cast<float *>(base);
-    HCand *res = reinterpret_cast<HCand *>(q_s + ld);
-    float *nb_d = reinterpret_cast<float *>(res + (ef + 1));
-    uint32_t *nb_slot = reinterpret_cast<uint32_t *>(nb_d + 32);
-    uint32_t *nb_new = nb_slot + 32;
-    for (int j = lane; j < ld; j += 32) q_s[j] = queries[(size_t)q * ld + j];
-    __syncwarp();
-    HCand *cands = cand_heaps + (size_t)q * cand_cap;
-    uint32_t *vis = visited + (size_t)q * vis_words;
-    long long evals = 0, expansions = 0;
+__device__ __forceinline__ float row_distance_rw(const float *row, const float *q_s, int ld) {
+    const float4 *x = reinterpret_cast<const float4 *>(row);
+    const float4 *q = reinterpret_cast<const float4 *>(q_s);
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < ld / 4; j++) {
+        float4 xv = x[j], qv = q[j];
+        acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+        acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+        acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+        acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+    }
+    return metric_finish<METRIC>(acc);
+}
 
-    // ---- phase 1: greedy descent, hnsw_index_search.go:271-296 ----
-    long long curr = entry_slot;
-    float curr_dist = 0.0f;
-    if (lane == 0) curr_dist = row_distance<METRIC, FMA>(rows + (size_t)curr * ld, q_s, ld);
-    curr_dist = __shfl_sync(0xffffffffu, curr_dist, 0);
-    evals++;
-    for (int lc = max_level; lc > 0; lc--) {
+// per-warp scratch in shared memory
+struct WarpScratch {
+    float *q_s;        // [ld] the query / the vector being inserted
+    HCand *res;        // [ef + 1] result max-heap
+    float *nb_d;       // [32]
+    uint32_t *nb_slot; // [32]
+    uint32_t *nb_new;  // [32]
+};
+__host__ __device__ inline size_t warp_scratch_bytes(int ld, int ef) {
+    return (((size_t)ld * 4 + (size_t)(ef + 1) * sizeof(HCand) + 32 * 12) + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ WarpScratch carve(uint8_t *base, int ld, int ef) {
+    WarpScratch w;
+    w.q_s = reinterpret_cast<float *>(base);
+    w.res = reinterpret_cast<HCand *>(w.q_s + ld);
+    w.nb_d = reinterpret_cast<float *>(w.res + (ef + 1));
+    w.nb_slot = reinterpret_cast<uint32_t *>(w.nb_d + 32);
+    w.nb_new = w.nb_slot + 32;
+    return w;
+}
+
+// greedy descent from `curr` through layers hi .. lo+1 (hnsw_index_search.go:271-296 / hnsw_index.go:498-521)
+template <int METRIC, bool FMA>
+__device__ __forceinline__ void greedy_descend(const GraphView &G, const float *q_s, int hi, int lo, long long &curr,
+                                               float &curr_dist, long long &evals, int lane) {
+    for (int lc = hi; lc > lo; lc--) {
         bool changed = true;
         while (changed) {
             changed = false;
-            if (lc > levels[curr]) break;                       // lc < len(node.Edges)
-            const long long pair = node_base[curr] + lc;
-            const long long e0 = edge_off[pair], deg = edge_off[pair + 1] - e0;
-            const long long node = curr;
-            (void)node;
-            for (long long b = 0; b < deg; b += 32) {
-                long long j = b + lane;
+            if (lc > G.levels[curr]) break;                     // lc < len(node.Edges)
+            int *degp;
+            const uint32_t *E = G.edges(curr, lc, &degp);
+            const int deg = *degp;
+            for (int b = 0; b < deg; b += 32) {
+                int j = b + lane;
                 uint32_t nb = 0;
                 bool valid = false;
                 float d = 0.0f;
                 if (j < deg) {
-                    nb = edges[e0 + j];
-                    valid = deleted[nb] == 0;
-                    if (valid) d = row_distance<METRIC, FMA>(rows + (size_t)nb * ld, q_s, ld);
+                    nb = E[j];
+                    valid = G.deleted[nb] == 0;
+                    if (valid) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, q_s, G.ld);
                 }
-                int cnt = (int)min(32LL, deg - b);
+                int cnt = min(32, deg - b);
                 for (int t = 0; t < cnt; t++) {
                     float dt = __shfl_sync(0xffffffffu, d, t);
                     bool vt = __shfl_sync(0xffffffffu, (int)valid, t) != 0;
@@ -166,67 +239,77 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
             }
         }
     }
+}
 
-    // ---- phase 2: searchLayer(query, curr, ef, 0), hnsw_index.go:565-629 ----
+// searchLayer(query, entry, ef, layer), hnsw_index.go:565-629.  Leaves the results ASCENDING in `sorted`
+// (= the cands buffer, whose heap is dead by then) and returns their number, or -1 on candidate-heap overflow.
+// touched (optional): every slot whose visited bit was set is appended, so the caller can clear the bits.
+template <int METRIC, bool FMA>
+__device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratch &W, long long entry, int ef, int layer,
+                                            uint32_t *vis, HCand *cands, int cand_cap, uint32_t *touched, int *n_touched,
+                                            long long &evals, long long &expansions, int lane) {
     int n_c = 0, n_r = 0;
     bool overflow = false;
-    if (deleted[curr] == 0) {
-        float d = 0.0f;
+    if (G.deleted[entry] == 0) {
         if (lane == 0) {
-            d = row_distance<METRIC, FMA>(rows + (size_t)curr * ld, q_s, ld);
-            HCand c{d, (uint32_t)curr};
+            float d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)entry * G.ld, W.q_s, G.ld);
+            HCand c{d, (uint32_t)entry};
             h_push<false>(cands, n_c, c);
-            h_push<true>(res, n_r, c);
+            h_push<true>(W.res, n_r, c);
         }
         evals++;
     }
-    if (lane == 0) atomicOr(&vis[curr >> 5], 1u << (curr & 31));
+    if (lane == 0) {
+        atomicOr(&vis[entry >> 5], 1u << (entry & 31));
+        if (touched) touched[(*n_touched)++] = (uint32_t)entry;
+    }
     __syncwarp();
     for (;;) {
-        // pop the nearest candidate (lane 0) and broadcast the decision
-        float cur_d = 0.0f;
         uint32_t cur_slot = 0;
         int go = 0;
-        if (lane == 0) {
-            if (n_c > 0) {
-                HCand cur = h_pop<false>(cands, n_c);
-                if (!(n_r >= ef && cur.d > res[0].d)) { go = 1; cur_d = cur.d; cur_slot = cur.slot; }
-            }
+        if (lane == 0 && n_c > 0) {
+            HCand cur = h_pop<false>(cands, n_c);
+            if (!(n_r >= ef && cur.d > W.res[0].d)) { go = 1; cur_slot = cur.slot; }
         }
         go = __shfl_sync(0xffffffffu, go, 0);
         if (!go) break;
         cur_slot = __shfl_sync(0xffffffffu, cur_slot, 0);
-        (void)cur_d;
         expansions++;
-        const long long pair = node_base[cur_slot];             // layer 0 always exists
-        const long long e0 = edge_off[pair], deg = edge_off[pair + 1] - e0;
-        for (long long b = 0; b < deg; b += 32) {
-            long long j = b + lane;
+        int deg = 0;
+        const uint32_t *E = nullptr;
+        if (layer <= G.levels[cur_slot]) {                          // layer < len(node.Edges)
+            int *degp;
+            E = G.edges(cur_slot, layer, &degp);
+            deg = *degp;
+        }
+        for (int b = 0; b < deg; b += 32) {
+            int j = b + lane;
             uint32_t nb = 0, isnew = 0;
             float d = 0.0f;
             if (j < deg) {
-                nb = edges[e0 + j];
-                if (deleted[nb] == 0) {
+                nb = E[j];
+                if (G.deleted[nb] == 0) {
                     uint32_t bit = 1u << (nb & 31);
                     uint32_t old = atomicOr(&vis[nb >> 5], bit);
                     isnew = (old & bit) == 0u;
                 }
-                if (isnew) d = row_distance<METRIC, FMA>(rows + (size_t)nb * ld, q_s, ld);
+                if (isnew) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, W.q_s, G.ld);
             }
-            nb_d[lane] = d; nb_slot[lane] = nb; nb_new[lane] = isnew;
+            W.nb_d[lane] = d; W.nb_slot[lane] = nb; W.nb_new[lane] = isnew;
             evals += __popc(__ballot_sync(0xffffffffu, isnew != 0u));
             __syncwarp();
             if (lane == 0) {
-                int cnt = (int)min(32LL, deg - b);
+                int cnt = min(32, deg - b);
                 for (int t = 0; t < cnt; t++) {
-                    if (!nb_new[t]) continue;
-                    float dt = nb_d[t];
-                    if (n_r < ef || dt < res[0].d) {
-                        HCand c{dt, nb_slot[t]};
+                    if (!W.nb_new[t]) continue;
+                    if (touched) touched[(*n_touched)++] = W.nb_slot[t];
+                    float dt = W.nb_d[t];
+                    if (n_r < ef || dt < W.res[0].d) {
+                        HCand c{dt, W.nb_slot[t]};
                         if (n_c >= cand_cap) { overflow = true; break; }
                         h_push<false>(cands, n_c, c);
-                        h_push<true>(res, n_r, c);
-                        if (n_r > ef) (void)h_pop<true>(res, n_r);
+                        h_push<true>(W.res, n_r, c);
+                        if (n_r > ef) (void)h_pop<true>(W.res, n_r);
                     }
                 }
             }
@@ -234,16 +317,50 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
         }
         if (__shfl_sync(0xffffffffu, (int)overflow, 0)) break;
     }
+    int n = -1;
+    if (lane == 0 && !overflow) {
+        n = n_r;
+        for (int i = n - 1; i >= 0; i--) cands[i] = h_pop<true>(W.res, n_r);     // :622-626 ascending
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();
+    return n;
+}
 
-    // ---- results: pop the max-heap back to front (ascending), post-filter, first k ----
+template <int METRIC, bool FMA>
+__global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
+    GraphView G, long long entry_slot, int max_level, const float *__restrict__ queries, int nq, int ef, long long k_req,
+    float threshold, const uint8_t *__restrict__ doc_skip, uint32_t *__restrict__ visited, long long vis_words,
+    HCand *__restrict__ cand_heaps, int cand_cap, long long out_stride, uint32_t *__restrict__ out_ids,
+    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts,
+    long long *__restrict__ work /* [nq][2]: distance evaluations, expansions */) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * HNSW_WARPS + warp;
+    if (q >= nq) return;
+    WarpScratch W = carve(smem + (size_t)warp * warp_scratch_bytes(G.ld, ef), G.ld, ef);
+    for (int j = lane; j < G.ld; j += 32) W.q_s[j] = queries[(size_t)q * G.ld + j];
+    __syncwarp();
+    HCand *cands = cand_heaps + (size_t)q * cand_cap;
+    uint32_t *vis = visited + (size_t)q * vis_words;
+    long long evals = 0, expansions = 0;
+
+    // phase 1: greedy descent, hnsw_index_search.go:271-296
+    long long curr = entry_slot;
+    float curr_dist = 0.0f;
+    if (lane == 0) curr_dist = row_distance_rw<METRIC, FMA>(G.rows + (size_t)curr * G.ld, W.q_s, G.ld);
+    curr_dist = __shfl_sync(0xffffffffu, curr_dist, 0);
+    evals++;
+    greedy_descend<METRIC, FMA>(G, W.q_s, max_level, 0, curr, curr_dist, evals, lane);
+
+    // phase 2: searchLayer(query, curr, ef, 0)
+    int n = search_layer<METRIC, FMA>(G, W, curr, ef, 0, vis, cands, cand_cap, nullptr, nullptr, evals, expansions, lane);
+
+    // results: post-filter (hnsw_index_search.go:321-335), already ascending, first k
     if (lane == 0) {
-        long long count = 0;
-        if (overflow) {
-            count = -1;
-        } else {
-            int n = n_r;
-            HCand *sorted = cands;                              // the candidate heap is dead: reuse as scratch
-            for (int i = n - 1; i >= 0; i--) sorted[i] = h_pop<true>(res, n_r);
+        long long count = -1;
+        if (n >= 0) {
+            HCand *sorted = cands;
             long long kept = 0;
             for (int i = 0; i < n; i++) {
                 uint32_t s = sorted[i].slot;
@@ -255,7 +372,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
             if (k > out_stride) k = out_stride;
             for (long long i = 0; i < k; i++) {
                 size_t o = (size_t)q * out_stride + i;
-                out_ids[o] = ids[sorted[i].slot];
+                out_ids[o] = G.ids[sorted[i].slot];
                 out_scores[o] = sorted[i].d;
                 if (out_pos) out_pos[o] = sorted[i].slot;
             }
@@ -263,6 +380,98 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
         }
         out_counts[q] = count;
         if (work) { work[(size_t)q * 2] = evals; work[(size_t)q * 2 + 1] = expansions; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// insertion: one warp inserts the slots [s0, s0 + m) one after the other (each insertion sees the graph
+// the previous ones left -- the reference holds idx.mu for the whole Add)
+// ------------------------------------------------------------------------------------------------
+// pruneConnections(nb, layer, M) (hnsw_index.go:658-694) while `skip` (the node being inserted) is not in
+// idx.nodes yet: its edge is dropped, the others are re-sorted by distance to nb (stable) and cut to M.
+template <int METRIC, bool FMA>
+__device__ __forceinline__ void prune(const GraphView &G, const WarpScratch &W, float *nbrow_s, long long nb, int layer, int M,
+                                      uint32_t skip, HCand *tmp, int lane) {
+    int *degp;
+    uint32_t *E = G.edges(nb, layer, &degp);
+    const int deg = *degp;
+    for (int j = lane; j < G.ld; j += 32) nbrow_s[j] = G.rows[(size_t)nb * G.ld + j];
+    __syncwarp();
+    for (int b = 0; b < deg; b += 32) {
+        int j = b + lane;
+        if (j < deg) {
+            uint32_t e = E[j];
+            float d = 0.0f;
+            if (e != skip) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)e * G.ld, nbrow_s, G.ld);
+            tmp[j] = HCand{d, e};
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int n = 0;
+        for (int j = 0; j < deg; j++) {                         // stable insertion sort of the known nodes
+            HCand c = tmp[j];
+            if (c.slot == skip) continue;
+            int i = n++;
+            while (i > 0 && tmp[deg + i - 1].d > c.d) { tmp[deg + i] = tmp[deg + i - 1]; i--; }
+            tmp[deg + i] = c;
+        }
+        int keep = n < M ? n : M;
+        for (int i = 0; i < keep; i++) E[i] = tmp[deg + i].slot;
+        *degp = keep;
+    }
+    __syncwarp();
+}
+
+template <int METRIC, bool FMA>
+__global__ void __launch_bounds__(32) hnsw_insert_kernel(GraphView G, long long s0, int m, long long entry_slot, int max_level,
+                                                         int M, int efc, uint32_t *__restrict__ vis, HCand *__restrict__ cands,
+                                                         int cand_cap, uint32_t *__restrict__ touched, HCand *__restrict__ tmp,
+                                                         int *__restrict__ status) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x;
+    WarpScratch W = carve(smem, G.ld, efc);
+    float *nbrow_s = reinterpret_cast<float *>(smem + warp_scratch_bytes(G.ld, efc));
+    int max_l = max_level;
+    for (int i = 0; i < m; i++) {
+        const long long s = s0 + i;
+        const int L = G.levels[s];
+        if (L > max_l) max_l = L;                               // hnsw_index.go:266-268: before insertNode
+        if (s == 0 && entry_slot < 0) continue;                 // :273-278 the first node only becomes the entry point
+        const long long entry = entry_slot < 0 ? 0 : entry_slot;
+        for (int j = lane; j < G.ld; j += 32) W.q_s[j] = G.rows[(size_t)s * G.ld + j];
+        __syncwarp();
+        long long evals = 0, expansions = 0;
+        long long curr = entry;
+        float curr_dist = 0.0f;
+        if (lane == 0) curr_dist = row_distance_rw<METRIC, FMA>(G.rows + (size_t)curr * G.ld, W.q_s, G.ld);
+        curr_dist = __shfl_sync(0xffffffffu, curr_dist, 0);
+        greedy_descend<METRIC, FMA>(G, W.q_s, max_l, L, curr, curr_dist, evals, lane);
+        for (int lc = L; lc >= 0; lc--) {
+            int n_touched = 0;
+            int nc = search_layer<METRIC, FMA>(G, W, curr, efc, lc, vis, cands, cand_cap, touched, &n_touched, evals, expansions, lane);
+            n_touched = __shfl_sync(0xffffffffu, n_touched, 0);
+            for (int t = lane; t < n_touched; t += 32) vis[touched[t] >> 5] = 0u;   // a fresh visited set per searchLayer
+            __syncwarp();
+            if (nc < 0) { if (lane == 0) *status = 1; return; }
+            const int Mx = lc == 0 ? 2 * M : M;
+            const int nsel = nc < Mx ? nc : Mx;                 // selectNeighbors: candidates are already ascending
+            int *my_degp;
+            uint32_t *my_E = G.edges(s, lc, &my_degp);
+            for (int t = 0; t < nsel; t++) {
+                const uint32_t nb = cands[t].slot;
+                if (lane == 0) { my_E[*my_degp] = nb; (*my_degp)++; }
+                if (lc <= G.levels[nb]) {
+                    int *degp;
+                    uint32_t *E = G.edges(nb, lc, &degp);
+                    if (lane == 0) { E[*degp] = (uint32_t)s; (*degp)++; }
+                    __syncwarp();
+                    if (*degp > Mx) prune<METRIC, FMA>(G, W, nbrow_s, nb, lc, Mx, (uint32_t)s, tmp, lane);
+                }
+                __syncwarp();
+            }
+            if (nc > 0) curr = cands[0].slot;                   // :548-550
+        }
     }
 }
 
@@ -281,7 +490,6 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
                     (long long)std::min<int64_t>(k_bound, ix.n));
     bool fma = rounding_mode() == CM_ROUND_FMA;
     const int ld = ix.ld;
-    // Distance.Preprocess on the queries
     float *qp = nullptr;
     int *qflags = nullptr;
     CM_TRY(ws_alloc((void **)&qp, (size_t)nq * ld * 4, st));
@@ -312,8 +520,7 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
     }
     const long long vis_words = (ix.n + 31) / 32;
     const int cand_cap = (int)std::min<int64_t>(ix.n + 1, (int64_t)16 * ef + 4096);
-    size_t per_warp = ((size_t)ld * 4 + (size_t)(ef + 1) * sizeof(HCand) + 32 * 12 + 15) & ~(size_t)15;
-    size_t smem = per_warp * HNSW_WARPS;
+    size_t smem = warp_scratch_bytes(ld, ef) * HNSW_WARPS;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "efSearch %d with dim %d does not fit shared memory", ef, ix.dim);
     // queries in groups so that the visited bitmaps stay bounded (<= 1 GiB)
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (vis_words * 4 + (int64_t)cand_cap * 8)));
@@ -321,20 +528,20 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
     HCand *heaps = nullptr;
     CM_TRY(ws_alloc((void **)&visited, (size_t)qgroup * vis_words * 4, st));
     CM_TRY(ws_alloc((void **)&heaps, (size_t)qgroup * cand_cap * sizeof(HCand), st));
+    GraphView G = ix.view();
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
         CM_CUDA(cudaMemsetAsync(visited, 0, (size_t)m * vis_words * 4, st));
         unsigned blocks = (unsigned)((m + HNSW_WARPS - 1) / HNSW_WARPS);
         ProfScope prof(CM_PROF_HNSW, st);
-#define CM_HNSW_LAUNCH(M, F)                                                                                          \
+#define CM_HNSW_LAUNCH(MM, F)                                                                                         \
     do {                                                                                                              \
-        CM_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        hnsw_search_kernel<M, F><<<blocks, HNSW_WARPS * 32, smem, st>>>(                                              \
-            ix.rows, ld, ix.ids, ix.deleted, ix.levels, ix.node_base, ix.edge_off, ix.edges, ix.entry_slot, ix.max_level, \
-            qp + (size_t)q0 * ld, (int)m, ef, (long long)p->k, p->threshold, doc_skip, visited, vis_words, heaps, cand_cap, \
-            (long long)out_stride, out_ids + (size_t)q0 * out_stride, out_scores + (size_t)q0 * out_stride,          \
-            out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr, (long long *)out_counts + q0,         \
-            work ? (long long *)work + (size_t)q0 * 2 : nullptr);                                                     \
+        CM_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<MM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hnsw_search_kernel<MM, F><<<blocks, HNSW_WARPS * 32, smem, st>>>(                                             \
+            G, ix.entry_slot, ix.max_level, qp + (size_t)q0 * ld, (int)m, ef, (long long)p->k, p->threshold, doc_skip, visited, \
+            vis_words, heaps, cand_cap, (long long)out_stride, out_ids + (size_t)q0 * out_stride,                     \
+            out_scores + (size_t)q0 * out_stride, out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,  \
+            (long long *)out_counts + q0, work ? (long long *)work + (size_t)q0 * 2 : nullptr);                       \
     } while (0)
         switch (ix.metric) {
         case CM_L2: if (fma) CM_HNSW_LAUNCH(CM_L2, true); else CM_HNSW_LAUNCH(CM_L2, false); break;
@@ -370,6 +577,8 @@ int cm_hnsw_create(int dim, int metric, int m, int ef_construction, int ef_searc
     h->ix.m = m > 0 ? m : 16;
     h->ix.efc = ef_construction > 0 ? ef_construction : 200;
     h->ix.efs = ef_search > 0 ? ef_search : h->ix.efc;
+    h->ix.E0 = 2 * h->ix.m + 1;
+    h->ix.EU = h->ix.m + 1;
     cudaGetDevice(&h->ix.device);
     *out = h;
     return CM_OK;
@@ -380,11 +589,11 @@ int cm_hnsw_destroy(cm_hnsw *h) {
 }
 int64_t cm_hnsw_size(const cm_hnsw *h) { return h ? h->ix.n : 0; }
 int cm_hnsw_ef_search(const cm_hnsw *h) { return h ? h->ix.efs : 0; }
+int cm_hnsw_max_level(const cm_hnsw *h) { return h ? h->ix.max_level : -1; }
 
-// Upload a graph built by HNSWIndex.Add / insertNode (hnsw_index.go:228-288, 493-552) -- by the Go
-// package's own builder (or any other host-side builder).  rows are the STORED vectors (already preprocessed by Add);
-// slots are insertion order; edge_off has sum(levels[i] + 1) + 1 entries, pairs ordered by (slot, layer);
-// edge_ids are neighbour node IDs.
+// Upload a graph built elsewhere by HNSWIndex.Add / insertNode (hnsw_index.go:228-288, 493-552), e.g. the state
+// decoded by HNSWIndex.ReadFrom.  rows are the STORED vectors (already preprocessed by Add); slots are insertion
+// order; edge_off has sum(levels[i] + 1) + 1 entries, pairs ordered by (slot, layer); edge_ids are neighbour IDs.
 int cm_hnsw_load_graph(cm_hnsw *h, int64_t n, const uint32_t *ids, const float *rows, const int32_t *levels,
                        const int64_t *edge_off, const uint32_t *edge_ids, uint32_t entry_id, int max_level) {
     if (!h || n < 0 || (n > 0 && (!ids || !rows || !levels || !edge_off || !edge_ids)))
@@ -392,43 +601,212 @@ int cm_hnsw_load_graph(cm_hnsw *h, int64_t n, const uint32_t *ids, const float *
     CM_CUDA(cudaSetDevice(h->ix.device));
     cm::HNSWIndex &ix = h->ix;
     ix.free_dev();
-    ix.slot_of.clear(); ix.deleted_ids.clear();
-    ix.n = 0; ix.entry_slot = -1; ix.max_level = -1;
+    ix.slot_of.clear(); ix.deleted_ids.clear(); ix.levels_host.clear();
+    ix.n = 0; ix.n_up = 0; ix.entry_slot = -1; ix.max_level = -1;
+    ix.E0 = 2 * ix.m + 1; ix.EU = ix.m + 1;
     if (n == 0) return CM_OK;
+    // slot map, per-layer degrees -> slot widths
     std::vector<long long> base((size_t)n + 1, 0);
+    int64_t n_up = 0;
     for (int64_t i = 0; i < n; i++) {
-        if (levels[i] < 0) return cm::fail(CM_ERR_INVALID_ARG, "negative level at slot %lld", (long long)i);
+        if (levels[i] < 0 || levels[i] >= cm::HNSW_MAX_LEVELS) return cm::fail(CM_ERR_INVALID_ARG, "level %d at slot %lld out of range", levels[i], (long long)i);
         base[(size_t)i + 1] = base[(size_t)i] + levels[i] + 1;
         ix.slot_of[ids[i]] = i;
+        if (levels[i] > 0) n_up++;
     }
-    long long pairs = base[(size_t)n], n_edges = edge_off[pairs];
-    std::vector<uint32_t> eslots((size_t)std::max<long long>(n_edges, 1));
-    for (long long e = 0; e < n_edges; e++) {
-        auto it = ix.slot_of.find(edge_ids[e]);
-        if (it == ix.slot_of.end()) return cm::fail(CM_ERR_NOT_FOUND, "edge %lld points to unknown node ID %u", e, edge_ids[e]);
-        eslots[(size_t)e] = (uint32_t)it->second;
-    }
+    for (int64_t i = 0; i < n; i++)
+        for (int l = 0; l <= levels[i]; l++) {
+            long long deg = edge_off[base[(size_t)i] + l + 1] - edge_off[base[(size_t)i] + l];
+            if (l == 0) ix.E0 = std::max<int>(ix.E0, (int)deg + 1); else ix.EU = std::max<int>(ix.EU, (int)deg + 1);
+        }
     auto ent = ix.slot_of.find(entry_id);
     if (ent == ix.slot_of.end()) return cm::fail(CM_ERR_NOT_FOUND, "entry point ID %u not in the graph", entry_id);
-    int ld = ix.ld;
-    CM_CUDA(cudaMalloc(&ix.rows, (size_t)n * ld * 4));
-    CM_CUDA(cudaMemset(ix.rows, 0, (size_t)n * ld * 4));
-    CM_CUDA(cudaMemcpy2D(ix.rows, (size_t)ld * 4, rows, (size_t)ix.dim * 4, (size_t)ix.dim * 4, (size_t)n, cudaMemcpyHostToDevice));
-    CM_CUDA(cudaMalloc(&ix.ids, (size_t)n * 4));
+    CM_TRY(ix.reserve(n, n_up));
+    std::vector<uint32_t> a0((size_t)n * ix.E0, 0), aU((size_t)std::max<int64_t>(n_up, 1) * cm::HNSW_MAX_LEVELS * ix.EU, 0);
+    std::vector<int> d0((size_t)n, 0), dU((size_t)std::max<int64_t>(n_up, 1) * cm::HNSW_MAX_LEVELS, 0), upof((size_t)n, -1);
+    int64_t u = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int my_u = -1;
+        if (levels[i] > 0) { my_u = (int)u++; upof[(size_t)i] = my_u; }
+        for (int l = 0; l <= levels[i]; l++) {
+            long long e0 = edge_off[base[(size_t)i] + l], e1 = edge_off[base[(size_t)i] + l + 1];
+            for (long long e = e0; e < e1; e++) {
+                auto it = ix.slot_of.find(edge_ids[e]);
+                if (it == ix.slot_of.end()) return cm::fail(CM_ERR_NOT_FOUND, "edge %lld points to unknown node ID %u", e, edge_ids[e]);
+                if (l == 0) a0[(size_t)i * ix.E0 + (e - e0)] = (uint32_t)it->second;
+                else aU[((size_t)my_u * cm::HNSW_MAX_LEVELS + l) * ix.EU + (e - e0)] = (uint32_t)it->second;
+            }
+            if (l == 0) d0[(size_t)i] = (int)(e1 - e0); else dU[(size_t)my_u * cm::HNSW_MAX_LEVELS + l] = (int)(e1 - e0);
+        }
+    }
+    CM_CUDA(cudaMemcpy2D(ix.rows, (size_t)ix.ld * 4, rows, (size_t)ix.dim * 4, (size_t)ix.dim * 4, (size_t)n, cudaMemcpyHostToDevice));
     CM_CUDA(cudaMemcpy(ix.ids, ids, (size_t)n * 4, cudaMemcpyHostToDevice));
-    CM_CUDA(cudaMalloc(&ix.deleted, (size_t)n));
-    CM_CUDA(cudaMemset(ix.deleted, 0, (size_t)n));
-    CM_CUDA(cudaMalloc(&ix.levels, (size_t)n * 4));
     CM_CUDA(cudaMemcpy(ix.levels, levels, (size_t)n * 4, cudaMemcpyHostToDevice));
-    CM_CUDA(cudaMalloc(&ix.node_base, (size_t)(n + 1) * 8));
-    CM_CUDA(cudaMemcpy(ix.node_base, base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
-    CM_CUDA(cudaMalloc(&ix.edge_off, (size_t)(pairs + 1) * 8));
-    CM_CUDA(cudaMemcpy(ix.edge_off, edge_off, (size_t)(pairs + 1) * 8, cudaMemcpyHostToDevice));
-    CM_CUDA(cudaMalloc(&ix.edges, eslots.size() * 4));
-    CM_CUDA(cudaMemcpy(ix.edges, eslots.data(), eslots.size() * 4, cudaMemcpyHostToDevice));
-    ix.n = n;
+    CM_CUDA(cudaMemcpy(ix.adj0, a0.data(), a0.size() * 4, cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMemcpy(ix.deg0, d0.data(), d0.size() * 4, cudaMemcpyHostToDevice));
+    CM_CUDA(cudaMemcpy(ix.up_of, upof.data(), upof.size() * 4, cudaMemcpyHostToDevice));
+    if (n_up > 0) {
+        CM_CUDA(cudaMemcpy(ix.adjU, aU.data(), (size_t)n_up * cm::HNSW_MAX_LEVELS * ix.EU * 4, cudaMemcpyHostToDevice));
+        CM_CUDA(cudaMemcpy(ix.degU, dU.data(), (size_t)n_up * cm::HNSW_MAX_LEVELS * 4, cudaMemcpyHostToDevice));
+    }
+    ix.levels_host.assign(levels, levels + n);
+    ix.n = n; ix.n_up = n_up;
     ix.entry_slot = ent->second;
     ix.max_level = max_level;
+    return CM_OK;
+}
+
+// n successive HNSWIndex.Add calls (hnsw_index.go:228-288) on the device: PreprocessInPlace (rows written back unless
+// writeback == 0), then insertNode with the caller's level draws (randomLevel, hnsw_index.go:474-484, stays with the
+// caller: the reference uses an unseeded global RNG).  IDs must be non-zero and new.
+int cm_hnsw_add(cm_hnsw *h, const uint32_t *ids, float *rows, const int32_t *levels, int64_t n, int writeback) {
+    if (!h || (n > 0 && (!ids || !rows || !levels))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (n <= 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    cm::HNSWIndex &ix = h->ix;
+    if (ix.E0 != 2 * ix.m + 1 || ix.EU != ix.m + 1)
+        return cm::fail(CM_ERR_UNSUPPORTED, "this graph was loaded with wider adjacency lists than M allows: insertion is not defined on it");
+    int64_t add_up = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (ids[i] == 0) return cm::fail(CM_ERR_INVALID_ARG, "node ID 0 is reserved (auto-assignment, hnsw_index.go:247-263)");
+        if (ix.slot_of.count(ids[i])) return cm::fail(CM_ERR_INVALID_ARG, "node ID %u already present", ids[i]);
+        if (levels[i] < 0 || levels[i] >= cm::HNSW_MAX_LEVELS) return cm::fail(CM_ERR_INVALID_ARG, "level %d out of range", levels[i]);
+        if (levels[i] > 0) add_up++;
+    }
+    bool fma = cm::rounding_mode() == CM_ROUND_FMA;
+    cudaStream_t st;
+    CM_TRY(cm::acquire_stream(&st));
+    int rc = ix.reserve(ix.n + n, ix.n_up + add_up);
+    float *raw = nullptr;
+    int *flags = nullptr, *status = nullptr;
+    uint32_t *vis = nullptr, *touched = nullptr;
+    cm::HCand *cands = nullptr, *tmp = nullptr;
+    const int cand_cap = (int)std::min<int64_t>(ix.n + n + 1, (int64_t)16 * ix.efc + 4096);
+    const int64_t vis_words = (ix.n + n + 31) / 32;
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&raw, (size_t)n * ix.dim * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&flags, (size_t)n * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&status, 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&vis, (size_t)vis_words * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&touched, (size_t)(ix.n + n + 1) * 4, st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&cands, (size_t)cand_cap * sizeof(cm::HCand), st);
+    if (rc == CM_OK) rc = cm::ws_alloc((void **)&tmp, (size_t)4 * (2 * ix.m + 2) * sizeof(cm::HCand), st);
+    int64_t good = n;
+    if (rc == CM_OK) {
+        cudaMemcpyAsync(raw, rows, (size_t)n * ix.dim * 4, cudaMemcpyHostToDevice, st);
+        rc = cm::launch_preprocess_rows(ix.metric, fma, raw, n, ix.dim, ix.dim, ix.rows + (size_t)ix.n * ix.ld, ix.ld, flags, st);
+    }
+    if (rc == CM_OK && ix.metric == CM_COSINE) {
+        std::vector<int> hf((size_t)n);
+        cudaMemcpyAsync(hf.data(), flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        for (int64_t i = 0; i < n; i++)
+            if (hf[(size_t)i]) { good = i; break; }
+        if (writeback && good > 0)
+            cudaMemcpy2DAsync(rows, (size_t)ix.dim * 4, ix.rows + (size_t)ix.n * ix.ld, (size_t)ix.ld * 4, (size_t)ix.dim * 4,
+                              (size_t)good, cudaMemcpyDeviceToHost, st);
+    }
+    if (rc == CM_OK && good > 0) {
+        // node records: id, level, empty adjacency, upper block for nodes above layer 0
+        std::vector<int> upof((size_t)good, -1);
+        int64_t u = ix.n_up;
+        for (int64_t i = 0; i < good; i++)
+            if (levels[i] > 0) upof[(size_t)i] = (int)u++;
+        cudaMemcpyAsync(ix.ids + ix.n, ids, (size_t)good * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(ix.levels + ix.n, levels, (size_t)good * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(ix.up_of + ix.n, upof.data(), (size_t)good * 4, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(ix.deg0 + ix.n, 0, (size_t)good * 4, st);
+        cudaMemsetAsync(ix.deleted + ix.n, 0, (size_t)good, st);
+        if (u > ix.n_up) cudaMemsetAsync(ix.degU + (size_t)ix.n_up * cm::HNSW_MAX_LEVELS, 0, (size_t)(u - ix.n_up) * cm::HNSW_MAX_LEVELS * 4, st);
+        cudaMemsetAsync(vis, 0, (size_t)vis_words * 4, st);
+        cudaMemsetAsync(status, 0, 4, st);
+        size_t smem = cm::warp_scratch_bytes(ix.ld, ix.efc) + (size_t)ix.ld * 4;
+        cm::GraphView G = ix.view();
+#define CM_HNSW_INS(MM, F)                                                                                            \
+    do {                                                                                                              \
+        cudaFuncSetAttribute(cm::hnsw_insert_kernel<MM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        cm::hnsw_insert_kernel<MM, F><<<1, 32, smem, st>>>(G, (long long)ix.n, (int)good, ix.entry_slot, ix.max_level, ix.m, ix.efc, \
+                                                           vis, cands, cand_cap, touched, tmp, status);               \
+    } while (0)
+        switch (ix.metric) {
+        case CM_L2: if (fma) CM_HNSW_INS(CM_L2, true); else CM_HNSW_INS(CM_L2, false); break;
+        case CM_L2SQ: if (fma) CM_HNSW_INS(CM_L2SQ, true); else CM_HNSW_INS(CM_L2SQ, false); break;
+        default: if (fma) CM_HNSW_INS(CM_COSINE, true); else CM_HNSW_INS(CM_COSINE, false); break;
+        }
+#undef CM_HNSW_INS
+        cm::count_launch();
+        int hstatus = 0;
+        cudaMemcpyAsync(&hstatus, status, 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "hnsw_add: %s", cudaGetErrorString(e));
+        else if (hstatus) rc = cm::fail(CM_ERR_UNSUPPORTED, "hnsw_add: candidate heap overflow (efConstruction %d)", ix.efc);
+        if (rc == CM_OK) {
+            for (int64_t i = 0; i < good; i++) {
+                ix.slot_of[ids[i]] = ix.n + i;
+                ix.levels_host.push_back(levels[i]);
+                if (levels[i] > ix.max_level) ix.max_level = levels[i];
+            }
+            if (ix.entry_slot < 0) ix.entry_slot = 0;
+            ix.n += good;
+            ix.n_up = u;
+        }
+    }
+    cm::ws_free(raw, st); cm::ws_free(flags, st); cm::ws_free(status, st); cm::ws_free(vis, st); cm::ws_free(touched, st);
+    cm::ws_free(cands, st); cm::ws_free(tmp, st);
+    cudaStreamSynchronize(st);
+    cm::release_stream(st);
+    if (rc == CM_OK && good < n) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (row %lld of this Add batch)", (long long)good);
+    return rc;
+}
+
+// the graph back to the host (HNSWIndex.WriteTo, tests): levels, and per (slot, layer) the neighbour IDs.
+// edge_off must hold sum(levels + 1) + 1 entries, edge_ids at least cm_hnsw_edge_count() entries.
+int64_t cm_hnsw_edge_count(const cm_hnsw *h) {
+    if (!h || h->ix.n == 0) return 0;
+    const cm::HNSWIndex &ix = h->ix;
+    cudaSetDevice(ix.device);
+    std::vector<int> d0((size_t)ix.n), dU((size_t)std::max<int64_t>(ix.n_up, 1) * cm::HNSW_MAX_LEVELS, 0);
+    if (cudaMemcpy(d0.data(), ix.deg0, (size_t)ix.n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (ix.n_up > 0 && cudaMemcpy(dU.data(), ix.degU, (size_t)ix.n_up * cm::HNSW_MAX_LEVELS * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t total = 0;
+    for (int v : d0) total += v;
+    int64_t u = 0;
+    for (int64_t i = 0; i < ix.n; i++)
+        if (ix.levels_host[(size_t)i] > 0) {
+            for (int l = 1; l <= ix.levels_host[(size_t)i]; l++) total += dU[(size_t)u * cm::HNSW_MAX_LEVELS + l];
+            u++;
+        }
+    return total;
+}
+int cm_hnsw_export_graph(const cm_hnsw *h, int32_t *levels, int64_t *edge_off, uint32_t *edge_ids, uint32_t *entry_id,
+                         int *max_level) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    const cm::HNSWIndex &ix = h->ix;
+    if (max_level) *max_level = ix.max_level;
+    if (ix.n == 0) { if (entry_id) *entry_id = 0; if (edge_off) edge_off[0] = 0; return CM_OK; }
+    CM_CUDA(cudaSetDevice(ix.device));
+    std::vector<uint32_t> a0((size_t)ix.n * ix.E0), aU((size_t)std::max<int64_t>(ix.n_up, 1) * cm::HNSW_MAX_LEVELS * ix.EU), hid((size_t)ix.n);
+    std::vector<int> d0((size_t)ix.n), dU((size_t)std::max<int64_t>(ix.n_up, 1) * cm::HNSW_MAX_LEVELS, 0);
+    CM_CUDA(cudaMemcpy(a0.data(), ix.adj0, a0.size() * 4, cudaMemcpyDeviceToHost));
+    CM_CUDA(cudaMemcpy(d0.data(), ix.deg0, d0.size() * 4, cudaMemcpyDeviceToHost));
+    CM_CUDA(cudaMemcpy(hid.data(), ix.ids, hid.size() * 4, cudaMemcpyDeviceToHost));
+    if (ix.n_up > 0) {
+        CM_CUDA(cudaMemcpy(aU.data(), ix.adjU, (size_t)ix.n_up * cm::HNSW_MAX_LEVELS * ix.EU * 4, cudaMemcpyDeviceToHost));
+        CM_CUDA(cudaMemcpy(dU.data(), ix.degU, (size_t)ix.n_up * cm::HNSW_MAX_LEVELS * 4, cudaMemcpyDeviceToHost));
+    }
+    int64_t pair = 0, e = 0, u = 0;
+    if (edge_off) edge_off[0] = 0;
+    for (int64_t i = 0; i < ix.n; i++) {
+        int L = ix.levels_host[(size_t)i];
+        if (levels) levels[i] = L;
+        for (int l = 0; l <= L; l++) {
+            int deg = l == 0 ? d0[(size_t)i] : dU[(size_t)u * cm::HNSW_MAX_LEVELS + l];
+            const uint32_t *src = l == 0 ? &a0[(size_t)i * ix.E0] : &aU[((size_t)u * cm::HNSW_MAX_LEVELS + l) * ix.EU];
+            for (int j = 0; j < deg; j++) edge_ids[e++] = hid[src[j]];
+            edge_off[++pair] = e;
+        }
+        if (L > 0) u++;
+    }
+    if (entry_id) *entry_id = hid[(size_t)ix.entry_slot];
     return CM_OK;
 }
 

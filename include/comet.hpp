@@ -427,18 +427,26 @@ inline std::unique_ptr<IVFPQIndex> NewIVFPQIndex(int dim, DistanceKind kind, int
     return std::make_unique<IVFPQIndex>(dim, kind, nlist, m, nbits);
 }
 
-// ---- HNSWIndex (hnsw_index.go): search on the device; the graph is built by the host package's own
-// insertNode (hnsw_index.go:493-552) and uploaded -- device-side insertion is the next row. ----
+// ---- HNSWIndex (hnsw_index.go): insertion and search on the device; LoadGraph restores a serialised graph ----
 class HNSWIndex : public VectorIndex {
 public:
     HNSWIndex(int dim, comet::DistanceKind kind, int m, int efConstruction, int efSearch) : VectorIndex(dim, kind) {
         check(cm_hnsw_create(dim, (int)kind, m, efConstruction, efSearch, &h_));
+        m_ = m > 0 ? m : 16;
     }
     ~HNSWIndex() override { cm_hnsw_destroy(h_); }
     void Train(const std::vector<VectorNode> &) override {}                                       // hnsw_index.go:215: no-op
-    void Add(VectorNode) override {
-        throw Error(CM_ERR_UNSUPPORTED, "HNSW insertion is not on the device path yet: build the graph with the host package and LoadGraph it");
+    // hnsw_index.go:228-288.  The level is drawn like randomLevel (:474-484: geometric, p = 1/M, capped at 16) from this
+    // index's own generator (the reference uses the unseeded global math/rand/v2; seed with SetLevelSeed for replays).
+    void Add(VectorNode v) override { AddWithLevel(v, randomLevel()); }
+    void AddWithLevel(VectorNode v, int level) {
+        checkDim(v);
+        uint32_t id = v.ID();
+        int32_t lv = level;
+        check(cm_hnsw_add(h_, &id, v.Vector().data(), &lv, 1, 1));
+        remember(v);
     }
+    void SetLevelSeed(uint64_t seed) { rng_state_ = seed ? seed : 0x9E3779B97F4A7C15ull; }
     // nodes in insertion order with their STORED vectors; edges per (node, layer) as neighbour IDs
     void LoadGraph(const std::vector<VectorNode> &nodes, const std::vector<int32_t> &levels, const std::vector<int64_t> &edge_off,
                    const std::vector<uint32_t> &edge_ids, uint32_t entry_id, int max_level) {
@@ -461,6 +469,19 @@ protected:
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_hnsw_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data(), nullptr));
     }
+    int randomLevel() {
+        int m = m_ > 0 ? m_ : 16, level = 0;
+        const double p = 1.0 / (double)m;
+        for (;;) {
+            rng_state_ ^= rng_state_ << 13; rng_state_ ^= rng_state_ >> 7; rng_state_ ^= rng_state_ << 17;   // xorshift64
+            double u = (double)(rng_state_ >> 11) * (1.0 / 9007199254740992.0);
+            if (!(u < p) || level >= 16) break;
+            level++;
+        }
+        return level;
+    }
+    int m_ = 16;
+    uint64_t rng_state_ = 0x9E3779B97F4A7C15ull;
     cm_hnsw *h_ = nullptr;
 };
 inline std::unique_ptr<HNSWIndex> NewHNSWIndex(int dim, DistanceKind kind, int m, int efConstruction, int efSearch) {   // hnsw_index.go:172

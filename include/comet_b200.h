@@ -263,6 +263,18 @@ int cm_hnsw_ef_search(const cm_hnsw *h);
  * pairs ordered by (slot, layer 0..level); edge_ids are neighbour node IDs in the reference's edge order. */
 int cm_hnsw_load_graph(cm_hnsw *h, int64_t n, const uint32_t *ids, const float *rows, const int32_t *levels,
                        const int64_t *edge_off, const uint32_t *edge_ids, uint32_t entry_id, int max_level);
+/* n successive HNSWIndex.Add calls ON THE DEVICE (hnsw_index.go:228-288 + insertNode / selectNeighbors /
+ * pruneConnections, :493-552, 637-694): PreprocessInPlace (rows written back unless writeback == 0), then the
+ * insertion with the caller's level draws (randomLevel, :474-484, stays with the caller: the reference draws
+ * from an unseeded global RNG).  IDs must be non-zero and new.  The graph is bit-identical to a sequential
+ * replay of the reference with the same levels. */
+int cm_hnsw_add(cm_hnsw *h, const uint32_t *ids, float *rows, const int32_t *levels, int64_t n, int writeback);
+int cm_hnsw_max_level(const cm_hnsw *h);
+/* the graph back to the host (HNSWIndex.WriteTo): levels[n]; edge_off[sum(levels+1)+1] and edge_ids
+ * [cm_hnsw_edge_count()] in the layout cm_hnsw_load_graph takes */
+int64_t cm_hnsw_edge_count(const cm_hnsw *h);
+int cm_hnsw_export_graph(const cm_hnsw *h, int32_t *levels, int64_t *edge_off, uint32_t *edge_ids, uint32_t *entry_id,
+                         int *max_level);
 int cm_hnsw_remove(cm_hnsw *h, uint32_t id);                         /* soft delete, hnsw_index.go:300-330 */
 /* nq independent searchSingleQuery calls (hnsw_index_search.go:248-354 + searchLayer hnsw_index.go:565-629);
  * p->ef_search as WithEfSearch.  out_stride >= min(k, ef, n).  out_work (optional, nq x 2): distance

@@ -113,6 +113,19 @@ static void test_trained_indexes() {
     EXPECT(throws([&] { NewIVFIndex(4, 50, Euclidean)->Train(nodes); NewIVFIndex(4, 500, Euclidean)->Train(nodes); }, "need at least 500"));
 }
 
+static void test_hnsw() {
+    // hnsw_index_search_test.go:123-203 style: after Add, the exact match ranks first
+    auto idx = NewHNSWIndex(4, Euclidean, 4, 20, 20);
+    idx->SetLevelSeed(7);
+    std::vector<VectorNode> nodes;
+    for (int i = 0; i < 20; i++) nodes.push_back(NewVectorNodeWithID((uint32_t)(i + 1), {(float)i, (float)(i % 3), (float)(i % 5), 1.0f}));
+    for (auto &n : nodes) idx->Add(n);
+    EXPECT(idx->Len() == 20 && idx->Kind() == "hnsw");
+    auto r = idx->NewSearch()->WithQuery({nodes[2].Vector()}).WithK(3).Execute();
+    EXPECT(r.size() == 3 && r[0].GetId() == 3 && r[0].Score == 0.0f);
+    EXPECT(throws([&] { idx->NewSearch()->WithQuery({{1, 2}}).Execute(); }, "query dimension mismatch: expected 4, got 2"));
+}
+
 int main(int argc, char **argv) {
     bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
     test_limiter_and_aggregation();
@@ -122,6 +135,7 @@ int main(int argc, char **argv) {
     } else {
         test_flat();
         test_trained_indexes();
+        test_hnsw();
     }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
     return failures ? 1 : 0;

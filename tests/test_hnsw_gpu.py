@@ -7,7 +7,7 @@ import pytest
 
 from comet_b200 import capi
 from oracle import oracle_py as O
-from tests.parity import assert_same_results
+from tests.parity import assert_same_results, bits
 
 pytestmark = pytest.mark.gpu
 
@@ -74,3 +74,51 @@ def test_hnsw_empty_and_errors():
         g.search(np.ones((1, 9), np.float32), k=1)
     assert e.value.code == capi.ERR_DIM_MISMATCH
     assert capi.HNSWIndex(8, capi.L2, 0, 0, 0).ef_search() == 200   # hnsw_index.go:178-190 defaults
+
+
+def oracle_flat_graph(o):
+    """(slot, layer)-ordered neighbour-ID lists of the oracle's graph, as cm_hnsw_export_graph lays them out."""
+    eids, elev, erows, layers = o.export()
+    off = [0]
+    chunks = []
+    for s in range(len(eids)):
+        for layer in range(int(elev[s]) + 1):
+            lo, nb = layers[layer]
+            seg = nb[lo[s]:lo[s + 1]]
+            chunks.append(seg)
+            off.append(off[-1] + len(seg))
+    flat = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+    return elev, np.asarray(off, np.int64), flat.astype(np.uint32)
+
+
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_hnsw_device_insertion_builds_the_oracles_graph(metric):
+    # SURVEY 8f N1: HNSWIndex.Add / insertNode / selectNeighbors / pruneConnections on the device, same level draws
+    rng = np.random.default_rng(31 + metric)
+    n, d, m, efc = 1200, 24, 6, 40
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    levels = O.hnsw_random_levels(n, m, 5)
+    levels[0] = 1
+    o = O.HNSW(d, metric, m, efc, 50)
+    o.add(ids, x.copy(), levels)
+    g = capi.HNSWIndex(d, metric, m, efc, 50)
+    xg = x.copy()
+    for a, b in [(0, 1), (1, 400), (400, 401), (401, n)]:          # several Add batches, incl. single nodes
+        g.add(ids[a:b], xg[a:b], levels[a:b])
+    assert len(g) == n and g.max_level() == o.max_level
+    if metric == capi.COSINE:                                       # Add normalised the caller's rows in place
+        assert np.array_equal(bits(xg), bits(np.stack([O.normalize(r) for r in x])))
+    glev, goff, gids, gentry, gml = g.export_graph()
+    olev, ooff, oflat = oracle_flat_graph(o)
+    assert gentry == o.entry_point and gml == o.max_level
+    assert np.array_equal(glev, olev)
+    assert np.array_equal(goff, ooff), "degrees differ"
+    assert np.array_equal(gids, oflat), "edges differ"
+    q = rng.standard_normal((11, d)).astype(np.float32)
+    check(g, o, q, 10)
+    check(g, o, q, 5, ef=30)
+    with pytest.raises(capi.CometError):
+        g.add([5], x[:1].copy(), [0])                               # duplicate ID
+    with pytest.raises(capi.CometError):
+        g.add([0], x[:1].copy(), [0])                               # ID 0 is reserved
