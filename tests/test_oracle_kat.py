@@ -414,3 +414,33 @@ def test_hnsw_reference_efsearch_recall_test():
     lo, _ = h.search(x[0], k=10, ef_search=10)
     hi, hs = h.search(x[0], k=10, ef_search=100)
     assert len(lo) > 0 and len(hi) > 0 and hi[0] == 1 and hs[0] == 0.0
+
+
+def test_golden_reference_kats_file():
+    """tests/golden/reference_kats.json (literals transcribed from the reference's tests) replayed on the oracle."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")
+    with open(path) as f:
+        kats = json.load(f)
+    codes = {"l2": 0, "l2_squared": 1, "cosine": 2}
+    for c in kats["distance"]:
+        got = O.distance(codes[c["metric"]], np.asarray(c["a"], np.float32), np.asarray(c["b"], np.float32))
+        assert abs(got - c["want"]) <= c["tol"], c
+    for c in kats["normalize"]:
+        if "error" in c:
+            with pytest.raises(Exception):
+                O.normalize(np.asarray(c["in"], np.float32))
+        else:
+            assert np.allclose(O.normalize(np.asarray(c["in"], np.float32)), c["want"], atol=c["tol"])
+    for c in kats["sanitize_k"]:
+        assert O.sanitize_k(c["k"], c["max"]) == c["want"], c
+    for c in kats["flat_search"]:
+        o = O.Flat(3, codes[c["metric"]])
+        for id_, row in c["rows"].items():
+            o.add([int(id_)], np.asarray([row], np.float32))
+        ids, sc = o.search(np.asarray(c["query"], np.float32), k=c["k"])
+        if "want_ids" in c:
+            assert ids.tolist() == c["want_ids"] and sc.tolist() == c["want_scores"]
+        else:
+            assert ids[0] == c["want_first_id"] and sc[0] == c["want_first_score"]
