@@ -12,12 +12,13 @@
 //   codes     u8  [cap][M]      arrival order;  ids u32 [cap];  deleted u8 [cap]
 //   IVFPQ adds: coarse FlatIndex of the nlist centroids (raw), members u32 [n] (store positions
 //   grouped by list, CSR) and list_off i64 [nlist+1].
-// One kernel, adc_scan_kernel, serves both: a CTA owns one (query, probe) pair and up to ADC_CHUNK
-// of its codes; it builds the pair's LUT in shared memory straight from the codebooks (only the
+// One kernel, adc_scan_kernel, serves both: a CTA owns one (query, probe) pair and a slice of its
+// codes; it builds the pair's LUT in shared memory straight from the codebooks (only the
 // 256 entries per sub-quantiser a uint8 code can address, pq_index.go:469), scans, and keeps its
 // K best keys (score, candidate number).  merge_topk_kernel + adc_emit_kernel finish the query.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -32,7 +33,7 @@
 namespace cm {
 
 static constexpr int ADC_THREADS = 256;
-static constexpr int ADC_CHUNK = 4096;      // codes per CTA
+static constexpr int ADC_CHUNK = 4096;      // fewest codes a CTA is given when a pair is sliced
 
 struct CodeStore {
     int M = 0;
@@ -200,19 +201,35 @@ __global__ void pq_encode_kernel(const float *__restrict__ rows, int ld, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// ADC scan.  blockIdx.y = pair = query * nprobes + probe, blockIdx.x = chunk of the pair's codes.
+// ADC scan.  blockIdx.y = pair = query * nprobes + probe, blockIdx.x = slice of the pair's codes.
 //   members == nullptr (PQ): the pair's codes are store positions [0, n), candidate number = position
 //   else (IVFPQ): list l = probe_list[pair]; codes at members[list_off[l] + j]; candidate number =
 //   q_off[query][probe] + j (the order of the reference's append loop)
+// A CTA builds the pair's table ONCE and then walks its whole slice of the codes (slices are sized on
+// the host so that a launch has a few waves of CTAs: 1M codes x 128 queries is 10 slices per query,
+// not 245 rebuilds of the same table).  The walk is in rounds of R code rows per thread: all R x MW
+// 16-byte code loads of a round are issued together (the rows of the NEXT round were prefetched to
+// L2 a round earlier, list positions two rounds earlier), the R table-sum chains are interleaved
+// (each chain is the reference's sequential m = 0..M-1 order), and the CTA meets at ONE barrier per
+// round, which also decides whether the candidate buffer must be compacted.
+//   MW = M / 16 (code bytes per row in 16-byte words) or 0 for the generic byte-wise path.
 // ------------------------------------------------------------------------------------------------
-template <bool FMA>
-__global__ void __launch_bounds__(ADC_THREADS) adc_scan_kernel(
+template <int MW> struct AdcRows { static constexpr int R = MW == 0 ? 1 : (MW <= 4 ? 4 : (MW <= 6 ? 3 : 2)); };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <bool FMA, int MW>
+__global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     const float *__restrict__ queries, int ld, int dim, int M, int Ksub, int dsub, int lut_n,
     const float *__restrict__ codebooks, const uint8_t *__restrict__ codes, long long n_store,
     const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
     const long long *__restrict__ q_off, const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
-    int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C, int n_chunks,
+    int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C, int n_slices,
     uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    constexpr int R = AdcRows<MW>::R;
+    constexpr int T = ADC_THREADS;
     extern __shared__ __align__(16) uint8_t smem[];
     float *lut = reinterpret_cast<float *>(smem);                       // [M][lut_n]
     float *res = lut + (size_t)M * lut_n;                               // [dim] query (residual)
@@ -235,83 +252,169 @@ __global__ void __launch_bounds__(ADC_THREADS) adc_scan_kernel(
         len = n_store;
         order0 = 0;
     }
-    const long long c0 = (long long)blockIdx.x * ADC_CHUNK;
-    const size_t part = (size_t)pair * n_chunks + blockIdx.x;
+    // this CTA's slice [c0, c1): equal shares of the pair's codes, rounded up to whole rounds
+    long long per = (len + n_slices - 1) / n_slices;
+    per = (per + (long long)R * T - 1) / ((long long)R * T) * ((long long)R * T);
+    const long long c0 = (long long)blockIdx.x * per;
+    const size_t part = (size_t)pair * n_slices + blockIdx.x;
     if (c0 >= len) return;                                              // part_counts was zeroed by the host
+    const long long c1 = min(len, c0 + per);
     if (tid == 0) { cnt = 0; tau = KEY_INF; }
     // query residual (ivfpq_index_search.go:285-296) or the query itself
-    for (int j = tid; j < dim; j += ADC_THREADS) {
+    for (int j = tid; j < dim; j += T) {
         float v = queries[(size_t)q * ld + j];
         res[j] = centroids ? __fsub_rn(v, centroids[(size_t)list * cld + j]) : v;
     }
     __syncthreads();
     // lookup table in the reference's summation order
-    for (int e = tid; e < M * lut_n; e += ADC_THREADS) {
-        int m = e / lut_n, c = e - m * lut_n;
-        const float *cb = codebooks + ((size_t)m * Ksub + c) * dsub;
-        const float *r = res + (size_t)m * dsub;
-        float dist = 0.0f;
-        if ((dsub & 3) == 0) {                       // 16-byte codebook loads; same summation order
-            const float4 *cb4 = reinterpret_cast<const float4 *>(cb);
-            for (int j = 0; j < dsub / 4; j++) {
-                float4 v = __ldg(cb4 + j);
-                dist = l2_step<FMA>(dist, r[4 * j + 0], v.x);
-                dist = l2_step<FMA>(dist, r[4 * j + 1], v.y);
-                dist = l2_step<FMA>(dist, r[4 * j + 2], v.z);
-                dist = l2_step<FMA>(dist, r[4 * j + 3], v.w);
+    if (dsub == 8 && lut_n == T) {
+        // thread = table column c, four sub-quantisers in flight (independent chains); the residual
+        // piece is a shared-memory broadcast, the codebook row a coalesced 32-byte load
+        const float4 *cb4 = reinterpret_cast<const float4 *>(codebooks) + (size_t)tid * 2;
+        const size_t m_stride4 = (size_t)Ksub * 2;
+        int m = 0;
+        for (; m + 4 <= M; m += 4) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                a[u] = __ldg(cb4 + (size_t)(m + u) * m_stride4);
+                b[u] = __ldg(cb4 + (size_t)(m + u) * m_stride4 + 1);
             }
-        } else {
-            for (int j = 0; j < dsub; j++) dist = l2_step<FMA>(dist, r[j], cb[j]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float4 r0 = *reinterpret_cast<const float4 *>(res + (m + u) * 8);
+                const float4 r1 = *reinterpret_cast<const float4 *>(res + (m + u) * 8 + 4);
+                float d = 0.0f;
+                d = l2_step<FMA>(d, r0.x, a[u].x); d = l2_step<FMA>(d, r0.y, a[u].y);
+                d = l2_step<FMA>(d, r0.z, a[u].z); d = l2_step<FMA>(d, r0.w, a[u].w);
+                d = l2_step<FMA>(d, r1.x, b[u].x); d = l2_step<FMA>(d, r1.y, b[u].y);
+                d = l2_step<FMA>(d, r1.z, b[u].z); d = l2_step<FMA>(d, r1.w, b[u].w);
+                lut[(m + u) * T + tid] = d;
+            }
         }
-        lut[e] = dist;
-    }
-    __syncthreads();
-    const long long c1 = min(len, c0 + ADC_CHUNK);
-    for (long long cbase = c0; cbase < c1; cbase += ADC_THREADS) {
-        long long j = cbase + tid;
-        bool live = j < c1;
-        uint32_t pos = 0;
-        float dist = 0.0f;
-        if (live) {
-            pos = mem ? mem[j] : (uint32_t)j;
-            const uint8_t *code = codes + (size_t)pos * M;
-            float sum = 0.0f;
-            if ((M & 15) == 0) {                     // 16 codes per load; table sums stay in sub-quantiser order
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(code);
-                const float *lp = lut;
-                for (int w = 0; w < M / 16; w++) {
-                    uint4 v = __ldg(c4 + w);
-                    uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            sum = __fadd_rn(sum, lp[(wd[t] >> (8 * b)) & 0xffu]);
-                            lp += lut_n;
-                        }
-                    }
+        for (; m < M; m++) {
+            const float4 a = __ldg(cb4 + (size_t)m * m_stride4), b = __ldg(cb4 + (size_t)m * m_stride4 + 1);
+            const float4 r0 = *reinterpret_cast<const float4 *>(res + m * 8);
+            const float4 r1 = *reinterpret_cast<const float4 *>(res + m * 8 + 4);
+            float d = 0.0f;
+            d = l2_step<FMA>(d, r0.x, a.x); d = l2_step<FMA>(d, r0.y, a.y);
+            d = l2_step<FMA>(d, r0.z, a.z); d = l2_step<FMA>(d, r0.w, a.w);
+            d = l2_step<FMA>(d, r1.x, b.x); d = l2_step<FMA>(d, r1.y, b.y);
+            d = l2_step<FMA>(d, r1.z, b.z); d = l2_step<FMA>(d, r1.w, b.w);
+            lut[m * T + tid] = d;
+        }
+    } else {
+        for (int e = tid; e < M * lut_n; e += T) {
+            int m = e / lut_n, c = e - m * lut_n;
+            const float *cb = codebooks + ((size_t)m * Ksub + c) * dsub;
+            const float *r = res + (size_t)m * dsub;
+            float dist = 0.0f;
+            if ((dsub & 3) == 0) {                       // 16-byte codebook loads; same summation order
+                const float4 *cb4 = reinterpret_cast<const float4 *>(cb);
+                for (int j = 0; j < dsub / 4; j++) {
+                    float4 v = __ldg(cb4 + j);
+                    dist = l2_step<FMA>(dist, r[4 * j + 0], v.x);
+                    dist = l2_step<FMA>(dist, r[4 * j + 1], v.y);
+                    dist = l2_step<FMA>(dist, r[4 * j + 2], v.z);
+                    dist = l2_step<FMA>(dist, r[4 * j + 3], v.w);
                 }
             } else {
-                for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+                for (int j = 0; j < dsub; j++) dist = l2_step<FMA>(dist, r[j], cb[j]);
             }
-            dist = __fsqrt_rn(sum);
-            if (skip != nullptr && skip[pos]) live = false;
-            if (threshold > 0.0f && dist > threshold) live = false;
-        }
-        // selection: append below the running bound, compact when the buffer may overflow
-        bar.sync();
-        bool need = cnt > C - ADC_THREADS;
-        bar.sync();
-        if (need) compact_topk(buf, C, K, &cnt, &tau, tid, ADC_THREADS, bar);
-        if (live) {
-            uint64_t key = make_key(dist, (uint32_t)(order0 + j));
-            if (key < tau) buf[atomicAdd(&cnt, 1)] = key;
+            lut[e] = dist;
         }
     }
-    compact_topk(buf, C, K, &cnt, &tau, tid, ADC_THREADS, bar);
+    __syncthreads();
+
+    const int limit = C - R * T;              // appends of one round always fit above this fill
+    // list positions: this round's and the next round's are in registers, those two rounds ahead in flight
+    uint32_t pos_cur[R], pos_nxt[R];
+    auto load_pos = [&](long long base, uint32_t (&out)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            long long j = base + (long long)r * T + tid;
+            out[r] = j < c1 ? (mem ? __ldg(mem + j) : (uint32_t)j) : 0u;
+        }
+    };
+    load_pos(c0, pos_cur);
+    load_pos(c0 + (long long)R * T, pos_nxt);
+    for (long long base = c0; base < c1; base += (long long)R * T) {
+        uint32_t pos_nn[R];
+        load_pos(base + 2ll * R * T, pos_nn);
+        bool live[R];
+        float dist[R];
+        if (MW > 0) {
+            uint32_t wd[R][MW > 0 ? MW * 4 : 1];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                live[r] = base + (long long)r * T + tid < c1;
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(codes + (size_t)pos_cur[r] * M);
+#pragma unroll
+                for (int w = 0; w < MW; w++) {
+                    uint4 v = __ldg(c4 + w);           // dead rows read row 0: harmless, never emitted
+                    wd[r][w * 4 + 0] = v.x; wd[r][w * 4 + 1] = v.y; wd[r][w * 4 + 2] = v.z; wd[r][w * 4 + 3] = v.w;
+                }
+            }
+            // next round's rows towards L2 while this round computes
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (base + (long long)(R + r) * T + tid < c1) {
+                    const uint8_t *p = codes + (size_t)pos_nxt[r] * M;
+                    prefetch_l2(p);
+                    prefetch_l2(p + MW * 16 - 1);
+                }
+            }
+            float sum[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) sum[r] = 0.0f;
+            const float *lp = lut;
+#pragma unroll
+            for (int w = 0; w < MW * 4; w++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) sum[r] = __fadd_rn(sum[r], lp[(wd[r][w] >> (8 * b)) & 0xffu]);
+                    lp += lut_n;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) dist[r] = __fsqrt_rn(sum[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                live[r] = base + (long long)r * T + tid < c1;
+                const uint8_t *code = codes + (size_t)pos_cur[r] * M;
+                float sum = 0.0f;
+                if (live[r])
+                    for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+                dist[r] = __fsqrt_rn(sum);
+            }
+        }
+        // selection: append below the running bound; one barrier per round decides on compaction
+        int top = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            bool ok = live[r];
+            if (ok && skip != nullptr && skip[pos_cur[r]]) ok = false;
+            if (ok && threshold > 0.0f && dist[r] > threshold) ok = false;
+            if (ok) {
+                uint64_t key = make_key(dist[r], (uint32_t)(order0 + base + (long long)r * T + tid));
+                if (key < tau) {
+                    int slot = atomicAdd(&cnt, 1);
+                    buf[slot] = key;
+                    top = max(top, slot + 1);
+                }
+            }
+        }
+        // the thread that took the highest slot sees the final fill, so the OR is exact
+        if (__syncthreads_or(top > limit)) compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+#pragma unroll
+        for (int r = 0; r < R; r++) { pos_cur[r] = pos_nxt[r]; pos_nxt[r] = pos_nn[r]; }
+    }
+    compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
     int mcount = cnt;
     uint64_t *dst = part_keys + part * K;
-    for (int i = tid; i < mcount; i += ADC_THREADS) dst[i] = buf[i];
+    for (int i = tid; i < mcount; i += T) dst[i] = buf[i];
     if (tid == 0) part_counts[part] = mcount;
 }
 
@@ -452,33 +555,49 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     CM_TRY(build_skip(S, p, &skip, &skip_buf, &filt_dev, st));
 
     const int K = (int)k_eff;
-    int C = next_pow2(K + 2 * ADC_THREADS);
+    // code bytes per row in 16-byte words -> kernel variant and rows per thread per round
+    int MW = ((ix.M & 15) == 0 && (ix.M / 16 == 1 || ix.M / 16 == 2 || ix.M / 16 == 4 || ix.M / 16 == 6 || ix.M / 16 == 8)) ? ix.M / 16 : 0;
+    if (const char *e = getenv("COMET_B200_ADC_GENERIC")) if (atoi(e)) MW = 0;
+    const int R = MW == 0 ? 1 : (MW <= 4 ? 4 : (MW <= 6 ? 3 : 2));
+    int C = next_pow2(K + R * ADC_THREADS);         // a round's appends always fit above a compacted buffer
     if (C < 1024) C = 1024;
     const int lut_n = ix.lut_entries();
     size_t smem = (size_t)ix.M * lut_n * 4 + (size_t)((ix.dim + 3) & ~3) * 4 + (size_t)C * 8;
     if (smem > max_smem_optin())
         return fail(CM_ERR_UNSUPPORTED, "M=%d x %d table entries + k=%d do not fit shared memory", ix.M, lut_n, K);
-    const int n_chunks = (int)std::max<int64_t>(1, (max_len + ADC_CHUNK - 1) / ADC_CHUNK);
-    const int64_t parts = (int64_t)nprobes * n_chunks;              // per query
+    // slices per pair: enough CTAs for a few waves (two CTAs per SM), but never so many that a CTA
+    // builds its table for less than one chunk of codes
+    int64_t n_slices = (8ll * sm_count() + nq * nprobes - 1) / (nq * nprobes);
+    n_slices = std::max<int64_t>(1, std::min<int64_t>(n_slices, (max_len + ADC_CHUNK - 1) / ADC_CHUNK));
+    if (const char *e = getenv("COMET_B200_ADC_SLICES")) n_slices = std::max<int64_t>(1, atoll(e));
+    const int64_t parts = (int64_t)nprobes * n_slices;              // per query
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 29) / (parts * K * 8)));
     if (qgroup * nprobes > 65535) qgroup = std::max<int64_t>(1, 65535 / nprobes);   // grid.y limit
     uint64_t *pk = nullptr;
     int *pc = nullptr;
     CM_TRY(ws_alloc((void **)&pk, (size_t)qgroup * parts * K * 8, st));
     CM_TRY(ws_alloc((void **)&pc, (size_t)qgroup * parts * 4, st));
-    auto kern = fma ? adc_scan_kernel<true> : adc_scan_kernel<false>;
+    using AdcKernel = void (*)(const float *, int, int, int, int, int, int, const float *, const uint8_t *, long long,
+                               const float *, int, const long long *, const long long *, const long long *, const uint32_t *,
+                               int, const uint8_t *, float, int, int, int, uint64_t *, int *);
+    AdcKernel kern = nullptr;
+#define CM_ADC_CASE(W) case W: kern = fma ? adc_scan_kernel<true, W> : adc_scan_kernel<false, W>; break;
+    switch (MW) {
+        CM_ADC_CASE(0) CM_ADC_CASE(1) CM_ADC_CASE(2) CM_ADC_CASE(4) CM_ADC_CASE(6) CM_ADC_CASE(8)
+    }
+#undef CM_ADC_CASE
     CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
         CM_CUDA(cudaMemsetAsync(pc, 0, (size_t)m * parts * 4, st));
-        dim3 grid((unsigned)n_chunks, (unsigned)(m * nprobes));
+        dim3 grid((unsigned)n_slices, (unsigned)(m * nprobes));
         {
             ProfScope prof(CM_PROF_PQ_SCAN, st);
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
                                                   ix.codebooks, S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
                                                   ix.coarse.ld, ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
                                                   ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
-                                                  ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, n_chunks, pk, pc);
+                                                  ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, (int)n_slices, pk, pc);
             count_launch();
             CM_CUDA(cudaGetLastError());
         }

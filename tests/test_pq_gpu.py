@@ -127,3 +127,33 @@ def test_ivfpq_m96_dim768_and_delete_flush():
     o.flush()
     assert len(g) == o.total()
     check_ivfpq(g, o, q, 100, 16)
+
+
+# The ADC kernel has one variant per code-row width (M / 16 sixteen-byte words, each with its own number
+# of rows per thread per round) plus a byte-wise generic one; a pair's codes are cut into slices when a
+# launch would otherwise have too few CTAs.  Every variant, several rounds, compaction and slicing:
+@pytest.mark.parametrize("d,M,nbits", [(64, 16, 8), (64, 32, 8), (128, 64, 8), (256, 128, 8), (96, 48, 8), (64, 16, 6)])
+def test_pq_every_code_width_sliced_scan(d, M, nbits):
+    g, o, rng = pq_pair(21000, d, capi.L2, M, nbits, 300 + M + nbits)
+    assert np.array_equal(g.codes(), o.codes())
+    q = rng.standard_normal((3, d)).astype(np.float32)
+    check_pq(g, o, q, 100)
+    check_pq(g, o, q[:2], 700)          # k above one round's appends: bigger candidate buffer
+    check_pq(g, o, q[:1], 40, filter_ids=np.arange(3, 21000, 11, dtype=np.uint32))
+
+
+def test_pq_m96_many_rounds_one_table_per_slice():
+    g, o, rng = pq_pair(30000, 768, capi.L2, 96, 8, 11)
+    q = rng.standard_normal((4, 768)).astype(np.float32)
+    check_pq(g, o, q, 100)
+
+
+def test_ivfpq_sliced_lists(monkeypatch):
+    g, o, rng, _ = ivfpq_pair(9000, 64, capi.L2, 2, 16, 8, 123)
+    q = rng.standard_normal((5, 64)).astype(np.float32)
+    for slices in ("1", "3", "7"):
+        monkeypatch.setenv("COMET_B200_ADC_SLICES", slices)
+        check_ivfpq(g, o, q, 60, 2)
+        check_ivfpq(g, o, q[:2], 0, 1)
+    monkeypatch.setenv("COMET_B200_ADC_GENERIC", "1")
+    check_ivfpq(g, o, q, 60, 2)

@@ -25,14 +25,100 @@ def timed(fn, reps=5):
     return (time.perf_counter() - t0) / reps
 
 
+def full_size(args):
+    """BASELINE.json configs[2] and configs[3] at their full sizes.  Rows are generated on the GPU with torch
+    (plumbing: a host numpy generator would dominate the box time) and handed to the C ABI's host entry points
+    in slabs, exactly like a caller that streams its corpus in."""
+    import torch
+    out = {}
+    d, nq = 768, 512
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(20261017)
+    only = set(args.only.split(","))
+
+    def blobs(centers, m):
+        idx = torch.randint(0, centers.shape[0], (m,), generator=g, device=dev)
+        return (centers[idx] + torch.randn((m, d), generator=g, device=dev)).cpu().numpy()
+
+    if "c3" in only:
+        n, nlist, nprobe, M = args.c3_n, 4096, 32, 96
+        centers = torch.randn((8192, d), generator=g, device=dev) * 2.0
+        ix = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
+        t0 = time.perf_counter(); ix.train(blobs(centers, nlist * 16)); t_train = time.perf_counter() - t0
+        t_add = 0.0
+        slab = 500_000
+        for s0 in range(0, n, slab):
+            m = min(slab, n - s0)
+            x = blobs(centers, m)
+            t0 = time.perf_counter()
+            ix.add(np.arange(s0 + 1, s0 + m + 1, dtype=np.uint32), x, writeback=False)
+            t_add += time.perf_counter() - t0
+            del x
+        q = blobs(centers, nq)
+        L = capi.lib()
+        L.cm_profile_reset(); L.cm_profile_enable(1)
+        dt = timed(lambda: ix.search(q, k=100, nprobes=nprobe), reps=5)
+        L.cm_profile_enable(0)
+        scan_ms, scan_n = capi.profile_get(capi.PROF_PQ_SCAN)
+        scanned = L.cm_ivfpq_last_scanned(ix.h) / nq
+        per = scan_ms / max(scan_n, 1) * 1e-3
+        out["c3_ivfpq"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "nq": nq,
+                           "train_s": t_train, "add_s": t_add, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3,
+                           "scanned_per_query": scanned, "adc_kernel_ms": per * 1e3,
+                           "adc_lookups_per_s": nq * scanned * M / per, "adc_code_GBps": nq * scanned * (M + 4) / per / 1e9,
+                           "lut_builds_per_s": nq * nprobe / per}
+        # single query latency (the reference's Execute() shape)
+        dt1 = timed(lambda: ix.search(q[:1], k=100, nprobes=nprobe), reps=20)
+        out["c3_ivfpq"]["ms_single_query"] = dt1 * 1e3
+        del ix
+        print(json.dumps(out), file=sys.stderr, flush=True)
+    if "c4" in only:
+        hn = args.c4_n
+        ids = np.arange(1, hn + 1, dtype=np.uint32)
+        Wk = torch.randn((24, d), generator=g, device=dev)
+        xk = (torch.randn((hn, 24), generator=g, device=dev) @ Wk).cpu().numpy()
+        qk = (torch.randn((nq, 24), generator=g, device=dev) @ Wk).cpu().numpy()
+        flat = capi.FlatIndex(d, capi.L2)
+        flat.add(ids, xk.copy())
+        nbr = np.zeros((hn, 32), np.uint32)
+        t0 = time.perf_counter()
+        for s0 in range(0, hn, 16384):
+            gi, _, _ = flat.search(xk[s0:s0 + 16384], k=33)
+            nbr[s0:s0 + 16384] = gi[:, 1:33]
+        t_knn = time.perf_counter() - t0
+        ti, _, _ = flat.search(qk, k=10)
+        del flat
+        levels = np.zeros(hn, np.int32)
+        off = np.arange(hn + 1, dtype=np.int64) * 32
+        gidx = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
+        gidx.load_graph(ids, xk, levels, [(off, nbr.ravel())], 1, 0)
+        res = {}
+
+        def run_knn():
+            res["r"] = gidx.search(qk, k=10, ef_search=128, with_work=True)
+        dt = timed(run_knn)
+        work = res["r"][3]
+        evals = float(work[:, 0].mean())
+        rec = float(np.mean([len(set(res["r"][0][i, :10].tolist()) & set(ti[i].tolist())) / 10 for i in range(nq)]))
+        out["c4_hnsw_knn_graph"] = {"n": hn, "dim": d, "degree": 32, "ef": 128, "k": 10, "nq": nq, "knn_graph_build_s": t_knn,
+                                    "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals,
+                                    "expansions_per_query": float(work[:, 1].mean()),
+                                    "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9, "recall_at_10_vs_flat": rec}
+    print(json.dumps(out, indent=1))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=500_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--nq", type=int, default=512)
     ap.add_argument("--hnsw-n", type=int, default=20_000)
-    ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw")
+    ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw,hnswknn,c3,c4")
+    ap.add_argument("--c3-n", type=int, default=10_000_000, help="rows of the BASELINE configs[2] run (IVFPQ)")
+    ap.add_argument("--c4-n", type=int, default=1_000_000, help="rows of the BASELINE configs[3] run (HNSW)")
     args = ap.parse_args()
+    if args.only in ("c3", "c4", "c3,c4"):
+        return full_size(args)
     only = set(args.only.split(",")) if args.only else {"ivf", "pq", "ivfpq", "hnsw"}
     rng = np.random.default_rng(1)
     n, d, nq = args.n, args.dim, args.nq
