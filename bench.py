@@ -107,7 +107,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop.set()
@@ -180,7 +180,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K},
+        "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K,
+                   "batch_per_gpu": BATCH, "global_batch": BATCH * max(1, args.gpus),
+                   "path": "reference CPU algorithm (C restatement of the Go loops), one query per host thread"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -366,9 +368,10 @@ def run_ours(args):
                                   "select_ms": sel_ms}
 
     # ---- e2e: host buffers through the public C ABI call ---------------------------------------
-    h_ids = np.zeros((nq, K), np.uint32)
-    h_sc = np.zeros((nq, K), np.float32)
-    h_cnt = np.zeros(nq, np.int64)
+    # result buffers in pinned host memory, like the query block: what a caller that cares about PCIe does
+    h_ids = torch.zeros((nq, K), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    h_sc = torch.zeros((nq, K), dtype=torch.float32, pin_memory=True).numpy()
+    h_cnt = torch.zeros((nq,), dtype=torch.int64, pin_memory=True).numpy()
     import ctypes as C
     p, keep = capi.make_params(k=K, path=path)
 
@@ -447,7 +450,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])

@@ -55,6 +55,7 @@ struct GemmPhase {
     int SA, SB;
     int n_tiles;      // tiles in this class
     int dbg;          // debugging aid: 1 = epilogue skips the accumulator scan, 2 = loads TMEM but does not compare
+    int dense;        // 1: (nearly) every score of this phase is a candidate (phase A): emit column by column
 };
 
 __device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
@@ -78,6 +79,22 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int c) {
 #undef CM_PICK
     default: return v[31];
     }
+}
+
+// The same pick as a 5-level select tree: 31 SELs, no divergence.  Used when many lanes of the warp hold a
+// hit in the same pass (the branch tree above then runs once per DISTINCT column, up to 32 times).
+__device__ __forceinline__ uint32_t pick32_sel(const uint32_t (&v)[32], int c) {
+    uint32_t a[16], b[8], d[4], e[2];
+    const bool p0 = (c & 1) != 0, p1 = (c & 2) != 0, p2 = (c & 4) != 0, p3 = (c & 8) != 0, p4 = (c & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = p1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = p2 ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) e[i] = p3 ? d[2 * i + 1] : d[2 * i];
+    return p4 ? e[1] : e[0];
 }
 
 template <int CG, bool HAS_H>
@@ -112,10 +129,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
         for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8 * CG); }
         fence_mbar_init();
     }
+    // fill counts live as [query][region] (region = CTA x lane quadrant): this CTA's four are one int4
     for (int i = tid; i < nq_pad; i += GT_THREADS) {
         g_s[i] = g_bound[i];
-#pragma unroll
-        for (int e = 0; e < 4; e++) cnt_s[e * GT_MAX_NQ + i] = cand_cnt[((size_t)blockIdx.x * 4 + e) * nq_pad + i];
+        const int4 c4 = *reinterpret_cast<const int4 *>(cand_cnt + ((size_t)i * n_cta_total + blockIdx.x) * 4);
+        cnt_s[0 * GT_MAX_NQ + i] = c4.x; cnt_s[1 * GT_MAX_NQ + i] = c4.y;
+        cnt_s[2 * GT_MAX_NQ + i] = c4.z; cnt_s[3 * GT_MAX_NQ + i] = c4.w;
     }
     if (warp == GT_WARP_ALLOC) tc::tmem_alloc<CG>(smem_u32(tmem_slot), 512);
     tc::fence_before_thread_sync();
@@ -240,13 +259,42 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                     mask = __funnelshift_l(__float_as_uint(t3), mask, 1);
                 }
                 uint32_t hits = cur_ok ? ~mask : 0u;       // bit (31 - c) set <=> column c is a candidate
-                while (hits != 0u) {                        // rare; usually one iteration for one or two lanes
-                    const int c = __clz(hits);
-                    hits &= ~(0x80000000u >> c);
-                    const float dot = __uint_as_float(pick32(vv, c));
-                    const int q = qbase + cb * 32 + c;
-                    const int slot = atomicAdd(&cnt_w[q], 1);   // counter private to this lane quadrant
-                    if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, cur_row);
+                if (phase.dense) {
+                    // Phase A: every live (row, query) pair is a candidate.  Column by column: the fill
+                    // count of (query, CTA, quadrant) belongs to this warp alone, so a ballot hands out the
+                    // slots -- the value is a named register (no pick), no atomics, no divergence.
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const bool h = (hits >> (31 - c)) & 1u;
+                        const uint32_t b = __ballot_sync(0xffffffffu, h);
+                        if (b != 0u) {
+                            const int q = qbase + cb * 32 + c;
+                            const int base = cnt_w[q];
+                            const int slot = base + __popc(b & lt_mask);
+                            if (h && slot < cand_slots)
+                                my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - __uint_as_float(vv[c]), cur_row);
+                            if (lane == 0) cnt_w[q] = base + __popc(b);
+                        }
+                    }
+                } else if (__popc(__ballot_sync(0xffffffffu, hits != 0u)) > 3) {
+                    // several lanes hold hits: one pass of this loop serves one hit of EVERY such lane
+                    while (hits != 0u) {
+                        const int c = __clz(hits);
+                        hits &= ~(0x80000000u >> c);
+                        const float dot = __uint_as_float(pick32_sel(vv, c));
+                        const int q = qbase + cb * 32 + c;
+                        const int slot = atomicAdd(&cnt_w[q], 1);   // counter private to this lane quadrant
+                        if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, cur_row);
+                    }
+                } else {
+                    while (hits != 0u) {                        // rare; usually one iteration for one or two lanes
+                        const int c = __clz(hits);
+                        hits &= ~(0x80000000u >> c);
+                        const float dot = __uint_as_float(pick32(vv, c));
+                        const int q = qbase + cb * 32 + c;
+                        const int slot = atomicAdd(&cnt_w[q], 1);   // counter private to this lane quadrant
+                        if (slot < cand_slots) my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - dot, cur_row);
+                    }
                 }
                 __syncwarp();
             }
@@ -259,10 +307,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     // ---- teardown: nobody exits (or frees TMEM) while the peer may still touch this CTA ----
     tc::fence_before_thread_sync();
     if (CG == 2) tc::cluster_sync_all(); else __syncthreads();
-    for (int i = tid; i < nq_pad; i += GT_THREADS) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) cand_cnt[((size_t)blockIdx.x * 4 + e) * nq_pad + i] = cnt_s[e * GT_MAX_NQ + i];
-    }
+    for (int i = tid; i < nq_pad; i += GT_THREADS)
+        *reinterpret_cast<int4 *>(cand_cnt + ((size_t)i * n_cta_total + blockIdx.x) * 4) =
+            make_int4(cnt_s[0 * GT_MAX_NQ + i], cnt_s[1 * GT_MAX_NQ + i], cnt_s[2 * GT_MAX_NQ + i], cnt_s[3 * GT_MAX_NQ + i]);
     if (warp == GT_WARP_ALLOC) {
         tc::fence_after_thread_sync();
         tc::tmem_dealloc<CG>(tmem_base, 512);
@@ -378,27 +425,26 @@ static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv
 // a radix select on (key - min), starting at the highest significant byte; the keys under the new
 // bound tau_K + 2E become the survivors for the next phase (ping-pong list) and the region counters
 // are reset.  After the last phase the survivors ARE the rows to re-score.
-static constexpr int SEL_THREADS = 1024;
-__global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
+static constexpr int SEL_THREADS = 768;     // >= candidate regions per query (4 x SMs); 2 CTAs per SM at <= 42 registers
+__global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
     const uint64_t *__restrict__ cand, int *__restrict__ cand_cnt, int nq_pad, int n_reg, int slots, int K, int dim,
     const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
     int *__restrict__ overflow, const uint64_t *__restrict__ surv_in, const int *__restrict__ surv_in_cnt,
     uint64_t *__restrict__ surv_out, int *__restrict__ surv_out_cnt, int surv_cap, int stage_cap, float e_scale) {
     extern __shared__ __align__(16) uint8_t sel_smem_raw[];
     uint64_t *key_s = reinterpret_cast<uint64_t *>(sel_smem_raw);                 // [stage_cap]
-    int *off_s = reinterpret_cast<int *>(key_s + stage_cap);                      // [n_reg + 1] (n_reg <= SEL_THREADS)
     __shared__ int hist[256];
     __shared__ int warp_tot[SEL_THREADS / 32];
     __shared__ uint32_t s_prefix, s_lo, s_hi;
-    __shared__ int s_rank, s_out, s_ovf;
+    __shared__ int s_rank, s_out, s_ovf, s_total;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_old = surv_in_cnt ? surv_in_cnt[q] : 0;
     if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; s_prefix = 0; s_rank = K; }
     // ---- region counts -> offsets behind the old survivors (block scan), counters reset for the next phase ----
     int c = 0;
     if (tid < n_reg) {
-        c = cand_cnt[(size_t)tid * nq_pad + q];
-        cand_cnt[(size_t)tid * nq_pad + q] = 0;
+        c = cand_cnt[(size_t)q * n_reg + tid];
+        cand_cnt[(size_t)q * n_reg + tid] = 0;
     }
     __syncthreads();
     if (c > slots) s_ovf = 1;
@@ -410,49 +456,58 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int wbase = n_old;
-    for (int w2 = 0; w2 < warp; w2++) wbase += warp_tot[w2];
-    if (tid < n_reg) off_s[tid + 1] = wbase + incl;
-    if (tid == 0) off_s[0] = n_old;
+    {   // exclusive scan of the 32 warp totals by every warp (one shuffle scan instead of a serial loop)
+        int wt = lane < SEL_THREADS / 32 ? warp_tot[lane] : 0, wi = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        const int total_all = __shfl_sync(0xffffffffu, wi, 31);
+        const int wbase = n_old + __shfl_sync(0xffffffffu, wi - wt, warp);
+        incl += wbase;
+        if (tid == 0) s_total = n_old + total_all;
+    }
     __syncthreads();
-    const int total = off_s[n_reg];
+    const int total = s_total;
     if (s_ovf || total > stage_cap) {
         if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; surv_out_cnt[q] = 0; }
         return;
     }
-    // ---- stage: old survivors, then the regions (a warp takes 4 regions at a time, loads before stores) ----
-    for (int i = tid; i < n_old; i += SEL_THREADS) key_s[i] = surv_in[(size_t)q * surv_cap + i];
-    const uint64_t *qcand = cand + (size_t)q * n_reg * slots;
-    for (int r0 = warp * 4; r0 < n_reg; r0 += (SEL_THREADS / 32) * 4) {
-        int o[4], cc[4], mc = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int r = r0 + u;
-            o[u] = r < n_reg ? off_s[r] : 0;
-            cc[u] = r < n_reg ? off_s[r + 1] - o[u] : 0;
-            mc = max(mc, cc[u]);
-        }
-        for (int i = lane; i < mc; i += 32) {
-            uint64_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = i < cc[u] ? __ldg(qcand + (size_t)(r0 + u) * slots + i) : 0ull;
+    // ---- stage: old survivors (all threads), then one region per thread: its keys are contiguous, so all of a
+    // thread's 16-byte loads are in flight together (the regions hold ~15 keys each in phases B and C, 32 in A).
+    // The range of the keys (radix base) is folded into the copy.
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n_old; i += SEL_THREADS) {
+        uint64_t v = surv_in[(size_t)q * surv_cap + i];
+        key_s[i] = v;
+        uint32_t h = (uint32_t)(v >> 32); lo = min(lo, h); hi = max(hi, h);
+    }
+    if (tid < n_reg && c > 0) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(cand + ((size_t)q * n_reg + tid) * slots);
+        uint64_t *dst = key_s + (incl - c);
+        for (int i0 = 0; i0 < c; i0 += 8) {
+            ulonglong2 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (i < cc[u]) key_s[o[u] + i] = v[u];
+                if (i0 + 2 * u < c) v[u] = __ldg(src + (i0 >> 1) + u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 2 * u;
+                if (i < c) { dst[i] = v[u].x; uint32_t h = (uint32_t)(v[u].x >> 32); lo = min(lo, h); hi = max(hi, h); }
+                if (i + 1 < c) { dst[i + 1] = v[u].y; uint32_t h = (uint32_t)(v[u].y >> 32); lo = min(lo, h); hi = max(hi, h); }
+            }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
     __syncthreads();
     float bound = INFINITY;
     if (total >= K) {
-        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-        for (int i = tid; i < total; i += SEL_THREADS) { uint32_t v = (uint32_t)(key_s[i] >> 32); lo = min(lo, v); hi = max(hi, v); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-        }
-        if (lane == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
-        __syncthreads();
         // digits are 8-bit windows counted from the HIGHEST SIGNIFICANT bit of the range, so the first
         // pass already spreads the keys over up to 256 bins (byte-aligned windows would put them all
         // into the one or two bins of the range's top byte and serialise the shared-memory atomics)
@@ -510,13 +565,20 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(
         bound = bound + fabsf(bound) * 1e-6f;
     }
     if (tid == 0) g[q] = -bound;
-    // ---- survivors: every staged key under the new bound ----
+    // ---- survivors: every staged key under the new bound (one shared-memory atomic per warp) ----
     const uint32_t bound_hi = float_to_ordered(bound);
-    for (int i = tid; i < total; i += SEL_THREADS) {
-        uint64_t key = key_s[i];
-        if ((uint32_t)(key >> 32) <= bound_hi) {
-            int slot = atomicAdd(&s_out, 1);
-            if (slot < surv_cap) surv_out[(size_t)q * surv_cap + slot] = key;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int i0 = 0; i0 < total; i0 += SEL_THREADS) {
+        const int i = i0 + tid;
+        const uint64_t key = i < total ? key_s[i] : 0ull;
+        const bool keep = i < total && (uint32_t)(key >> 32) <= bound_hi;
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+        if (b != 0u) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_out, __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(b & lt_mask);
+            if (keep && slot < surv_cap) surv_out[(size_t)q * surv_cap + slot] = key;
         }
     }
     __syncthreads();
@@ -713,9 +775,9 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
             S[(size_t)i] = S[(size_t)i + 1] * R;
         }
         auto mult = [&](int stride) { return (int)((T + stride - 1) / stride); };   // multiples of stride in [0, T)
-        ph[n_ph++] = GemmPhase{0, S[0], S[0], mult(S[0]), 0};
-        for (int i = 1; i < L; i++) ph[n_ph++] = GemmPhase{1, S[(size_t)i - 1], S[(size_t)i], mult(S[(size_t)i]) - mult(S[(size_t)i - 1]), 0};
-        ph[n_ph++] = GemmPhase{2, S[(size_t)L - 1], S[(size_t)L - 1], T - mult(S[(size_t)L - 1]), 0};
+        ph[n_ph++] = GemmPhase{0, S[0], S[0], mult(S[0]), 0, 1};
+        for (int i = 1; i < L; i++) ph[n_ph++] = GemmPhase{1, S[(size_t)i - 1], S[(size_t)i], mult(S[(size_t)i]) - mult(S[(size_t)i - 1]), 0, 0};
+        ph[n_ph++] = GemmPhase{2, S[(size_t)L - 1], S[(size_t)L - 1], T - mult(S[(size_t)L - 1]), 0, 0};
         if (ph[0].n_tiles > n_clusters)
             return fail(CM_ERR_UNSUPPORTED, "phase plan: %d first-phase tiles for %d clusters", ph[0].n_tiles, n_clusters);
     }
@@ -729,6 +791,7 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     int passes = 0;
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
+    if (const char *e = getenv("COMET_B200_NO_DENSE")) if (atoi(e)) for (int p = 0; p < n_ph; p++) ph[p].dense = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
         int nqc = (int)std::min<int64_t>(GT_MAX_NQ, nq - q0);
         int nq_pad = (nqc + GT_QBLK - 1) / GT_QBLK * GT_QBLK;
