@@ -147,21 +147,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
         if (lane == 0) {
             prefetch_tmap(&tmap_x);
             prefetch_tmap(&tmap_q);
-            uint32_t it = 0;
+            // ring position and phase are loop-carried (no division in the issue loop: this one thread has to
+            // stay ahead of the tensor pipe, 512 cycles per k-block)
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t stage0 = smem_u32(stage_base), full0 = smem_u32(&full_bar[0]);
+            const uint32_t full0_leader = (CG == 2) ? tc::mapa(full0, 0) : full0;
             for (int w = cluster; w < n_work; w += n_clusters) {
                 int t = phase_tile(phase, w / n_qblk), nb = w % n_qblk;
                 int row0 = t * (GT_ROWS * CG) + (int)cta_rank * GT_ROWS;
                 int q0 = nb * GT_QBLK + (int)cta_rank * B_ROWS;
-                for (int kb = 0; kb < k_blocks; kb++, it++) {
-                    int s = it % stages;
-                    uint32_t ph = (it / stages) & 1;
+                for (int kb = 0; kb < k_blocks; kb++) {
                     mbar_wait_parked(&empty_bar[s], ph ^ 1);
-                    uint32_t bar = smem_u32(&full_bar[s]);
-                    if (CG == 2) bar = tc::mapa(bar, 0);
-                    if (cta_rank == 0) tc::mbar_arrive_expect_tx_addr(smem_u32(&full_bar[s]), STAGE_BYTES * CG);
-                    uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+                    const uint32_t bar = full0_leader + (uint32_t)s * 8u;
+                    if (cta_rank == 0) tc::mbar_arrive_expect_tx_addr(full0 + (uint32_t)s * 8u, STAGE_BYTES * CG);
+                    const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE_BYTES;
                     tc::tma_load_2d_cg<CG>(sa, &tmap_x, kb * GT_BK, row0, bar);
                     tc::tma_load_2d_cg<CG>(sa + GT_A_BYTES, &tmap_q, kb * GT_BK, q0, bar);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -169,18 +172,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
     } else if (warp == GT_WARP_MMA) {
         // ===== MMA issuer (one lane of the leader CTA) =====
         if (cta_rank == 0 && lane == 0) {
-            uint32_t it = 0, wi = 0;
+            uint32_t wi = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t stage0 = smem_u32(stage_base), empty0 = smem_u32(&empty_bar[0]);
             for (int w = cluster; w < n_work; w += n_clusters, wi++) {
                 uint32_t acc = wi & 1, aph = (wi >> 1) & 1;
                 mbar_wait_parked(&tempty_bar[acc], aph ^ 1);
                 tc::fence_after_thread_sync();
                 uint32_t d_tmem = tmem_base + acc * GT_QBLK;
-                for (int kb = 0; kb < k_blocks; kb++, it++) {
-                    int s = it % stages;
-                    uint32_t ph = (it / stages) & 1;
+                for (int kb = 0; kb < k_blocks; kb++) {
                     mbar_wait_parked(&full_bar[s], ph);
                     tc::fence_after_thread_sync();
-                    uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+                    const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE_BYTES;
                     uint64_t adesc = tc::make_smem_desc_sw128(sa);
                     uint64_t bdesc = tc::make_smem_desc_sw128(sa + GT_A_BYTES);
 #pragma unroll
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                         tc::mma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC,
                                          (uint32_t)((kb | k) != 0));
                     }
-                    tc::mma_commit<CG>(smem_u32(&empty_bar[s]));       // frees the smem slot (both CTAs)
+                    tc::mma_commit<CG>(empty0 + (uint32_t)s * 8u);     // frees the smem slot (both CTAs)
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
                 tc::mma_commit<CG>(smem_u32(&tfull_bar[acc]));         // accumulator ready (both CTAs)
             }
