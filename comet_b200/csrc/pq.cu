@@ -11,7 +11,7 @@
 //   codebooks f32 [M][Ksub][dsub]
 //   codes     u8  [cap][M]      arrival order;  ids u32 [cap];  deleted u8 [cap]
 //   IVFPQ adds: coarse FlatIndex of the nlist centroids (raw), members u32 [n] (store positions
-//   grouped by list, CSR) and list_off i64 [nlist+1].
+//   grouped by list, CSR), list_off i64 [nlist+1] and codes_by_list u8 [n][M] (the codes in CSR order).
 // One kernel, adc_scan_kernel, serves both: a CTA owns one (query, probe) pair and a slice of its
 // codes; it builds the pair's LUT in shared memory straight from the codebooks (only the
 // 256 entries per sub-quantiser a uint8 code can address, pq_index.go:469), scans, and keeps its
@@ -134,15 +134,34 @@ struct PQCore {
     uint32_t *members = nullptr;
     long long *list_off = nullptr;
     int64_t members_cap = 0;
+    uint8_t *codes_by_list = nullptr;   // [n][M] codes in CSR (list) order: a probed list is one contiguous stream
     bool csr_dirty = true;
     std::vector<int64_t> sizes_desc;
     std::mutex csr_mu;
     unsigned long long *scanned_total = nullptr;   // device: codes scanned by the last IVFPQ search (all queries)
 
-    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); }
+    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); cudaFree(codes_by_list); }
     int lut_entries() const { return Ksub < 256 ? Ksub : 256; }
     int sync_csr(cudaStream_t st);
 };
+
+// codes_by_list[i] = codes[members[i]]: 16 bytes per thread when M is a multiple of 16
+__global__ void gather_codes_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ members, long long n,
+                                    int M, uint8_t *__restrict__ out) {
+    if ((M & 15) == 0) {
+        const int w = M / 16;
+        long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        if (t >= n * w) return;
+        long long i = t / w;
+        int k = (int)(t - i * w);
+        reinterpret_cast<uint4 *>(out)[t] = __ldg(reinterpret_cast<const uint4 *>(codes + (size_t)members[i] * M) + k);
+    } else {
+        long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        if (t >= n * M) return;
+        long long i = t / M;
+        out[t] = codes[(size_t)members[i] * M + (t - i * M)];
+    }
+}
 
 int PQCore::sync_csr(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(csr_mu);
@@ -150,8 +169,11 @@ int PQCore::sync_csr(cudaStream_t st) {
     int64_t n = store.n;
     if (n > members_cap || !members) {
         cudaFree(members);
+        cudaFree(codes_by_list);
+        codes_by_list = nullptr;
         members_cap = std::max<int64_t>(n + n / 2, 1024);
         CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
+        CM_CUDA(cudaMalloc(&codes_by_list, (size_t)members_cap * M));
     }
     if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
     std::vector<uint32_t> flat;
@@ -167,6 +189,12 @@ int PQCore::sync_csr(cudaStream_t st) {
     std::sort(sizes_desc.begin(), sizes_desc.end(), std::greater<int64_t>());
     if (!flat.empty()) CM_CUDA(cudaMemcpyAsync(members, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(list_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        const long long work = (M & 15) == 0 ? (long long)n * (M / 16) : (long long)n * M;
+        gather_codes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, codes_by_list);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
     CM_CUDA(cudaStreamSynchronize(st));
     csr_dirty = false;
     return CM_OK;
@@ -209,7 +237,8 @@ __global__ void pq_encode_kernel(const float *__restrict__ rows, int ld, long lo
 // the host so that a launch has a few waves of CTAs: 1M codes x 128 queries is 10 slices per query,
 // not 245 rebuilds of the same table).  The walk is in rounds of R code rows per thread: all R x MW
 // 16-byte code loads of a round are issued together (the rows of the NEXT round were prefetched to
-// L2 a round earlier, list positions two rounds earlier), the R table-sum chains are interleaved
+// L2 a round earlier; a pair's rows are one contiguous stream -- IVFPQ scans a list-ordered copy of
+// the codes, rebuilt with the CSR after Add / Flush), the R table-sum chains are interleaved
 // (each chain is the reference's sequential m = 0..M-1 order), and the CTA meets at ONE barrier per
 // round, which also decides whether the candidate buffer must be compacted.
 //   MW = M / 16 (code bytes per row in 16-byte words) or 0 for the generic byte-wise path.
@@ -327,42 +356,29 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     __syncthreads();
 
     const int limit = C - R * T;              // appends of one round always fit above this fill
-    // list positions: this round's and the next round's are in registers, those two rounds ahead in flight
-    uint32_t pos_cur[R], pos_nxt[R];
-    auto load_pos = [&](long long base, uint32_t (&out)[R]) {
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            long long j = base + (long long)r * T + tid;
-            out[r] = j < c1 ? (mem ? __ldg(mem + j) : (uint32_t)j) : 0u;
-        }
-    };
-    load_pos(c0, pos_cur);
-    load_pos(c0 + (long long)R * T, pos_nxt);
+    // the pair's code rows are one contiguous stream: the store itself (PQ) or the list's slice of the
+    // list-ordered copy (IVFPQ; `codes` then points at codes_by_list)
+    const uint8_t *rows = codes + (mem ? (size_t)list_off[list] * M : 0);
     for (long long base = c0; base < c1; base += (long long)R * T) {
-        uint32_t pos_nn[R];
-        load_pos(base + 2ll * R * T, pos_nn);
         bool live[R];
         float dist[R];
         if (MW > 0) {
             uint32_t wd[R][MW > 0 ? MW * 4 : 1];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                live[r] = base + (long long)r * T + tid < c1;
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(codes + (size_t)pos_cur[r] * M);
+                const long long j = base + (long long)r * T + tid;
+                live[r] = j < c1;
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(rows + (size_t)(live[r] ? j : c0) * M);
 #pragma unroll
                 for (int w = 0; w < MW; w++) {
-                    uint4 v = __ldg(c4 + w);           // dead rows read row 0: harmless, never emitted
+                    uint4 v = __ldg(c4 + w);           // dead rows re-read row c0: harmless, never emitted
                     wd[r][w * 4 + 0] = v.x; wd[r][w * 4 + 1] = v.y; wd[r][w * 4 + 2] = v.z; wd[r][w * 4 + 3] = v.w;
                 }
             }
-            // next round's rows towards L2 while this round computes
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (base + (long long)(R + r) * T + tid < c1) {
-                    const uint8_t *p = codes + (size_t)pos_nxt[r] * M;
-                    prefetch_l2(p);
-                    prefetch_l2(p + MW * 16 - 1);
-                }
+            // next round's rows towards L2 while this round computes (one 128-byte line per 128 bytes of rows)
+            {
+                const long long nb = (base + (long long)R * T) * M, ne = min(c1, base + 2ll * R * T) * M;
+                for (long long o = nb + (long long)tid * 128; o < ne; o += (long long)T * 128) prefetch_l2(rows + o);
             }
             float sum[R];
 #pragma unroll
@@ -382,8 +398,9 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                live[r] = base + (long long)r * T + tid < c1;
-                const uint8_t *code = codes + (size_t)pos_cur[r] * M;
+                const long long j = base + (long long)r * T + tid;
+                live[r] = j < c1;
+                const uint8_t *code = rows + (size_t)(live[r] ? j : c0) * M;
                 float sum = 0.0f;
                 if (live[r])
                     for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
@@ -395,10 +412,11 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
 #pragma unroll
         for (int r = 0; r < R; r++) {
             bool ok = live[r];
-            if (ok && skip != nullptr && skip[pos_cur[r]]) ok = false;
+            const long long j = base + (long long)r * T + tid;
+            if (ok && skip != nullptr && skip[mem ? mem[j] : (uint32_t)j]) ok = false;
             if (ok && threshold > 0.0f && dist[r] > threshold) ok = false;
             if (ok) {
-                uint64_t key = make_key(dist[r], (uint32_t)(order0 + base + (long long)r * T + tid));
+                uint64_t key = make_key(dist[r], (uint32_t)(order0 + j));
                 if (key < tau) {
                     int slot = atomicAdd(&cnt, 1);
                     buf[slot] = key;
@@ -408,8 +426,6 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
         }
         // the thread that took the highest slot sees the final fill, so the OR is exact
         if (__syncthreads_or(top > limit)) compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
-#pragma unroll
-        for (int r = 0; r < R; r++) { pos_cur[r] = pos_nxt[r]; pos_nxt[r] = pos_nn[r]; }
     }
     compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
     int mcount = cnt;
@@ -594,7 +610,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         {
             ProfScope prof(CM_PROF_PQ_SCAN, st);
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
-                                                  ix.codebooks, S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
+                                                  ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
                                                   ix.coarse.ld, ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
                                                   ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
                                                   ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, (int)n_slices, pk, pc);

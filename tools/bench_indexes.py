@@ -42,7 +42,17 @@ def full_size(args):
 
     if "c3" in only:
         n, nlist, nprobe, M = args.c3_n, 4096, 32, 96
-        centers = torch.randn((8192, d), generator=g, device=dev) * 2.0
+        # fewer blobs than lists: every blob is represented among the 65,536 training rows, so no blob's rows fall
+        # into a far-away "hub" list at Add time (with 8,192 blobs a query scanned 18 % of the corpus)
+        centers = torch.randn((args.c3_blobs, d), generator=g, device=dev) * 2.0
+        if args.c3_data == "manifold":
+            # rows on a 32-dimensional linear manifold + small isotropic noise: one connected cloud, so the
+            # reference's deterministic k-means yields lists of comparable length (no blob / hub structure)
+            W3 = torch.randn((32, d), generator=g, device=dev)
+
+            def blobs(_c, m):   # noqa: F811
+                z = torch.randn((m, 32), generator=g, device=dev)
+                return (z @ W3 + 0.05 * torch.randn((m, d), generator=g, device=dev)).cpu().numpy()
         ix = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
         t0 = time.perf_counter(); ix.train(blobs(centers, nlist * 16)); t_train = time.perf_counter() - t0
         t_add = 0.0
@@ -62,7 +72,7 @@ def full_size(args):
         scan_ms, scan_n = capi.profile_get(capi.PROF_PQ_SCAN)
         scanned = L.cm_ivfpq_last_scanned(ix.h) / nq
         per = scan_ms / max(scan_n, 1) * 1e-3
-        out["c3_ivfpq"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "nq": nq,
+        out["c3_ivfpq"] = {"data": args.c3_data, "n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "M": M, "nbits": 8, "k": 100, "nq": nq,
                            "train_s": t_train, "add_s": t_add, "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3,
                            "scanned_per_query": scanned, "adc_kernel_ms": per * 1e3,
                            "adc_lookups_per_s": nq * scanned * M / per, "adc_code_GBps": nq * scanned * (M + 4) / per / 1e9,
@@ -115,6 +125,8 @@ def main():
     ap.add_argument("--hnsw-n", type=int, default=20_000)
     ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw,hnswknn,c3,c4")
     ap.add_argument("--c3-n", type=int, default=10_000_000, help="rows of the BASELINE configs[2] run (IVFPQ)")
+    ap.add_argument("--c3-blobs", type=int, default=1024)
+    ap.add_argument("--c3-data", default="manifold", choices=["manifold", "blobs"])
     ap.add_argument("--c4-n", type=int, default=1_000_000, help="rows of the BASELINE configs[3] run (HNSW)")
     args = ap.parse_args()
     if args.only in ("c3", "c4", "c3,c4"):
