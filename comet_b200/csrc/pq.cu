@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     uint64_t *buf = reinterpret_cast<uint64_t *>(res + ((dim + 3) & ~3));   // [C]
     __shared__ int cnt;
     __shared__ uint64_t tau;
+    __shared__ int sel_hist[256];
+    __shared__ uint32_t sel_red[4];
     const CtaBarrier bar;
     const int tid = threadIdx.x;
     const long long pair = blockIdx.y;
@@ -356,6 +358,10 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     __syncthreads();
 
     const int limit = C - R * T;              // appends of one round always fit above this fill
+    const int keep_mid = K + (limit - K) / 2; // keys a mid-stream compaction may leave (K <= keep_mid <= limit)
+    int keep_end = 64;
+    while (keep_end < K) keep_end <<= 1;
+    if (keep_end > limit) keep_end = K;
     // the pair's code rows are one contiguous stream: the store itself (PQ) or the list's slice of the
     // list-ordered copy (IVFPQ; `codes` then points at codes_by_list)
     const uint8_t *rows = codes + (mem ? (size_t)list_off[list] * M : 0);
@@ -425,8 +431,14 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
             }
         }
         // the thread that took the highest slot sees the final fill, so the OR is exact
-        if (__syncthreads_or(top > limit)) compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+        // (a radix-select compaction: no sort; it leaves up to keep_mid keys and a bound just above them)
+        if (__syncthreads_or(top > limit)) {
+            if (!compact_select(buf, C, K, keep_mid, &cnt, &tau, tid, T, sel_hist, sel_red))
+                compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+        }
     }
+    // the CTA's answer: exactly the K smallest -- select down to at most next_pow2(K) keys, sort those
+    if (!compact_select(buf, C, K, keep_end, &cnt, &tau, tid, T, sel_hist, sel_red)) { /* ties: sort them all */ }
     compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
     int mcount = cnt;
     uint64_t *dst = part_keys + part * K;

@@ -41,7 +41,7 @@ def full_size(args):
         return (centers[idx] + torch.randn((m, d), generator=g, device=dev)).cpu().numpy()
 
     if "c3" in only:
-        n, nlist, nprobe, M = args.c3_n, 4096, 32, 96
+        n, nlist, nprobe, M = args.c3_n, args.c3_nlist, 32, 96
         # fewer blobs than lists: every blob is represented among the 65,536 training rows, so no blob's rows fall
         # into a far-away "hub" list at Add time (with 8,192 blobs a query scanned 18 % of the corpus)
         centers = torch.randn((args.c3_blobs, d), generator=g, device=dev) * 2.0
@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw,hnswknn,c3,c4")
     ap.add_argument("--c3-n", type=int, default=10_000_000, help="rows of the BASELINE configs[2] run (IVFPQ)")
     ap.add_argument("--c3-blobs", type=int, default=1024)
+    ap.add_argument("--c3-nlist", type=int, default=4096)
     ap.add_argument("--c3-data", default="manifold", choices=["manifold", "blobs"])
     ap.add_argument("--c4-n", type=int, default=1_000_000, help="rows of the BASELINE configs[3] run (HNSW)")
     args = ap.parse_args()
