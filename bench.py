@@ -447,6 +447,75 @@ def run_ours(args):
     return 0
 
 
+# -------------------------------------------------------------------------------------------------
+# --workload c1 / b1: the single-query shapes (not the driver's bench line; parity-test configs measured
+# for DESIGN.md).  c1 = BASELINE.json configs[0], Flat L2Squared 10K x 128, K=10, one query per call: latency
+# of one host-API call next to the CPU restatement on one thread (what one Go Execute() does).
+# b1 = one to eight queries against the headline corpus: the exact TMA scan, one pass over 3.07 GB.
+# -------------------------------------------------------------------------------------------------
+def run_single_query_shapes(args):
+    import torch
+    from comet_b200 import capi
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    rng = np.random.default_rng(SEED)
+    out = {}
+    if args.workload == "c1":
+        from oracle import oracle_py as O          # cpu_baseline leg + in-run parity check
+        n, d, k = 10_000, 128, 10
+        x = rng.standard_normal((n, d), dtype=np.float32)
+        q = rng.standard_normal((64, d), dtype=np.float32)
+        ids = np.arange(1, n + 1, dtype=np.uint32)
+        g = capi.FlatIndex(d, capi.L2SQ)
+        g.add(ids, x.copy())
+        o = O.Flat(d, capi.L2SQ)
+        o.add(ids, x.copy())
+        gi, gs, gc = g.search(q[:1], k=k)
+        oi, os_ = o.search(q[0], k=k)
+        O.set_threads(1)
+        cpu_s = timed(lambda: o.search(q[0], k=k), 50)
+        out = {"metric": "latency of one single-query Execute()", "unit": "us", "higher_is_better": False,
+               "config": {"workload": "flat_l2sq_10Kx128_k10_b1"}, "dtype": "f32", "data": "synthetic",
+               "value": timed(lambda: g.search(q[:1], k=k), 300) * 1e6,
+               "us_per_call_b8": timed(lambda: g.search(q[:8], k=k), 300) * 1e6,
+               "us_per_call_b64": timed(lambda: g.search(q[:64], k=k), 300) * 1e6,
+               "algorithmic_bytes_per_query": n * d * 4 + d * 4 + k * 8,
+               "cpu_baseline": {"value": cpu_s * 1e6, "unit": "us", "cores": 1, "kind": "port",
+                                "sample": "the same query, CPU restatement of the Go loops, one thread"},
+               "parity": {"ids_bit_exact": bool(np.array_equal(gi[0], oi)),
+                          "scores_bit_exact": bool(np.array_equal(gs[0].view(np.uint32), os_.view(np.uint32)))}}
+    else:
+        n2, d2 = N_ROWS, DIM
+        dev = torch.device("cuda", 0)
+        g2 = capi.FlatIndex(d2, capi.COSINE)
+        g2.reserve(n2)
+        x = gen_rows_device(torch, n2, d2, SEED, dev)
+        g2.add_device(np.arange(1, n2 + 1, dtype=np.uint32), x.data_ptr(), n2)
+        torch.cuda.synchronize()
+        del x
+        q2 = rng.standard_normal((8, d2), dtype=np.float32)
+        L = capi.lib()
+        hbm = measured_peaks()[0]
+        out = {"metric": "exact scan, small batches", "config": {"workload": "flat_cosine_1Mx768_k100_b1..8"}}
+        for b in (1, 2, 4, 8):
+            L.cm_profile_reset(); L.cm_profile_enable(1)
+            dt = timed(lambda: g2.search(q2[:b], k=K), 20)
+            L.cm_profile_enable(0)
+            ms, cnt = capi.profile_get(capi.PROF_FLAT_SCAN)
+            per = ms / max(cnt, 1)
+            gbs = (n2 * d2 * 4 + b * d2 * 4) / (per * 1e-3) / 1e9
+            out[f"b{b}"] = {"host_call_ms": dt * 1e3, "scan_kernel_ms": per, "scan_GBps": gbs, "frac_of_hbm_peak": gbs / hbm}
+    emit(out)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,6 +528,8 @@ def main():
     ap.add_argument("--sharding", default="auto", choices=["auto", "rows", "queries"])
     ap.add_argument("--rows", type=int, default=0, help="corpus rows (default 1M = BASELINE configs[1]); 12500000 = one 1/8 shard of the 100M x 768 config")
     ap.add_argument("--metric-kind", default="cosine", choices=["cosine", "l2", "l2_squared"])
+    ap.add_argument("--workload", default="headline", choices=["headline", "c1", "b1"],
+                    help="headline = the driver's bench line; c1 / b1 = single-query shapes (see run_single_query_shapes)")
     args = ap.parse_args()
     if args.rows > 0:
         global N_ROWS
@@ -467,6 +538,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "headline":
+        return run_single_query_shapes(args)
     return run_ours(args)
 
 

@@ -110,6 +110,7 @@ int FlatIndex::reserve(int64_t want) {
 
 FlatIndex::~FlatIndex() {
     cudaFree(rows); cudaFree(ids); cudaFree(deleted);
+    cudaFree(rescored_dev);
     free_shadow();
 }
 
@@ -608,6 +609,12 @@ int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out) {
     if (!h || !out) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(const_cast<cm_flat *>(h)->ix.stats_mu);
     *out = h->ix.last_stats;
+    if (out->candidates < 0) {       // tensor path: the count lives on the device until somebody asks
+        unsigned long long c = 0;
+        out->candidates = 0;
+        if (h->ix.rescored_dev && cudaMemcpy(&c, h->ix.rescored_dev, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            out->candidates = (int64_t)c;
+    }
     return CM_OK;
 }
 

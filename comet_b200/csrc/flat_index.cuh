@@ -41,6 +41,7 @@ struct FlatIndex {
 
     std::mutex stats_mu;
     cm_flat_stats last_stats{};
+    unsigned long long *rescored_dev = nullptr;   // device: candidates re-scored by the last tensor-path search (all queries)
 
     ~FlatIndex();
     int reserve(int64_t want);

@@ -48,6 +48,7 @@ static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
 static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
 static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
+static constexpr int RS_GRID_X = 2;        // re-score CTAs per query (each loops over its 128-candidate chunks)
 static constexpr int SEL_STAGE_CAP = 12288; // keys (old survivors + new candidates) staged in smem by the select kernel (96 KB)
 
 struct GemmPhase {
@@ -435,7 +436,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
     const uint64_t *__restrict__ cand, int *__restrict__ cand_cnt, int nq_pad, int n_reg, int slots, int K, int dim,
     const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
     int *__restrict__ overflow, const uint64_t *__restrict__ surv_in, const int *__restrict__ surv_in_cnt,
-    uint64_t *__restrict__ surv_out, int *__restrict__ surv_out_cnt, int surv_cap, int stage_cap, float e_scale) {
+    uint64_t *__restrict__ surv_out, int *__restrict__ surv_out_cnt, int surv_cap, int stage_cap, float e_scale,
+    int *__restrict__ dbg_staged_max) {
     extern __shared__ __align__(16) uint8_t sel_smem_raw[];
     uint64_t *key_s = reinterpret_cast<uint64_t *>(sel_smem_raw);                 // [stage_cap]
     __shared__ int hist[256];
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
     }
     __syncthreads();
     const int total = s_total;
+    if (dbg_staged_max && tid == 0) atomicMax(dbg_staged_max, total);
     if (s_ovf || total > stage_cap) {
         if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; surv_out_cnt[q] = 0; }
         return;
@@ -607,61 +610,64 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
     __shared__ uint32_t pos_s[128];
     const int q = blockIdx.y, tid = threadIdx.x;
     const int cnt = min(rs_cnt[q], rs_cap);
-    const int base = blockIdx.x * 128;
-    if (base >= cnt) return;
-    const int mine = base + tid;
-    const bool live = mine < cnt;
-    const uint32_t pos = key_pos(rs[(size_t)q * rs_cap + (live ? mine : base)]);
-    pos_s[tid] = pos;
     for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
-    __syncthreads();
     const int n_chunks = ld / 32;
-    auto issue = [&](int c) {
-        uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
-#pragma unroll
-        for (int p = 0; p < 8; p++) {
-            int idx = p * 128 + tid;
-            int r = idx >> 3, piece = idx & 7;
-            const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
-            uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    issue(0);
-    float acc = 0.0f;
-    for (int c = 0; c < n_chunks; c++) {
-        if (c + 1 < n_chunks) {
-            issue(c + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+    // a few CTAs per query, each walking its 128-candidate chunks (a (RS_CAP / 128) x nq grid would launch
+    // mostly empty CTAs: ~230 candidates per query survive on the headline workload)
+    for (int base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+        const int mine = base + tid;
+        const bool live = mine < cnt;
+        const uint32_t pos = key_pos(rs[(size_t)q * rs_cap + (live ? mine : base)]);
+        __syncthreads();            // previous chunk's readers of pos_s / stage are done; q_s is staged
+        pos_s[tid] = pos;
         __syncthreads();
-        const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
-        const float *qc = q_s + c * 32;
+        auto issue = [&](int c) {
+            uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
-            float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
-            acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
-            acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
-            acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
-            acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+            for (int p = 0; p < 8; p++) {
+                int idx = p * 128 + tid;
+                int r = idx >> 3, piece = idx & 7;
+                const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
+                uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+        float acc = 0.0f;
+        for (int c = 0; c < n_chunks; c++) {
+            if (c + 1 < n_chunks) {
+                issue(c + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
+            const float *qc = q_s + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
+                float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
+                acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+                acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+                acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+                acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    float dist = metric_finish<METRIC>(acc);
-    if (live && !(threshold > 0.0f && dist > threshold)) {
-        int slot = atomicAdd(&out_cnt[q], 1);
-        out_keys[(size_t)q * rs_cap + slot] = make_key(dist, pos);
+        float dist = metric_finish<METRIC>(acc);
+        if (live && !(threshold > 0.0f && dist > threshold)) {
+            int slot = atomicAdd(&out_cnt[q], 1);
+            out_keys[(size_t)q * rs_cap + slot] = make_key(dist, pos);
+        }
     }
 }
 
 static int launch_rescore(int metric, bool fma, const float *rows, int ld, const float *queries, int nq,
                           const uint64_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
                           cudaStream_t st) {
-    dim3 grid(RS_CAP / 128, (unsigned)nq);
+    dim3 grid(RS_GRID_X, (unsigned)nq);
     size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
     ProfScope prof(CM_PROF_RESCORE, st);
 #define CM_RS_CASE(M)                                                                                                 \
@@ -692,9 +698,15 @@ __global__ void init_bounds_kernel(float *__restrict__ g, int nq, int nq_pad) {
 }
 
 // queries that overflowed a candidate list get count -1 (the host entry point redoes them exactly)
-__global__ void mark_overflow_kernel(const int *__restrict__ overflow, int nq, long long *__restrict__ out_counts) {
+__global__ void mark_overflow_kernel(const int *__restrict__ overflow, int nq, long long *__restrict__ out_counts,
+                                     const int *__restrict__ rs_cnt, unsigned long long *__restrict__ rescored) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq && overflow[q]) out_counts[q] = -1;
+    // statistics: candidates that went through the exact re-score (cm_flat_last_stats reads the sum lazily)
+    int c = q < nq ? rs_cnt[q] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c > 0 && rescored) atomicAdd(rescored, (unsigned long long)c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -795,6 +807,13 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8 + (size_t)(n_reg + 1) * 4;
     CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     int passes = 0;
+    int *dbg_staged = nullptr;           // COMET_B200_DBG_STAGED=1: most keys any query staged, per phase (stderr)
+    if (getenv("COMET_B200_DBG_STAGED")) {
+        CM_CUDA(cudaMalloc(&dbg_staged, MAX_PH * sizeof(int)));
+        CM_CUDA(cudaMemsetAsync(dbg_staged, 0, MAX_PH * sizeof(int), st));
+    }
+    if (!rescored_dev) CM_CUDA(cudaMalloc(&rescored_dev, 8));
+    CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
     if (const char *e = getenv("COMET_B200_NO_DENSE")) if (atoi(e)) for (int p = 0; p < n_ph; p++) ph[p].dense = 0;
     for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
@@ -842,7 +861,8 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
                 cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(
                     cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf,
                     p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP, p == 0 ? nullptr : rcnt + (size_t)in * nq_pad,
-                    rs + (size_t)out * nq_pad * RS_CAP, rcnt + (size_t)out * nq_pad, RS_CAP, SEL_STAGE_CAP, e_scale);
+                    rs + (size_t)out * nq_pad * RS_CAP, rcnt + (size_t)out * nq_pad, RS_CAP, SEL_STAGE_CAP, e_scale,
+                    dbg_staged ? dbg_staged + p : nullptr);
                 count_launch();
                 CM_CUDA(cudaGetLastError());
             }
@@ -854,14 +874,25 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
                                  out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
                                  out_counts + q0, st));
-        mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0));
+        mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0),
+                                                                rcnt + (size_t)last * nq_pad, rescored_dev);
         count_launch();
         CM_CUDA(cudaGetLastError());
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);
     }
+    if (dbg_staged) {
+        int h[MAX_PH] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_staged, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[comet_b200] staged keys (max over queries) per phase:");
+        for (int p = 0; p < n_ph; p++) fprintf(stderr, " %d", h[p]);
+        fprintf(stderr, "  (cap %d)\n", SEL_STAGE_CAP);
+        cudaFree(dbg_staged);
+    }
     stats->path_used = CM_PATH_TENSOR;
     stats->passes = passes;
+    stats->candidates = -1;      // on the device: cm_flat_last_stats fetches it
     return CM_OK;
 }
 

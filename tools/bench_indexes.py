@@ -1,9 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the IVF / PQ / IVFPQ / HNSW device search paths at moderate sizes (the BASELINE.json
 configs[2..3] are parity-test cases; this script characterises their kernels for DESIGN.md / profiles/).
-Indexes are trained and filled through the C ABI on the GPU; the HNSW graph comes from a host builder
-(the CPU checker under oracle/, used here only as a graph BUILDER for measurement input, never on the
-timed path)."""
+Indexes are trained, filled and -- for HNSW -- built through the C ABI on the GPU."""
 import argparse
 import json
 import os
@@ -211,19 +209,16 @@ def main():
         # HNSW: graph from the host builder, search on the device.  Rows on a 24-dimensional manifold: with i.i.d.
         # 768-d Gaussian rows all pairwise distances coincide and the reference's build (entry point never promoted,
         # plain "M nearest" selection) leaves only a few dozen nodes reachable from the entry point.
-        from oracle import oracle_py as O
         hn = args.hnsw_n
         z = rng.standard_normal((hn, 24), dtype=np.float32)
         W = rng.standard_normal((24, d), dtype=np.float32)
         xh = (z @ W + 0.05 * rng.standard_normal((hn, d), dtype=np.float32)).astype(np.float32)
         qh = (rng.standard_normal((nq, 24), dtype=np.float32) @ W).astype(np.float32)
-        lv = O.hnsw_random_levels(hn, 16, 3)
+        # the reference's level draw, floor(-ln(U) / ln(M)) (hnsw_index.go:474-484), with numpy's generator
+        lv = np.minimum(np.floor(-np.log(1.0 - rng.random(hn)) / np.log(16.0)), 16).astype(np.int32)
         lv[0] = 0
-        o = O.HNSW(d, capi.L2, 16, 100, 128)
-        t0 = time.perf_counter(); o.add(ids[:hn], xh.copy(), lv); t_build = time.perf_counter() - t0
-        eids, elev, erows, layers = o.export()
         g = capi.HNSWIndex(d, capi.L2, 16, 100, 128)
-        g.load_graph(eids, erows, elev, layers, o.entry_point, o.max_level)
+        t0 = time.perf_counter(); g.add(ids[:hn], xh.copy(), lv, writeback=False); t_build = time.perf_counter() - t0
         res = {}
 
         def run():
@@ -231,7 +226,7 @@ def main():
         dt = timed(run)
         work = res["r"][3]
         evals = float(work[:, 0].mean())
-        out["hnsw"] = {"n": hn, "dim": d, "M": 16, "ef": 128, "k": 10, "host_build_s": t_build, "qps_host_api": nq / dt,
+        out["hnsw"] = {"n": hn, "dim": d, "M": 16, "ef": 128, "k": 10, "device_build_s": t_build, "qps_host_api": nq / dt,
                        "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
                        "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9}
     print(json.dumps(out, indent=1))
