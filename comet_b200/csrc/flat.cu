@@ -111,6 +111,8 @@ int FlatIndex::reserve(int64_t want) {
 FlatIndex::~FlatIndex() {
     cudaFree(rows); cudaFree(ids); cudaFree(deleted);
     cudaFree(rescored_dev);
+    cudaFree(staged_dev);
+    cudaFreeHost(staged_host);
     free_shadow();
 }
 

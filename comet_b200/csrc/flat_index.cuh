@@ -42,6 +42,8 @@ struct FlatIndex {
     std::mutex stats_mu;
     cm_flat_stats last_stats{};
     unsigned long long *rescored_dev = nullptr;   // device: candidates re-scored by the last tensor-path search (all queries)
+    int *staged_dev = nullptr;              // device [8]: most keys any query staged in the select of phase p (this search)
+    int *staged_host = nullptr;             // pinned copy of the previous search's values (-1: unknown): picks the select shape
 
     ~FlatIndex();
     int reserve(int64_t want);

@@ -49,6 +49,7 @@ static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem
 static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
 static constexpr int RS_GRID_X = 2;        // re-score CTAs per query (each loops over its 128-candidate chunks)
+static constexpr int MAX_PH = 6;           // phases of the candidate pass
 static constexpr int SEL_STAGE_CAP = 12288; // keys (old survivors + new candidates) staged in smem by the select kernel (96 KB)
 
 struct GemmPhase {
@@ -431,79 +432,107 @@ static int launch_to_bf16(const float *src, int64_t n, int dim, int ld_src, __nv
 // a radix select on (key - min), starting at the highest significant byte; the keys under the new
 // bound tau_K + 2E become the survivors for the next phase (ping-pong list) and the region counters
 // are reset.  After the last phase the survivors ARE the rows to re-score.
+// Two launch shapes: <768, 2> stages up to SEL_STAGE_CAP keys (96 KB, two CTAs per SM: 296 CTAs in flight, so
+// 512 queries take two rounds) and <512, 4> stages up to SEL_STAGE_CAP_SMALL keys (48 KB, four CTAs per SM: all
+// 512 queries in ONE round).  The host picks the small shape for a phase when the keys it staged on the previous
+// call (and, for phase A, the rows it is about to emit) fit with margin.
 static constexpr int SEL_THREADS = 768;     // >= candidate regions per query (4 x SMs); 2 CTAs per SM at <= 42 registers
-__global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
+static constexpr int SEL_THREADS_SMALL = 512;
+static constexpr int SEL_STAGE_CAP_SMALL = 6144;
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) cand_select_kernel(
     const uint64_t *__restrict__ cand, int *__restrict__ cand_cnt, int nq_pad, int n_reg, int slots, int K, int dim,
     const float2 *__restrict__ q_norms, const unsigned int *__restrict__ max_bits, float *__restrict__ g,
     int *__restrict__ overflow, const uint64_t *__restrict__ surv_in, const int *__restrict__ surv_in_cnt,
     uint64_t *__restrict__ surv_out, int *__restrict__ surv_out_cnt, int surv_cap, int stage_cap, float e_scale,
-    int *__restrict__ dbg_staged_max) {
+    int *__restrict__ staged_max) {
+    constexpr int NW = NT / 32;
+    constexpr int NRB = NT >= 768 ? 1 : 2;     // region blocks of NT regions each (n_reg <= NRB * NT, checked on the host)
     extern __shared__ __align__(16) uint8_t sel_smem_raw[];
     uint64_t *key_s = reinterpret_cast<uint64_t *>(sel_smem_raw);                 // [stage_cap]
     __shared__ int hist[256];
-    __shared__ int warp_tot[SEL_THREADS / 32];
+    __shared__ int warp_tot[NRB][32];
     __shared__ uint32_t s_prefix, s_lo, s_hi;
     __shared__ int s_rank, s_out, s_ovf, s_total;
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_old = surv_in_cnt ? surv_in_cnt[q] : 0;
     if (tid == 0) { s_ovf = overflow[q]; s_out = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; s_prefix = 0; s_rank = K; }
     // ---- region counts -> offsets behind the old survivors (block scan), counters reset for the next phase ----
-    int c = 0;
-    if (tid < n_reg) {
-        c = cand_cnt[(size_t)q * n_reg + tid];
-        cand_cnt[(size_t)q * n_reg + tid] = 0;
-    }
-    __syncthreads();
-    if (c > slots) s_ovf = 1;
-    int incl = c;
+    int c[NRB], incl[NRB];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    for (int rb = 0; rb < NRB; rb++) {
+        const int r = rb * NT + tid;
+        c[rb] = 0;
+        if (r < n_reg) {
+            c[rb] = cand_cnt[(size_t)q * n_reg + r];
+            cand_cnt[(size_t)q * n_reg + r] = 0;
+        }
     }
-    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    {   // exclusive scan of the 32 warp totals by every warp (one shuffle scan instead of a serial loop)
-        int wt = lane < SEL_THREADS / 32 ? warp_tot[lane] : 0, wi = wt;
+#pragma unroll
+    for (int rb = 0; rb < NRB; rb++) {
+        if (c[rb] > slots) s_ovf = 1;
+        int v = c[rb];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
+            int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
         }
-        const int total_all = __shfl_sync(0xffffffffu, wi, 31);
-        const int wbase = n_old + __shfl_sync(0xffffffffu, wi - wt, warp);
-        incl += wbase;
-        if (tid == 0) s_total = n_old + total_all;
+        incl[rb] = v;
+        if (lane == 31) warp_tot[rb][warp] = v;
+    }
+    __syncthreads();
+    {   // exclusive scan of the warp totals of both region blocks by every warp (shuffle scan)
+        int carry = n_old;
+#pragma unroll
+        for (int rb = 0; rb < NRB; rb++) {
+            int wt = lane < NW ? warp_tot[rb][lane] : 0, wi = wt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            incl[rb] += carry + __shfl_sync(0xffffffffu, wi - wt, warp);
+            carry += __shfl_sync(0xffffffffu, wi, 31);
+        }
+        if (tid == 0) s_total = carry;
     }
     __syncthreads();
     const int total = s_total;
-    if (dbg_staged_max && tid == 0) atomicMax(dbg_staged_max, total);
+    if (staged_max && tid == 0) atomicMax(staged_max, total);
     if (s_ovf || total > stage_cap) {
         if (tid == 0) { overflow[q] = 1; g[q] = INFINITY; surv_out_cnt[q] = 0; }
         return;
     }
     // ---- stage: old survivors (all threads), then one region per thread: its keys are contiguous, so all of a
     // thread's 16-byte loads are in flight together (the regions hold ~15 keys each in phases B and C, 32 in A).
-    // The range of the keys (radix base) is folded into the copy.
+    // The range of the keys (radix base) is folded into the copy.  (Key-by-key 8-byte cp.async, which needs no
+    // registers and keeps every key in flight, measured slower in phases B and C: 24.0 / 28.4 us against 21.7 /
+    // 25.4 us.)
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < n_old; i += SEL_THREADS) {
+    for (int i = tid; i < n_old; i += NT) {
         uint64_t v = surv_in[(size_t)q * surv_cap + i];
         key_s[i] = v;
         uint32_t h = (uint32_t)(v >> 32); lo = min(lo, h); hi = max(hi, h);
     }
-    if (tid < n_reg && c > 0) {
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(cand + ((size_t)q * n_reg + tid) * slots);
-        uint64_t *dst = key_s + (incl - c);
-        for (int i0 = 0; i0 < c; i0 += 8) {
-            ulonglong2 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (i0 + 2 * u < c) v[u] = __ldg(src + (i0 >> 1) + u);
+    for (int rb = 0; rb < NRB; rb++) {
+        const int r = rb * NT + tid, cc = c[rb];
+        if (r < n_reg && cc > 0) {
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(cand + ((size_t)q * n_reg + r) * slots);
+            uint64_t *dst = key_s + (incl[rb] - cc);
+            constexpr int VB = MINB >= 4 ? 2 : 4;       // 16-byte loads in flight per thread (register budget)
+            for (int i0 = 0; i0 < cc; i0 += 2 * VB) {
+                ulonglong2 v[VB];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + 2 * u;
-                if (i < c) { dst[i] = v[u].x; uint32_t h = (uint32_t)(v[u].x >> 32); lo = min(lo, h); hi = max(hi, h); }
-                if (i + 1 < c) { dst[i + 1] = v[u].y; uint32_t h = (uint32_t)(v[u].y >> 32); lo = min(lo, h); hi = max(hi, h); }
+                for (int u = 0; u < VB; u++)
+                    if (i0 + 2 * u < cc) v[u] = __ldg(src + (i0 >> 1) + u);
+#pragma unroll
+                for (int u = 0; u < VB; u++) {
+                    const int i = i0 + 2 * u;
+                    if (i < cc) { dst[i] = v[u].x; uint32_t h = (uint32_t)(v[u].x >> 32); lo = min(lo, h); hi = max(hi, h); }
+                    if (i + 1 < cc) { dst[i + 1] = v[u].y; uint32_t h = (uint32_t)(v[u].y >> 32); lo = min(lo, h); hi = max(hi, h); }
+                }
             }
         }
     }
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
             const uint32_t prefix = s_prefix;
             const uint32_t mask = (shift + width) >= 32 ? 0u : (0xFFFFFFFFu << (shift + width));
             const uint32_t dmask = (1u << width) - 1u;
-            for (int i = tid; i < total; i += SEL_THREADS) {
+            for (int i = tid; i < total; i += NT) {
                 uint32_t v = (uint32_t)(key_s[i] >> 32) - base;
                 if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & dmask], 1);
             }
@@ -576,7 +605,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 2) cand_select_kernel(
     // ---- survivors: every staged key under the new bound (one shared-memory atomic per warp) ----
     const uint32_t bound_hi = float_to_ordered(bound);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int i0 = 0; i0 < total; i0 += SEL_THREADS) {
+    for (int i0 = 0; i0 < total; i0 += NT) {
         const int i = i0 + tid;
         const uint64_t key = i < total ? key_s[i] : 0ull;
         const bool keep = i < total && (uint32_t)(key >> 32) <= bound_hi;
@@ -770,7 +799,6 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     // it is within 25x of the rows already seen.  A phase then emits ~ 2 K x (its rows / rows seen
     // before) keys per query whatever n is (sweep on 1M and 12.5M x 768: profiles/r01_tensor_path.md).
     // Tile t belongs to the first level whose stride divides t (strides nest: S_0 | S_1 | ... ).
-    constexpr int MAX_PH = 6;
     GemmPhase ph[MAX_PH];
     int n_ph = 0;
     {
@@ -803,15 +831,34 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     float e_scale = 1.0f;
     if (const char *es = getenv("COMET_B200_E_SCALE")) e_scale = std::max(1.0f, (float)atof(es));
     const int n_reg = n_cta * 4;   // candidate regions per query: (CTA, lane quadrant)
-    if (n_reg > SEL_THREADS) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
-    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8 + (size_t)(n_reg + 1) * 4;
-    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    if (n_reg > SEL_THREADS || n_reg > 2 * SEL_THREADS_SMALL) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
+    const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8, sel_smem_small = (size_t)SEL_STAGE_CAP_SMALL * 8;
+    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel<SEL_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel<SEL_THREADS_SMALL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_small));
     int passes = 0;
-    int *dbg_staged = nullptr;           // COMET_B200_DBG_STAGED=1: most keys any query staged, per phase (stderr)
-    if (getenv("COMET_B200_DBG_STAGED")) {
-        CM_CUDA(cudaMalloc(&dbg_staged, MAX_PH * sizeof(int)));
-        CM_CUDA(cudaMemsetAsync(dbg_staged, 0, MAX_PH * sizeof(int), st));
+    // keys staged per phase: counted on the device, copied to pinned memory after the last phase; the NEXT search
+    // reads them (no synchronisation: a stale or missing value only means the roomier launch shape is used)
+    if (!staged_dev) {
+        CM_CUDA(cudaMalloc(&staged_dev, 8 * sizeof(int)));
+        CM_CUDA(cudaHostAlloc(&staged_host, 8 * sizeof(int), cudaHostAllocDefault));
+        for (int p = 0; p < 8; p++) staged_host[p] = -1;
     }
+    CM_CUDA(cudaMemsetAsync(staged_dev, 0, 8 * sizeof(int), st));
+    const int small_ok = SEL_STAGE_CAP_SMALL - SEL_STAGE_CAP_SMALL / 12;      // 8 % headroom
+    bool sel_small[MAX_PH];
+    for (int p = 0; p < n_ph; p++) {
+        const int prev = staged_host[p];
+        sel_small[p] = prev >= 0 && prev <= small_ok;
+        if (p == 0) sel_small[p] = (int64_t)ph[0].n_tiles * tile_rows <= small_ok;   // phase A stages exactly its rows
+    }
+    // Measured on 512 x 1M x 768 (ncu, profiles/): 33.8 / 19.4 / 25.9 us in the one-round shape against 35.8 / 21.7 /
+    // 25.4 us -- the kernel is issue-bound, not round-bound -- so the roomier shape stays the default.
+    {
+        const char *e = getenv("COMET_B200_SEL_SMALL");
+        const bool want_small = e && atoi(e) != 0;
+        for (int p = 0; p < n_ph; p++) sel_small[p] = sel_small[p] && want_small;
+    }
+    const bool dbg_staged = getenv("COMET_B200_DBG_STAGED") != nullptr;
     if (!rescored_dev) CM_CUDA(cudaMalloc(&rescored_dev, 8));
     CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
@@ -858,11 +905,18 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
             {
                 ProfScope prof(CM_PROF_SELECT, st);
                 const int in = (p + 1) & 1, out = p & 1;
-                cand_select_kernel<<<nqc, SEL_THREADS, sel_smem, st>>>(
-                    cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf,
-                    p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP, p == 0 ? nullptr : rcnt + (size_t)in * nq_pad,
-                    rs + (size_t)out * nq_pad * RS_CAP, rcnt + (size_t)out * nq_pad, RS_CAP, SEL_STAGE_CAP, e_scale,
-                    dbg_staged ? dbg_staged + p : nullptr);
+                const uint64_t *s_in = p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP;
+                const int *s_in_cnt = p == 0 ? nullptr : rcnt + (size_t)in * nq_pad;
+                uint64_t *s_out = rs + (size_t)out * nq_pad * RS_CAP;
+                int *s_out_cnt = rcnt + (size_t)out * nq_pad;
+                if (sel_small[p])
+                    cand_select_kernel<SEL_THREADS_SMALL, 4><<<nqc, SEL_THREADS_SMALL, sel_smem_small, st>>>(
+                        cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
+                        RS_CAP, SEL_STAGE_CAP_SMALL, e_scale, staged_dev + p);
+                else
+                    cand_select_kernel<SEL_THREADS, 2><<<nqc, SEL_THREADS, sel_smem, st>>>(
+                        cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
+                        RS_CAP, SEL_STAGE_CAP, e_scale, staged_dev + p);
                 count_launch();
                 CM_CUDA(cudaGetLastError());
             }
@@ -881,14 +935,12 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);
     }
+    CM_CUDA(cudaMemcpyAsync(staged_host, staged_dev, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (dbg_staged) {
-        int h[MAX_PH] = {0};
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg_staged, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[comet_b200] staged keys (max over queries) per phase:");
-        for (int p = 0; p < n_ph; p++) fprintf(stderr, " %d", h[p]);
-        fprintf(stderr, "  (cap %d)\n", SEL_STAGE_CAP);
-        cudaFree(dbg_staged);
+        for (int p = 0; p < n_ph; p++) fprintf(stderr, " %d%s", staged_host[p], sel_small[p] ? "s" : "");
+        fprintf(stderr, "  (caps %d / %d)\n", SEL_STAGE_CAP_SMALL, SEL_STAGE_CAP);
     }
     stats->path_used = CM_PATH_TENSOR;
     stats->passes = passes;
