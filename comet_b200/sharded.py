@@ -63,3 +63,53 @@ def device_merge(k: int, stream_ptr: int = 0):
         return out_ids, out_sc, out_cnt
 
     return merge
+
+
+def query_bounds(nq: int, world: int, rank: int) -> Tuple[int, int]:
+    """Queries [q0, q0 + m) answered by `rank` when every rank holds a REPLICA of the index: equal contiguous
+    shares, remainder spread over the first ranks."""
+    per, rem = divmod(nq, world)
+    q0 = rank * per + min(rank, rem)
+    return q0, per + (1 if rank < rem else 0)
+
+
+class ReplicatedSearch:
+    """Query-sharded search over replicas: the layout for every index whose device state fits one GPU
+    (IVF / PQ / IVFPQ codes and lists, the HNSW graph -- SURVEY 8e "replicas only" -- and the flat corpus of
+    the headline config).  Queries are the independent units of the path, so there is NO data-path
+    collective: rank r answers its own contiguous share with `search_local`, and the result is exactly what
+    one index would return, ties included (nothing is merged).  `gather=True` additionally assembles the
+    full [nq, K] result on every rank (one all-gather of padded shares) for callers that want it in one place.
+
+    search_local(queries[m, d]) -> (ids[m, K], scores[m, K], counts[m]) tensors."""
+
+    def __init__(self, search_local: Callable, group=None):
+        self.search_local = search_local
+        self.group = group
+
+    def search(self, queries, gather: bool = True):
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        nq = int(queries.shape[0])
+        q0, m = query_bounds(nq, world, rank)
+        ids, scores, counts = self.search_local(queries[q0:q0 + m])
+        if world == 1 or not gather:
+            return ids, scores, counts
+        share = (nq + world - 1) // world            # padded share: all_gather needs equal shapes
+
+        def pad(t):
+            out = torch.zeros((share,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            out[:m] = t
+            return out
+        parts = []
+        for t in (ids, scores, counts):
+            buf = torch.empty((world * share,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(buf, pad(t).contiguous(), group=self.group)
+            rows = []
+            for r in range(world):
+                _, mr = query_bounds(nq, world, r)
+                rows.append(buf[r * share:r * share + mr])
+            parts.append(torch.cat(rows, dim=0))
+        return tuple(parts)

@@ -98,3 +98,18 @@ def test_auto_path_picks_tensor_for_large_batches():
     assert g.last_stats()["path_used"] == capi.PATH_TENSOR
     g.search(q[:8], k=10)
     assert g.last_stats()["path_used"] == capi.PATH_EXACT
+
+
+def test_tensor_path_select_shapes_and_candidate_count(monkeypatch):
+    # The select kernel has two launch shapes (two CTAs per SM staging up to 12288 keys; opt-in: four CTAs per SM
+    # staging up to 6144, chosen from the previous call's staged-key counts).  Both must give the oracle's answer,
+    # call after call, and the device-side count of re-scored candidates must be at least K per query.
+    g, o, rng = make_pair(40_000, 96, capi.COSINE, 31, 2)
+    q = rng.standard_normal((130, 96)).astype(np.float32)
+    for small in ("0", "1", "1"):
+        monkeypatch.setenv("COMET_B200_SEL_SMALL", small)
+        st = check(g, o, q, 25)
+        assert st["fallback_queries"] == 0
+        assert st["candidates"] >= 25 * len(q)
+    monkeypatch.setenv("COMET_B200_NO_DENSE", "1")      # phase A through the sparse emission path
+    check(g, o, q, 25)

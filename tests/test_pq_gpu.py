@@ -157,3 +157,33 @@ def test_ivfpq_sliced_lists(monkeypatch):
         check_ivfpq(g, o, q[:2], 0, 1)
     monkeypatch.setenv("COMET_B200_ADC_GENERIC", "1")
     check_ivfpq(g, o, q, 60, 2)
+
+
+def test_adc_selection_under_heavy_ties():
+    # A handful of distinct vectors repeated thousands of times: every ADC score is shared by thousands of codes, the
+    # radix-select compaction cannot separate them (it must report that and let the sort decide), and the answer is
+    # still the oracle's (score, candidate number) order.
+    rng = np.random.default_rng(77)
+    d, M, nbits = 64, 16, 8
+    base = rng.standard_normal((5, d)).astype(np.float32)
+    x = base[rng.integers(0, 5, 12_000)]
+    x[::97] += rng.standard_normal((len(x[::97]), d)).astype(np.float32) * 0.01
+    ids = np.arange(1, len(x) + 1, dtype=np.uint32)
+    train = rng.standard_normal((600, d)).astype(np.float32)
+    o = O.PQ(d, capi.L2, M, nbits)
+    o.train(train.copy())
+    g = capi.PQIndex(d, capi.L2, M, nbits)
+    g.set_codebooks(o.codebooks())
+    o.add(ids, x.copy())
+    g.add(ids, x.copy())
+    q = np.concatenate([base[:2], rng.standard_normal((2, d)).astype(np.float32)])
+    check_pq(g, o, q, 50)
+    check_pq(g, o, q, 300)
+    oi = O.IVFPQ(d, capi.L2, 4, M, nbits)
+    oi.train(np.concatenate([train, x[:400]]).copy())
+    gi = capi.IVFPQIndex(d, capi.L2, 4, M, nbits)
+    gi.set_trained(oi.centroids(), oi.codebooks())
+    oi.add(ids, x.copy())
+    gi.add(ids, x.copy())
+    check_ivfpq(gi, oi, q, 50, 2)
+    check_ivfpq(gi, oi, q[:2], 3000, 1)

@@ -106,3 +106,112 @@ def test_shard_bounds_cover_rows_contiguously():
             assert r0 == nxt and m >= 0
             nxt = r0 + m
         assert nxt == n
+
+
+# ---- the other layouts of SURVEY 8e on CPU: PQ row shards (same exchange step as flat) and query-sharded replicas ----
+def _pq_worker(rank, world, port, out_q):
+    from oracle import oracle_py as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, q = _data()
+    train = x[:600]
+    row0, rows = shard_bounds(N, world, rank)
+    o = O.PQ(D, 0, 4, 4)
+    o.train(train.copy())                                    # codebooks are replicated: same training set on every rank
+    o.add(np.arange(row0 + 1, row0 + rows + 1, dtype=np.uint32), x[row0:row0 + rows].copy())
+
+    def search_local(queries):
+        ids = np.zeros((len(queries), K), np.int64)
+        sc = np.zeros((len(queries), K), np.float32)
+        cnt = np.zeros(len(queries), np.int64)
+        for i, qq in enumerate(queries):
+            a, b = o.search(qq, k=K)
+            ids[i, :len(a)], sc[i, :len(a)], cnt[i] = a, b, len(a)
+        return torch.from_numpy(ids), torch.from_numpy(sc), torch.from_numpy(cnt)
+
+    ids, sc, cnt = ShardedSearch(search_local, _merge_rule).search(q)
+    if rank == 0:
+        out_q.put((ids.numpy(), sc.numpy(), cnt.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_pq_row_shards_match_single_index():
+    """ADC scores tie often (few distinct table sums): the (score, shard, rank-in-list) merge must reproduce the
+    single index's (score, position) order across the shard boundary."""
+    from oracle import oracle_py as O
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pq_worker, args=(r, 2, port, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0, "a gloo rank failed"
+    ids, sc, cnt = out_q.get(timeout=10)
+    x, q = _data()
+    whole = O.PQ(D, 0, 4, 4)
+    whole.train(x[:600].copy())
+    whole.add(np.arange(1, N + 1, dtype=np.uint32), x.copy())
+    for i in range(NQ):
+        oi, os_ = whole.search(q[i], k=K)
+        assert cnt[i] == len(oi)
+        assert np.array_equal(sc[i, :cnt[i]].view(np.uint32), os_.view(np.uint32))
+        assert np.array_equal(ids[i, :cnt[i]], oi.astype(np.int64)), f"query {i}"
+
+
+def _replica_worker(rank, world, port, out_q):
+    from oracle import oracle_py as O
+    from comet_b200.sharded import ReplicatedSearch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, q = _data()
+    o = O.IVF(D, 8, 0)
+    o.train(x[:400].copy())
+    o.add(np.arange(1, N + 1, dtype=np.uint32), x.copy())
+
+    def search_local(queries):
+        ids = np.zeros((len(queries), K), np.int64)
+        sc = np.zeros((len(queries), K), np.float32)
+        cnt = np.zeros(len(queries), np.int64)
+        for i, qq in enumerate(queries):
+            a, b = o.search(qq, k=K, nprobes=3)
+            ids[i, :len(a)], sc[i, :len(a)], cnt[i] = a, b, len(a)
+        return torch.from_numpy(ids), torch.from_numpy(sc), torch.from_numpy(cnt)
+
+    ids, sc, cnt = ReplicatedSearch(search_local).search(torch.from_numpy(q).numpy())
+    if rank == 1:                                            # every rank holds the full result
+        out_q.put((ids.numpy(), sc.numpy(), cnt.numpy()))
+    dist.destroy_process_group()
+
+
+def test_three_rank_replicas_answer_their_own_queries():
+    from oracle import oracle_py as O
+    from comet_b200.sharded import query_bounds
+    covered = []
+    for r in range(3):
+        q0, m = query_bounds(NQ, 3, r)
+        covered += list(range(q0, q0 + m))
+    assert covered == list(range(NQ))
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_replica_worker, args=(r, 3, port, out_q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0, "a gloo rank failed"
+    ids, sc, cnt = out_q.get(timeout=10)
+    x, q = _data()
+    o = O.IVF(D, 8, 0)
+    o.train(x[:400].copy())
+    o.add(np.arange(1, N + 1, dtype=np.uint32), x.copy())
+    assert ids.shape == (NQ, K)
+    for i in range(NQ):
+        oi, os_ = o.search(q[i], k=K, nprobes=3)
+        assert cnt[i] == len(oi)
+        assert np.array_equal(sc[i, :cnt[i]].view(np.uint32), os_.view(np.uint32))
+        assert np.array_equal(ids[i, :cnt[i]], oi.astype(np.int64)), f"query {i}"
