@@ -628,19 +628,24 @@ __global__ void __launch_bounds__(NT, MINB) cand_select_kernel(
 // ------------------------------------------------------------------------------------------------
 // exact re-score of the candidates in reference order (distance.go loops), 128 candidates per block
 // ------------------------------------------------------------------------------------------------
-template <int METRIC, bool FMA>
+// CH = floats of a row fetched per step: 32 (one 128-byte line) or 64 (two consecutive lines, when ld % 64 == 0 --
+// longer DRAM bursts for the same bytes in flight).
+template <int METRIC, bool FMA, int CH>
 __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
                                                       const uint64_t *__restrict__ rs, const int *__restrict__ rs_cnt,
                                                       int rs_cap, float threshold, uint64_t *__restrict__ out_keys,
                                                       int *__restrict__ out_cnt) {
+    constexpr int PCS = CH / 4;                      // 16-byte pieces per row per step
+    constexpr int ROW_B = CH * 4;                    // bytes of a row in a stage
+    constexpr int STAGE_B = 128 * ROW_B;
     extern __shared__ __align__(16) uint8_t smem[];
     float *q_s = reinterpret_cast<float *>(smem);                    // [ld]
-    uint8_t *stage = smem + (size_t)ld * 4;                          // [2][128 rows][128 B], 16-byte pieces XOR-swizzled
+    uint8_t *stage = smem + (size_t)ld * 4;                          // [2][128 rows][ROW_B], 16-byte pieces XOR-swizzled
     __shared__ uint32_t pos_s[128];
     const int q = blockIdx.y, tid = threadIdx.x;
     const int cnt = min(rs_cnt[q], rs_cap);
     for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
-    const int n_chunks = ld / 32;
+    const int n_chunks = ld / CH;
     // a few CTAs per query, each walking its 128-candidate chunks (a (RS_CAP / 128) x nq grid would launch
     // mostly empty CTAs: ~230 candidates per query survive on the headline workload)
     for (int base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
@@ -651,13 +656,13 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
         pos_s[tid] = pos;
         __syncthreads();
         auto issue = [&](int c) {
-            uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
+            uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
 #pragma unroll
-            for (int p = 0; p < 8; p++) {
+            for (int p = 0; p < PCS; p++) {
                 int idx = p * 128 + tid;
-                int r = idx >> 3, piece = idx & 7;
-                const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
-                uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+                int r = idx / PCS, piece = idx % PCS;
+                const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
+                uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -672,10 +677,10 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
-            const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
-            const float *qc = q_s + c * 32;
+            const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
+            const float *qc = q_s + c * CH;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < PCS; j++) {
                 float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
                 float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
                 acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
@@ -693,21 +698,32 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
     }
 }
 
+template <int METRIC, bool FMA, int CH>
+static int launch_rescore_t(const float *rows, int ld, const float *queries, int nq, const uint64_t *rs, const int *rs_cnt,
+                            float threshold, uint64_t *out_keys, int *out_cnt, cudaStream_t st) {
+    dim3 grid(RS_GRID_X, (unsigned)nq);
+    size_t smem = (size_t)ld * 4 + 2 * 128 * (size_t)CH * 4;
+    auto kern = rescore_kernel<METRIC, FMA, CH>;
+    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt);
+    return CM_OK;
+}
+
 static int launch_rescore(int metric, bool fma, const float *rows, int ld, const float *queries, int nq,
                           const uint64_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
                           cudaStream_t st) {
-    dim3 grid(RS_GRID_X, (unsigned)nq);
-    size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
+    int ch = (ld % 64 == 0) ? 64 : 32;
+    if (const char *e = getenv("COMET_B200_RS_CH")) ch = (atoi(e) == 64 && ld % 64 == 0) ? 64 : 32;
     ProfScope prof(CM_PROF_RESCORE, st);
-#define CM_RS_CASE(M)                                                                                                 \
-    case M:                                                                                                           \
-        if (fma) {                                                                                                    \
-            CM_CUDA(cudaFuncSetAttribute(rescore_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            rescore_kernel<M, true><<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt); \
-        } else {                                                                                                      \
-            CM_CUDA(cudaFuncSetAttribute(rescore_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            rescore_kernel<M, false><<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt); \
-        }                                                                                                             \
+#define CM_RS_CASE(M)                                                                                                  \
+    case M:                                                                                                            \
+        if (ch == 64) {                                                                                                \
+            if (fma) CM_TRY((launch_rescore_t<M, true, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));   \
+            else CM_TRY((launch_rescore_t<M, false, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));      \
+        } else {                                                                                                       \
+            if (fma) CM_TRY((launch_rescore_t<M, true, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));   \
+            else CM_TRY((launch_rescore_t<M, false, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));      \
+        }                                                                                                              \
         break;
     switch (metric) {
         CM_RS_CASE(CM_L2)
