@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                         const uint32_t b = __ballot_sync(0xffffffffu, h);
                         if (b != 0u) {
                             const int q = qbase + cb * 32 + c;
-                            const int base = cnt_w[q];
+                            // only lane 0 ever touches the counter (read here, written below): no lane can
+                            // overtake another one's read under independent thread scheduling
+                            const int base = __shfl_sync(0xffffffffu, lane == 0 ? cnt_w[q] : 0, 0);
                             const int slot = base + __popc(b & lt_mask);
                             if (h && slot < cand_slots)
                                 my_cand[(size_t)q * q_stride + slot] = make_key(cur_hx - __uint_as_float(vv[c]), cur_row);
@@ -569,6 +571,7 @@ __global__ void __launch_bounds__(NT, MINB) cand_select_kernel(
             if (warp == 0) {
                 // bin holding rank s_rank: warp scan over 8 bins per lane
                 int h[8], sum = 0;
+                const int r = s_rank;              // read before the shuffles: they order it against the write below
 #pragma unroll
                 for (int u = 0; u < 8; u++) { h[u] = hist[lane * 8 + u]; sum += h[u]; }
                 int inc = sum;
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(NT, MINB) cand_select_kernel(
                     int t = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += t;
                 }
-                int r = s_rank, before = inc - sum;
+                int before = inc - sum;
                 bool mine = r > before && r <= inc;
                 if (mine) {
                     int rr = r - before, bb = 0;

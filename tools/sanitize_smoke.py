@@ -29,6 +29,31 @@ pq = capi.PQIndex(d, capi.L2, 8, 4)
 pq.train(x[:2000].copy()); pq.add(ids[:5000], x[:5000].copy()); pq.search(q[:9], k=10)
 ip = capi.IVFPQIndex(d, capi.L2, 8, 8, 4)
 ip.train(x[:2000].copy()); ip.add(ids[:5000], x[:5000].copy()); ip.search(q[:9], k=10, nprobes=3)
+# the ADC kernel's wide-row variants (M / 16 = 1 and 6: rounds of 4 / 3 rows per thread, table fast path for dsub 8),
+# enough codes per (query, probe) for several rounds, the radix-select compaction and the list-ordered code copy
+for (d2, M2, n2) in ((64, 16, 6000), (768, 96, 2600)):
+    x2 = rng.standard_normal((n2, d2)).astype(np.float32)
+    q2 = rng.standard_normal((5, d2)).astype(np.float32)
+    ids2 = np.arange(1, n2 + 1, dtype=np.uint32)
+    pq2 = capi.PQIndex(d2, capi.L2, M2, 8)
+    pq2.train(x2[:600].copy()); pq2.add(ids2, x2.copy()); pq2.search(q2, k=20); pq2.search(q2[:1], k=300)
+    ip2 = capi.IVFPQIndex(d2, capi.L2, 2, M2, 8)
+    ip2.train(x2[:600].copy()); ip2.add(ids2, x2.copy()); ip2.search(q2, k=20, nprobes=2)
+    ip2.remove(3); ip2.search(q2[:2], k=20, nprobes=1); ip2.flush(); ip2.search(q2[:2], k=20, nprobes=2)
+# tensor path with 256-byte re-score pieces (row pitch a multiple of 64 floats) and both select launch shapes
+x3 = rng.standard_normal((17000, 128)).astype(np.float32)
+f3 = capi.FlatIndex(128, capi.L2)
+f3.add(np.arange(1, 17001, dtype=np.uint32), x3)
+q3 = rng.standard_normal((70, 128)).astype(np.float32)
+f3.search(q3, k=10, path=capi.PATH_TENSOR)
+os.environ["COMET_B200_SEL_SMALL"] = "1"
+f3.search(q3, k=10, path=capi.PATH_TENSOR)
+f3.search(q3, k=10, path=capi.PATH_TENSOR)
+os.environ.pop("COMET_B200_SEL_SMALL")
+# HNSW insertion on the device
+hb = capi.HNSWIndex(d, capi.L2, 4, 20, 16)
+hb.add(ids[:200], x[:200].copy(), np.minimum(np.floor(-np.log(1.0 - rng.random(200)) / np.log(4.0)), 5).astype(np.int32))
+hb.search(q[:4], k=5)
 # a hand-made HNSW graph: a ring with chords on layer 0, a few nodes on layer 1
 n = 300
 levels = np.zeros(n, np.int32); levels[::50] = 1
