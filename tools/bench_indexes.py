@@ -108,7 +108,13 @@ def full_size(args):
         work = res["r"][3]
         evals = float(work[:, 0].mean())
         rec = float(np.mean([len(set(res["r"][0][i, :10].tolist()) & set(ti[i].tolist())) / 10 for i in range(nq)]))
-        out["c4_hnsw_knn_graph"] = {"n": hn, "dim": d, "degree": 32, "ef": 128, "k": 10, "nq": nq, "knn_graph_build_s": t_knn,
+        # the traversal is a latency-bound chain per query: throughput comes from queries in flight
+        sweep = {}
+        for nq2 in [int(v) for v in args.c4_nq.split(",") if v]:
+            qq = (torch.randn((nq2, 24), generator=g, device=dev) @ Wk).cpu().numpy()
+            dt2 = timed(lambda: gidx.search(qq, k=10, ef_search=128), reps=3)
+            sweep[str(nq2)] = {"ms_per_batch": dt2 * 1e3, "qps_host_api": nq2 / dt2}
+        out["c4_hnsw_knn_graph"] = {"queries_in_flight_sweep": sweep, "n": hn, "dim": d, "degree": 32, "ef": 128, "k": 10, "nq": nq, "knn_graph_build_s": t_knn,
                                     "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "dist_evals_per_query": evals,
                                     "expansions_per_query": float(work[:, 1].mean()),
                                     "algorithmic_GBps": nq * evals * (d * 4 + 4) / dt / 1e9, "recall_at_10_vs_flat": rec}
@@ -123,6 +129,7 @@ def main():
     ap.add_argument("--hnsw-n", type=int, default=20_000)
     ap.add_argument("--only", default="", help="comma list of ivf,pq,ivfpq,hnsw,hnswknn,c3,c4")
     ap.add_argument("--c3-n", type=int, default=10_000_000, help="rows of the BASELINE configs[2] run (IVFPQ)")
+    ap.add_argument("--c4-nq", default="2048,8192", help="extra batch sizes for the HNSW run")
     ap.add_argument("--c3-blobs", type=int, default=1024)
     ap.add_argument("--c3-nlist", type=int, default=4096)
     ap.add_argument("--c3-data", default="manifold", choices=["manifold", "blobs"])
