@@ -183,6 +183,66 @@ __device__ __forceinline__ float row_distance_rw(const float *row, const float *
     return metric_finish<METRIC>(acc);
 }
 
+// Distances of up to 32 rows (one per lane, `need` = this lane's row counts) to the vector in q_s, each in the
+// reference's order, with the rows STAGED through shared memory: per step the warp copies the next 128 bytes of every
+// needed row with 16-byte cp.async (a quarter-warp per row: coalesced, two steps in flight) and each lane then walks
+// its own row's piece.  The per-lane `row_distance` walk keeps only 64 bytes per lane in flight and re-fetches lines
+// through L1 when many warps share an SM.  Must be called by all 32 lanes; rows must not be written by this kernel.
+template <int METRIC, bool FMA>
+__device__ __forceinline__ float warp_row_distances(const float *__restrict__ rows, int ld, uint32_t nb, bool need,
+                                                    const float *__restrict__ q_s, uint8_t *stage, int lane) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, need);
+    if (mask == 0u) return 0.0f;
+    // the eight (row, piece) pairs this lane copies every step: rows p*4 + lane/8, piece lane%8
+    const int piece = lane & 7;
+    const float *src[8];
+    uint32_t dst_off[8];
+    bool cp[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int r = p * 4 + (lane >> 3);
+        const uint32_t nbr = __shfl_sync(0xffffffffu, nb, r);
+        cp[p] = (mask >> r) & 1u;
+        src[p] = rows + (size_t)nbr * ld + piece * 4;
+        dst_off[p] = (uint32_t)(r * 128 + ((piece ^ (r & 7)) << 4));
+    }
+    const int n_ch = ld / 32;
+    const uint32_t stage_u = smem_u32(stage);
+    auto issue = [&](int c) {
+        const uint32_t base = stage_u + (uint32_t)(c & 1) * 4096u;
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+            if (cp[p]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[p]), "l"(src[p] + c * 32) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    float acc = 0.0f;
+    for (int c = 0; c < n_ch; c++) {
+        if (c + 1 < n_ch) {
+            issue(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        if (need) {
+            const uint8_t *sp = stage + (size_t)(c & 1) * 4096 + lane * 128;
+            const float *qc = q_s + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (lane & 7)) << 4));
+                const float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
+                acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+                acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+                acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+                acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+            }
+        }
+        __syncwarp();
+    }
+    return metric_finish<METRIC>(acc);
+}
+
 // per-warp scratch in shared memory
 struct WarpScratch {
     float *q_s;        // [ld] the query / the vector being inserted
@@ -190,10 +250,13 @@ struct WarpScratch {
     float *nb_d;       // [32]
     uint32_t *nb_slot; // [32]
     uint32_t *nb_new;  // [32]
+    uint8_t *stage;    // [2][32 rows][128 B] row pieces of one expansion's neighbours (16-byte pieces XOR-swizzled)
 };
-__host__ __device__ inline size_t warp_scratch_bytes(int ld, int ef) {
+static constexpr int HNSW_STAGE_BYTES = 2 * 32 * 128;
+__host__ __device__ inline size_t warp_scratch_head(int ld, int ef) {
     return (((size_t)ld * 4 + (size_t)(ef + 1) * sizeof(HCand) + 32 * 12) + 15) & ~(size_t)15;
 }
+__host__ __device__ inline size_t warp_scratch_bytes(int ld, int ef) { return warp_scratch_head(ld, ef) + HNSW_STAGE_BYTES; }
 __device__ __forceinline__ WarpScratch carve(uint8_t *base, int ld, int ef) {
     WarpScratch w;
     w.q_s = reinterpret_cast<float *>(base);
@@ -201,6 +264,7 @@ __device__ __forceinline__ WarpScratch carve(uint8_t *base, int ld, int ef) {
     w.nb_d = reinterpret_cast<float *>(w.res + (ef + 1));
     w.nb_slot = reinterpret_cast<uint32_t *>(w.nb_d + 32);
     w.nb_new = w.nb_slot + 32;
+    w.stage = base + warp_scratch_head(ld, ef);
     return w;
 }
 
@@ -244,7 +308,7 @@ __device__ __forceinline__ void greedy_descend(const GraphView &G, const float *
 // searchLayer(query, entry, ef, layer), hnsw_index.go:565-629.  Leaves the results ASCENDING in `sorted`
 // (= the cands buffer, whose heap is dead by then) and returns their number, or -1 on candidate-heap overflow.
 // touched (optional): every slot whose visited bit was set is appended, so the caller can clear the bits.
-template <int METRIC, bool FMA>
+template <int METRIC, bool FMA, bool STAGED>
 __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratch &W, long long entry, int ef, int layer,
                                             uint32_t *vis, HCand *cands, int cand_cap, uint32_t *touched, int *n_touched,
                                             long long &evals, long long &expansions, int lane) {
@@ -293,8 +357,9 @@ __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratc
                     uint32_t old = atomicOr(&vis[nb >> 5], bit);
                     isnew = (old & bit) == 0u;
                 }
-                if (isnew) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, W.q_s, G.ld);
+                if (!STAGED && isnew) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, W.q_s, G.ld);
             }
+            if (STAGED) d = warp_row_distances<METRIC, FMA>(G.rows, G.ld, nb, isnew != 0u, W.q_s, W.stage, lane);
             W.nb_d[lane] = d; W.nb_slot[lane] = nb; W.nb_new[lane] = isnew;
             evals += __popc(__ballot_sync(0xffffffffu, isnew != 0u));
             __syncwarp();
@@ -354,7 +419,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
     greedy_descend<METRIC, FMA>(G, W.q_s, max_level, 0, curr, curr_dist, evals, lane);
 
     // phase 2: searchLayer(query, curr, ef, 0)
-    int n = search_layer<METRIC, FMA>(G, W, curr, ef, 0, vis, cands, cand_cap, nullptr, nullptr, evals, expansions, lane);
+    int n = search_layer<METRIC, FMA, true>(G, W, curr, ef, 0, vis, cands, cand_cap, nullptr, nullptr, evals, expansions, lane);
 
     // results: post-filter (hnsw_index_search.go:321-335), already ascending, first k
     if (lane == 0) {
@@ -449,7 +514,7 @@ __global__ void __launch_bounds__(32) hnsw_insert_kernel(GraphView G, long long 
         greedy_descend<METRIC, FMA>(G, W.q_s, max_l, L, curr, curr_dist, evals, lane);
         for (int lc = L; lc >= 0; lc--) {
             int n_touched = 0;
-            int nc = search_layer<METRIC, FMA>(G, W, curr, efc, lc, vis, cands, cand_cap, touched, &n_touched, evals, expansions, lane);
+            int nc = search_layer<METRIC, FMA, false>(G, W, curr, efc, lc, vis, cands, cand_cap, touched, &n_touched, evals, expansions, lane);
             n_touched = __shfl_sync(0xffffffffu, n_touched, 0);
             for (int t = lane; t < n_touched; t += 32) vis[touched[t] >> 5] = 0u;   // a fresh visited set per searchLayer
             __syncwarp();
