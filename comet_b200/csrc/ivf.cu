@@ -143,7 +143,8 @@ __device__ __forceinline__ uint32_t ivf_locate(const long long *__restrict__ qo,
 }
 
 // 128 candidates of one query per CTA: gather rows, reference-order distance, filters, keys out
-template <int METRIC, bool FMA>
+// CH = floats of a row fetched per step: 32, or 64 (two consecutive 128-byte lines) when ld % 64 == 0
+template <int METRIC, bool FMA, int CH>
 __global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
                                                        const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
                                                        const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
@@ -167,15 +168,16 @@ __global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__
     if (tid == 0) s_cnt = 0;
     for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
     __syncthreads();
-    const int n_ch = ld / 32;
+    constexpr int PCS = CH / 4, ROW_B = CH * 4, STAGE_B = 128 * ROW_B;
+    const int n_ch = ld / CH;
     auto issue = [&](int c) {
-        uint8_t *dst = stage + (size_t)(c & 1) * (128 * 128);
+        uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
+        for (int p = 0; p < PCS; p++) {
             int idx = p * 128 + tid;
-            int r = idx >> 3, piece = idx & 7;
-            const float *src = rows + (size_t)pos_s[r] * ld + c * 32 + piece * 4;
-            uint32_t d = smem_u32(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+            int r = idx / PCS, piece = idx % PCS;
+            const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
+            uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -190,10 +192,10 @@ __global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const uint8_t *sp = stage + (size_t)(c & 1) * (128 * 128) + tid * 128;
-        const float *qc = q_s + c * 32;
+        const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
+        const float *qc = q_s + c * CH;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < PCS; j++) {
             float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
             float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
             acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
@@ -234,15 +236,17 @@ static int launch_ivf_scan_m(bool fma, dim3 grid, size_t smem, cudaStream_t st, 
                              const long long *probe_list, const long long *q_off, const long long *list_off,
                              const uint32_t *members, int nprobes, const uint8_t *skip, float threshold, long long cap_c,
                              int n_chunks, uint64_t *out_keys, int *out_cnt) {
-    if (fma) {
-        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ivf_scan_kernel<METRIC, true><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes,
-                                                               skip, threshold, cap_c, n_chunks, out_keys, out_cnt);
-    } else {
-        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ivf_scan_kernel<METRIC, false><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes,
-                                                                skip, threshold, cap_c, n_chunks, out_keys, out_cnt);
-    }
+    const bool wide = ld % 64 == 0;
+    smem = (size_t)ld * 4 + 2 * 128 * (size_t)(wide ? 256 : 128);
+#define CM_IVF_GO(F, C)                                                                                                   \
+    do {                                                                                                                 \
+        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, F, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ivf_scan_kernel<METRIC, F, C><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes, \
+                                                               skip, threshold, cap_c, n_chunks, out_keys, out_cnt);     \
+    } while (0)
+    if (fma) { if (wide) CM_IVF_GO(true, 64); else CM_IVF_GO(true, 32); }
+    else { if (wide) CM_IVF_GO(false, 64); else CM_IVF_GO(false, 32); }
+#undef CM_IVF_GO
     count_launch();
     CM_CUDA(cudaGetLastError());
     return CM_OK;
