@@ -303,8 +303,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
+    t_enq0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    host_enqueue_ms = (time.perf_counter() - t_enq0) * 1e3 / args.steps   # CPU time to ENQUEUE one step (no sync inside)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -438,7 +440,7 @@ def run_ours(args):
                        "path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
                        "l2_policy": "inputs (%.2f GB fp32 corpus + bf16 shadow per GPU) larger than the 126 MB L2; no flush needed" % (shard * DIM * 4 / 1e9),
                        "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,
         }
         emit(line)

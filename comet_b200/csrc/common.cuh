@@ -43,6 +43,8 @@ struct ProfScope {
 };
 
 int ensure_device();            // CM_OK when a CUDA device is usable
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when this kernel needs more than it was last given
+int set_dyn_smem(const void *func, size_t bytes);
 int sm_count();
 int rounding_mode();            // CM_ROUND_*
 size_t max_smem_optin();

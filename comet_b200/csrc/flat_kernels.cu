@@ -241,7 +241,7 @@ static int launch_scan_t(const ScanLaunch &L, const CUtensorMap &tmap, const flo
                          int64_t n_rows, const uint8_t *skip, float threshold, uint64_t *part_keys,
                          int *part_counts, int n_groups, cudaStream_t stream) {
     auto kern = flat_scan_kernel<METRIC, FMA, QB>;
-    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    CM_TRY(set_dyn_smem((const void *)kern, L.smem));
     int n_tiles = (int)((n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS);
     ProfScope prof(CM_PROF_FLAT_SCAN, stream);
     kern<<<dim3((unsigned)L.grid, (unsigned)n_groups), SCAN_THREADS, L.smem, stream>>>(tmap, queries, ld, (long long)n_rows, n_tiles, L.stages, skip,
@@ -340,7 +340,7 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
     if (C < 2048) C = 2048;
     size_t smem = (size_t)C * 8;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
-    CM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CM_TRY(set_dyn_smem((const void *)merge_topk_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
     merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(part_keys, part_counts, parts, Kp, K, C, row_ids,
                                                            (long long)out_stride, out_ids, out_scores,
@@ -394,7 +394,7 @@ int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t 
     if (C < 512) C = 512;
     size_t smem = (size_t)C * 8;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "%d shards x k=%lld too large for the shard merge", world, (long long)in_stride);
-    CM_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CM_TRY(set_dyn_smem((const void *)merge_shards_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
     merge_shards_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>(ids, scores, (const long long *)counts, world,
                                                                       (long long)nq, (long long)in_stride, K, C,

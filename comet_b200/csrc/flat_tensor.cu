@@ -337,7 +337,7 @@ static int launch_gemm_t(const CUtensorMap &tx, const CUtensorMap &tq, const Gem
     int stages = CG == 2 ? 6 : 4;
     size_t smem = gemm_smem_bytes(CG, stages);
     auto kern = flat_gemm_kernel<CG, HAS_H>;
-    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CM_TRY(set_dyn_smem((const void *)kern, smem));
     int n_work = ph.n_tiles * n_qblk;
     if (n_work <= 0) return CM_OK;
     int clusters = std::min(sm_count() / CG, n_work);
@@ -707,7 +707,7 @@ static int launch_rescore_t(const float *rows, int ld, const float *queries, int
     dim3 grid(RS_GRID_X, (unsigned)nq);
     size_t smem = (size_t)ld * 4 + 2 * 128 * (size_t)CH * 4;
     auto kern = rescore_kernel<METRIC, FMA, CH>;
-    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CM_TRY(set_dyn_smem((const void *)kern, smem));
     kern<<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt);
     return CM_OK;
 }
@@ -852,8 +852,8 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     const int n_reg = n_cta * 4;   // candidate regions per query: (CTA, lane quadrant)
     if (n_reg > SEL_THREADS || n_reg > 2 * SEL_THREADS_SMALL) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
     const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8, sel_smem_small = (size_t)SEL_STAGE_CAP_SMALL * 8;
-    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel<SEL_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    CM_CUDA(cudaFuncSetAttribute(cand_select_kernel<SEL_THREADS_SMALL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_small));
+    CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS, 2>, sel_smem));
+    CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS_SMALL, 4>, sel_smem_small));
     int passes = 0;
     // keys staged per phase: counted on the device, copied to pinned memory after the last phase; the NEXT search
     // reads them (no synchronisation: a stale or missing value only means the roomier launch shape is used)

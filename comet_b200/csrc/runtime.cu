@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +28,22 @@ int fail(int code, const char *fmt, ...) {
     vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
     va_end(ap);
     return code;
+}
+
+// dynamic shared memory opt-in per (device, kernel): the runtime call is made only when a launch needs more than
+// the kernel was last given on that device (a search step launches the same dozen kernels over and over)
+static std::mutex g_smem_mu;
+static std::map<std::pair<int, const void *>, size_t> g_smem_set;
+int set_dyn_smem(const void *func, size_t bytes) {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t &have = g_smem_set[std::make_pair(dev, func)];
+    if (bytes > have) {
+        CM_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return CM_OK;
 }
 
 static std::once_flag g_dev_once;
