@@ -306,7 +306,7 @@ def run_ours(args):
     t_enq0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
-    host_enqueue_ms = (time.perf_counter() - t_enq0) * 1e3 / args.steps   # CPU time to ENQUEUE one step (no sync inside)
+    host_enqueue_ms = (time.perf_counter() - t_enq0) * 1e3 / args.steps   # CPU time to ENQUEUE one step (no sync inside; beyond ~75 steps the driver's launch queue fills and this includes waiting for the GPU)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

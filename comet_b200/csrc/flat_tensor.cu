@@ -770,6 +770,12 @@ void FlatIndex::free_shadow() {
 
 int FlatIndex::ensure_shadow(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(shadow_mu);
+    if (!staged_dev) {          // statistics words of the tensor path (concurrent searches share them)
+        CM_CUDA(cudaMalloc(&rescored_dev, 8));
+        CM_CUDA(cudaHostAlloc(&staged_host, 8 * sizeof(int), cudaHostAllocDefault));
+        for (int p = 0; p < 8; p++) staged_host[p] = -1;
+        CM_CUDA(cudaMalloc(&staged_dev, 8 * sizeof(int)));
+    }
     if (rows_bf16 && shadow_rows == n && shadow_cap == cap) return CM_OK;
     ldb = (dim + GT_BK - 1) / GT_BK * GT_BK;
     if (!rows_bf16 || shadow_cap != cap) {
@@ -857,12 +863,7 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     int passes = 0;
     // keys staged per phase: counted on the device, copied to pinned memory after the last phase; the NEXT search
     // reads them (no synchronisation: a stale or missing value only means the roomier launch shape is used)
-    if (!staged_dev) {
-        CM_CUDA(cudaMalloc(&staged_dev, 8 * sizeof(int)));
-        CM_CUDA(cudaHostAlloc(&staged_host, 8 * sizeof(int), cudaHostAllocDefault));
-        for (int p = 0; p < 8; p++) staged_host[p] = -1;
-    }
-    CM_CUDA(cudaMemsetAsync(staged_dev, 0, 8 * sizeof(int), st));
+    CM_CUDA(cudaMemsetAsync(staged_dev, 0, 8 * sizeof(int), st));      // allocated by ensure_shadow (under its lock)
     const int small_ok = SEL_STAGE_CAP_SMALL - SEL_STAGE_CAP_SMALL / 12;      // 8 % headroom
     bool sel_small[MAX_PH];
     for (int p = 0; p < n_ph; p++) {
@@ -878,7 +879,6 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         for (int p = 0; p < n_ph; p++) sel_small[p] = sel_small[p] && want_small;
     }
     const bool dbg_staged = getenv("COMET_B200_DBG_STAGED") != nullptr;
-    if (!rescored_dev) CM_CUDA(cudaMalloc(&rescored_dev, 8));
     CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
     if (const char *e = getenv("COMET_B200_NO_DENSE")) if (atoi(e)) for (int p = 0; p < n_ph; p++) ph[p].dense = 0;
