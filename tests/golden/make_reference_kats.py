@@ -21,6 +21,25 @@ KATS = {
         {"src": "distance_test.go:417-491", "in": [3, 4], "want": [0.6, 0.8], "tol": 1e-6},
         {"src": "distance_test.go:417-491", "in": [0, 0, 0], "error": "ErrZeroVector"},
     ],
+    # Norm / Normalize / NormalizeInPlace helpers (distance.go:312-428).  For a ZERO vector the helpers return the
+    # vector unchanged, while cosine.Preprocess -- the call on the search path -- returns ErrZeroVector (above).
+    "norm": [
+        {"src": "distance_test.go:533-579", "in": [3, 4], "want": 5.0}, {"src": "distance_test.go:533-579", "in": [1, 0, 0], "want": 1.0},
+        {"src": "distance_test.go:533-579", "in": [0, 0, 0], "want": 0.0}, {"src": "distance_test.go:533-579", "in": [-3, -4], "want": 5.0},
+        {"src": "distance_test.go:533-579", "in": [7], "want": 7.0}, {"src": "distance_test.go:533-579", "in": [1, 1, 1, 1], "want": 2.0},
+    ],
+    "normalize_helper": [
+        {"src": "distance_test.go:656-722", "in": [3, 4], "want": [0.6, 0.8]}, {"src": "distance_test.go:656-722", "in": [1, 0, 0], "want": [1, 0, 0]},
+        {"src": "distance_test.go:656-722", "in": [-3, -4], "want": [-0.6, -0.8]},
+        {"src": "distance_test.go:656-722", "in": [1, 1, 1, 1], "want": [0.5, 0.5, 0.5, 0.5]},
+        {"src": "distance_test.go:724-781", "in": [2, 2, 2, 2], "want": [0.5, 0.5, 0.5, 0.5]},
+    ],
+    # TestHighDimensionalVectors (distance_test.go:786-816): a[i] = i % 10, b[i] = (i + 1) % 10, dim 768; every metric finite
+    "high_dimensional": {"src": "distance_test.go:786-816", "dim": 768},
+    # TestCalculateBatchConsistency (distance_test.go:886-925): per-query Calculate == batch, target all zeros
+    "batch_consistency": {"src": "distance_test.go:886-925", "queries": [[1, 2, 3], [4, 5, 6], [7, 8, 9]], "target": [0, 0, 0]},
+    # TestDistanceKindConstants (distance_test.go:870-884)
+    "kind_constants": {"src": "distance_test.go:870-884", "l2": "l2", "l2_squared": "l2_squared", "cosine": "cosine"},
     "sanitize_k": [
         {"src": "limiter_test.go:7-73", "k": 0, "max": 5, "want": 5}, {"src": "limiter_test.go:7-73", "k": -1, "max": 5, "want": 5},
         {"src": "limiter_test.go:7-73", "k": 3, "max": 5, "want": 3}, {"src": "limiter_test.go:7-73", "k": 10, "max": 5, "want": 5},

@@ -433,6 +433,24 @@ def test_golden_reference_kats_file():
                 O.normalize(np.asarray(c["in"], np.float32))
         else:
             assert np.allclose(O.normalize(np.asarray(c["in"], np.float32)), c["want"], atol=c["tol"])
+    for c in kats["norm"]:
+        assert abs(O.norm(np.asarray(c["in"], np.float32)) - c["want"]) <= EPS, c
+    for c in kats["normalize_helper"]:
+        assert np.allclose(O.normalize(np.asarray(c["in"], np.float32)), c["want"], atol=EPS), c
+    hd = kats["high_dimensional"]["dim"]
+    a = (np.arange(hd) % 10).astype(np.float32)
+    b = ((np.arange(hd) + 1) % 10).astype(np.float32)
+    assert np.isfinite(O.distance(0, a, b)) and np.isfinite(O.distance(1, a, b))
+    assert O.distance(1, a, b) == 692.0 * 1.0 + 76.0 * 81.0                       # 692 elements differ by 1, 76 by 9 (exact in fp32)
+    assert np.isfinite(O.distance(2, O.normalize(a), O.normalize(b)))
+    bc = kats["batch_consistency"]
+    for qv in bc["queries"]:
+        qv = np.asarray(qv, np.float32)
+        assert O.distance(0, qv, np.asarray(bc["target"], np.float32)) == O.norm(qv)          # |q - 0| is the norm, same loop
+        assert O.distance(1, qv, np.asarray(bc["target"], np.float32)) == float(np.float32(np.dot(qv, qv)))
+    from comet_b200 import capi
+    kc = kats["kind_constants"]
+    assert capi.METRICS == {kc["l2"]: capi.L2, kc["l2_squared"]: capi.L2SQ, kc["cosine"]: capi.COSINE}
     for c in kats["sanitize_k"]:
         assert O.sanitize_k(c["k"], c["max"]) == c["want"], c
     for c in kats["flat_search"]:
