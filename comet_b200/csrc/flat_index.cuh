@@ -30,14 +30,15 @@ struct FlatIndex {
 
     // tensor-core candidate pass state (flat_tensor.cu)
     __nv_bfloat16 *rows_bf16 = nullptr;     // [cap][ldb] bf16 shadow of rows, ldb = dim padded to 64
-    float *row_h = nullptr;                 // [cap] |x|^2 / 2 for L2 / L2^2, 0 for cosine (candidate key offset)
+    float *row_h = nullptr;                 // [cap + 128] |x|^2 / 2 for L2 / L2^2, 0 for cosine (candidate key offset); +inf behind row n
     unsigned int *max_bits = nullptr;       // device [2]: bits of max_row |x| and max_row |x - bf16(x)| (error bound)
     int ldb = 0;
     int64_t shadow_rows = 0;                // rows [0, shadow_rows) of the shadow are current
     int64_t shadow_cap = 0;
     int tensor_cta_group = 2;               // 2: CTA pairs (UMMA M=256), 1: single-CTA UMMA M=128
     std::mutex shadow_mu;
-    CUtensorMap tmap_bf16;
+    CUtensorMap tmap_bf16;                  // box 64 x 128 rows (both operands staged in shared memory)
+    CUtensorMap tmap_bf16_ts;               // box 64 x 32 rows (query-resident pass, flat_gemm_ts.cu)
 
     std::mutex stats_mu;
     cm_flat_stats last_stats{};

@@ -32,6 +32,7 @@
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+#include "flat_tensor.cuh"
 #include "select.cuh"
 #include "tcgen05.cuh"
 
@@ -49,55 +50,7 @@ static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem
 static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
 static constexpr int RS_CAP = 2048;        // candidates re-scored per query
 static constexpr int RS_GRID_X = 2;        // re-score CTAs per query (each loops over its 128-candidate chunks)
-static constexpr int MAX_PH = 6;           // phases of the candidate pass
 static constexpr int SEL_STAGE_CAP = 12288; // keys (old survivors + new candidates) staged in smem by the select kernel (96 KB)
-
-struct GemmPhase {
-    int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
-    int SA, SB;
-    int n_tiles;      // tiles in this class
-    int dbg;          // debugging aid: 1 = epilogue skips the accumulator scan, 2 = loads TMEM but does not compare
-    int dense;        // 1: (nearly) every score of this phase is a candidate (phase A): emit column by column
-};
-
-__device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
-    switch (p.cls) {
-    case 0: return i * p.SA;
-    case 1: { int R = p.SA / p.SB; int j = i + i / (R - 1) + 1; return j * p.SB; }
-    case 2: return i + i / (p.SB - 1) + 1;
-    default: return i;
-    }
-}
-
-// v[c] for a run-time c without spilling the register array: a 32-way switch (taken only on the rare
-// candidate path)
-__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int c) {
-    switch (c) {
-#define CM_PICK(i) case i: return v[i];
-        CM_PICK(0) CM_PICK(1) CM_PICK(2) CM_PICK(3) CM_PICK(4) CM_PICK(5) CM_PICK(6) CM_PICK(7)
-        CM_PICK(8) CM_PICK(9) CM_PICK(10) CM_PICK(11) CM_PICK(12) CM_PICK(13) CM_PICK(14) CM_PICK(15)
-        CM_PICK(16) CM_PICK(17) CM_PICK(18) CM_PICK(19) CM_PICK(20) CM_PICK(21) CM_PICK(22) CM_PICK(23)
-        CM_PICK(24) CM_PICK(25) CM_PICK(26) CM_PICK(27) CM_PICK(28) CM_PICK(29) CM_PICK(30)
-#undef CM_PICK
-    default: return v[31];
-    }
-}
-
-// The same pick as a 5-level select tree: 31 SELs, no divergence.  Used when many lanes of the warp hold a
-// hit in the same pass (the branch tree above then runs once per DISTINCT column, up to 32 times).
-__device__ __forceinline__ uint32_t pick32_sel(const uint32_t (&v)[32], int c) {
-    uint32_t a[16], b[8], d[4], e[2];
-    const bool p0 = (c & 1) != 0, p1 = (c & 2) != 0, p2 = (c & 4) != 0, p3 = (c & 8) != 0, p4 = (c & 16) != 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = p0 ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = p1 ? a[2 * i + 1] : a[2 * i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) d[i] = p2 ? b[2 * i + 1] : b[2 * i];
-#pragma unroll
-    for (int i = 0; i < 2; i++) e[i] = p3 ? d[2 * i + 1] : d[2 * i];
-    return p4 ? e[1] : e[0];
-}
 
 template <int CG, bool HAS_H>
 __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
@@ -155,6 +108,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
             uint32_t ph = 0;
             const uint32_t stage0 = smem_u32(stage_base), full0 = smem_u32(&full_bar[0]);
             const uint32_t full0_leader = (CG == 2) ? tc::mapa(full0, 0) : full0;
+            // timing probes (results are garbage): dbg bit 64 / 128 = stop loading the corpus / query operand
+            // once the ring has been filled once -- what the mainloop costs with half (or none) of its L2 traffic
+            int fills = 0;
             for (int w = cluster; w < n_work; w += n_clusters) {
                 int t = phase_tile(phase, w / n_qblk), nb = w % n_qblk;
                 int row0 = t * (GT_ROWS * CG) + (int)cta_rank * GT_ROWS;
@@ -162,10 +118,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) flat_gemm_kernel(
                 for (int kb = 0; kb < k_blocks; kb++) {
                     mbar_wait_parked(&empty_bar[s], ph ^ 1);
                     const uint32_t bar = full0_leader + (uint32_t)s * 8u;
-                    if (cta_rank == 0) tc::mbar_arrive_expect_tx_addr(full0 + (uint32_t)s * 8u, STAGE_BYTES * CG);
+                    const bool ld_a = !(phase.dbg & 64) || fills < stages, ld_b = !(phase.dbg & 128) || fills < stages;
+                    if (fills < stages) fills++;
+                    if (cta_rank == 0)
+                        tc::mbar_arrive_expect_tx_addr(full0 + (uint32_t)s * 8u, ((ld_a ? GT_A_BYTES : 0) + (ld_b ? B_BYTES : 0)) * CG);
                     const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE_BYTES;
-                    tc::tma_load_2d_cg<CG>(sa, &tmap_x, kb * GT_BK, row0, bar);
-                    tc::tma_load_2d_cg<CG>(sa + GT_A_BYTES, &tmap_q, kb * GT_BK, q0, bar);
+                    if (ld_a) tc::tma_load_2d_cg<CG>(sa, &tmap_x, kb * GT_BK, row0, bar);
+                    if (ld_b) tc::tma_load_2d_cg<CG>(sa + GT_A_BYTES, &tmap_q, kb * GT_BK, q0, bar);
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -740,9 +699,21 @@ static int launch_rescore(int metric, bool fma, const float *rows, int ld, const
     return CM_OK;
 }
 
-__global__ void init_bounds_kernel(float *__restrict__ g, int nq, int nq_pad) {
+__global__ void init_bounds_kernel(float *__restrict__ g, int nq, int nq_pad, float first) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq_pad) g[q] = q < nq ? -INFINITY : INFINITY;
+    if (q < nq_pad) g[q] = q < nq ? first : INFINITY;
+}
+
+// key offsets as the query-resident pass reads them: +inf for rows that must not become candidates
+// (soft-deleted / filtered out / beyond the last row)
+__global__ void fill_inf_kernel(float *__restrict__ h, long long from, long long to) {
+    long long i = from + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < to) h[i] = INFINITY;
+}
+__global__ void masked_h_kernel(const float *__restrict__ row_h, const uint8_t *__restrict__ skip, long long n,
+                                long long n_pad, float *__restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_pad) out[i] = (i < n && !skip[i]) ? row_h[i] : INFINITY;
 }
 
 // queries that overflowed a candidate list get count -1 (the host entry point redoes them exactly)
@@ -781,18 +752,26 @@ int FlatIndex::ensure_shadow(cudaStream_t st) {
     if (!rows_bf16 || shadow_cap != cap) {
         free_shadow();
         CM_CUDA(cudaMalloc(&rows_bf16, (size_t)cap * ldb * sizeof(__nv_bfloat16)));
-        CM_CUDA(cudaMalloc(&row_h, (size_t)cap * sizeof(float)));
+        CM_CUDA(cudaMalloc(&row_h, (size_t)(cap + 2 * TS_N) * sizeof(float)));
         CM_CUDA(cudaMalloc(&max_bits, 2 * sizeof(unsigned int)));
         CM_CUDA(cudaMemsetAsync(max_bits, 0, 2 * sizeof(unsigned int), st));
         shadow_cap = cap;
         shadow_rows = 0;
         CM_TRY(make_tmap_2d(&tmap_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_bf16, (uint64_t)ldb, (uint64_t)cap,
                             (uint64_t)ldb * 2, GT_BK, GT_ROWS, CU_TENSOR_MAP_SWIZZLE_128B));
+        CM_TRY(make_tmap_2d(&tmap_bf16_ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows_bf16, (uint64_t)ldb, (uint64_t)cap,
+                            (uint64_t)ldb * 2, GT_BK, TS_N / 2, CU_TENSOR_MAP_SWIZZLE_128B));
     }
     if (shadow_rows == 0) CM_CUDA(cudaMemsetAsync(max_bits, 0, 2 * sizeof(unsigned int), st));
     float h_scale = metric == CM_COSINE ? 0.0f : 0.5f;
     CM_TRY(launch_to_bf16(rows + (size_t)shadow_rows * ld, n - shadow_rows, dim, ld, rows_bf16 + (size_t)shadow_rows * ldb,
                           ldb, h_scale, row_h + shadow_rows, nullptr, max_bits, st));
+    {   // rows behind the last one read as +inf offsets: the query-resident pass walks whole 64-row tiles
+        const long long to = cap + 2 * TS_N;
+        fill_inf_kernel<<<(unsigned)((to - n + 255) / 256), 256, 0, st>>>(row_h, (long long)n, to);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
     CM_CUDA(cudaStreamSynchronize(st));
     shadow_rows = n;
     return CM_OK;
@@ -808,55 +787,65 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     if (k_eff > RS_CAP / 2) return fail(CM_ERR_UNSUPPORTED, "tensor path supports k <= %d", RS_CAP / 2);
     CM_TRY(ensure_shadow(st));
     const int cg = tensor_cta_group;
-    const int tile_rows = GT_ROWS * cg;
+    // Query-resident candidate pass (flat_gemm_ts.cu) whenever a query row fits in tensor memory beside the
+    // accumulators; wider rows (and the single-CTA debugging shape) stage both operands in shared memory.
+    bool use_ts = cg == 2 && ldb <= TS_MAX_LDB;
+    if (const char *e = getenv("COMET_B200_NO_TS")) if (atoi(e)) use_ts = false;
+    const int tile_rows = use_ts ? TS_N : GT_ROWS * cg;
     const int T = (int)((n + tile_rows - 1) / tile_rows);
     const int K = (int)k_eff;
     bool fma = rounding_mode() == CM_ROUND_FMA;
 
-    // ---- phase plan (see the header comment) ----
-    // Phase A gives every cluster at most one tile (its rows all become candidates: <= 128 per
-    // (query, CTA) region); B is sized so that it emits about as many candidates as A did.
     if (n < 16384) return fail(CM_ERR_UNSUPPORTED, "the tensor path needs at least 16384 rows (have %lld)", (long long)n);
     const int n_cta = sm_count();
     const int n_clusters = n_cta / cg;
-    // Geometric phases: A ~ 50 K rows (at most one tile per cluster, so its all-candidate rows fit the
-    // per-CTA regions), every later phase ~ 10x the rows seen so far, the last one takes the rest once
-    // it is within 25x of the rows already seen.  A phase then emits ~ 2 K x (its rows / rows seen
-    // before) keys per query whatever n is (sweep on 1M and 12.5M x 768: profiles/r01_tensor_path.md).
-    // Tile t belongs to the first level whose stride divides t (strides nest: S_0 | S_1 | ... ).
+    // ---- phase plan (see the header comment) ----
+    // Geometric phases: A ~ 50 K rows (all of them candidates, so they have to fit the candidate regions), every
+    // later phase ~ 10x the rows seen so far, the last one takes the rest once it is within 25x of the rows already
+    // seen.  A phase then emits ~ 2 K x (its rows / rows seen before) keys per query whatever n is (sweep on 1M and
+    // 12.5M x 768: profiles/r01_tensor_path.md).  Tile t belongs to the first level whose stride divides t
+    // (strides nest: S_0 | S_1 | ... ).
+    // Region capacity bounds phase A: shared-memory staging gives every cluster at most one 128/256-row tile
+    // (128 slots per lane quadrant); the query-resident pass puts 32 keys per tile into a 256-slot region and a
+    // query block is served by at least n_clusters / 4 clusters.
+    const int max_tiles_a = use_ts ? (TS_SLOTS / (TS_N / 2) - 2) * std::max(1, n_clusters / (GT_MAX_NQ / TS_QBLK))
+                                   : std::max(1, n_clusters / 2);
     GemmPhase ph[MAX_PH];
     int n_ph = 0;
     {
         int64_t rows_a = std::min<int64_t>(std::max<int64_t>(50 * (int64_t)K, 2048), 8192);
         if (const char *e = getenv("COMET_B200_ROWS_A")) rows_a = atoll(e);
-        int tA = std::min((int)((rows_a + tile_rows - 1) / tile_rows), std::max(1, n_clusters / 2));
         int64_t growth = 10;
         if (const char *e = getenv("COMET_B200_PHASE_GROWTH")) growth = std::max<int64_t>(2, atoll(e));
-        // cumulative tile targets of the sampled levels
-        std::vector<int64_t> cum;
-        cum.push_back(tA);
-        while ((int)cum.size() < MAX_PH - 1 && (T - cum.back()) > 25 * cum.back()) cum.push_back(cum.back() * (growth + 1));
-        // strides from the finest level up, each a multiple of the next
-        int L = (int)cum.size();
-        std::vector<int> S((size_t)L);
-        S[(size_t)L - 1] = (int)std::max<int64_t>(2, T / cum[(size_t)L - 1]);
-        for (int i = L - 2; i >= 0; i--) {
-            int R = (int)std::max<int64_t>(2, (cum[(size_t)i + 1] + cum[(size_t)i] / 2) / cum[(size_t)i]);
-            S[(size_t)i] = S[(size_t)i + 1] * R;
+        int tA = std::min((int)((rows_a + tile_rows - 1) / tile_rows), max_tiles_a);
+        for (;;) {
+            n_ph = 0;
+            // cumulative tile targets of the sampled levels
+            std::vector<int64_t> cum;
+            cum.push_back(tA);
+            while ((int)cum.size() < MAX_PH - 1 && (T - cum.back()) > 25 * cum.back()) cum.push_back(cum.back() * (growth + 1));
+            // strides from the finest level up, each a multiple of the next
+            int L = (int)cum.size();
+            std::vector<int> S((size_t)L);
+            S[(size_t)L - 1] = (int)std::max<int64_t>(2, T / cum[(size_t)L - 1]);
+            for (int i = L - 2; i >= 0; i--) {
+                int R = (int)std::max<int64_t>(2, (cum[(size_t)i + 1] + cum[(size_t)i] / 2) / cum[(size_t)i]);
+                S[(size_t)i] = S[(size_t)i + 1] * R;
+            }
+            auto mult = [&](int stride) { return (int)((T + stride - 1) / stride); };   // multiples of stride in [0, T)
+            ph[n_ph++] = GemmPhase{0, S[0], S[0], mult(S[0]), 0, 1};
+            for (int i = 1; i < L; i++) ph[n_ph++] = GemmPhase{1, S[(size_t)i - 1], S[(size_t)i], mult(S[(size_t)i]) - mult(S[(size_t)i - 1]), 0, 0};
+            ph[n_ph++] = GemmPhase{2, S[(size_t)L - 1], S[(size_t)L - 1], T - mult(S[(size_t)L - 1]), 0, 0};
+            const int cap_a = use_ts ? (TS_SLOTS / (TS_N / 2)) * std::max(1, n_clusters / (GT_MAX_NQ / TS_QBLK)) : n_clusters;
+            if (ph[0].n_tiles <= cap_a) break;
+            if (tA <= 1) return fail(CM_ERR_UNSUPPORTED, "phase plan: %d first-phase tiles for %d clusters", ph[0].n_tiles, n_clusters);
+            tA = tA * 3 / 4;     // stride rounding made phase A larger than asked for: ask for less
         }
-        auto mult = [&](int stride) { return (int)((T + stride - 1) / stride); };   // multiples of stride in [0, T)
-        ph[n_ph++] = GemmPhase{0, S[0], S[0], mult(S[0]), 0, 1};
-        for (int i = 1; i < L; i++) ph[n_ph++] = GemmPhase{1, S[(size_t)i - 1], S[(size_t)i], mult(S[(size_t)i]) - mult(S[(size_t)i - 1]), 0, 0};
-        ph[n_ph++] = GemmPhase{2, S[(size_t)L - 1], S[(size_t)L - 1], T - mult(S[(size_t)L - 1]), 0, 0};
-        if (ph[0].n_tiles > n_clusters)
-            return fail(CM_ERR_UNSUPPORTED, "phase plan: %d first-phase tiles for %d clusters", ph[0].n_tiles, n_clusters);
     }
 
     // debugging aid: widen the candidate band (>= 1 keeps the result exact)
     float e_scale = 1.0f;
     if (const char *es = getenv("COMET_B200_E_SCALE")) e_scale = std::max(1.0f, (float)atof(es));
-    const int n_reg = n_cta * 4;   // candidate regions per query: (CTA, lane quadrant)
-    if (n_reg > SEL_THREADS || n_reg > 2 * SEL_THREADS_SMALL) return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
     const size_t sel_smem = (size_t)SEL_STAGE_CAP * 8, sel_smem_small = (size_t)SEL_STAGE_CAP_SMALL * 8;
     CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS, 2>, sel_smem));
     CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS_SMALL, 4>, sel_smem_small));
@@ -882,10 +871,26 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
     if (const char *e = getenv("COMET_B200_NO_DENSE")) if (atoi(e)) for (int p = 0; p < n_ph; p++) ph[p].dense = 0;
+    // key offsets with the skip mask folded in (query-resident pass: +inf = never a candidate)
+    const float *h_eff = row_h;
+    float *h_masked = nullptr;
+    if (use_ts && skip != nullptr) {
+        const long long n_pad = (long long)T * TS_N;
+        CM_TRY(ws_alloc((void **)&h_masked, (size_t)n_pad * 4, st));
+        masked_h_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(row_h, skip, (long long)n, n_pad, h_masked);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+        h_eff = h_masked;
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += GT_MAX_NQ) {
         int nqc = (int)std::min<int64_t>(GT_MAX_NQ, nq - q0);
         int nq_pad = (nqc + GT_QBLK - 1) / GT_QBLK * GT_QBLK;
         int n_qblk = nq_pad / GT_QBLK;
+        // candidate regions per query: (CTA, lane quadrant) / (cluster of the query's block, column half)
+        const int n_reg = use_ts ? ts_regions(n_clusters, n_qblk) : n_cta * 4;
+        const int slots = use_ts ? TS_SLOTS : CAND_SLOTS;
+        if (n_reg > SEL_THREADS || n_reg > 2 * SEL_THREADS_SMALL)
+            return fail(CM_ERR_UNSUPPORTED, "%d SMs: more candidate regions than the select kernel scans", n_cta);
         // ---- workspace ----
         __nv_bfloat16 *q16 = nullptr;
         float2 *qn = nullptr;
@@ -896,24 +901,28 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
         CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
-        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * CAND_SLOTS * 8, st));
+        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * slots * 8, st));
         CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 4) * 4, st));
         ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
         CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
         CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 4) * 4, st));
         CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
-        // g: phase A bound is -inf for real queries (everything is a candidate), +inf for padding
-        init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad);
+        // g = -(bound): phase A lets everything through for real queries (a large FINITE value for the query-resident
+        // pass, whose invalid rows carry +inf offsets: inf - inf would be NaN), nothing for padding
+        init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad, use_ts ? -3.0e38f : -INFINITY);
         count_launch();
         CM_CUDA(cudaGetLastError());
         CM_TRY(launch_to_bf16(qp + (size_t)q0 * ld, nqc, dim, ld, q16, ldb, 0.0f, nullptr, qn, nullptr, st));
         CUtensorMap tq;
-        CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
-                            (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
+        if (!use_ts)
+            CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
+                                (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
         for (int p = 0; p < n_ph; p++) {
             const bool has_h = metric != CM_COSINE;   // cosine keys are -dot: no per-row offset
-            if (cg == 2 && has_h)
+            if (use_ts)
+                CM_TRY(launch_gemm_ts(tmap_bf16_ts, ph[p], n_qblk, ldb, q16, h_eff, has_h || h_masked != nullptr, n, g, cand, ccnt, st));
+            else if (cg == 2 && has_h)
                 CM_TRY((launch_gemm_t<2, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else if (cg == 2)
                 CM_TRY((launch_gemm_t<2, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
@@ -930,11 +939,11 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
                 int *s_out_cnt = rcnt + (size_t)out * nq_pad;
                 if (sel_small[p])
                     cand_select_kernel<SEL_THREADS_SMALL, 4><<<nqc, SEL_THREADS_SMALL, sel_smem_small, st>>>(
-                        cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
+                        cand, ccnt, nq_pad, n_reg, slots, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
                         RS_CAP, SEL_STAGE_CAP_SMALL, e_scale, staged_dev + p);
                 else
                     cand_select_kernel<SEL_THREADS, 2><<<nqc, SEL_THREADS, sel_smem, st>>>(
-                        cand, ccnt, nq_pad, n_reg, CAND_SLOTS, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
+                        cand, ccnt, nq_pad, n_reg, slots, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
                         RS_CAP, SEL_STAGE_CAP, e_scale, staged_dev + p);
                 count_launch();
                 CM_CUDA(cudaGetLastError());
@@ -954,6 +963,7 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);
     }
+    ws_free(h_masked, st);
     CM_CUDA(cudaMemcpyAsync(staged_host, staged_dev, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (dbg_staged) {
         cudaStreamSynchronize(st);

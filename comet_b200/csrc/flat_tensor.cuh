@@ -1,0 +1,75 @@
+// flat_tensor.cuh -- pieces shared by the two candidate-pass kernels of the tensor path (flat_tensor.cu: both
+// operands streamed through shared memory; flat_gemm_ts.cu: queries resident in tensor memory).
+#pragma once
+
+#include "common.cuh"
+
+namespace cm {
+
+static constexpr int MAX_PH = 6;           // phases of the candidate pass
+
+struct GemmPhase {
+    int cls;          // 0: tiles t % SA == 0; 1: t % SB == 0 && t % SA != 0; 2: t % SB != 0; 3: all tiles
+    int SA, SB;
+    int n_tiles;      // tiles in this class
+    int dbg;          // debugging aid: 1 = epilogue skips the accumulator scan, 2 = loads TMEM but does not compare
+    int dense;        // 1: (nearly) every score of this phase is a candidate (phase A): emit column by column
+};
+
+__device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
+    switch (p.cls) {
+    case 0: return i * p.SA;
+    case 1: { int R = p.SA / p.SB; int j = i + i / (R - 1) + 1; return j * p.SB; }
+    case 2: return i + i / (p.SB - 1) + 1;
+    default: return i;
+    }
+}
+
+// v[c] for a run-time c without spilling the register array: a 32-way switch (taken only on the rare
+// candidate path)
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int c) {
+    switch (c) {
+#define CM_PICK(i) case i: return v[i];
+        CM_PICK(0) CM_PICK(1) CM_PICK(2) CM_PICK(3) CM_PICK(4) CM_PICK(5) CM_PICK(6) CM_PICK(7)
+        CM_PICK(8) CM_PICK(9) CM_PICK(10) CM_PICK(11) CM_PICK(12) CM_PICK(13) CM_PICK(14) CM_PICK(15)
+        CM_PICK(16) CM_PICK(17) CM_PICK(18) CM_PICK(19) CM_PICK(20) CM_PICK(21) CM_PICK(22) CM_PICK(23)
+        CM_PICK(24) CM_PICK(25) CM_PICK(26) CM_PICK(27) CM_PICK(28) CM_PICK(29) CM_PICK(30)
+#undef CM_PICK
+    default: return v[31];
+    }
+}
+
+// The same pick as a 5-level select tree: 31 SELs, no divergence.  Used when many lanes of the warp hold a
+// hit in the same pass (the branch tree above then runs once per DISTINCT column, up to 32 times).
+__device__ __forceinline__ uint32_t pick32_sel(const uint32_t (&v)[32], int c) {
+    uint32_t a[16], b[8], d[4], e[2];
+    const bool p0 = (c & 1) != 0, p1 = (c & 2) != 0, p2 = (c & 4) != 0, p3 = (c & 8) != 0, p4 = (c & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = p1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = p2 ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) e[i] = p3 ? d[2 * i + 1] : d[2 * i];
+    return p4 ? e[1] : e[0];
+}
+
+// ---- query-resident candidate pass (flat_gemm_ts.cu) ----
+static constexpr int TS_N = 64;            // corpus rows per work item (UMMA N; 32 per CTA of the pair)
+static constexpr int TS_QBLK = 256;        // queries per CTA pair (UMMA M; 128 TMEM lanes per CTA)
+static constexpr int TS_SLOTS = 256;       // candidate slots per (query, cluster, column half) region
+static constexpr int TS_MAX_LDB = 768;     // bf16 elements of a query row that fit beside two accumulators in TMEM
+
+// regions per query for a launch over n_qblk query blocks on n_clusters CTA pairs
+inline int ts_regions(int n_clusters, int n_qblk) { return 2 * ((n_clusters + n_qblk - 1) / n_qblk); }
+
+// One phase of the candidate pass over the tiles of `phase`: keys under the per-query bound go to
+// cand[q][region][slot], fill counts to cand_cnt[q][region] (overwritten, not accumulated).
+// has_h: row_h holds the key offsets [>= n_tiles_total * TS_N], +inf for rows that must not become candidates;
+// !has_h (cosine, nothing masked): offsets are zero and rows >= n_rows are cut from the hit masks.
+int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk, int ldb, const void *q16,
+                   const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, uint64_t *cand, int *cand_cnt,
+                   cudaStream_t st);
+
+}  // namespace cm

@@ -38,9 +38,14 @@ def check(g, o, q, k, **kw):
     return st
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+# cta_group 2 runs the query-resident candidate pass (queries in tensor memory, flat_gemm_ts.cu); 1 and "2s"
+# (COMET_B200_NO_TS) the pass that stages both operands in shared memory (the one rows wider than 768 use)
+@pytest.mark.parametrize("cta_group", [1, 2, "2s"])
 @pytest.mark.parametrize("metric", [capi.L2SQ, capi.COSINE, capi.L2])
-def test_tensor_path_matches_oracle(metric, cta_group):
+def test_tensor_path_matches_oracle(metric, cta_group, monkeypatch):
+    if cta_group == "2s":
+        monkeypatch.setenv("COMET_B200_NO_TS", "1")
+        cta_group = 2
     g, o, rng = make_pair(33_000, 128, metric, 11 + metric, cta_group)
     q = rng.standard_normal((260, 128)).astype(np.float32)
     st = check(g, o, q, 10)
@@ -48,8 +53,11 @@ def test_tensor_path_matches_oracle(metric, cta_group):
     check(g, o, q[:70], 100)
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
-def test_tensor_path_dim768_k100(cta_group):
+@pytest.mark.parametrize("cta_group", [1, 2, "2s"])
+def test_tensor_path_dim768_k100(cta_group, monkeypatch):
+    if cta_group == "2s":
+        monkeypatch.setenv("COMET_B200_NO_TS", "1")
+        cta_group = 2
     g, o, rng = make_pair(24_000, 768, capi.COSINE, 5, cta_group)
     q = rng.standard_normal((300, 768)).astype(np.float32)
     st = check(g, o, q, 100)
@@ -113,3 +121,17 @@ def test_tensor_path_select_shapes_and_candidate_count(monkeypatch):
         assert st["candidates"] >= 25 * len(q)
     monkeypatch.setenv("COMET_B200_NO_DENSE", "1")      # phase A through the sparse emission path
     check(g, o, q, 25)
+
+
+def test_tensor_path_rows_wider_than_tensor_memory():
+    # 800 dims: a query row no longer fits beside the accumulators in tensor memory -> both operands are staged
+    g, o, rng = make_pair(17_000, 800, capi.L2SQ, 41, 2)
+    q = rng.standard_normal((64, 800)).astype(np.float32)
+    check(g, o, q, 10)
+
+
+def test_tensor_path_many_query_blocks():
+    # 1030 queries: two device chunks (1024 + 6), the first with four query blocks spread over the CTA pairs
+    g, o, rng = make_pair(20_000, 64, capi.COSINE, 43, 2)
+    q = rng.standard_normal((1030, 64)).astype(np.float32)
+    check(g, o, q, 5)
