@@ -178,6 +178,27 @@ __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, u
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// Programmatic dependent launch: a kernel launched with PdlLaunch may be scheduled while its predecessor in the
+// stream is still running (once every CTA of the predecessor has called pdl_trigger() or exited).  It must call
+// pdl_wait() before it touches anything the predecessor reads or writes; pdl_wait() returns when the predecessor
+// grid has completed and its writes are visible.  EVERY kernel of a chain launched this way calls pdl_wait()
+// (completion is then transitive along the stream).
+// What the predecessor wrote must be read with ordinary (coherent) loads AFTER pdl_wait(): a `const __restrict__`
+// pointer or __ldg() turns a load into ld.global.nc, which the compiler may hoist above the wait -- it assumes the
+// data does not change while the kernel runs, and under PDL it does.  ld_pdl_*() are volatile loads for the first
+// reads behind a wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ float ld_pdl_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_pdl_s32(const int *p) {
+    int v;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -190,6 +211,27 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 #endif
+
+// host: launch configuration with the programmatic-dependent-launch attribute (and optionally a cluster shape)
+struct PdlLaunch {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[2];
+    PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x = 0, bool pdl = true) {
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        int n = 0;
+        if (cluster_x > 0) {
+            attr[n].id = cudaLaunchAttributeClusterDimension;
+            attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+            n++;
+        }
+        if (pdl) {
+            attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[n].val.programmaticStreamSerializationAllowed = 1;
+            n++;
+        }
+        cfg.attrs = attr; cfg.numAttrs = (unsigned)n;
+    }
+};
 
 // host: encode a 2-D row-major tensor map (driver entry point fetched at run time, no -lcuda)
 int make_tmap_2d(CUtensorMap *out, CUtensorMapDataType dtype, uint32_t elem_bytes, const void *base,

@@ -110,7 +110,6 @@ int FlatIndex::reserve(int64_t want) {
 
 FlatIndex::~FlatIndex() {
     cudaFree(rows); cudaFree(ids); cudaFree(deleted);
-    cudaFree(rescored_dev);
     cudaFree(staged_dev);
     cudaFreeHost(staged_host);
     free_shadow();
@@ -230,21 +229,7 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
     }
     bool fma = rounding_mode() == CM_ROUND_FMA;
 
-    // 1. Distance.Preprocess on every query (flat_index_search.go:236) into a zero-padded [nq_pad][ld] block
-    int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
-    float *qp = nullptr;
-    int *qflags = nullptr;
-    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
-    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
-    if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
-    CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp, ld, qflags, st));
-    if (check_zero_queries && metric == CM_COSINE) {
-        // the host entry point reads these flags after its final synchronise: a zero query is reported
-        // then (its row of results is garbage by then, and discarded) without stalling the pipeline here
-        CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-    }
-
-    // 2. soft deletes + document filter -> per-row skip mask (flat_index_search.go:255-263)
+    // 1. soft deletes + document filter -> per-row skip mask (flat_index_search.go:255-263)
     const uint8_t *skip = nullptr;
     uint8_t *skip_buf = nullptr;
     uint32_t *filt_dev = nullptr;
@@ -262,15 +247,30 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
         skip = deleted;
     }
 
-    // 3. pick the pipeline
+    // 2. pick the pipeline
     int path = p->path;
     if (path == CM_PATH_AUTO)
         path = tensor_path_eligible(nq, k_eff, p->filter_ids && p->nfilter > 0, p->threshold) ? CM_PATH_TENSOR : CM_PATH_EXACT;
+
+    // 3. Distance.Preprocess on every query (flat_index_search.go:236) into a zero-padded [nq_pad][ld] block (the
+    //    tensor path folds it into its own query-preparation kernel), then the search proper
+    int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
+    float *qp = nullptr;
+    int *qflags = nullptr;
+    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
+    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
     int rc = CM_OK;
     if (path == CM_PATH_TENSOR) {
-        rc = search_tensor(qp, nq, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
+        rc = search_tensor(q_dev, qp, qflags, nq, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
     } else {
+        if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
+        CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp, ld, qflags, st));
         rc = search_exact(qp, nq, nq_pad, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
+    }
+    if (rc == CM_OK && check_zero_queries && metric == CM_COSINE) {
+        // the host entry point reads these flags after its final synchronise: a zero query is reported
+        // then (its row of results is garbage by then, and discarded) without stalling the pipeline here
+        CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     ws_free(qp, st); ws_free(qflags, st); ws_free(skip_buf, st); ws_free(filt_dev, st);
     stats.kernel_launches = g_kernel_launches.load() - launches0;

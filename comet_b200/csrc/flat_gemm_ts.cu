@@ -64,7 +64,7 @@ template <bool HAS_H>
 __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     const __grid_constant__ CUtensorMap tmap_x, GemmPhase phase, int n_qblk, int k_atoms,
     const __nv_bfloat16 *__restrict__ q16, int ldb, const float *__restrict__ row_h, long long n_rows,
-    const float *__restrict__ g_bound, int n_regions, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
+    const float *g_bound, int n_regions, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *stage_base = smem;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)TS_STAGES * TS_STAGE_BYTES);
@@ -96,6 +96,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     tc::cluster_sync_all();
     tc::fence_after_thread_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: this grid may have started while the previous kernel of the search (query
+    // preparation or a selection) was still running; the next one may be scheduled as soon as SMs free up.  Only
+    // the epilogue warps touch what the predecessor produces (bounds) or reads (candidate regions): they wait
+    // below, after the query block -- written two or more kernels ago -- is in tensor memory.
+    pdl_trigger();
 
     if (warp == TS_WARP_TMA) {
         // ===== corpus producer: the only stream of the kernel (whole warp walks the loop, one elected lane issues) =====
@@ -169,6 +174,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
         const int q = nb * TS_QBLK + (int)cta_rank * (TS_QBLK / 2) + ew * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
         // ---- the query block goes to tensor memory: column j of lane m = bf16 pair (2j, 2j+1) of query m ----
+        // First phase: the predecessor IS the kernel that writes the bf16 queries -- wait for it here.  Later phases
+        // follow a selection kernel that triggers only after ITS wait, i.e. after the previous candidate pass (and,
+        // transitively, the query preparation) has completed: the query block can be loaded while that selection
+        // is still running.
+        if (phase.cls == 0) pdl_wait();
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(q16 + (size_t)q * ldb);
             const int n_chunks = ldb / 64;                 // chunks of 32 columns (64 bf16, 128 bytes)
@@ -186,7 +196,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(smem_u32(qready_bar), 0));
         }
-        const float gq = g_bound[q];                       // -(bound): a key is a candidate iff (dot - gq) - h >= 0
+        pdl_wait();
+        const float gq = ld_pdl_f32(g_bound + q);          // -(bound): a key is a candidate iff (dot - gq) - h >= 0
         const int region = 2 * j0 + half;
         uint64_t *my_cand = cand + ((size_t)q * n_regions + region) * TS_SLOTS;
         int cnt = 0;
@@ -295,20 +306,9 @@ int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk,
     auto kern = has_h ? flat_gemm_ts_kernel<true> : flat_gemm_ts_kernel<false>;
     CM_TRY(set_dyn_smem((const void *)kern, smem));
     const int n_clusters = sm_count() / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(n_clusters * 2));
-    cfg.blockDim = dim3(TS_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    PdlLaunch L(dim3((unsigned)(n_clusters * 2)), dim3(TS_THREADS), smem, st, 2);
     ProfScope prof(CM_PROF_FLAT_GEMM, st);
-    CM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap_x32, ph, n_qblk, ldb / 64, (const __nv_bfloat16 *)q16, ldb, row_h,
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, tmap_x32, ph, n_qblk, ldb / 64, (const __nv_bfloat16 *)q16, ldb, row_h,
                                (long long)n_rows, g_bound, ts_regions(n_clusters, n_qblk), cand, cand_cnt));
     count_launch();
     return CM_OK;

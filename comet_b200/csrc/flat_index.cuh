@@ -64,8 +64,8 @@ struct FlatIndex {
                           int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats);
     // flat_tensor.cu
     bool tensor_path_eligible(int64_t nq, int64_t k_eff, bool has_skip, float threshold) const;
-    int search_tensor(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
-                      int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+    int search_tensor(const float *q_raw, float *qp, int *qflags, int64_t nq, int64_t k_eff, const uint8_t *skip,
+                      float threshold, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                       int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats);
     void free_shadow();
     int ensure_shadow(cudaStream_t st);

@@ -48,7 +48,7 @@ static constexpr int GT_WARP_ALLOC = 8, GT_WARP_TMA = 10, GT_WARP_MMA = 11;
 static constexpr int GT_A_BYTES = GT_ROWS * GT_BK * 2;
 static constexpr int GT_MAX_NQ = 1024;     // queries per launch (bounds in smem)
 static constexpr int CAND_SLOTS = 128;     // candidate slots per (query, CTA, lane quadrant) region
-static constexpr int RS_CAP = 2048;        // candidates re-scored per query
+static constexpr int RS_CAP = TS_RS_CAP;   // candidates re-scored per query
 static constexpr int RS_GRID_X = 2;        // re-score CTAs per query (each loops over its 128-candidate chunks)
 static constexpr int SEL_STAGE_CAP = 12288; // keys (old survivors + new candidates) staged in smem by the select kernel (96 KB)
 
@@ -704,6 +704,80 @@ __global__ void init_bounds_kernel(float *__restrict__ g, int nq, int nq_pad, fl
     if (q < nq_pad) g[q] = q < nq ? first : INFINITY;
 }
 
+// Everything a query chunk needs before the first candidate pass, in ONE launch (it used to be three kernels and
+// four memsets): Distance.Preprocess in the reference's order (distance.go:269-290; cosine: sequential sum of
+// squares by one lane, then x * (1 / norm)), the zero-padded fp32 copy the re-score reads, the bf16 copy + |q|,
+// |q - bf16(q)| for the error bound, the first bound, and the zeroed counters of the chunk.
+// One warp per query row; rows [nq, nq_pad) are padding (zero bf16 row, bound +inf = never a candidate).
+template <bool FMA>
+__global__ void __launch_bounds__(128) prep_queries_kernel(
+    int metric, const float *__restrict__ src, int nq, int nq_pad, int dim, float *__restrict__ qp, int ld,
+    int *__restrict__ zero_flags, __nv_bfloat16 *__restrict__ q16, int ldb, float2 *__restrict__ qn,
+    float *__restrict__ g, float g_first, uint4 *__restrict__ zero_a, long long zero_a_n, uint4 *__restrict__ zero_b,
+    long long zero_b_n) {
+    extern __shared__ float prow[];
+    pdl_wait();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    {   // counters of this chunk (16-byte words)
+        const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = gridDim.x * (long long)blockDim.x;
+        for (long long i = t; i < zero_a_n; i += nt) zero_a[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (long long i = t; i < zero_b_n; i += nt) zero_b[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int i = blockIdx.x * (blockDim.x >> 5) + w;
+    if (i >= nq_pad) return;
+    uint2 *d16 = reinterpret_cast<uint2 *>(q16 + (size_t)i * ldb);
+    if (i >= nq) {
+        for (int j = lane * 4; j < ldb; j += 128) d16[j >> 2] = make_uint2(0u, 0u);
+        if (lane == 0) { g[i] = INFINITY; qn[i] = make_float2(0.0f, 0.0f); }
+        return;
+    }
+    float *r = prow + (size_t)w * ldb;
+    const float *sp = src + (size_t)i * dim;
+    for (int j = lane; j < ldb; j += 32) r[j] = j < dim ? sp[j] : 0.0f;
+    __syncwarp();
+    float scale = 1.0f;
+    int zero = 0;
+    if (metric == CM_COSINE) {
+        if (lane == 0) {
+            float sum = 0.0f;
+            for (int j = 0; j < dim; j++) sum = dot_step<FMA>(sum, r[j], r[j]);
+            float norm = __fsqrt_rn(sum);
+            zero = norm == 0.0f;
+            scale = __fdiv_rn(1.0f, norm);
+        }
+        scale = __shfl_sync(0xffffffffu, scale, 0);
+        zero = __shfl_sync(0xffffffffu, zero, 0);
+    }
+    if (zero_flags && lane == 0) zero_flags[i] = zero;
+    const bool do_scale = metric == CM_COSINE && !zero;
+    float *dp = qp + (size_t)i * ld;
+    for (int j = lane; j < ld; j += 32) {
+        float v = 0.0f;
+        if (j < dim) { v = do_scale ? __fmul_rn(r[j], scale) : r[j]; r[j] = v; }
+        dp[j] = v;
+    }
+    __syncwarp();
+    float sq = 0.0f, rsq = 0.0f;
+    for (int j = lane * 4; j < ldb; j += 128) {
+        const float4 v = *reinterpret_cast<const float4 *>(r + j);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+        float2 r0 = __bfloat1622float2(p0), r1 = __bfloat1622float2(p1);
+        float ex = v.x - r0.x, ey = v.y - r0.y, ez = v.z - r1.x, ew = v.w - r1.y;
+        sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        rsq += ex * ex + ey * ey + ez * ez + ew * ew;
+        d16[j >> 2] = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
+    }
+    if (lane == 0) {
+        qn[i] = make_float2(sqrtf(sq) * 1.0001f, sqrtf(rsq) * 1.0001f);
+        g[i] = g_first;
+    }
+}
+
 // key offsets as the query-resident pass reads them: +inf for rows that must not become candidates
 // (soft-deleted / filtered out / beyond the last row)
 __global__ void fill_inf_kernel(float *__restrict__ h, long long from, long long to) {
@@ -742,10 +816,11 @@ void FlatIndex::free_shadow() {
 int FlatIndex::ensure_shadow(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(shadow_mu);
     if (!staged_dev) {          // statistics words of the tensor path (concurrent searches share them)
-        CM_CUDA(cudaMalloc(&rescored_dev, 8));
+        // one 48-byte block: staged_dev[8] then the re-scored counter, so that one kernel can zero both
+        CM_CUDA(cudaMalloc(&staged_dev, 48));
+        rescored_dev = reinterpret_cast<unsigned long long *>(staged_dev + 8);
         CM_CUDA(cudaHostAlloc(&staged_host, 8 * sizeof(int), cudaHostAllocDefault));
         for (int p = 0; p < 8; p++) staged_host[p] = -1;
-        CM_CUDA(cudaMalloc(&staged_dev, 8 * sizeof(int)));
     }
     if (rows_bf16 && shadow_rows == n && shadow_cap == cap) return CM_OK;
     ldb = (dim + GT_BK - 1) / GT_BK * GT_BK;
@@ -781,8 +856,10 @@ bool FlatIndex::tensor_path_eligible(int64_t nq, int64_t k_eff, bool has_filter,
     return nq >= 64 && k_eff <= 256 && n >= 65536 && !has_filter;
 }
 
-int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
-                             int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+// q_raw: the caller's queries [nq][dim]; qp: [>= nq][ld] receives their preprocessed, zero-padded copy
+// (Distance.Preprocess, flat_index_search.go:236), qflags[i] = 1 for a zero vector under cosine.
+int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t nq, int64_t k_eff, const uint8_t *skip,
+                             float threshold, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                              int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
     if (k_eff > RS_CAP / 2) return fail(CM_ERR_UNSUPPORTED, "tensor path supports k <= %d", RS_CAP / 2);
     CM_TRY(ensure_shadow(st));
@@ -850,9 +927,10 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
     CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS, 2>, sel_smem));
     CM_TRY(set_dyn_smem((const void *)cand_select_kernel<SEL_THREADS_SMALL, 4>, sel_smem_small));
     int passes = 0;
+    if (!use_ts) CM_TRY(launch_preprocess_rows(metric, fma, q_raw, nq, dim, dim, qp, ld, qflags, st));
     // keys staged per phase: counted on the device, copied to pinned memory after the last phase; the NEXT search
     // reads them (no synchronisation: a stale or missing value only means the roomier launch shape is used)
-    CM_CUDA(cudaMemsetAsync(staged_dev, 0, 8 * sizeof(int), st));      // allocated by ensure_shadow (under its lock)
+    if (!use_ts) CM_CUDA(cudaMemsetAsync(staged_dev, 0, 8 * sizeof(int), st));      // allocated by ensure_shadow (under its lock)
     const int small_ok = SEL_STAGE_CAP_SMALL - SEL_STAGE_CAP_SMALL / 12;      // 8 % headroom
     bool sel_small[MAX_PH];
     for (int p = 0; p < n_ph; p++) {
@@ -868,7 +946,8 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         for (int p = 0; p < n_ph; p++) sel_small[p] = sel_small[p] && want_small;
     }
     const bool dbg_staged = getenv("COMET_B200_DBG_STAGED") != nullptr;
-    CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
+    int *stat_words = staged_dev;      // staged_dev[8] + the re-scored counter: 48 bytes
+    if (!use_ts) CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
     if (const char *e = getenv("COMET_B200_NO_DENSE")) if (atoi(e)) for (int p = 0; p < n_ph; p++) ph[p].dense = 0;
     // key offsets with the skip mask folded in (query-resident pass: +inf = never a candidate)
@@ -906,18 +985,30 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
         ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
         CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
-        CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 4) * 4, st));
-        CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
-        // g = -(bound): phase A lets everything through for real queries (a large FINITE value for the query-resident
-        // pass, whose invalid rows carry +inf offsets: inf - inf would be NaN), nothing for padding
-        init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad, use_ts ? -3.0e38f : -INFINITY);
-        count_launch();
-        CM_CUDA(cudaGetLastError());
-        CM_TRY(launch_to_bf16(qp + (size_t)q0 * ld, nqc, dim, ld, q16, ldb, 0.0f, nullptr, qn, nullptr, st));
         CUtensorMap tq;
-        if (!use_ts)
+        if (use_ts) {
+            // one launch: Preprocess + padded fp32 copy + bf16 copy and norms + first bound + zeroed counters.
+            // g = -(bound): phase A lets everything through for real queries -- a large FINITE value, because rows
+            // that must not become candidates carry +inf offsets and inf - inf would be NaN -- nothing for padding.
+            const size_t cnt_bytes = (size_t)nq_pad * (n_reg + 4) * 4;       // multiple of 16: nq_pad % 256 == 0
+            const size_t smem = 4 * (size_t)ldb * 4;
+            auto kern = fma ? prep_queries_kernel<true> : prep_queries_kernel<false>;
+            CM_TRY(set_dyn_smem((const void *)kern, smem));
+            PdlLaunch L(dim3((unsigned)((nq_pad + 3) / 4)), dim3(128), smem, st);
+            CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, metric, q_raw + (size_t)q0 * dim, nqc, nq_pad, dim, qp + (size_t)q0 * ld, ld,
+                                       qflags + q0, q16, ldb, qn, g, -3.0e38f, (uint4 *)ccnt, (long long)(cnt_bytes / 16),
+                                       (uint4 *)stat_words, (long long)(q0 == 0 ? 3 : 0)));
+            count_launch();
+        } else {
+            CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 4) * 4, st));
+            CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
+            init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad, -INFINITY);
+            count_launch();
+            CM_CUDA(cudaGetLastError());
+            CM_TRY(launch_to_bf16(qp + (size_t)q0 * ld, nqc, dim, ld, q16, ldb, 0.0f, nullptr, qn, nullptr, st));
             CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
                                 (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
+        }
         for (int p = 0; p < n_ph; p++) {
             const bool has_h = metric != CM_COSINE;   // cosine keys are -dot: no per-row offset
             if (use_ts)
@@ -930,13 +1021,28 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
                 CM_TRY((launch_gemm_t<1, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else
                 CM_TRY((launch_gemm_t<1, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
-            {
+            const int in = (p + 1) & 1, out = p & 1;
+            const uint64_t *s_in = p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP;
+            const int *s_in_cnt = p == 0 ? nullptr : rcnt + (size_t)in * nq_pad;
+            uint64_t *s_out = rs + (size_t)out * nq_pad * RS_CAP;
+            int *s_out_cnt = rcnt + (size_t)out * nq_pad;
+            if (use_ts) {
+                // selection per query; after the last phase the same kernel re-scores, sorts and writes the result
+                const bool finish = p == n_ph - 1;
+                ProfScope prof(finish ? CM_PROF_RESCORE : CM_PROF_SELECT, st);
+                TsSelectArgs a{};
+                a.nq = nqc; a.cand = cand; a.cand_cnt = ccnt; a.n_reg = n_reg; a.slots = slots; a.K = K; a.dim = dim;
+                a.q_norms = qn; a.max_bits = max_bits; a.g = g; a.overflow = ovf;
+                a.surv_in = s_in; a.surv_in_cnt = s_in_cnt; a.surv_out = s_out; a.surv_out_cnt = s_out_cnt;
+                a.e_scale = e_scale; a.staged_max = staged_dev + p;
+                a.rows = rows; a.ld = ld; a.ch = (ld % 64 == 0) ? 64 : 32; a.queries = qp + (size_t)q0 * ld;
+                a.threshold = threshold; a.row_ids = ids; a.out_stride = out_stride;
+                a.out_ids = out_ids + (size_t)q0 * out_stride; a.out_scores = out_scores + (size_t)q0 * out_stride;
+                a.out_pos = out_pos ? out_pos + (size_t)q0 * out_stride : nullptr; a.out_counts = out_counts + q0;
+                a.rescored = rescored_dev;
+                CM_TRY(launch_ts_select(a, finish, metric, fma, st));
+            } else {
                 ProfScope prof(CM_PROF_SELECT, st);
-                const int in = (p + 1) & 1, out = p & 1;
-                const uint64_t *s_in = p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP;
-                const int *s_in_cnt = p == 0 ? nullptr : rcnt + (size_t)in * nq_pad;
-                uint64_t *s_out = rs + (size_t)out * nq_pad * RS_CAP;
-                int *s_out_cnt = rcnt + (size_t)out * nq_pad;
                 if (sel_small[p])
                     cand_select_kernel<SEL_THREADS_SMALL, 4><<<nqc, SEL_THREADS_SMALL, sel_smem_small, st>>>(
                         cand, ccnt, nq_pad, n_reg, slots, K, dim, qn, max_bits, g, ovf, s_in, s_in_cnt, s_out, s_out_cnt,
@@ -950,16 +1056,18 @@ int FlatIndex::search_tensor(const float *qp, int64_t nq, int64_t k_eff, const u
             }
             passes++;
         }
-        const int last = (n_ph - 1) & 1;
-        CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs + (size_t)last * nq_pad * RS_CAP,
-                              rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st));
-        CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
-                                 out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
-                                 out_counts + q0, st));
-        mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0),
-                                                                rcnt + (size_t)last * nq_pad, rescored_dev);
-        count_launch();
-        CM_CUDA(cudaGetLastError());
+        if (!use_ts) {
+            const int last = (n_ph - 1) & 1;
+            CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs + (size_t)last * nq_pad * RS_CAP,
+                                  rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st));
+            CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
+                                     out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
+                                     out_counts + q0, st));
+            mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0),
+                                                                    rcnt + (size_t)last * nq_pad, rescored_dev);
+            count_launch();
+            CM_CUDA(cudaGetLastError());
+        }
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);
     }

@@ -72,4 +72,24 @@ int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk,
                    const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, uint64_t *cand, int *cand_cnt,
                    cudaStream_t st);
 
+// ---- per-query selection / fused finish for that pass (flat_finish.cu) ----
+static constexpr int TS_RS_CAP = 2048;          // survivors (candidates re-scored) per query
+static constexpr int TS_SEL_STAGE_CAP = 11264;  // keys (old survivors + new candidates) staged in shared memory (88 KB)
+
+struct TsSelectArgs {
+    int nq;
+    const uint64_t *cand; int *cand_cnt; int n_reg, slots, K, dim;
+    const float2 *q_norms; const unsigned int *max_bits; float *g; int *overflow;
+    const uint64_t *surv_in; const int *surv_in_cnt; uint64_t *surv_out; int *surv_out_cnt;   // lists of TS_RS_CAP keys
+    float e_scale; int *staged_max;
+    // finish only
+    const float *rows; int ld, ch; const float *queries; float threshold; const uint32_t *row_ids;
+    int64_t out_stride; uint32_t *out_ids; float *out_scores; int64_t *out_pos; int64_t *out_counts;
+    unsigned long long *rescored;
+};
+// finish = false: K-th smallest staged key -> g[q], survivors -> surv_out.  finish = true: the same selection, then
+// the survivors are re-scored in reference order, sorted by (score, scan position) and written as the query's
+// result; out_counts[q] = -1 when a candidate list overflowed (the caller redoes that query exactly).
+int launch_ts_select(const TsSelectArgs &a, bool finish, int metric, bool fma, cudaStream_t st);
+
 }  // namespace cm
