@@ -64,7 +64,7 @@ template <bool HAS_H>
 __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     const __grid_constant__ CUtensorMap tmap_x, GemmPhase phase, int n_qblk, int k_atoms,
     const __nv_bfloat16 *__restrict__ q16, int ldb, const float *__restrict__ row_h, long long n_rows,
-    const float *g_bound, int n_regions, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
+    const float *g_bound, TsBound tsb, int n_regions, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *stage_base = smem;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)TS_STAGES * TS_STAGE_BYTES);
@@ -197,7 +197,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
             if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(smem_u32(qready_bar), 0));
         }
         pdl_wait();
-        const float gq = ld_pdl_f32(g_bound + q);          // -(bound): a key is a candidate iff (dot - gq) - h >= 0
+        float gq = ld_pdl_f32(g_bound + q);                // -(bound): a key is a candidate iff (dot - gq) - h >= 0
+        const bool padding = gq == INFINITY;               // query slot behind the batch: never a candidate
+        if (tsb.read_bits && !padding) {                   // bound from the sampling phase (see TsBound)
+            const unsigned int b = (unsigned int)ld_pdl_s32(reinterpret_cast<const int *>(tsb.gmax_bits + q));
+            gq = b == 0u ? INFINITY : -ordered_to_float(b);
+        }
+        float sm[TS_BOUND_J];                              // sampling phase: this thread's smallest keys, ascending
+#pragma unroll
+        for (int u = 0; u < TS_BOUND_J; u++) sm[u] = INFINITY;
         const int region = 2 * j0 + half;
         uint64_t *my_cand = cand + ((size_t)q * n_regions + region) * TS_SLOTS;
         int cnt = 0;
@@ -235,7 +243,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
                 const long long left = n_rows - (long long)row0;
                 live = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ~(0xFFFFFFFFu >> (int)left));
             }
-            if (phase.dense) {
+            if (phase.dense == 2) {
+                // sampling phase: no candidates, only the thread's TS_BOUND_J smallest keys (insertions are rare
+                // after the first few dozen values: one compare per value on the common path)
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const float key = (HAS_H ? hh[c] : 0.0f) - __uint_as_float(vv[c]);
+                    if (key < sm[TS_BOUND_J - 1] && ((live >> (31 - c)) & 1u)) {
+                        sm[TS_BOUND_J - 1] = key;
+#pragma unroll
+                        for (int u = TS_BOUND_J - 1; u > 0; u--)
+                            if (sm[u] < sm[u - 1]) { const float t = sm[u]; sm[u] = sm[u - 1]; sm[u - 1] = t; }
+                    }
+                }
+            } else if (phase.dense) {
                 // phase A: (nearly) every value is a candidate -- straight-line predicated appends
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
@@ -286,7 +307,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
             }
             if (HAS_H && it + 1 < n_items) fetch_h(tw.t);
         }
-        cand_cnt[(size_t)q * n_regions + region] = cnt;    // > TS_SLOTS: the select kernel flags the overflow
+        if (phase.dense == 2) {
+            if (!padding) {
+                const float kth = tsb.j <= 1 ? sm[0] : (tsb.j == 2 ? sm[1] : (tsb.j == 3 ? sm[2] : sm[3]));
+                const float2 qn = tsb.q_norms[q];
+                const float nq = qn.x, dq = qn.y, X = __uint_as_float(tsb.max_bits[0]), Dx = __uint_as_float(tsb.max_bits[1]);
+                const float E = 1.001f * (nq * Dx + dq * X + dq * Dx) +
+                                1.01f * (float)(tsb.dim + 8) * 1.1920929e-07f * (nq * X + 0.5f * (nq + X) * (nq + X));
+                float bound = kth + 2.0f * E * tsb.e_scale;
+                bound = bound + fabsf(bound) * 1e-6f;
+                atomicMax(tsb.gmax_bits + q, float_to_ordered(bound));
+            }
+        } else {
+            cand_cnt[(size_t)q * n_regions + region] = cnt;    // > TS_SLOTS: the select kernel flags the overflow
+        }
     }
 
     // ---- teardown: nobody exits (or frees TMEM) while the peer may still touch this CTA ----
@@ -299,8 +333,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
 }
 
 int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk, int ldb, const void *q16,
-                   const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, uint64_t *cand, int *cand_cnt,
-                   cudaStream_t st) {
+                   const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, const TsBound &tsb, uint64_t *cand,
+                   int *cand_cnt, cudaStream_t st) {
     if (ldb % 64 != 0 || ldb > TS_MAX_LDB) return fail(CM_ERR_UNSUPPORTED, "query-resident pass: ldb %d", ldb);
     const size_t smem = (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)(2 * TS_STAGES + 5) * 8 + 16;
     auto kern = has_h ? flat_gemm_ts_kernel<true> : flat_gemm_ts_kernel<false>;
@@ -309,7 +343,7 @@ int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk,
     PdlLaunch L(dim3((unsigned)(n_clusters * 2)), dim3(TS_THREADS), smem, st, 2);
     ProfScope prof(CM_PROF_FLAT_GEMM, st);
     CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, tmap_x32, ph, n_qblk, ldb / 64, (const __nv_bfloat16 *)q16, ldb, row_h,
-                               (long long)n_rows, g_bound, ts_regions(n_clusters, n_qblk), cand, cand_cnt));
+                               (long long)n_rows, g_bound, tsb, ts_regions(n_clusters, n_qblk), cand, cand_cnt));
     count_launch();
     return CM_OK;
 }

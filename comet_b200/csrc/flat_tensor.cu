@@ -946,6 +946,14 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
         for (int p = 0; p < n_ph; p++) sel_small[p] = sel_small[p] && want_small;
     }
     const bool dbg_staged = getenv("COMET_B200_DBG_STAGED") != nullptr;
+    bool sample_ok = n_ph >= 2;        // first phase only samples a bound (see TsBound) when the batch allows it
+    if (const char *e = getenv("COMET_B200_NO_SAMPLE")) if (atoi(e)) sample_ok = false;
+    // Last selection + re-score + sort in one kernel (flat_finish.cu), or as selection, re-score and merge kernels.
+    // Measured on 512 x 1M x 768, K = 100: fused 146 us against 25 + 82 + 16 us -- one CTA per query serialises
+    // its selection, its two gather rounds and its sort, and 512 such CTAs are 1.7 waves; the split kernels
+    // spread the gathers over 1024 small CTAs.  The fused kernel stays selectable (COMET_B200_FINISH=1).
+    bool fused_finish = false;
+    if (const char *e = getenv("COMET_B200_FINISH")) fused_finish = atoi(e) != 0;
     int *stat_words = staged_dev;      // staged_dev[8] + the re-scored counter: 48 bytes
     if (!use_ts) CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
@@ -981,7 +989,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
         CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
         CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * slots * 8, st));
-        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 4) * 4, st));
+        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 5) * 4, st));
         ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
         CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
@@ -990,7 +998,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
             // one launch: Preprocess + padded fp32 copy + bf16 copy and norms + first bound + zeroed counters.
             // g = -(bound): phase A lets everything through for real queries -- a large FINITE value, because rows
             // that must not become candidates carry +inf offsets and inf - inf would be NaN -- nothing for padding.
-            const size_t cnt_bytes = (size_t)nq_pad * (n_reg + 4) * 4;       // multiple of 16: nq_pad % 256 == 0
+            const size_t cnt_bytes = (size_t)nq_pad * (n_reg + 5) * 4;       // multiple of 16: nq_pad % 256 == 0
             const size_t smem = 4 * (size_t)ldb * 4;
             auto kern = fma ? prep_queries_kernel<true> : prep_queries_kernel<false>;
             CM_TRY(set_dyn_smem((const void *)kern, smem));
@@ -1000,7 +1008,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                                        (uint4 *)stat_words, (long long)(q0 == 0 ? 3 : 0)));
             count_launch();
         } else {
-            CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 4) * 4, st));
+            CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 5) * 4, st));
             CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
             init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad, -INFINITY);
             count_launch();
@@ -1009,11 +1017,43 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
             CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
                                 (uint64_t)ldb * 2, GT_BK, GT_QBLK / cg, CU_TENSOR_MAP_SWIZZLE_128B));
         }
+        // Sampling first phase (query-resident pass): instead of emitting every row of phase A as a candidate and
+        // selecting among them, the pass only derives a bound (TsBound) and the next phase covers A's tiles again
+        // (+0.5 % of the rows): one launch boundary, one selection and the densest emission less.
+        GemmPhase phc[MAX_PH];
+        for (int p = 0; p < n_ph; p++) phc[p] = ph[p];
+        TsBound tsb{};
+        unsigned int *gmax = reinterpret_cast<unsigned int *>(kcnt + nq_pad);      // [nq_pad] words zeroed with the counters
+        bool sampled = false;
+        if (use_ts && sample_ok) {
+            const int step_min = n_clusters / n_qblk, step_max = (n_clusters + n_qblk - 1) / n_qblk;
+            const int j = (K + 2 * step_min - 1) / (2 * step_min);
+            if (j <= TS_BOUND_J && ph[0].n_tiles >= step_max) {     // every epilogue thread sees at least 32 sample rows
+                sampled = true;
+                tsb.j = j; tsb.q_norms = qn; tsb.max_bits = max_bits; tsb.dim = dim; tsb.e_scale = e_scale; tsb.gmax_bits = gmax;
+                phc[0].dense = 2;
+                if (ph[1].cls == 1) {
+                    // The sampled bound is the max over ~74 threads of a low order statistic of what each thread saw:
+                    // it needs a few hundred rows per thread to get near the quantile an exact selection over phase A
+                    // gave (64 rows per thread left the worst queries at the 28 % quantile: 16 K keys in the next
+                    // phase).  Every third tile of the next phase: ~290 rows per thread at 1M rows, bound ~2.5 %.
+                    const int s_a = 3 * ph[1].SB;
+                    phc[0] = GemmPhase{0, s_a, s_a, (T + s_a - 1) / s_a, ph[0].dbg, 2};
+                    phc[1] = GemmPhase{0, ph[1].SB, ph[1].SB, ph[1].n_tiles + ph[0].n_tiles, ph[1].dbg, 0};
+                } else {
+                    phc[1] = GemmPhase{3, 1, 1, T, ph[1].dbg, 0};
+                }
+            }
+        }
+        int n_sel = 0;              // selections done: survivor lists ping-pong between rs[0] and rs[1]
         for (int p = 0; p < n_ph; p++) {
             const bool has_h = metric != CM_COSINE;   // cosine keys are -dot: no per-row offset
-            if (use_ts)
-                CM_TRY(launch_gemm_ts(tmap_bf16_ts, ph[p], n_qblk, ldb, q16, h_eff, has_h || h_masked != nullptr, n, g, cand, ccnt, st));
-            else if (cg == 2 && has_h)
+            if (use_ts) {
+                TsBound b = tsb;
+                b.read_bits = sampled && p == 1;
+                if (!sampled) b.j = 0;
+                CM_TRY(launch_gemm_ts(tmap_bf16_ts, phc[p], n_qblk, ldb, q16, h_eff, has_h || h_masked != nullptr, n, g, b, cand, ccnt, st));
+            } else if (cg == 2 && has_h)
                 CM_TRY((launch_gemm_t<2, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else if (cg == 2)
                 CM_TRY((launch_gemm_t<2, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
@@ -1021,14 +1061,17 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                 CM_TRY((launch_gemm_t<1, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else
                 CM_TRY((launch_gemm_t<1, false>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
-            const int in = (p + 1) & 1, out = p & 1;
-            const uint64_t *s_in = p == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP;
-            const int *s_in_cnt = p == 0 ? nullptr : rcnt + (size_t)in * nq_pad;
+            passes++;
+            if (sampled && p == 0) continue;          // the sampling phase leaves no candidates to select from
+            const int in = (n_sel + 1) & 1, out = n_sel & 1;
+            const uint64_t *s_in = n_sel == 0 ? nullptr : rs + (size_t)in * nq_pad * RS_CAP;
+            const int *s_in_cnt = n_sel == 0 ? nullptr : rcnt + (size_t)in * nq_pad;
             uint64_t *s_out = rs + (size_t)out * nq_pad * RS_CAP;
             int *s_out_cnt = rcnt + (size_t)out * nq_pad;
+            n_sel++;
             if (use_ts) {
                 // selection per query; after the last phase the same kernel re-scores, sorts and writes the result
-                const bool finish = p == n_ph - 1;
+                const bool finish = p == n_ph - 1 && fused_finish;
                 ProfScope prof(finish ? CM_PROF_RESCORE : CM_PROF_SELECT, st);
                 TsSelectArgs a{};
                 a.nq = nqc; a.cand = cand; a.cand_cnt = ccnt; a.n_reg = n_reg; a.slots = slots; a.K = K; a.dim = dim;
@@ -1054,10 +1097,9 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                 count_launch();
                 CM_CUDA(cudaGetLastError());
             }
-            passes++;
         }
-        if (!use_ts) {
-            const int last = (n_ph - 1) & 1;
+        if (!use_ts || !fused_finish) {
+            const int last = (n_sel - 1) & 1;
             CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs + (size_t)last * nq_pad * RS_CAP,
                                   rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st));
             CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,

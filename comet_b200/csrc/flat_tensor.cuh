@@ -13,7 +13,8 @@ struct GemmPhase {
     int SA, SB;
     int n_tiles;      // tiles in this class
     int dbg;          // debugging aid: 1 = epilogue skips the accumulator scan, 2 = loads TMEM but does not compare
-    int dense;        // 1: (nearly) every score of this phase is a candidate (phase A): emit column by column
+    int dense;        // 1: (nearly) every score of this phase is a candidate (phase A): emit column by column;
+                      // 2 (query-resident pass only): emit nothing, only derive a first bound from a row sample
 };
 
 __device__ __forceinline__ int phase_tile(const GemmPhase &p, int i) {
@@ -64,13 +65,30 @@ static constexpr int TS_MAX_LDB = 768;     // bf16 elements of a query row that 
 // regions per query for a launch over n_qblk query blocks on n_clusters CTA pairs
 inline int ts_regions(int n_clusters, int n_qblk) { return 2 * ((n_clusters + n_qblk - 1) / n_qblk); }
 
+// Bound hand-over of the sampling phase (GemmPhase::dense == 2).  A query is served by n_threads = 2 x (CTA pairs
+// of its query block) epilogue threads, each seeing its own rows.  Every thread keeps its j smallest keys,
+// j = ceil(K / n_threads): the union of those lists holds >= K distinct rows, all with key <= max over threads of
+// the j-th smallest, so that maximum bounds the K-th smallest key of the sample -- and of the corpus.  It is
+// looser than an exact selection over the sample (the ~5 % quantile instead of 2 % at K = 100), but it needs no
+// candidate lists, no selection kernel and no second launch boundary.
+struct TsBound {
+    int j;                        // 1..TS_BOUND_J; 0: this launch neither produces nor consumes a sampled bound
+    int read_bits;                // this phase takes its bound from gmax_bits (the phase after the sampling phase)
+    const float2 *q_norms;        // |q|, |q - bf16(q)| per query (error bound E_q, header of flat_tensor.cu)
+    const unsigned int *max_bits; // max row norm, max row residual norm
+    int dim;
+    float e_scale;
+    unsigned int *gmax_bits;      // [nq_pad] float_to_ordered(bound), combined with atomicMax; 0 = no bound (padding)
+};
+static constexpr int TS_BOUND_J = 4;
+
 // One phase of the candidate pass over the tiles of `phase`: keys under the per-query bound go to
 // cand[q][region][slot], fill counts to cand_cnt[q][region] (overwritten, not accumulated).
 // has_h: row_h holds the key offsets [>= n_tiles_total * TS_N], +inf for rows that must not become candidates;
 // !has_h (cosine, nothing masked): offsets are zero and rows >= n_rows are cut from the hit masks.
 int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk, int ldb, const void *q16,
-                   const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, uint64_t *cand, int *cand_cnt,
-                   cudaStream_t st);
+                   const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, const TsBound &tsb, uint64_t *cand,
+                   int *cand_cnt, cudaStream_t st);
 
 // ---- per-query selection / fused finish for that pass (flat_finish.cu) ----
 static constexpr int TS_RS_CAP = 2048;          // survivors (candidates re-scored) per query
