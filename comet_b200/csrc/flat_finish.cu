@@ -13,6 +13,8 @@
 //     flatIndexSearch.searchSingleQuery returns (flat_index_search.go:277-291).
 // Compared with select + re-score + merge + mark as four launches this keeps the survivor list on chip and lets
 // the selection of one query overlap the row gathers of another on the same SM.
+#include <algorithm>
+
 #include "flat_tensor.cuh"
 #include "select.cuh"
 
@@ -291,6 +293,147 @@ __global__ void __launch_bounds__(FIN_THREADS, 2) ts_select_kernel(
     if (lane == 0 && kept) atomicAdd(&s_out, kept);
     __syncthreads();
     if (tid == 0) out_counts[q] = s_out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split tail: the survivors of the last selection are re-scored by RSF_GRID_X small CTAs per query (the row
+// gathers of a 512-query batch are spread over 1024 CTAs, three per SM, 32 KB in flight each), and the CTA
+// that finishes LAST for a query sorts that query's exact keys and writes its result -- no merge kernel, no
+// overflow-marking kernel, no launch boundaries behind the gathers.
+// ------------------------------------------------------------------------------------------------
+static constexpr int RSF_GRID_X = 2;
+template <int METRIC, bool FMA, int CH>
+__global__ void __launch_bounds__(128) rescore_finish_kernel(
+    const float *__restrict__ rows, int ld, const float *queries, const uint64_t *rs, const int *rs_cnt, int rs_cap,
+    float threshold, uint64_t *keys2, int *keys2_cnt, int *done, const int *overflow, int K,
+    const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
+    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts,
+    unsigned long long *rescored) {
+    constexpr int PCS = CH / 4;                      // 16-byte pieces per row per step
+    constexpr int ROW_B = CH * 4;                    // bytes of a row in a stage
+    constexpr int STAGE_B = 128 * ROW_B;
+    extern __shared__ __align__(16) uint8_t rsf_smem[];
+    float *q_s = reinterpret_cast<float *>(rsf_smem);                    // [ld]
+    uint8_t *stage = rsf_smem + (size_t)ld * 4;                          // [2][128 rows][ROW_B], 16-byte pieces XOR-swizzled
+    __shared__ uint32_t pos_s[128];
+    __shared__ int s_last;
+    const int q = blockIdx.y, tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    const int cnt = min(ld_pdl_s32(rs_cnt + q), rs_cap);
+    for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
+    const int n_chunks = ld / CH;
+    for (int base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+        const int mine = base + tid;
+        const bool live = mine < cnt;
+        const uint32_t pos = key_pos(rs[(size_t)q * rs_cap + (live ? mine : base)]);
+        __syncthreads();            // previous chunk's readers of pos_s / stage are done; q_s is staged
+        pos_s[tid] = pos;
+        __syncthreads();
+        auto issue = [&](int c) {
+            uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
+#pragma unroll
+            for (int p = 0; p < PCS; p++) {
+                int idx = p * 128 + tid;
+                int r = idx / PCS, piece = idx % PCS;
+                const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
+                uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+        float acc = 0.0f;
+        for (int c = 0; c < n_chunks; c++) {
+            if (c + 1 < n_chunks) {
+                issue(c + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
+            const float *qc = q_s + c * CH;
+#pragma unroll
+            for (int j = 0; j < PCS; j++) {
+                float4 xv = *reinterpret_cast<const float4 *>(sp + ((j ^ (tid & 7)) << 4));
+                float4 qv = *reinterpret_cast<const float4 *>(qc + j * 4);
+                acc = metric_step<METRIC, FMA>(acc, qv.x, xv.x);
+                acc = metric_step<METRIC, FMA>(acc, qv.y, xv.y);
+                acc = metric_step<METRIC, FMA>(acc, qv.z, xv.z);
+                acc = metric_step<METRIC, FMA>(acc, qv.w, xv.w);
+            }
+            __syncthreads();
+        }
+        const float dist = metric_finish<METRIC>(acc);
+        // flat_index_search.go:265-271: a threshold > 0 drops rows farther than it
+        if (live && !(threshold > 0.0f && dist > threshold)) {
+            const int slot = atomicAdd(&keys2_cnt[q], 1);
+            keys2[(size_t)q * rs_cap + slot] = make_key(dist, pos);
+        }
+    }
+    // ---- the last CTA of this query to get here sorts and writes the result ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&done[q], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (ld_pdl_s32(overflow + q)) {              // a candidate list overflowed in some phase: the caller redoes the query
+        if (tid == 0) out_counts[q] = -1;
+        return;
+    }
+    if (tid == 0 && rescored && cnt > 0) atomicAdd(rescored, (unsigned long long)cnt);
+    const int m = min(ld_pdl_s32(keys2_cnt + q), rs_cap);
+    uint64_t *sort_s = reinterpret_cast<uint64_t *>(rsf_smem);          // the gather stages are free now
+    int P = 64;
+    while (P < m) P <<= 1;
+    __syncthreads();
+    for (int i = tid; i < P; i += 128) {
+        uint64_t v = KEY_INF;
+        if (i < m) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(keys2 + (size_t)q * rs_cap + i) : "memory");
+        sort_s[i] = v;
+    }
+    __syncthreads();
+    bitonic_sort_smem(sort_s, P, tid, 128, CtaBarrier());
+    const int want = min(K, m);
+    for (int i = tid; i < want; i += 128) {
+        const uint64_t key = sort_s[i];
+        const uint32_t pos = key_pos(key);
+        const size_t o = (size_t)q * out_stride + i;
+        out_ids[o] = row_ids ? row_ids[pos] : pos;
+        out_scores[o] = key_score(key);
+        if (out_pos) out_pos[o] = pos;
+    }
+    if (tid == 0) out_counts[q] = want;
+}
+
+template <int METRIC, bool FMA, int CH>
+static int launch_rescore_finish_t(const RescoreFinishArgs &a, cudaStream_t st) {
+    const size_t smem = std::max((size_t)a.ld * 4 + 2 * 128 * (size_t)CH * 4, (size_t)TS_RS_CAP * 8);
+    auto kern = rescore_finish_kernel<METRIC, FMA, CH>;
+    CM_TRY(set_dyn_smem((const void *)kern, smem));
+    PdlLaunch L(dim3(RSF_GRID_X, (unsigned)a.nq), dim3(128), smem, st);
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, a.rows, a.ld, a.queries, a.rs, a.rs_cnt, (int)TS_RS_CAP, a.threshold, a.keys2,
+                               a.keys2_cnt, a.done, a.overflow, a.K, a.row_ids, (long long)a.out_stride, a.out_ids,
+                               a.out_scores, (long long *)a.out_pos, (long long *)a.out_counts, a.rescored));
+    count_launch();
+    return CM_OK;
+}
+
+int launch_rescore_finish(const RescoreFinishArgs &a, int metric, bool fma, cudaStream_t st) {
+    const bool wide = a.ld % 64 == 0;
+#define CM_RSF_CASE(M)                                                                                                \
+    case M:                                                                                                           \
+        if (wide) return fma ? launch_rescore_finish_t<M, true, 64>(a, st) : launch_rescore_finish_t<M, false, 64>(a, st); \
+        return fma ? launch_rescore_finish_t<M, true, 32>(a, st) : launch_rescore_finish_t<M, false, 32>(a, st);
+    switch (metric) {
+        CM_RSF_CASE(CM_L2)
+        CM_RSF_CASE(CM_L2SQ)
+        CM_RSF_CASE(CM_COSINE)
+    default: return fail(CM_ERR_INVALID_ARG, "unknown metric %d", metric);
+    }
+#undef CM_RSF_CASE
 }
 
 size_t ts_select_smem(bool finish) {

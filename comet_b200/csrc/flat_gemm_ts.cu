@@ -62,8 +62,8 @@ struct TileWalk {
 
 template <bool HAS_H>
 __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
-    const __grid_constant__ CUtensorMap tmap_x, GemmPhase phase, int n_qblk, int k_atoms,
-    const __nv_bfloat16 *__restrict__ q16, int ldb, const float *__restrict__ row_h, long long n_rows,
+    const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q, GemmPhase phase, int n_qblk,
+    int k_atoms, const float *__restrict__ row_h, long long n_rows,
     const float *g_bound, TsBound tsb, int n_regions, uint64_t *__restrict__ cand, int *__restrict__ cand_cnt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *stage_base = smem;
@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     uint64_t *empty_bar = full_bar + TS_STAGES;
     uint64_t *tfull_bar = empty_bar + TS_STAGES;
     uint64_t *tempty_bar = tfull_bar + 2;
-    uint64_t *qready_bar = tempty_bar + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qready_bar + 1);
+    uint64_t *qready_bar = tempty_bar + 2;          // leader CTA: both CTAs' query blocks are in tensor memory
+    uint64_t *qload_bar = qready_bar + 1;           // this CTA's query block has landed in the (still idle) stage ring
+    uint64_t *qdone_bar = qload_bar + 1;            // this CTA's epilogue warps have read it: the ring is free
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(qdone_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // cluster = CTA pair along x: rank and cluster index from blockIdx (ptxas knows they are warp-uniform; the
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
         for (int s = 0; s < TS_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
         mbar_init(qready_bar, 16);
+        mbar_init(qload_bar, 1);
+        mbar_init(qdone_bar, 8);
         fence_mbar_init();
     }
     if (warp == TS_WARP_ALLOC) tc::tmem_alloc<2>(smem_u32(tmem_slot), 512);
@@ -105,6 +109,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     if (warp == TS_WARP_TMA) {
         // ===== corpus producer: the only stream of the kernel (whole warp walks the loop, one elected lane issues) =====
         prefetch_tmap(&tmap_x);
+        // The CTA's 128 query rows first: one 128-row box per k-atom into the idle stage ring (an atom of 128 rows
+        // x 128 bytes is exactly one 16 KB stage), from where the epilogue warps move them into tensor memory.
+        // First phase: the predecessor IS the kernel that writes the bf16 queries -- wait for it.  Later phases follow
+        // a selection kernel that triggers only after ITS wait, i.e. after the previous candidate pass (and,
+        // transitively, the query preparation) has completed: the block can be fetched while that selection runs.
+        if (phase.cls == 0 || phase.cls == 3) pdl_wait();
+        if (lane == 0) {
+            prefetch_tmap(&tmap_q);
+            mbar_arrive_expect_tx(qload_bar, (uint32_t)k_atoms * TS_STAGE_BYTES);
+            const int qrow0 = nb * TS_QBLK + (int)cta_rank * (TS_QBLK / 2);
+            for (int a = 0; a < k_atoms; a++) tma_load_2d(stage_base + (size_t)a * TS_STAGE_BYTES, &tmap_q, a * 64, qrow0, qload_bar);
+        }
+        __syncwarp();
+        mbar_wait_parked(qdone_bar, 0);             // the ring belongs to the corpus stream from here on
         int s = 0;
         uint32_t ph = 0;
         const uint32_t stage0 = smem_u32(stage_base), full0 = smem_u32(&full_bar[0]);
@@ -174,27 +192,27 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
         const int q = nb * TS_QBLK + (int)cta_rank * (TS_QBLK / 2) + ew * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
         // ---- the query block goes to tensor memory: column j of lane m = bf16 pair (2j, 2j+1) of query m ----
-        // First phase: the predecessor IS the kernel that writes the bf16 queries -- wait for it here.  Later phases
-        // follow a selection kernel that triggers only after ITS wait, i.e. after the previous candidate pass (and,
-        // transitively, the query preparation) has completed: the query block can be loaded while that selection
-        // is still running.
-        if (phase.cls == 0) pdl_wait();
+        // (row m of a k-atom is 128 bytes in the SWIZZLE_128B box: its 16-byte chunk j sits at chunk j ^ (m & 7))
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(q16 + (size_t)q * ldb);
-            const int n_chunks = ldb / 64;                 // chunks of 32 columns (64 bf16, 128 bytes)
-            for (int ch = half; ch < n_chunks; ch += 2) {
+            mbar_wait_parked(qload_bar, 0);
+            const int m = ew * 32 + lane;
+            for (int a = half; a < k_atoms; a += 2) {      // an atom = 32 columns (64 bf16)
+                const uint8_t *rowp = stage_base + (size_t)a * TS_STAGE_BYTES + (size_t)m * 128;
                 uint32_t v[32];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    const uint4 t = __ldg(src + ch * 8 + u);
+                    const uint4 t = *reinterpret_cast<const uint4 *>(rowp + ((u ^ (m & 7)) << 4));
                     v[4 * u + 0] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
                 }
-                tc::tmem_st_32x32(lane_addr + (uint32_t)ch * 32u, v);
+                tc::tmem_st_32x32(lane_addr + (uint32_t)a * 32u, v);
             }
             tc::tmem_st_wait();
             tc::fence_before_thread_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(smem_u32(qready_bar), 0));
+            if (lane == 0) {
+                mbar_arrive(qdone_bar);
+                tc::mbar_arrive_cluster(tc::mapa(smem_u32(qready_bar), 0));
+            }
         }
         pdl_wait();
         float gq = ld_pdl_f32(g_bound + q);                // -(bound): a key is a candidate iff (dot - gq) - h >= 0
@@ -332,17 +350,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
     }
 }
 
-int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk, int ldb, const void *q16,
+int launch_gemm_ts(const CUtensorMap &tmap_x32, const CUtensorMap &tmap_q128, const GemmPhase &ph, int n_qblk, int ldb,
                    const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, const TsBound &tsb, uint64_t *cand,
                    int *cand_cnt, cudaStream_t st) {
     if (ldb % 64 != 0 || ldb > TS_MAX_LDB) return fail(CM_ERR_UNSUPPORTED, "query-resident pass: ldb %d", ldb);
-    const size_t smem = (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)(2 * TS_STAGES + 5) * 8 + 16;
+    const size_t smem = (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)(2 * TS_STAGES + 7) * 8 + 16;
     auto kern = has_h ? flat_gemm_ts_kernel<true> : flat_gemm_ts_kernel<false>;
     CM_TRY(set_dyn_smem((const void *)kern, smem));
     const int n_clusters = sm_count() / 2;
     PdlLaunch L(dim3((unsigned)(n_clusters * 2)), dim3(TS_THREADS), smem, st, 2);
     ProfScope prof(CM_PROF_FLAT_GEMM, st);
-    CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, tmap_x32, ph, n_qblk, ldb / 64, (const __nv_bfloat16 *)q16, ldb, row_h,
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, tmap_x32, tmap_q128, ph, n_qblk, ldb / 64, row_h,
                                (long long)n_rows, g_bound, tsb, ts_regions(n_clusters, n_qblk), cand, cand_cnt));
     count_launch();
     return CM_OK;

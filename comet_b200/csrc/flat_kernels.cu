@@ -284,7 +284,7 @@ int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *
 // merge of per-CTA partial lists -> final sorted top-K per query
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
-    const uint64_t *__restrict__ part_keys, const int *__restrict__ part_counts, int parts, int Kp, int K, int C,
+    const uint64_t *part_keys, const int *part_counts, int parts, int Kp, int K, int C,    // (no __restrict__: see pdl_wait())
     const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
     float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
     const CtaBarrier bar;
     const int tid = threadIdx.x;
     const int q = blockIdx.x;
+    pdl_wait();             // no-op unless launched with the programmatic-dependent-launch attribute
+    pdl_trigger();
     if (tid == 0) { cnt = 0; tau = KEY_INF; }
     __syncthreads();
     const uint64_t *pk = part_keys + (size_t)q * parts * Kp;
@@ -335,18 +337,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
 
 int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int K,
                       const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores,
-                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream) {
+                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream, bool pdl) {
     int C = next_pow2(K + Kp);
     if (C < 2048) C = 2048;
     size_t smem = (size_t)C * 8;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
     CM_TRY(set_dyn_smem((const void *)merge_topk_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
-    merge_topk_kernel<<<nq, MERGE_THREADS, smem, stream>>>(part_keys, part_counts, parts, Kp, K, C, row_ids,
-                                                           (long long)out_stride, out_ids, out_scores,
-                                                           (long long *)out_pos, (long long *)out_counts);
+    PdlLaunch L(dim3((unsigned)nq), dim3(MERGE_THREADS), smem, stream, 0, pdl);
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, merge_topk_kernel, part_keys, part_counts, parts, Kp, K, C, row_ids,
+                               (long long)out_stride, out_ids, out_scores, (long long *)out_pos, (long long *)out_counts));
     count_launch();
-    CM_CUDA(cudaGetLastError());
     return CM_OK;
 }
 

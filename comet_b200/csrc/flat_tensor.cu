@@ -593,10 +593,9 @@ __global__ void __launch_bounds__(NT, MINB) cand_select_kernel(
 // CH = floats of a row fetched per step: 32 (one 128-byte line) or 64 (two consecutive lines, when ld % 64 == 0 --
 // longer DRAM bursts for the same bytes in flight).
 template <int METRIC, bool FMA, int CH>
-__global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ rows, int ld, const float *__restrict__ queries,
-                                                      const uint64_t *__restrict__ rs, const int *__restrict__ rs_cnt,
-                                                      int rs_cap, float threshold, uint64_t *__restrict__ out_keys,
-                                                      int *__restrict__ out_cnt) {
+__global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ rows, int ld, const float *queries,
+                                                      const uint64_t *rs, const int *rs_cnt,      // (no __restrict__: see pdl_wait())
+                                                      int rs_cap, float threshold, uint64_t *out_keys, int *out_cnt) {
     constexpr int PCS = CH / 4;                      // 16-byte pieces per row per step
     constexpr int ROW_B = CH * 4;                    // bytes of a row in a stage
     constexpr int STAGE_B = 128 * ROW_B;
@@ -605,7 +604,9 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
     uint8_t *stage = smem + (size_t)ld * 4;                          // [2][128 rows][ROW_B], 16-byte pieces XOR-swizzled
     __shared__ uint32_t pos_s[128];
     const int q = blockIdx.y, tid = threadIdx.x;
-    const int cnt = min(rs_cnt[q], rs_cap);
+    pdl_wait();             // no-op unless launched with the programmatic-dependent-launch attribute
+    pdl_trigger();
+    const int cnt = min(ld_pdl_s32(rs_cnt + q), rs_cap);
     for (int j = tid; j < ld; j += 128) q_s[j] = queries[(size_t)q * ld + j];
     const int n_chunks = ld / CH;
     // a few CTAs per query, each walking its 128-candidate chunks (a (RS_CAP / 128) x nq grid would launch
@@ -662,29 +663,30 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float *__restrict__ 
 
 template <int METRIC, bool FMA, int CH>
 static int launch_rescore_t(const float *rows, int ld, const float *queries, int nq, const uint64_t *rs, const int *rs_cnt,
-                            float threshold, uint64_t *out_keys, int *out_cnt, cudaStream_t st) {
+                            float threshold, uint64_t *out_keys, int *out_cnt, cudaStream_t st, bool pdl) {
     dim3 grid(RS_GRID_X, (unsigned)nq);
     size_t smem = (size_t)ld * 4 + 2 * 128 * (size_t)CH * 4;
     auto kern = rescore_kernel<METRIC, FMA, CH>;
     CM_TRY(set_dyn_smem((const void *)kern, smem));
-    kern<<<grid, 128, smem, st>>>(rows, ld, queries, rs, rs_cnt, RS_CAP, threshold, out_keys, out_cnt);
+    PdlLaunch L(grid, dim3(128), smem, st, 0, pdl);
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, kern, rows, ld, queries, rs, rs_cnt, (int)RS_CAP, threshold, out_keys, out_cnt));
     return CM_OK;
 }
 
 static int launch_rescore(int metric, bool fma, const float *rows, int ld, const float *queries, int nq,
                           const uint64_t *rs, const int *rs_cnt, float threshold, uint64_t *out_keys, int *out_cnt,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool pdl = false) {
     int ch = (ld % 64 == 0) ? 64 : 32;
     if (const char *e = getenv("COMET_B200_RS_CH")) ch = (atoi(e) == 64 && ld % 64 == 0) ? 64 : 32;
     ProfScope prof(CM_PROF_RESCORE, st);
 #define CM_RS_CASE(M)                                                                                                  \
     case M:                                                                                                            \
         if (ch == 64) {                                                                                                \
-            if (fma) CM_TRY((launch_rescore_t<M, true, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));   \
-            else CM_TRY((launch_rescore_t<M, false, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));      \
+            if (fma) CM_TRY((launch_rescore_t<M, true, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st, pdl)));   \
+            else CM_TRY((launch_rescore_t<M, false, 64>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st, pdl)));      \
         } else {                                                                                                       \
-            if (fma) CM_TRY((launch_rescore_t<M, true, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));   \
-            else CM_TRY((launch_rescore_t<M, false, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st)));      \
+            if (fma) CM_TRY((launch_rescore_t<M, true, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st, pdl)));   \
+            else CM_TRY((launch_rescore_t<M, false, 32>(rows, ld, queries, nq, rs, rs_cnt, threshold, out_keys, out_cnt, st, pdl)));      \
         }                                                                                                              \
         break;
     switch (metric) {
@@ -791,9 +793,10 @@ __global__ void masked_h_kernel(const float *__restrict__ row_h, const uint8_t *
 }
 
 // queries that overflowed a candidate list get count -1 (the host entry point redoes them exactly)
-__global__ void mark_overflow_kernel(const int *__restrict__ overflow, int nq, long long *__restrict__ out_counts,
-                                     const int *__restrict__ rs_cnt, unsigned long long *__restrict__ rescored) {
+__global__ void mark_overflow_kernel(const int *overflow, int nq, long long *out_counts, const int *rs_cnt,
+                                     unsigned long long *rescored) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();             // no-op unless launched with the programmatic-dependent-launch attribute
     if (q < nq && overflow[q]) out_counts[q] = -1;
     // statistics: candidates that went through the exact re-score (cm_flat_last_stats reads the sum lazily)
     int c = q < nq ? rs_cnt[q] : 0;
@@ -948,12 +951,15 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
     const bool dbg_staged = getenv("COMET_B200_DBG_STAGED") != nullptr;
     bool sample_ok = n_ph >= 2;        // first phase only samples a bound (see TsBound) when the batch allows it
     if (const char *e = getenv("COMET_B200_NO_SAMPLE")) if (atoi(e)) sample_ok = false;
-    // Last selection + re-score + sort in one kernel (flat_finish.cu), or as selection, re-score and merge kernels.
-    // Measured on 512 x 1M x 768, K = 100: fused 146 us against 25 + 82 + 16 us -- one CTA per query serialises
-    // its selection, its two gather rounds and its sort, and 512 such CTAs are 1.7 waves; the split kernels
-    // spread the gathers over 1024 small CTAs.  The fused kernel stays selectable (COMET_B200_FINISH=1).
-    bool fused_finish = false;
-    if (const char *e = getenv("COMET_B200_FINISH")) fused_finish = atoi(e) != 0;
+    // Tail of the search: 0 = selection, re-score, merge and overflow-marking kernels; 1 = ONE kernel per query for
+    // the last selection + re-score + sort (flat_finish.cu); 2 = selection + re-score whose last CTA per query sorts
+    // and writes.  Measured on 512 x 1M x 768, K = 100 (step, ms): 0.673 / 0.692 / 0.680 -- a CTA per query
+    // serialises its selection, gather rounds and sort (512 such CTAs are 1.7 waves), and the last-CTA sort runs on
+    // 128 threads behind the gathers; 1024 small gather CTAs followed by a 13 us merge win.  All selectable
+    // (COMET_B200_TAIL).
+    int tail_mode = 0;
+    if (const char *e = getenv("COMET_B200_TAIL")) tail_mode = std::max(0, std::min(2, atoi(e)));
+    const bool fused_finish = tail_mode == 1;
     int *stat_words = staged_dev;      // staged_dev[8] + the re-scored counter: 48 bytes
     if (!use_ts) CM_CUDA(cudaMemsetAsync(rescored_dev, 0, 8, st));
     if (const char *dbg = getenv("COMET_B200_DBG_EPI")) for (int p = 0; p < n_ph; p++) ph[p].dbg = atoi(dbg);
@@ -989,7 +995,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
         CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
         CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
         CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * slots * 8, st));
-        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 5) * 4, st));
+        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 6) * 4, st));
         ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
         CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
         CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
@@ -998,7 +1004,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
             // one launch: Preprocess + padded fp32 copy + bf16 copy and norms + first bound + zeroed counters.
             // g = -(bound): phase A lets everything through for real queries -- a large FINITE value, because rows
             // that must not become candidates carry +inf offsets and inf - inf would be NaN -- nothing for padding.
-            const size_t cnt_bytes = (size_t)nq_pad * (n_reg + 5) * 4;       // multiple of 16: nq_pad % 256 == 0
+            const size_t cnt_bytes = (size_t)nq_pad * (n_reg + 6) * 4;       // multiple of 16: nq_pad % 256 == 0
             const size_t smem = 4 * (size_t)ldb * 4;
             auto kern = fma ? prep_queries_kernel<true> : prep_queries_kernel<false>;
             CM_TRY(set_dyn_smem((const void *)kern, smem));
@@ -1007,8 +1013,10 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                                        qflags + q0, q16, ldb, qn, g, -3.0e38f, (uint4 *)ccnt, (long long)(cnt_bytes / 16),
                                        (uint4 *)stat_words, (long long)(q0 == 0 ? 3 : 0)));
             count_launch();
+            CM_TRY(make_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q16, (uint64_t)ldb, (uint64_t)nq_pad,
+                                (uint64_t)ldb * 2, GT_BK, TS_QBLK / 2, CU_TENSOR_MAP_SWIZZLE_128B));
         } else {
-            CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 5) * 4, st));
+            CM_CUDA(cudaMemsetAsync(ccnt, 0, (size_t)nq_pad * (n_reg + 6) * 4, st));
             CM_CUDA(cudaMemsetAsync(q16, 0, (size_t)nq_pad * ldb * 2, st));
             init_bounds_kernel<<<(nq_pad + 255) / 256, 256, 0, st>>>(g, nqc, nq_pad, -INFINITY);
             count_launch();
@@ -1052,7 +1060,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                 TsBound b = tsb;
                 b.read_bits = sampled && p == 1;
                 if (!sampled) b.j = 0;
-                CM_TRY(launch_gemm_ts(tmap_bf16_ts, phc[p], n_qblk, ldb, q16, h_eff, has_h || h_masked != nullptr, n, g, b, cand, ccnt, st));
+                CM_TRY(launch_gemm_ts(tmap_bf16_ts, tq, phc[p], n_qblk, ldb, h_eff, has_h || h_masked != nullptr, n, g, b, cand, ccnt, st));
             } else if (cg == 2 && has_h)
                 CM_TRY((launch_gemm_t<2, true>(tmap_bf16, tq, ph[p], n_qblk, ldb / GT_BK, n, row_h, skip, g, nq_pad, cand, ccnt, st)));
             else if (cg == 2)
@@ -1098,17 +1106,29 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                 CM_CUDA(cudaGetLastError());
             }
         }
-        if (!use_ts || !fused_finish) {
+        if (use_ts && tail_mode == 2) {
+            const int last = (n_sel - 1) & 1;
+            ProfScope prof(CM_PROF_RESCORE, st);
+            RescoreFinishArgs a{};
+            a.nq = nqc; a.K = K; a.rows = rows; a.ld = ld; a.queries = qp + (size_t)q0 * ld;
+            a.rs = rs + (size_t)last * nq_pad * RS_CAP; a.rs_cnt = rcnt + (size_t)last * nq_pad; a.threshold = threshold;
+            a.keys2 = keys2; a.keys2_cnt = kcnt; a.done = kcnt + 2 * nq_pad; a.overflow = ovf;
+            a.row_ids = ids; a.out_stride = out_stride; a.out_ids = out_ids + (size_t)q0 * out_stride;
+            a.out_scores = out_scores + (size_t)q0 * out_stride;
+            a.out_pos = out_pos ? out_pos + (size_t)q0 * out_stride : nullptr; a.out_counts = out_counts + q0;
+            a.rescored = rescored_dev;
+            CM_TRY(launch_rescore_finish(a, metric, fma, st));
+        } else if (!use_ts || tail_mode == 0) {
             const int last = (n_sel - 1) & 1;
             CM_TRY(launch_rescore(metric, fma, rows, ld, qp + (size_t)q0 * ld, nqc, rs + (size_t)last * nq_pad * RS_CAP,
-                                  rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st));
+                                  rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st, use_ts));
             CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
                                      out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
-                                     out_counts + q0, st));
-            mark_overflow_kernel<<<(nqc + 255) / 256, 256, 0, st>>>(ovf, nqc, (long long *)(out_counts + q0),
-                                                                    rcnt + (size_t)last * nq_pad, rescored_dev);
+                                     out_counts + q0, st, use_ts));
+            PdlLaunch L(dim3((unsigned)((nqc + 255) / 256)), dim3(256), 0, st, 0, use_ts);
+            CM_CUDA(cudaLaunchKernelEx(&L.cfg, mark_overflow_kernel, (const int *)ovf, nqc, (long long *)(out_counts + q0),
+                                       (const int *)(rcnt + (size_t)last * nq_pad), rescored_dev));
             count_launch();
-            CM_CUDA(cudaGetLastError());
         }
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);

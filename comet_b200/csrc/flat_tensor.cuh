@@ -86,7 +86,8 @@ static constexpr int TS_BOUND_J = 4;
 // cand[q][region][slot], fill counts to cand_cnt[q][region] (overwritten, not accumulated).
 // has_h: row_h holds the key offsets [>= n_tiles_total * TS_N], +inf for rows that must not become candidates;
 // !has_h (cosine, nothing masked): offsets are zero and rows >= n_rows are cut from the hit masks.
-int launch_gemm_ts(const CUtensorMap &tmap_x32, const GemmPhase &ph, int n_qblk, int ldb, const void *q16,
+// tmap_q128: the bf16 queries [nq_pad][ldb], box 64 x 128 rows, SWIZZLE_128B.
+int launch_gemm_ts(const CUtensorMap &tmap_x32, const CUtensorMap &tmap_q128, const GemmPhase &ph, int n_qblk, int ldb,
                    const float *row_h, bool has_h, int64_t n_rows, const float *g_bound, const TsBound &tsb, uint64_t *cand,
                    int *cand_cnt, cudaStream_t st);
 
@@ -109,5 +110,18 @@ struct TsSelectArgs {
 // the survivors are re-scored in reference order, sorted by (score, scan position) and written as the query's
 // result; out_counts[q] = -1 when a candidate list overflowed (the caller redoes that query exactly).
 int launch_ts_select(const TsSelectArgs &a, bool finish, int metric, bool fma, cudaStream_t st);
+
+// Re-score of the last selection's survivors in reference order + per-query sort and output by the last CTA of
+// each query.  keys2 [nq][TS_RS_CAP], keys2_cnt [nq] and done [nq] must be zero on entry.
+struct RescoreFinishArgs {
+    int nq, K;
+    const float *rows; int ld; const float *queries;
+    const uint64_t *rs; const int *rs_cnt;             // survivor lists of TS_RS_CAP keys
+    float threshold;
+    uint64_t *keys2; int *keys2_cnt; int *done; const int *overflow;
+    const uint32_t *row_ids; int64_t out_stride; uint32_t *out_ids; float *out_scores; int64_t *out_pos; int64_t *out_counts;
+    unsigned long long *rescored;
+};
+int launch_rescore_finish(const RescoreFinishArgs &a, int metric, bool fma, cudaStream_t st);
 
 }  // namespace cm
