@@ -82,6 +82,23 @@ __device__ __forceinline__ float metric_finish(float acc) {
     return acc;
 }
 
+#ifdef __CUDACC__
+// packed fp32x2 helpers (sm_100a FADD2 / FMUL2): lane by lane identical to the scalar round-to-nearest operations
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // ordering keys: (score, scan position) ascending == ascending u64.  Scores on this path are
 // never -0.0 (sums of squares, 1 - clamp(dot), sqrt), so the sign-flip transform keeps ties equal.

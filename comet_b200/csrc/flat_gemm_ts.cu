@@ -287,15 +287,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1) flat_gemm_ts_kernel(
                 }
             } else {
                 // sign bits of t through four independent funnel-shift chains (one chain of 32 is ~150 dependent cycles)
+                // (the subtractions two values at a time: FADD2 -- every instruction of this loop is paid ~400 times
+                // per CTA and microsecond)
                 uint32_t m[4] = {0u, 0u, 0u, 0u};
+                const uint64_t gq2 = pk2(gq, gq);
 #pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) {
+                for (int c8 = 0; c8 < 8; c8 += 2) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const int c = k * 8 + c8;
-                        float t = __uint_as_float(vv[c]) - gq;
-                        if (HAS_H) t -= hh[c];
-                        m[k] = __funnelshift_l(__float_as_uint(t), m[k], 1);
+                        uint64_t t2 = sub2_rn(pk2(__uint_as_float(vv[c]), __uint_as_float(vv[c + 1])), gq2);
+                        if (HAS_H) t2 = sub2_rn(t2, pk2(hh[c], hh[c + 1]));
+                        float t0, t1;
+                        unpk2(t2, t0, t1);
+                        m[k] = __funnelshift_l(__float_as_uint(t0), m[k], 1);
+                        m[k] = __funnelshift_l(__float_as_uint(t1), m[k], 1);
                     }
                 }
                 const uint32_t mask = (m[0] << 24) | ((m[1] & 0xFFu) << 16) | ((m[2] & 0xFFu) << 8) | (m[3] & 0xFFu);

@@ -27,19 +27,6 @@ namespace cm {
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn and --fmad=false, which would fuse the
 // two roundings the reference performs separately.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-    uint64_t d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-    return d;
-}
-__device__ __forceinline__ void unpk2(uint64_t v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -286,7 +273,8 @@ int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *
 __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
     const uint64_t *part_keys, const int *part_counts, int parts, int Kp, int K, int C,    // (no __restrict__: see pdl_wait())
     const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
-    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts) {
+    float *__restrict__ out_scores, long long *__restrict__ out_pos, long long *__restrict__ out_counts,
+    const int *overflow, const int *stat_cnt, unsigned long long *stat_sum) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);
     __shared__ int cnt;
@@ -332,12 +320,18 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
         out_scores[o] = key_score(key);
         if (out_pos) out_pos[o] = pos;
     }
-    if (tid == 0) out_counts[q] = m;
+    if (tid == 0) {
+        // tensor path: a query whose candidate lists overflowed gets count -1 (the host entry point redoes it with the
+        // exact scan); stat_sum accumulates the candidates that went through the exact re-score
+        out_counts[q] = (overflow && ld_pdl_s32(overflow + q)) ? -1 : m;
+        if (stat_sum && stat_cnt) { const int c = ld_pdl_s32(stat_cnt + q); if (c > 0) atomicAdd(stat_sum, (unsigned long long)c); }
+    }
 }
 
 int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int K,
                       const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores,
-                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream, bool pdl) {
+                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream, bool pdl, const int *overflow,
+                      const int *stat_cnt, unsigned long long *stat_sum) {
     int C = next_pow2(K + Kp);
     if (C < 2048) C = 2048;
     size_t smem = (size_t)C * 8;
@@ -346,7 +340,8 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
     ProfScope prof(CM_PROF_SELECT, stream);
     PdlLaunch L(dim3((unsigned)nq), dim3(MERGE_THREADS), smem, stream, 0, pdl);
     CM_CUDA(cudaLaunchKernelEx(&L.cfg, merge_topk_kernel, part_keys, part_counts, parts, Kp, K, C, row_ids,
-                               (long long)out_stride, out_ids, out_scores, (long long *)out_pos, (long long *)out_counts));
+                               (long long)out_stride, out_ids, out_scores, (long long *)out_pos, (long long *)out_counts,
+                               overflow, stat_cnt, stat_sum));
     count_launch();
     return CM_OK;
 }

@@ -35,7 +35,8 @@ int launch_flat_scan(const ScanLaunch &L, const CUtensorMap &tmap, const float *
 // part_keys: [nq][parts][Kp]; outputs are [nq][out_stride].
 int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int K,
                       const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores,
-                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream, bool pdl = false);
+                      int64_t *out_pos, int64_t *out_counts, cudaStream_t stream, bool pdl = false,
+                      const int *overflow = nullptr, const int *stat_cnt = nullptr, unsigned long long *stat_sum = nullptr);
 
 // Merge `world` per-shard sorted result lists per query ([world][nq][in_stride], counts [world][nq] or
 // NULL = full) into the global top-K ordered by (score, shard, rank within the shard).

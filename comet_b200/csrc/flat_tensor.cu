@@ -792,19 +792,6 @@ __global__ void masked_h_kernel(const float *__restrict__ row_h, const uint8_t *
     if (i < n_pad) out[i] = (i < n && !skip[i]) ? row_h[i] : INFINITY;
 }
 
-// queries that overflowed a candidate list get count -1 (the host entry point redoes them exactly)
-__global__ void mark_overflow_kernel(const int *overflow, int nq, long long *out_counts, const int *rs_cnt,
-                                     unsigned long long *rescored) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    pdl_wait();             // no-op unless launched with the programmatic-dependent-launch attribute
-    if (q < nq && overflow[q]) out_counts[q] = -1;
-    // statistics: candidates that went through the exact re-score (cm_flat_last_stats reads the sum lazily)
-    int c = q < nq ? rs_cnt[q] : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c > 0 && rescored) atomicAdd(rescored, (unsigned long long)c);
-}
-
 // ------------------------------------------------------------------------------------------------
 // FlatIndex glue
 // ------------------------------------------------------------------------------------------------
@@ -1124,11 +1111,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                                   rcnt + (size_t)last * nq_pad, threshold, keys2, kcnt, st, use_ts));
             CM_TRY(launch_merge_topk(keys2, kcnt, nqc, 1, RS_CAP, K, ids, out_stride, out_ids + (size_t)q0 * out_stride,
                                      out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
-                                     out_counts + q0, st, use_ts));
-            PdlLaunch L(dim3((unsigned)((nqc + 255) / 256)), dim3(256), 0, st, 0, use_ts);
-            CM_CUDA(cudaLaunchKernelEx(&L.cfg, mark_overflow_kernel, (const int *)ovf, nqc, (long long *)(out_counts + q0),
-                                       (const int *)(rcnt + (size_t)last * nq_pad), rescored_dev));
-            count_launch();
+                                     out_counts + q0, st, use_ts, ovf, rcnt + (size_t)last * nq_pad, rescored_dev));
         }
         ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
         ws_free(keys2, st);

@@ -7,7 +7,7 @@ dev = torch.device("cuda", 0)
 n, d, K, nq = 1_000_000, 768, 100, 512
 g = torch.Generator(device=dev); g.manual_seed(1)
 x = torch.randn((n, d), generator=g, device=dev)
-ix = capi.FlatIndex(d, capi.COSINE)
+ix = capi.FlatIndex(d, capi.METRICS[os.environ.get("DBG_METRIC", "cosine")])
 ix.add_device(np.arange(1, n + 1, dtype=np.uint32), x.data_ptr(), n)
 del x
 q = torch.randn((nq, d), generator=g, device=dev)
