@@ -864,6 +864,16 @@ int co_ivfpq_add_batch(co_ivfpq *x, const uint32_t *ids, float *rows, long n) {
     }
     return CO_OK;
 }
+/* Restore path (IVFPQIndex.ReadFrom, ivfpq_index.go:700+): compressed vectors return to the lists they were
+ * stored in, in stored order, without being re-encoded -- what a search then scans is exactly the saved state. */
+int co_ivfpq_load_codes(co_ivfpq *x, const uint32_t *ids, const uint8_t *codes, const int *list_of, long n) {
+    if (!x->trained) return CO_ERR_NOT_TRAINED;
+    for (long i = 0; i < n; i++) {
+        if (list_of[i] < 0 || list_of[i] >= x->nlist) return CO_ERR_ARG;
+        list_push(&x->lists[list_of[i]], ids[i], NULL, 0, codes + (size_t)i * x->M, x->M);
+    }
+    return CO_OK;
+}
 int co_ivfpq_remove(co_ivfpq *x, uint32_t id) {
     if (!lists_contain(x->lists, x->nlist, id)) return CO_ERR_NOT_FOUND;
     if (idset_contains(&x->deleted, id)) return CO_ERR_NOT_FOUND;
@@ -1220,6 +1230,31 @@ int co_hnsw_add_batch(co_hnsw *h, const uint32_t *ids, float *rows, const int *l
         int rc = co_hnsw_add(h, ids[i], rows + (size_t)i * h->dim, levels[i]);
         if (rc) return rc;
     }
+    return CO_OK;
+}
+/* Restore path (HNSWIndex.ReadFrom, hnsw_index.go:898-1096): nodes with their stored (already preprocessed)
+ * vectors, levels and per-layer edge lists, entry point and max level as saved.  edge_off has one entry per
+ * (slot, layer <= level) pair in that order, plus the end. */
+int co_hnsw_load_graph(co_hnsw *h, long n, const uint32_t *ids, const float *rows, const int *levels,
+                       const long long *edge_off, const uint32_t *edge_ids, uint32_t entry, int max_level) {
+    if (h->n != 0) return CO_ERR_ARG;
+    int d = h->dim;
+    h->cap = n > 0 ? n : 1;
+    h->nodes = xrealloc(h->nodes, (size_t)h->cap * sizeof(hnode));
+    h->rows = xrealloc(h->rows, (size_t)h->cap * d * sizeof(float));
+    memcpy(h->rows, rows, (size_t)n * d * sizeof(float));
+    long pair = 0;
+    for (long s = 0; s < n; s++) {
+        if (levels[s] < 0 || levels[s] > 16 || ids[s] == 0) return CO_ERR_ARG;
+        hnode *node = &h->nodes[s];
+        node->id = ids[s]; node->level = levels[s];
+        node->edges = calloc((size_t)levels[s] + 1, sizeof(edge_list));
+        for (int l = 0; l <= levels[s]; l++, pair++)
+            for (long long e = edge_off[pair]; e < edge_off[pair + 1]; e++) edges_push(&node->edges[l], edge_ids[e]);
+        hmap_insert(h, ids[s], s);
+        h->n++;
+    }
+    h->entry = entry; h->max_level = max_level;
     return CO_OK;
 }
 /* hnsw_index.go:300-318 Remove (soft) */

@@ -134,6 +134,7 @@ int   co_ivfpq_train(co_ivfpq *, const float *rows, long n);
 int   co_ivfpq_set_trained(co_ivfpq *, const float *centroids, const float *codebooks);
 int   co_ivfpq_add(co_ivfpq *, uint32_t id, float *vec);
 int   co_ivfpq_add_batch(co_ivfpq *, const uint32_t *ids, float *rows, long n);
+int   co_ivfpq_load_codes(co_ivfpq *, const uint32_t *ids, const uint8_t *codes, const int *list_of, long n);  /* ReadFrom */
 int   co_ivfpq_remove(co_ivfpq *, uint32_t id);
 int   co_ivfpq_flush(co_ivfpq *);
 int   co_ivfpq_default_nprobes(const co_ivfpq *);
@@ -154,6 +155,8 @@ void  co_hnsw_free(co_hnsw *);
 /* level = what randomLevel() drew (hnsw_index.go:474-484); the caller owns the RNG (F8). id != 0. */
 int   co_hnsw_add(co_hnsw *, uint32_t id, float *vec, int level);
 int   co_hnsw_add_batch(co_hnsw *, const uint32_t *ids, float *rows, const int *levels, long n);
+int   co_hnsw_load_graph(co_hnsw *, long n, const uint32_t *ids, const float *rows, const int *levels,
+                         const long long *edge_off, const uint32_t *edge_ids, uint32_t entry, int max_level);  /* ReadFrom */
 int   co_hnsw_remove(co_hnsw *, uint32_t id);
 long  co_hnsw_size(const co_hnsw *);
 int   co_hnsw_max_level(const co_hnsw *);

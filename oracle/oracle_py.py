@@ -110,6 +110,7 @@ def lib():
         "co_ivfpq_set_trained": (C.c_int, [vp, f32p, f32p]),
         "co_ivfpq_add": (C.c_int, [vp, C.c_uint32, f32p]),
         "co_ivfpq_add_batch": (C.c_int, [vp, u32p, f32p, C.c_long]),
+        "co_ivfpq_load_codes": (C.c_int, [vp, u32p, u8p, i32p, C.c_long]),
         "co_ivfpq_remove": (C.c_int, [vp, C.c_uint32]),
         "co_ivfpq_flush": (C.c_int, [vp]),
         "co_ivfpq_default_nprobes": (C.c_int, [vp]),
@@ -123,6 +124,7 @@ def lib():
         "co_hnsw_free": (None, [vp]),
         "co_hnsw_add": (C.c_int, [vp, C.c_uint32, f32p, C.c_int]),
         "co_hnsw_add_batch": (C.c_int, [vp, u32p, f32p, i32p, C.c_long]),
+        "co_hnsw_load_graph": (C.c_int, [vp, C.c_long, u32p, f32p, i32p, C.POINTER(C.c_longlong), u32p, C.c_uint32, C.c_int]),
         "co_hnsw_remove": (C.c_int, [vp, C.c_uint32]),
         "co_hnsw_size": (C.c_long, [vp]),
         "co_hnsw_max_level": (C.c_int, [vp]),
@@ -444,6 +446,13 @@ class IVFPQ(_Index):
         c, cb = _f32(centroids), _f32(codebooks)
         _check(lib().co_ivfpq_set_trained(self.h, _p(c, f32p), _p(cb, f32p)))
 
+    def load_codes(self, ids, codes, list_of):
+        """Restore path (IVFPQIndex.ReadFrom): stored codes go back to their lists without re-encoding."""
+        ids = _u32(np.atleast_1d(ids))
+        c = np.ascontiguousarray(codes, dtype=np.uint8).reshape(len(ids), -1)
+        lo = np.ascontiguousarray(list_of, dtype=np.int32)
+        _check(lib().co_ivfpq_load_codes(self.h, _p(ids, u32p), _p(c, u8p), _p(lo, i32p), len(ids)), "ivfpq_load_codes")
+
     def add(self, ids, rows):
         ids = _u32(np.atleast_1d(ids))
         rows = rows if (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous) else _f32(rows)
@@ -524,6 +533,17 @@ class HNSW(_Index):
         rows = rows if (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous) else _f32(rows)
         _check(lib().co_hnsw_add_batch(self.h, _p(ids, u32p), _p(rows.reshape(len(ids), self.dim), f32p),
                                        _p(levels, i32p), len(ids)), "hnsw_add")
+
+    def load_graph(self, ids, rows, levels, edge_off, edge_ids, entry_id, max_level):
+        """Restore path (HNSWIndex.ReadFrom): stored vectors, levels, per-(slot, layer) edge lists, entry point."""
+        ids = _u32(np.atleast_1d(ids))
+        rows = rows if (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous) else _f32(rows)
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        eo = np.ascontiguousarray(edge_off, dtype=np.int64)
+        ei = _u32(edge_ids) if len(edge_ids) else np.zeros(1, np.uint32)
+        _check(lib().co_hnsw_load_graph(self.h, len(ids), _p(ids, u32p), _p(rows.reshape(len(ids), self.dim), f32p),
+                                        _p(levels, i32p), _p(eo, C.POINTER(C.c_longlong)), _p(ei, u32p), int(entry_id),
+                                        int(max_level)), "hnsw_load_graph")
 
     def remove(self, id_):
         _check(lib().co_hnsw_remove(self.h, int(id_)), "hnsw_remove")
