@@ -73,6 +73,23 @@ SIGNATURES = {
                                  i64p, i64p]),
     "cm_flat_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                         vp, vp, vp]),
+    "cm_flat_sharded_create": (C.c_int, [C.c_int, C.c_int, i32p, C.c_int, C.c_int64, C.POINTER(vp)]),
+    "cm_flat_sharded_destroy": (C.c_int, [vp]),
+    "cm_flat_sharded_shards": (C.c_int, [vp]),
+    "cm_flat_sharded_size": (C.c_int64, [vp]),
+    "cm_flat_sharded_shard_size": (C.c_int, [vp, C.c_int, i64p]),
+    "cm_flat_sharded_reserve": (C.c_int, [vp, C.c_int64]),
+    "cm_flat_sharded_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
+    "cm_flat_sharded_add_device": (C.c_int, [vp, C.c_int, u32p, vp, C.c_int64, vp]),
+    "cm_flat_sharded_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_flat_sharded_flush": (C.c_int, [vp]),
+    "cm_flat_sharded_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p,
+                                         i64p]),
+    "cm_flat_sharded_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp,
+                                                vp, vp, vp]),
+    "cm_flat_sharded_last_exchange_bytes": (C.c_int64, [vp]),
+    "cm_flat_sharded_last_timing": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cm_flat_sharded_last_stats": (C.c_int, [vp, C.POINTER(FlatStats)]),
     "cm_flat_batcher_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_flat_batcher_destroy": (C.c_int, [vp]),
     "cm_flat_batcher_search": (C.c_int, [vp, f32p, C.c_int, C.c_int64, C.c_float, C.c_int64, u32p, f32p, i64p]),
@@ -321,6 +338,85 @@ class FlatIndex:
     def last_stats(self):
         s = FlatStats()
         check(lib().cm_flat_last_stats(self.h, C.byref(s)))
+        return {"path_used": s.path_used, "passes": s.passes, "candidates": s.candidates,
+                "fallback_queries": s.fallback_queries, "kernel_launches": s.kernel_launches}
+
+
+class ShardedFlatIndex:
+    """Thin owner of a cm_flat_sharded handle: one process, one shard per entry of `devices`."""
+
+    def __init__(self, dim, metric, devices, rows_per_shard):
+        self.h = vp()
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        check(lib().cm_flat_sharded_create(int(dim), int(metric), ptr(dv, i32p), len(dv), int(rows_per_shard),
+                                           C.byref(self.h)))
+        self.dim, self.metric, self.devices = dim, metric, list(devices)
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().cm_flat_sharded_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(lib().cm_flat_sharded_size(self.h))
+
+    def shard_size(self, r):
+        n = C.c_int64(0)
+        check(lib().cm_flat_sharded_shard_size(self.h, int(r), C.byref(n)))
+        return n.value
+
+    def reserve(self, n):
+        check(lib().cm_flat_sharded_reserve(self.h, int(n)))
+
+    def add(self, ids, rows, writeback=True):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        check(lib().cm_flat_sharded_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
+
+    def add_device(self, shard, ids, rows_dev_ptr, n, stream=0):
+        ids = _u32(ids)
+        check(lib().cm_flat_sharded_add_device(self.h, int(shard), ptr(ids, u32p), vp(rows_dev_ptr), int(n), vp(stream)))
+
+    def remove(self, id_):
+        check(lib().cm_flat_sharded_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_flat_sharded_flush(self.h))
+
+    def search(self, queries, k=10, threshold=0.0, filter_ids=None, path=PATH_AUTO):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        n = len(self)
+        ke = max(n if (k <= 0 or k > n) else k, 1)
+        ids = np.zeros((nq, ke), np.uint32)
+        sc = np.zeros((nq, ke), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, filter_ids=filter_ids, path=path)
+        check(lib().cm_flat_sharded_search(self.h, ptr(q, f32p), nq, d, C.byref(p), ke, ptr(ids, u32p),
+                                           ptr(sc, f32p), ptr(cnt, i64p)))
+        return ids, sc, cnt
+
+    def search_device(self, q_ptr, nq, k, out_ids_ptr, out_scores_ptr, out_counts_ptr, out_stride, stream=0,
+                      threshold=0.0, path=PATH_AUTO):
+        p, keep = make_params(k=k, threshold=threshold, path=path)
+        check(lib().cm_flat_sharded_search_device(self.h, vp(q_ptr), int(nq), self.dim, C.byref(p), int(out_stride),
+                                                  vp(out_ids_ptr), vp(out_scores_ptr), vp(out_counts_ptr), vp(stream)))
+
+    def exchange_bytes(self):
+        return int(lib().cm_flat_sharded_last_exchange_bytes(self.h))
+
+    def last_timing(self):
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        check(lib().cm_flat_sharded_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"search_ms_max": a.value, "gather_ms_max": b.value, "merge_ms": c.value}
+
+    def last_stats(self):
+        s = FlatStats()
+        check(lib().cm_flat_sharded_last_stats(self.h, C.byref(s)))
         return {"path_used": s.path_used, "passes": s.passes, "candidates": s.candidates,
                 "fallback_queries": s.fallback_queries, "kernel_launches": s.kernel_launches}
 

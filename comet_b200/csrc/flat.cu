@@ -9,7 +9,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <set>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -21,37 +23,50 @@ namespace cm {
 
 // ---- small stream pool so concurrent searches (RLock holders) do not serialise ---------------
 static std::mutex g_stream_mu;
-static std::vector<cudaStream_t> g_stream_pool;
+static std::map<int, std::vector<cudaStream_t>> g_stream_pool;
+static std::map<cudaStream_t, int> g_stream_home;     // per device: a stream belongs to the device it was made on
 
 int acquire_stream(cudaStream_t *out) {
+    int dev = 0;
+    CM_CUDA(cudaGetDevice(&dev));
     {
         std::lock_guard<std::mutex> lk(g_stream_mu);
-        if (!g_stream_pool.empty()) {
-            *out = g_stream_pool.back();
-            g_stream_pool.pop_back();
+        std::vector<cudaStream_t> &pool = g_stream_pool[dev];
+        if (!pool.empty()) {
+            *out = pool.back();
+            pool.pop_back();
             return CM_OK;
         }
     }
     CM_CUDA(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    g_stream_home[*out] = dev;
     return CM_OK;
 }
 void release_stream(cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_stream_mu);
-    g_stream_pool.push_back(s);
+    g_stream_pool[g_stream_home[s]].push_back(s);
 }
 
-static std::once_flag g_pool_once;
+static std::set<int> g_pool_tuned;
 static void tune_mempool() {
-    cudaMemPool_t pool;
     int dev = 0;
     cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        if (!g_pool_tuned.insert(dev).second) return;
+    }
+    cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t thresh = ~0ull;   // keep freed workspace cached: searches reuse it
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
 }
 int ws_alloc(void **p, size_t bytes, cudaStream_t s) {
-    std::call_once(g_pool_once, tune_mempool);
+    static thread_local int tuned_dev = -1;   // the lock above is taken once per (thread, device change), not per call
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != tuned_dev) { tune_mempool(); tuned_dev = dev; }
     CM_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, s));
     return CM_OK;
 }
@@ -102,6 +117,9 @@ int FlatIndex::reserve(int64_t want) {
         CM_CUDA(cudaMemcpy(nids, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
         CM_CUDA(cudaMemcpy(ndel, deleted, (size_t)n, cudaMemcpyDeviceToDevice));
     }
+    // the memset / copies above ran on the legacy default stream, which the library's non-blocking streams do not
+    // synchronise with: make them complete before anything else can touch the new buffers
+    CM_CUDA(cudaDeviceSynchronize());
     cudaFree(rows); cudaFree(ids); cudaFree(deleted);
     rows = nrows; ids = nids; deleted = ndel; cap = ncap;
     shadow_rows = 0;   // tensor-path shadow must be rebuilt against the new buffers
@@ -223,11 +241,23 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
     if (k_eff <= 0 || k_eff > n) k_eff = n;                      // limiter.go:12-17 on len(idx.vectors)
     if (out_stride < k_eff)
         return fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)k_eff);
+    bool fma = rounding_mode() == CM_ROUND_FMA;
     if (n == 0 || k_eff == 0) {
         CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
+        if (metric == CM_COSINE) {
+            // the reference preprocesses the query before it looks at the index (flat_index_search.go:236): a zero
+            // query fails with ErrZeroVector on an empty index too
+            float *qp0 = nullptr;
+            int *qf0 = nullptr;
+            CM_TRY(ws_alloc((void **)&qp0, (size_t)nq * ld * 4, st));
+            CM_TRY(ws_alloc((void **)&qf0, (size_t)nq * sizeof(int), st));
+            CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp0, ld, qf0, st));
+            if (check_zero_queries) CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qf0, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+            else CM_TRY(launch_mark_zero_queries(qf0, nq, out_counts, st));
+            ws_free(qp0, st); ws_free(qf0, st);
+        }
         return CM_OK;
     }
-    bool fma = rounding_mode() == CM_ROUND_FMA;
 
     // 1. soft deletes + document filter -> per-row skip mask (flat_index_search.go:255-263)
     const uint8_t *skip = nullptr;
@@ -271,6 +301,9 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
         // the host entry point reads these flags after its final synchronise: a zero query is reported
         // then (its row of results is garbage by then, and discarded) without stalling the pipeline here
         CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qflags, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    } else if (rc == CM_OK && metric == CM_COSINE) {
+        // device entry point: nobody reads the flags on the host -- a zero query is reported as count -2
+        CM_TRY(launch_mark_zero_queries(qflags, nq, out_counts, st));
     }
     ws_free(qp, st); ws_free(qflags, st); ws_free(skip_buf, st); ws_free(filt_dev, st);
     stats.kernel_launches = g_kernel_launches.load() - launches0;
@@ -561,7 +594,7 @@ int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const 
     cm::release_stream(st);
     if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "flat_search: %s", cudaGetErrorString(e));
     if (rc != CM_OK) return rc;
-    if (h->ix.metric == CM_COSINE && h->ix.n > 0) {           // distance.go:269-290: Preprocess fails on a zero query
+    if (h->ix.metric == CM_COSINE) {                          // distance.go:269-290: Preprocess fails on a zero query
         int64_t z = cm::first_zero_query();
         cm::tl_zero_n = 0;
         if (z >= 0) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)z);

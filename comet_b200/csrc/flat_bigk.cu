@@ -2,6 +2,8 @@
 // k > 4096 (limiter.go:12-17 turns k <= 0 into "all").  The reference sorts all N results anyway
 // (flat_index_search.go:277); here every row's key goes to HBM and one radix sort per query orders
 // them.  Not a hot path: a result of >4096 rows per query is dominated by returning it.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "flat_index.cuh"
@@ -95,6 +97,65 @@ int FlatIndex::search_exact_bigk(const float *qp, int64_t nq, int64_t k_eff, con
     ws_free(keys, st); ws_free(sorted, st); ws_free(tmp, st);
     stats->path_used = CM_PATH_EXACT;
     stats->passes = (int)nq;
+    return CM_OK;
+}
+
+// ---- shard merge when world x k does not fit the shared-memory merge (k <= 0 / huge k on a sharded index) ------
+__global__ void merge_keys_kernel(const float *__restrict__ scores, const long long *__restrict__ counts, int world,
+                                  long long nq, long long q, long long in_stride, uint64_t *__restrict__ keys) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= world * in_stride) return;
+    long long r = i / in_stride, j = i % in_stride;
+    long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
+    keys[i] = j < c ? make_key(scores[((size_t)r * nq + q) * in_stride + j], (uint32_t)i) : KEY_INF;
+}
+__global__ void merge_emit_kernel(const uint64_t *__restrict__ keys, long long total, long long k, const uint32_t *__restrict__ ids,
+                                  const long long *__restrict__ counts, int world, long long nq, long long q, long long in_stride,
+                                  uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, long long *__restrict__ out_count) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i == 0 && out_count) {
+        long long bad = 0, have = 0;
+        for (int r = 0; r < world; r++) {
+            long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
+            bad = min(bad, c);
+            have += c < in_stride ? (c > 0 ? c : 0) : in_stride;
+        }
+        *out_count = bad < 0 ? bad : (have < k ? have : k);
+    }
+    if (i >= k || i >= total) return;
+    uint64_t key = keys[i];
+    if (key == KEY_INF) return;
+    uint32_t src = key_pos(key);
+    long long r = src / in_stride, j = src % in_stride;
+    out_ids[i] = ids[((size_t)r * nq + q) * in_stride + j];
+    out_scores[i] = key_score(key);
+}
+
+int merge_shards_bigk(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
+                      int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                      int64_t *out_counts, cudaStream_t st) {
+    const int64_t total = (int64_t)world * in_stride;
+    if (total >= (1ll << 32)) return fail(CM_ERR_UNSUPPORTED, "%d shards x k=%lld too large for the shard merge", world, (long long)in_stride);
+    uint64_t *keys = nullptr, *sorted = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, sorted, total, 0, 64, st);
+    CM_TRY(ws_alloc((void **)&keys, (size_t)total * 8, st));
+    CM_TRY(ws_alloc((void **)&sorted, (size_t)total * 8, st));
+    CM_TRY(ws_alloc(&tmp, tmp_bytes, st));
+    for (int64_t q = 0; q < nq; q++) {
+        merge_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scores, (const long long *)counts, world, (long long)nq,
+                                                                          (long long)q, (long long)in_stride, keys);
+        CM_CUDA(cudaGetLastError());
+        CM_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, sorted, total, 0, 64, st));
+        merge_emit_kernel<<<(unsigned)((std::min(k, total) + 255) / 256), 256, 0, st>>>(
+            sorted, (long long)total, (long long)k, ids, (const long long *)counts, world, (long long)nq, (long long)q,
+            (long long)in_stride, out_ids + (size_t)q * out_stride, out_scores + (size_t)q * out_stride,
+            out_counts ? (long long *)out_counts + q : nullptr);
+        CM_CUDA(cudaGetLastError());
+        count_launch(5);
+    }
+    ws_free(keys, st); ws_free(sorted, st); ws_free(tmp, st);
     return CM_OK;
 }
 

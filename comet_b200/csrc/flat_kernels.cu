@@ -364,6 +364,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
     const long long q = blockIdx.x;
     if (tid == 0) { cnt = 0; tau = KEY_INF; }
     __syncthreads();
+    // A shard that could not answer a query (tensor-path candidate overflow: count -1, see cm_flat_search_device)
+    // makes the merged answer unknown too: the -1 is passed on, never silently treated as an empty list.
+    if (counts) {
+        long long bad = 0;          // -2 (zero query under cosine: every non-empty shard says so) wins over -1
+        for (int r = 0; r < world; r++) bad = min(bad, counts[(size_t)r * nq + q]);
+        if (bad < 0) {
+            if (tid == 0 && out_counts) out_counts[q] = bad;
+            return;
+        }
+    }
     for (int r = 0; r < world; r++) {
         long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
         if (c > in_stride) c = in_stride;
@@ -389,7 +399,8 @@ int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t 
     int C = next_pow2((int)(world * in_stride));
     if (C < 512) C = 512;
     size_t smem = (size_t)C * 8;
-    if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "%d shards x k=%lld too large for the shard merge", world, (long long)in_stride);
+    if (smem > max_smem_optin())    // k <= 0 / huge k: one radix sort per query over the gathered lists (flat_bigk.cu)
+        return merge_shards_bigk(ids, scores, counts, world, nq, in_stride, (int64_t)K, out_stride, out_ids, out_scores, out_counts, stream);
     CM_TRY(set_dyn_smem((const void *)merge_shards_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
     merge_shards_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>(ids, scores, (const long long *)counts, world,
@@ -522,6 +533,19 @@ int launch_distance_pairs(int metric, bool fma, const float *a, const float *b, 
     default: return fail(CM_ERR_INVALID_ARG, "unknown metric %d", metric);
     }
 #undef CM_PAIR_CASE
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// device entry points report a zero query under cosine (ErrZeroVector, distance.go:269-290) as count -2
+__global__ void mark_zero_queries_kernel(const int *__restrict__ flags, long long nq, long long *__restrict__ out_counts) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q < nq && flags[q]) out_counts[q] = -2;
+}
+int launch_mark_zero_queries(const int *flags, int64_t nq, int64_t *out_counts, cudaStream_t stream) {
+    if (nq <= 0) return CM_OK;
+    mark_zero_queries_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(flags, (long long)nq, (long long *)out_counts);
     count_launch();
     CM_CUDA(cudaGetLastError());
     return CM_OK;

@@ -43,6 +43,10 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
 int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
                         int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                         int64_t *out_counts, cudaStream_t stream);
+// the same for world x in_stride beyond the shared-memory merge: one radix sort per query (flat_bigk.cu)
+int merge_shards_bigk(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
+                      int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                      int64_t *out_counts, cudaStream_t stream);
 
 // Distance.Preprocess / PreprocessInPlace on n rows (one thread per row, reference order).
 // dst rows have leading dimension ld_dst (zero padded beyond dim); flags[i] = 1 for a zero vector.
@@ -52,6 +56,9 @@ int launch_preprocess_rows(int metric, bool fma, const float *src, int64_t n, in
 // Distance.Calculate over n pairs (one thread per pair, reference order).
 int launch_distance_pairs(int metric, bool fma, const float *a, const float *b, int64_t n, int dim, float *out,
                           cudaStream_t stream);
+
+// out_counts[q] = -2 where flags[q] != 0 (zero query under cosine, reported by the device entry points)
+int launch_mark_zero_queries(const int *flags, int64_t nq, int64_t *out_counts, cudaStream_t stream);
 
 // skip[row] = deleted[row] | (filter given && id[row] not in sorted filter)
 int launch_build_skip(const uint32_t *row_ids, const uint8_t *deleted, int64_t n, const uint32_t *filter_sorted,

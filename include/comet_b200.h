@@ -74,6 +74,7 @@ typedef struct cm_pq cm_pq;
 typedef struct cm_ivfpq cm_ivfpq;
 typedef struct cm_hnsw cm_hnsw;
 typedef struct cm_flat_batcher cm_flat_batcher;
+typedef struct cm_flat_sharded cm_flat_sharded;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 int cm_init(const int *device_ids, int n_devices); /* NULL/0: use the current device */
@@ -139,6 +140,12 @@ int cm_flat_get_rows(const cm_flat *h, const int64_t *positions, int64_t n, floa
 int cm_flat_search(cm_flat *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
                    int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                    int64_t *out_counts);
+/* Device-pointer variant: enqueues on `stream`, never synchronises, so it cannot do what the host entry point
+ * does after its synchronise.  Two per-query conditions are therefore REPORTED in out_counts_dev instead:
+ *   -1  the tensor path's candidate lists overflowed for this query (adversarial ties): its row of results is
+ *       undefined and the caller must redo the query with p->path = CM_PATH_EXACT (cm_flat_search does);
+ *   -2  cosine: the query is a zero vector (Distance.Preprocess fails with ErrZeroVector, distance.go:269-290):
+ *       its row of results is undefined (cm_flat_search returns CM_ERR_ZERO_VECTOR). */
 int cm_flat_search_device(cm_flat *h, const float *queries_dev, int64_t nq, int dim,
                           const cm_search_params *p, int64_t out_stride, uint32_t *out_ids_dev,
                           float *out_scores_dev, int64_t *out_pos_dev, int64_t *out_counts_dev,
@@ -152,6 +159,46 @@ int cm_flat_search_device(cm_flat *h, const float *queries_dev, int64_t nq, int 
 int cm_merge_shards_device(const uint32_t *ids_dev, const float *scores_dev, const int64_t *counts_dev, int world,
                            int64_t nq, int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids_dev,
                            float *out_scores_dev, int64_t *out_counts_dev, void *stream);
+/* ---- row-sharded FlatIndex over the GPUs of one box, ONE host process ---------- */
+/* The Go host is a single process, so the multi-GPU layout lives behind this ABI: NewFlatIndex on a box with W
+ * GPUs binds cm_flat_sharded_create instead of cm_flat_create and nothing else changes for its callers.
+ * Shard r lives on devices[r] (the same device may appear more than once) and holds up to rows_per_shard rows;
+ * rows fill shard 0 first, then shard 1, ...: the reference's result order (score, scan position) is then
+ * (score, shard, rank within the shard's list), so the per-shard top-K lists merge without touching a row again.
+ * One search = queries to every shard over NVLink peer copies, cm_flat_search_device on every shard concurrently
+ * (one stream per device, CUDA events for ordering), the [nq][K] lists back to devices[0], one merge kernel
+ * (flat_index_search.go:277-291 on the union).  No NCCL: a single process owns the devices.
+ * Searches on one handle are serialised (they share the gather buffers); mutators need external exclusion. */
+int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_devices, int64_t rows_per_shard,
+                           cm_flat_sharded **out);
+int cm_flat_sharded_destroy(cm_flat_sharded *h);
+int cm_flat_sharded_shards(const cm_flat_sharded *h);
+int64_t cm_flat_sharded_size(const cm_flat_sharded *h);                 /* len(idx.vectors) over all shards */
+int cm_flat_sharded_shard_size(const cm_flat_sharded *h, int shard, int64_t *rows);
+int cm_flat_sharded_reserve(cm_flat_sharded *h, int64_t n_rows);
+/* n successive FlatIndex.Add calls (flat_index.go:169-189); rows written back like cm_flat_add */
+int cm_flat_sharded_add(cm_flat_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
+/* rows already resident on the device of shard `shard` (filling several shards in parallel is allowed as long as
+ * every shard before the last non-empty one is full before the first search) */
+int cm_flat_sharded_add_device(cm_flat_sharded *h, int shard, const uint32_t *ids_host, const float *rows_dev,
+                               int64_t n, void *stream);
+int cm_flat_sharded_remove(cm_flat_sharded *h, uint32_t id);            /* flat_index.go:219-250 */
+int cm_flat_sharded_flush(cm_flat_sharded *h);                          /* flat_index.go:266-299, shard by shard */
+/* nq independent searchSingleQuery calls against the whole sharded corpus; same contract as cm_flat_search
+ * (a query a shard's tensor path could not answer is redone on the exact path of every shard; a zero query under
+ * cosine fails the call with CM_ERR_ZERO_VECTOR). */
+int cm_flat_sharded_search(cm_flat_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                           int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_counts);
+/* queries / outputs on devices[0], enqueued on `stream` (a stream of devices[0]); never synchronises; per-query
+ * conditions are reported as counts -1 / -2 exactly like cm_flat_search_device */
+int cm_flat_sharded_search_device(cm_flat_sharded *h, const float *queries_dev, int64_t nq, int dim,
+                                  const cm_search_params *p, int64_t out_stride, uint32_t *out_ids_dev,
+                                  float *out_scores_dev, int64_t *out_counts_dev, void *stream);
+/* bytes that crossed NVLink in the last search (queries out + lists back; shards on devices[0] move nothing) */
+int64_t cm_flat_sharded_last_exchange_bytes(const cm_flat_sharded *h);
+/* device-side durations of the last search (CUDA events; waits for the search to finish): the slowest shard's
+ * local search, the slowest shard's copy of its lists to devices[0], the merge kernel */
+int cm_flat_sharded_last_timing(cm_flat_sharded *h, double *search_ms_max, double *gather_ms_max, double *merge_ms);
 /* Cross-call dynamic batching.  The reference's callers issue one query per Execute()
  * (flat_index_search.go:109-165), often from many goroutines; cm_flat_batcher_search blocks its caller while a
  * worker coalesces the concurrent requests that share (k, threshold) into ONE device batch (at most max_batch
@@ -171,6 +218,8 @@ typedef struct {
     int64_t kernel_launches;
 } cm_flat_stats;
 int cm_flat_last_stats(const cm_flat *h, cm_flat_stats *out);
+/* summed over the shards of the last sharded search */
+int cm_flat_sharded_last_stats(const cm_flat_sharded *h, cm_flat_stats *out);
 
 /* ---- ivf_index.go / ivf_index_search.go ----------------------------------------------------- */
 int cm_ivf_create(int dim, int nlist, int metric, cm_ivf **out);     /* NewIVFIndex ivf_index.go:147 */
