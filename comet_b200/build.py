@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs
+        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lz"]
         subprocess.check_call(cmd)
     return OUT
 

@@ -157,6 +157,29 @@ SIGNATURES = {
                                  i64p, i64p, i64p]),
     "cm_hnsw_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp,
                                         vp, vp, vp, vp]),
+    "cm_flat_get_ids": (C.c_int, [vp, C.c_int64, C.c_int64, u32p]),
+    "cm_hnsw_flush": (C.c_int, [vp]),
+    "cm_debug_decode_roaring": (C.c_int, [u8p, C.c_int64, u32p, C.c_int64, i64p]),
+    "cm_flat_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_flat_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_flat_save_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_flat_load_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_ivf_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_ivf_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_ivf_save_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_ivf_load_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_pq_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_pq_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_pq_save_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_pq_load_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_ivfpq_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_ivfpq_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_ivfpq_save_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_ivfpq_load_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_hnsw_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_hnsw_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),
+    "cm_hnsw_save_file": (C.c_int, [vp, C.c_char_p]),
+    "cm_hnsw_load_file": (C.c_int, [vp, C.c_char_p]),
     "cm_merge_shards_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp]),
 }
 
@@ -253,6 +276,42 @@ def preprocess_rows(metric, rows):
     return rows
 
 
+
+def save_bytes(kind, handle):
+    """WriteTo of index type `kind` ("flat" | "ivf" | "pq" | "ivfpq" | "hnsw") -> bytes (flushes the index)."""
+    L = lib()
+    n = C.c_int64(0)
+    check(getattr(L, f"cm_{kind}_save")(handle, None, 0, C.byref(n)))
+    buf = np.zeros(max(n.value, 1), np.uint8)
+    check(getattr(L, f"cm_{kind}_save")(handle, ptr(buf, u8p), n.value, C.byref(n)))
+    return buf[:n.value].tobytes()
+
+
+def load_bytes(kind, handle, data):
+    """ReadFrom: replaces the state of the pre-constructed index; returns the number of bytes consumed."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    used = C.c_int64(0)
+    check(getattr(lib(), f"cm_{kind}_load")(handle, ptr(buf, u8p), len(buf), C.byref(used)))
+    return used.value
+
+
+def save_file(kind, handle, path):
+    check(getattr(lib(), f"cm_{kind}_save_file")(handle, str(path).encode()))
+
+
+def load_file(kind, handle, path):
+    check(getattr(lib(), f"cm_{kind}_load_file")(handle, str(path).encode()))
+
+
+def decode_roaring(blob):
+    b = np.frombuffer(blob, dtype=np.uint8)
+    n = C.c_int64(0)
+    check(lib().cm_debug_decode_roaring(ptr(b, u8p) if len(b) else None, len(b), None, 0, C.byref(n)))
+    out = np.zeros(max(n.value, 1), np.uint32)
+    check(lib().cm_debug_decode_roaring(ptr(b, u8p) if len(b) else None, len(b), ptr(out, u32p), n.value, C.byref(n)))
+    return out[:n.value]
+
+
 class FlatIndex:
     """Thin owner of a cm_flat handle."""
 
@@ -294,6 +353,12 @@ class FlatIndex:
 
     def __len__(self):
         return int(lib().cm_flat_size(self.h))
+
+    def get_ids(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        out = np.zeros(max(n, 1), np.uint32)
+        check(lib().cm_flat_get_ids(self.h, int(first), int(n), ptr(out, u32p)))
+        return out[:n]
 
     def get_vector(self, id_):
         out = np.empty(self.dim, np.float32)
@@ -692,6 +757,9 @@ class HNSWIndex:
 
     def remove(self, id_):
         check(lib().cm_hnsw_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_hnsw_flush(self.h))
 
     def search(self, queries, k=10, ef_search=0, threshold=0.0, filter_ids=None, with_work=False):
         q = _f32(queries)

@@ -18,6 +18,7 @@
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+#include "wire.cuh"
 
 namespace cm {
 
@@ -346,6 +347,99 @@ int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t
     return CM_OK;
 }
 
+
+// stored (already preprocessed) rows appended as they are
+int FlatIndex::load_stored_rows(const uint32_t *ids_h, const float *rows_h, int64_t n_add) {
+    cudaStream_t st;
+    CM_TRY(acquire_stream(&st));
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)dim * 4));
+    float *stage = nullptr;
+    int rc = ws_alloc((void **)&stage, (size_t)std::min(slab, n_add) * dim * 4, st);
+    if (rc == CM_OK) rc = reserve(n + n_add);
+    const bool was_raw = raw_rows;
+    raw_rows = true;
+    for (int64_t i0 = 0; rc == CM_OK && i0 < n_add; i0 += slab) {
+        int64_t m = std::min(slab, n_add - i0);
+        cudaError_t e = cudaMemcpyAsync(stage, rows_h + (size_t)i0 * dim, (size_t)m * dim * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = fail(CM_ERR_CUDA, "load_rows: %s", cudaGetErrorString(e)); break; }
+        rc = add_from_device(ids_h + i0, stage, m, nullptr, st);
+    }
+    raw_rows = was_raw;
+    ws_free(stage, st);
+    cudaStreamSynchronize(st);
+    release_stream(st);
+    return rc;
+}
+
+// back to the state NewFlatIndex leaves: no vectors, nothing deleted (buffers are kept)
+int FlatIndex::reset() {
+    if (deleted && cap > 0) CM_CUDA(cudaMemset(deleted, 0, (size_t)cap));
+    n = 0;
+    n_deleted_rows = 0;
+    ids_host_mirror.clear();
+    deleted_ids.clear();
+    shadow_rows = 0;
+    return CM_OK;
+}
+
+// stored rows [first, first + m) to a dense host buffer (m x dim)
+int FlatIndex::read_rows(int64_t first, int64_t m, float *out) const {
+    if (m <= 0) return CM_OK;
+    CM_CUDA(cudaMemcpy2D(out, (size_t)dim * 4, rows + (size_t)first * ld, (size_t)ld * 4, (size_t)dim * 4, (size_t)m, cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+
+// FlatIndex.WriteTo (flat_index.go:366-470): Flush, then magic "FLAT", version, dim, distance kind, vector count,
+// per vector (ID, dimension, data), roaring blob of the (now empty) deleted set.
+int FlatIndex::save(wire::Sink &s) {
+    CM_TRY(flush());
+    CM_TRY(wire::write_header(s, "FLAT", dim, metric));
+    CM_WIRE_PUT(s.u32((uint32_t)n), "vector count");
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(64u << 20) / ((int64_t)dim * 4));
+    std::vector<float> host((size_t)std::min(slab, std::max<int64_t>(n, 1)) * dim);
+    std::vector<uint8_t> rec;
+    for (int64_t i0 = 0; i0 < n; i0 += slab) {
+        const int64_t m = std::min(slab, n - i0);
+        CM_TRY(read_rows(i0, m, host.data()));
+        const size_t per = 8 + (size_t)dim * 4;
+        rec.resize((size_t)m * per);
+        for (int64_t i = 0; i < m; i++) {
+            uint8_t *r = rec.data() + (size_t)i * per;
+            const uint32_t id = ids_host_mirror[(size_t)(i0 + i)], d = (uint32_t)dim;
+            memcpy(r, &id, 4);
+            memcpy(r + 4, &d, 4);
+            memcpy(r + 8, &host[(size_t)i * dim], (size_t)dim * 4);
+        }
+        CM_WIRE_PUT(s.put(rec.data(), rec.size()), "vector data");
+    }
+    CM_WIRE_PUT(wire::write_empty_bitmap(s), "bitmap");
+    return CM_OK;
+}
+
+// FlatIndex.ReadFrom (flat_index.go:488-614): the whole stream is decoded and validated first; only then does the
+// index state change (vectors and deleted set are REPLACED, as in the reference).
+int FlatIndex::load(wire::Source &s) {
+    CM_TRY(wire::read_header(s, "FLAT", dim, metric));
+    uint32_t count = 0;
+    CM_WIRE_GET(s.u32(&count), "vector count");
+    std::vector<uint32_t> ids_h(count);
+    std::vector<float> rows_h((size_t)count * dim);
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t vd = 0;
+        CM_WIRE_GET(s.u32(&ids_h[i]), "vector ID");
+        CM_WIRE_GET(s.u32(&vd), "vector dimension");
+        if ((int64_t)vd != dim) return fail(CM_ERR_DIM_MISMATCH, "vector %u has dimension %u, expected %d", i, vd, dim);
+        CM_WIRE_GET(s.get(&rows_h[(size_t)i * dim], (size_t)dim * 4), "vector data");
+    }
+    std::vector<uint32_t> dead;
+    CM_TRY(wire::read_bitmap(s, &dead));
+    CM_TRY(reset());
+    if (count > 0) CM_TRY(load_stored_rows(ids_h.data(), rows_h.data(), (int64_t)count));
+    for (uint32_t id : dead)
+        if (remove(id) != CM_OK) deleted_ids.insert(id);      // an ID the stream marks deleted without holding it: kept in the set
+    return CM_OK;
+}
+
 }  // namespace cm
 
 // ------------------------------------------------------------------------------------------------
@@ -472,25 +566,33 @@ int cm_flat_load_rows(cm_flat *h, const uint32_t *ids, const float *rows, int64_
     if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     if (n <= 0) return CM_OK;
     CM_CUDA(cudaSetDevice(h->ix.device));
-    cudaStream_t st;
-    CM_TRY(cm::acquire_stream(&st));
-    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)h->ix.dim * 4));
-    float *stage = nullptr;
-    int rc = cm::ws_alloc((void **)&stage, (size_t)std::min(slab, n) * h->ix.dim * 4, st);
-    if (rc == CM_OK) rc = h->ix.reserve(h->ix.n + n);
-    const bool was_raw = h->ix.raw_rows;
-    h->ix.raw_rows = true;
-    for (int64_t i0 = 0; rc == CM_OK && i0 < n; i0 += slab) {
-        int64_t m = std::min(slab, n - i0);
-        cudaError_t e = cudaMemcpyAsync(stage, rows + (size_t)i0 * h->ix.dim, (size_t)m * h->ix.dim * 4, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { rc = cm::fail(CM_ERR_CUDA, "load_rows: %s", cudaGetErrorString(e)); break; }
-        rc = h->ix.add_from_device(ids + i0, stage, m, nullptr, st);
-    }
-    h->ix.raw_rows = was_raw;
-    cm::ws_free(stage, st);
-    cudaStreamSynchronize(st);
-    cm::release_stream(st);
-    return rc;
+    return h->ix.load_stored_rows(ids, rows, n);
+}
+// WriteTo / ReadFrom (flat_index.go:366-614) on caller bytes or a file (".gz" = gzip, storage_provider.go:163-166)
+int cm_flat_save(cm_flat *h, uint8_t *buf, int64_t cap, int64_t *bytes) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_buffer([&](cm::wire::Sink &s) { return h->ix.save(s); }, buf, cap, bytes);
+}
+int cm_flat_load(cm_flat *h, const uint8_t *buf, int64_t len, int64_t *consumed) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_buffer([&](cm::wire::Source &s) { return h->ix.load(s); }, buf, len, consumed);
+}
+int cm_flat_save_file(cm_flat *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_file([&](cm::wire::Sink &s) { return h->ix.save(s); }, path);
+}
+int cm_flat_load_file(cm_flat *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_file([&](cm::wire::Source &s) { return h->ix.load(s); }, path);
+}
+int cm_flat_get_ids(const cm_flat *h, int64_t first, int64_t n, uint32_t *out) {
+    if (!h || first < 0 || n < 0 || first + n > h->ix.n || (n > 0 && !out)) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n > 0) memcpy(out, h->ix.ids_host_mirror.data() + first, (size_t)n * 4);
+    return CM_OK;
 }
 int cm_flat_add_device(cm_flat *h, const uint32_t *ids_host, const float *rows_dev, int64_t n, void *stream) {
     if (!h || (n > 0 && (!ids_host || !rows_dev))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");

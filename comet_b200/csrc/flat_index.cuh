@@ -14,6 +14,7 @@ namespace cm {
 int acquire_stream(cudaStream_t *out);
 void release_stream(cudaStream_t s);
 int ws_alloc(void **p, size_t bytes, cudaStream_t s);
+namespace wire { struct Sink; struct Source; }
 void ws_free(void *p, cudaStream_t s);
 
 struct FlatIndex {
@@ -53,6 +54,11 @@ struct FlatIndex {
                         cudaStream_t st);
     int remove(uint32_t id);
     int flush();
+    int reset();
+    int load_stored_rows(const uint32_t *ids_host, const float *rows_host, int64_t n_add);
+    int read_rows(int64_t first, int64_t m, float *out) const;
+    int save(wire::Sink &s);       // FlatIndex.WriteTo
+    int load(wire::Source &s);     // FlatIndex.ReadFrom
     int search_device(const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                       uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
                       bool check_zero_queries);

@@ -538,6 +538,18 @@ int launch_distance_pairs(int metric, bool fma, const float *a, const float *b, 
     return CM_OK;
 }
 
+__global__ void fill_counts_kernel(long long *__restrict__ counts, long long nq, long long v) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q < nq) counts[q] = v;
+}
+int launch_fill_counts(int64_t *counts, int64_t nq, int64_t value, cudaStream_t stream) {
+    if (nq <= 0) return CM_OK;
+    fill_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>((long long *)counts, (long long)nq, (long long)value);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
 // device entry points report a zero query under cosine (ErrZeroVector, distance.go:269-290) as count -2
 __global__ void mark_zero_queries_kernel(const int *__restrict__ flags, long long nq, long long *__restrict__ out_counts) {
     long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;

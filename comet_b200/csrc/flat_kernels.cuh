@@ -57,6 +57,8 @@ int launch_preprocess_rows(int metric, bool fma, const float *src, int64_t n, in
 int launch_distance_pairs(int metric, bool fma, const float *a, const float *b, int64_t n, int dim, float *out,
                           cudaStream_t stream);
 
+// counts[q] = value (a kernel rather than a memset: the array may live on a peer device)
+int launch_fill_counts(int64_t *counts, int64_t nq, int64_t value, cudaStream_t stream);
 // out_counts[q] = -2 where flags[q] != 0 (zero query under cosine, reported by the device entry points)
 int launch_mark_zero_queries(const int *flags, int64_t nq, int64_t *out_counts, cudaStream_t stream);
 

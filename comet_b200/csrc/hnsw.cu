@@ -25,6 +25,7 @@
 // each lane walks its own row in the reference's sequential order -- and lane 0 replays the heap
 // operations in edge order.  Visited set: one bit per node (global memory, atomicOr).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <unordered_map>
 #include <unordered_set>
@@ -32,6 +33,7 @@
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+#include "wire.cuh"
 
 namespace cm {
 
@@ -939,6 +941,196 @@ int cm_hnsw_search(cm_hnsw *h, const float *queries, int64_t nq, int dim, const 
         for (int64_t q = 0; q < nq; q++)
             if (out_counts[q] < 0) return cm::fail(CM_ERR_UNSUPPORTED, "candidate heap overflow on query %lld (efSearch too small a bound)", (long long)q);
     return rc;
+}
+
+// ---- HNSWIndex.Flush (hnsw_index.go:348-430), WriteTo / ReadFrom (hnsw_index.go:734-1096) ----------------------
+// the whole graph on the host, in slot (insertion) order
+struct HostGraph {
+    std::vector<uint32_t> ids;
+    std::vector<float> rows;
+    std::vector<int32_t> levels;
+    std::vector<int64_t> edge_off;
+    std::vector<uint32_t> edge_ids;
+    uint32_t entry = 0;
+    int max_level = -1;
+};
+static int hnsw_to_host(cm_hnsw *h, HostGraph *g) {
+    cm::HNSWIndex &ix = h->ix;
+    const int64_t n = ix.n;
+    g->ids.resize((size_t)n);
+    g->rows.resize((size_t)n * ix.dim);
+    g->levels.resize((size_t)n);
+    int64_t pairs = 0;
+    for (int64_t i = 0; i < n; i++) pairs += ix.levels_host[(size_t)i] + 1;
+    g->edge_off.assign((size_t)pairs + 1, 0);
+    g->edge_ids.resize((size_t)std::max<int64_t>(cm_hnsw_edge_count(h), 1));
+    g->entry = 0;
+    g->max_level = ix.max_level;
+    if (n == 0) return CM_OK;
+    CM_CUDA(cudaMemcpy(g->ids.data(), ix.ids, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CM_CUDA(cudaMemcpy2D(g->rows.data(), (size_t)ix.dim * 4, ix.rows, (size_t)ix.ld * 4, (size_t)ix.dim * 4, (size_t)n, cudaMemcpyDeviceToHost));
+    return cm_hnsw_export_graph(h, g->levels.data(), g->edge_off.data(), g->edge_ids.data(), &g->entry, &g->max_level);
+}
+
+// Flush: (1) every live node drops its edges to deleted nodes; (2) a deleted entry point is replaced by a live node at
+// maxLevel, else by a node of the highest level left (maxLevel follows), else the index is empty; (3) deleted nodes go;
+// (4) the deleted set is cleared.  The reference walks a Go map in phase 2, so WHICH of several eligible nodes becomes
+// the entry point is random there; here it is the earliest inserted one (lowest slot) -- one of the outcomes the
+// reference can produce, chosen deterministically.
+int cm_hnsw_flush(cm_hnsw *h) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    cm::HNSWIndex &ix = h->ix;
+    if (ix.deleted_ids.empty()) return CM_OK;
+    CM_CUDA(cudaSetDevice(ix.device));
+    HostGraph g;
+    CM_TRY(hnsw_to_host(h, &g));
+    const std::unordered_set<uint32_t> dead = ix.deleted_ids;
+    const int64_t n = (int64_t)g.ids.size();
+    uint32_t entry = g.entry;
+    int max_level = g.max_level;
+    if (dead.count(entry)) {
+        bool found = false;
+        for (int64_t i = 0; i < n && !found; i++)
+            if (!dead.count(g.ids[(size_t)i]) && g.levels[(size_t)i] == max_level) { entry = g.ids[(size_t)i]; found = true; }
+        if (!found) {
+            int best = -1;
+            for (int64_t i = 0; i < n; i++)
+                if (!dead.count(g.ids[(size_t)i]) && g.levels[(size_t)i] > best) { best = g.levels[(size_t)i]; entry = g.ids[(size_t)i]; }
+            if (best >= 0) max_level = best;
+            else { entry = 0; max_level = -1; }
+        }
+    }
+    HostGraph out;
+    out.edge_off.push_back(0);
+    int64_t pair = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int L = g.levels[(size_t)i];
+        if (!dead.count(g.ids[(size_t)i])) {
+            out.ids.push_back(g.ids[(size_t)i]);
+            out.levels.push_back(L);
+            out.rows.insert(out.rows.end(), g.rows.begin() + (size_t)i * ix.dim, g.rows.begin() + (size_t)(i + 1) * ix.dim);
+            for (int l = 0; l <= L; l++) {
+                for (int64_t e = g.edge_off[(size_t)(pair + l)]; e < g.edge_off[(size_t)(pair + l + 1)]; e++)
+                    if (!dead.count(g.edge_ids[(size_t)e])) out.edge_ids.push_back(g.edge_ids[(size_t)e]);
+                out.edge_off.push_back((int64_t)out.edge_ids.size());
+            }
+        }
+        pair += L + 1;
+    }
+    if (out.edge_ids.empty()) out.edge_ids.push_back(0);
+    return cm_hnsw_load_graph(h, (int64_t)out.ids.size(), out.ids.data(), out.rows.data(), out.levels.data(), out.edge_off.data(),
+                              out.edge_ids.data(), entry, max_level);
+}
+
+// WriteTo: Flush; header; M, efConstruction, efSearch, levelMult (float64, 1 / ln M); maxLevel (int32), entryPoint;
+// node count; per node (ID, level, vector dimension, vector, edge layer count, per layer edge count + IDs); roaring
+// blob.  The reference writes nodes in Go map order (random); here in insertion order -- ReadFrom accepts any order.
+static int hnsw_save(cm_hnsw *h, cm::wire::Sink &s) {
+    cm::HNSWIndex &ix = h->ix;
+    CM_TRY(cm_hnsw_flush(h));
+    HostGraph g;
+    CM_TRY(hnsw_to_host(h, &g));
+    CM_TRY(cm::wire::write_header(s, "HNSW", ix.dim, ix.metric));
+    CM_WIRE_PUT(s.u32((uint32_t)ix.m), "M");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.efc), "efConstruction");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.efs), "efSearch");
+    CM_WIRE_PUT(s.f64(1.0 / std::log((double)ix.m)), "levelMult");          // hnsw_index.go:206
+    CM_WIRE_PUT(s.i32((int32_t)g.max_level), "maxLevel");
+    CM_WIRE_PUT(s.u32(g.ids.empty() ? 0u : g.entry), "entryPoint");
+    CM_WIRE_PUT(s.u32((uint32_t)g.ids.size()), "node count");
+    int64_t pair = 0;
+    std::vector<uint8_t> rec;
+    for (size_t i = 0; i < g.ids.size(); i++) {
+        const int L = g.levels[i];
+        rec.clear();
+        auto app = [&](const void *p, size_t nbytes) { rec.insert(rec.end(), (const uint8_t *)p, (const uint8_t *)p + nbytes); };
+        const uint32_t id = g.ids[i], d = (uint32_t)ix.dim, layers = (uint32_t)(L + 1);
+        const int32_t lvl = L;
+        app(&id, 4); app(&lvl, 4); app(&d, 4);
+        app(&g.rows[i * (size_t)ix.dim], (size_t)ix.dim * 4);
+        app(&layers, 4);
+        for (int l = 0; l <= L; l++) {
+            const int64_t e0 = g.edge_off[(size_t)(pair + l)], e1 = g.edge_off[(size_t)(pair + l + 1)];
+            const uint32_t cnt = (uint32_t)(e1 - e0);
+            app(&cnt, 4);
+            if (cnt) app(&g.edge_ids[(size_t)e0], (size_t)cnt * 4);
+        }
+        pair += L + 1;
+        CM_WIRE_PUT(s.put(rec.data(), rec.size()), "node");
+    }
+    CM_WIRE_PUT(cm::wire::write_empty_bitmap(s), "bitmap");
+    return CM_OK;
+}
+
+static int hnsw_load(cm_hnsw *h, cm::wire::Source &s) {
+    cm::HNSWIndex &ix = h->ix;
+    CM_TRY(cm::wire::read_header(s, "HNSW", ix.dim, ix.metric));
+    uint32_t M = 0, efc = 0, efs = 0, entry = 0, count = 0;
+    int32_t max_level = 0;
+    double level_mult = 0.0;
+    CM_WIRE_GET(s.u32(&M), "M");
+    CM_WIRE_GET(s.u32(&efc), "efConstruction");
+    CM_WIRE_GET(s.u32(&efs), "efSearch");
+    if ((int64_t)M != ix.m) return cm::fail(CM_ERR_INVALID_ARG, "m parameter mismatch: index has m=%d, serialized data has m=%u", ix.m, M);
+    if ((int64_t)efc != ix.efc) return cm::fail(CM_ERR_INVALID_ARG, "efConstruction mismatch: index has %d, serialized data has %u", ix.efc, efc);
+    if ((int64_t)efs != ix.efs) return cm::fail(CM_ERR_INVALID_ARG, "efSearch mismatch: index has %d, serialized data has %u", ix.efs, efs);
+    CM_WIRE_GET(s.f64(&level_mult), "levelMult");      // randomLevel stays with the caller (cm_hnsw_add takes the level draws)
+    CM_WIRE_GET(s.i32(&max_level), "maxLevel");
+    CM_WIRE_GET(s.u32(&entry), "entryPoint");
+    CM_WIRE_GET(s.u32(&count), "node count");
+    HostGraph g;
+    g.ids.resize(count);
+    g.levels.resize(count);
+    g.rows.resize((size_t)count * ix.dim);
+    g.edge_off.push_back(0);
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t vd = 0, layers = 0;
+        CM_WIRE_GET(s.u32(&g.ids[i]), "node ID");
+        CM_WIRE_GET(s.i32(&g.levels[i]), "node level");
+        CM_WIRE_GET(s.u32(&vd), "vector dimension");
+        if ((int64_t)vd != ix.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "node %u has dimension %u, expected %d", g.ids[i], vd, ix.dim);
+        CM_WIRE_GET(s.get(&g.rows[(size_t)i * ix.dim], (size_t)ix.dim * 4), "vector data");
+        CM_WIRE_GET(s.u32(&layers), "edge layer count");
+        if ((int64_t)layers != (int64_t)g.levels[i] + 1)
+            return cm::fail(CM_ERR_INVALID_ARG, "node %u has %u edge layers at level %d", g.ids[i], layers, g.levels[i]);
+        for (uint32_t l = 0; l < layers; l++) {
+            uint32_t cnt = 0;
+            CM_WIRE_GET(s.u32(&cnt), "edge count");
+            const size_t at = g.edge_ids.size();
+            g.edge_ids.resize(at + cnt);
+            CM_WIRE_GET(cnt == 0 || s.get(&g.edge_ids[at], (size_t)cnt * 4), "edge IDs");
+            g.edge_off.push_back((int64_t)g.edge_ids.size());
+        }
+    }
+    std::vector<uint32_t> dead;
+    CM_TRY(cm::wire::read_bitmap(s, &dead));
+    if (g.edge_ids.empty()) g.edge_ids.push_back(0);
+    CM_TRY(cm_hnsw_load_graph(h, (int64_t)count, g.ids.data(), g.rows.data(), g.levels.data(), g.edge_off.data(), g.edge_ids.data(),
+                              entry, (int)max_level));
+    for (uint32_t id : dead)
+        if (cm_hnsw_remove(h, id) != CM_OK) ix.deleted_ids.insert(id);
+    return CM_OK;
+}
+
+int cm_hnsw_save(cm_hnsw *h, uint8_t *buf, int64_t cap, int64_t *bytes) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_buffer([&](cm::wire::Sink &s) { return hnsw_save(h, s); }, buf, cap, bytes);
+}
+int cm_hnsw_load(cm_hnsw *h, const uint8_t *buf, int64_t len, int64_t *consumed) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_buffer([&](cm::wire::Source &s) { return hnsw_load(h, s); }, buf, len, consumed);
+}
+int cm_hnsw_save_file(cm_hnsw *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_file([&](cm::wire::Sink &s) { return hnsw_save(h, s); }, path);
+}
+int cm_hnsw_load_file(cm_hnsw *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_file([&](cm::wire::Source &s) { return hnsw_load(h, s); }, path);
 }
 
 }  // extern "C"

@@ -29,6 +29,7 @@
 #include "flat_kernels.cuh"
 #include "kmeans.cuh"
 #include "select.cuh"
+#include "wire.cuh"
 
 namespace cm {
 
@@ -676,6 +677,131 @@ int cm_ivf_search(cm_ivf *h, const float *queries, int64_t nq, int dim, const cm
     cm::release_stream(st);
     if (rc == CM_OK && e != cudaSuccess) return cm::fail(CM_ERR_CUDA, "ivf_search: %s", cudaGetErrorString(e));
     return rc;
+}
+
+// ---- wire format "IVFX" (ivf_index.go:468-785) ------------------------------------------------------------------
+// back to the state NewIVFIndex leaves: untrained, no vectors
+static int ivf_reset(cm_ivf *h) {
+    cm::IVFIndex &ix = h->ix;
+    CM_TRY(ix.store.reset());
+    CM_TRY(ix.coarse.reset());
+    for (auto &l : ix.lists) l.clear();
+    ix.list_of.clear();
+    ix.trained = false;
+    ix.csr_dirty = true;
+    return CM_OK;
+}
+
+// IVFIndex.WriteTo: Flush, header, nlist, trained flag, centroids (size + data each), list count, per list (size, per
+// vector ID + data), roaring blob.
+static int ivf_save(cm_ivf *h, cm::wire::Sink &s) {
+    cm::IVFIndex &ix = h->ix;
+    CM_TRY(cm_ivf_flush(h));
+    CM_TRY(cm::wire::write_header(s, "IVFX", ix.dim, ix.metric));
+    CM_WIRE_PUT(s.u32((uint32_t)ix.nlist), "nlist");
+    CM_WIRE_PUT(s.u8(ix.trained ? 1 : 0), "trained flag");
+    if (ix.trained) {
+        std::vector<float> c((size_t)ix.nlist * ix.dim);
+        CM_TRY(cm_ivf_get_centroids(h, c.data()));
+        for (int l = 0; l < ix.nlist; l++) {
+            CM_WIRE_PUT(s.u32((uint32_t)ix.dim), "centroid size");
+            CM_WIRE_PUT(s.put(&c[(size_t)l * ix.dim], (size_t)ix.dim * 4), "centroid data");
+        }
+    }
+    CM_WIRE_PUT(s.u32((uint32_t)ix.lists.size()), "list count");
+    const size_t per = 4 + (size_t)ix.dim * 4;
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)per);
+    std::vector<float> rows;
+    std::vector<int64_t> pos;
+    std::vector<uint8_t> rec;
+    for (size_t l = 0; l < ix.lists.size(); l++) {
+        const std::vector<uint32_t> &L = ix.lists[l];
+        CM_WIRE_PUT(s.u32((uint32_t)L.size()), "list size");
+        for (int64_t i0 = 0; i0 < (int64_t)L.size(); i0 += slab) {
+            const int64_t m = std::min<int64_t>(slab, (int64_t)L.size() - i0);
+            pos.assign(L.begin() + i0, L.begin() + i0 + m);
+            rows.resize((size_t)m * ix.dim);
+            CM_TRY(cm_ivf_get_rows(h, pos.data(), m, rows.data()));
+            rec.resize((size_t)m * per);
+            for (int64_t i = 0; i < m; i++) {
+                const uint32_t id = ix.store.ids_host_mirror[(size_t)pos[(size_t)i]];
+                memcpy(&rec[(size_t)i * per], &id, 4);
+                memcpy(&rec[(size_t)i * per + 4], &rows[(size_t)i * ix.dim], (size_t)ix.dim * 4);
+            }
+            CM_WIRE_PUT(s.put(rec.data(), rec.size()), "list data");
+        }
+    }
+    CM_WIRE_PUT(cm::wire::write_empty_bitmap(s), "bitmap");
+    return CM_OK;
+}
+
+// IVFIndex.ReadFrom: everything is decoded and validated before the index state is replaced.  The store keeps the
+// stream's order (list by list); the search only depends on the order inside each list.
+static int ivf_load(cm_ivf *h, cm::wire::Source &s) {
+    cm::IVFIndex &ix = h->ix;
+    CM_TRY(cm::wire::read_header(s, "IVFX", ix.dim, ix.metric));
+    uint32_t nlist = 0, list_count = 0;
+    uint8_t trained = 0;
+    CM_WIRE_GET(s.u32(&nlist), "nlist");
+    if ((int64_t)nlist != ix.nlist) return cm::fail(CM_ERR_INVALID_ARG, "nlist mismatch: index has nlist=%d, serialized data has nlist=%u", ix.nlist, nlist);
+    CM_WIRE_GET(s.u8(&trained), "trained flag");
+    std::vector<float> cent;
+    if (trained == 1) {
+        cent.resize((size_t)ix.nlist * ix.dim);
+        for (int l = 0; l < ix.nlist; l++) {
+            uint32_t sz = 0;
+            CM_WIRE_GET(s.u32(&sz), "centroid size");
+            if ((int64_t)sz != ix.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "centroid %d has dimension %u, expected %d", l, sz, ix.dim);
+            CM_WIRE_GET(s.get(&cent[(size_t)l * ix.dim], (size_t)ix.dim * 4), "centroid data");
+        }
+    }
+    CM_WIRE_GET(s.u32(&list_count), "list count");
+    if (list_count > (uint32_t)ix.nlist) return cm::fail(CM_ERR_INVALID_ARG, "serialized data has %u lists, index has nlist=%d", list_count, ix.nlist);
+    std::vector<uint32_t> ids;
+    std::vector<int32_t> list_of;
+    std::vector<float> rows;
+    for (uint32_t l = 0; l < list_count; l++) {
+        uint32_t sz = 0;
+        CM_WIRE_GET(s.u32(&sz), "list size");
+        const size_t at = ids.size();
+        ids.resize(at + sz);
+        list_of.resize(at + sz, (int32_t)l);
+        rows.resize((at + sz) * (size_t)ix.dim);
+        for (uint32_t i = 0; i < sz; i++) {
+            CM_WIRE_GET(s.u32(&ids[at + i]), "list vector ID");
+            CM_WIRE_GET(s.get(&rows[(at + i) * (size_t)ix.dim], (size_t)ix.dim * 4), "list vector data");
+        }
+    }
+    std::vector<uint32_t> dead;
+    CM_TRY(cm::wire::read_bitmap(s, &dead));
+    if (!ids.empty() && trained != 1) return cm::fail(CM_ERR_NOT_TRAINED, "serialized data holds vectors but no centroids");
+    CM_TRY(ivf_reset(h));
+    if (trained == 1) CM_TRY(cm_ivf_set_centroids(h, cent.data()));
+    if (!ids.empty()) CM_TRY(cm_ivf_load_lists(h, ids.data(), rows.data(), list_of.data(), (int64_t)ids.size()));
+    for (uint32_t id : dead)
+        if (ix.store.remove(id) != CM_OK) ix.store.deleted_ids.insert(id);
+    return CM_OK;
+}
+
+int cm_ivf_save(cm_ivf *h, uint8_t *buf, int64_t cap, int64_t *bytes) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_buffer([&](cm::wire::Sink &s) { return ivf_save(h, s); }, buf, cap, bytes);
+}
+int cm_ivf_load(cm_ivf *h, const uint8_t *buf, int64_t len, int64_t *consumed) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_buffer([&](cm::wire::Source &s) { return ivf_load(h, s); }, buf, len, consumed);
+}
+int cm_ivf_save_file(cm_ivf *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::save_to_file([&](cm::wire::Sink &s) { return ivf_save(h, s); }, path);
+}
+int cm_ivf_load_file(cm_ivf *h, const char *path) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    return cm::wire::load_from_file([&](cm::wire::Source &s) { return ivf_load(h, s); }, path);
 }
 
 }  // extern "C"

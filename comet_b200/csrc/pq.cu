@@ -29,6 +29,7 @@
 #include "flat_kernels.cuh"
 #include "kmeans.cuh"
 #include "select.cuh"
+#include "wire.cuh"
 
 namespace cm {
 
@@ -874,6 +875,152 @@ static int core_get_trained(const PQCore &ix, float *centroids, float *codebooks
     return CM_OK;
 }
 
+// ---- wire formats "PQIX" (pq_index.go:509-846) and "IVPQ" (ivfpq_index.go:544-960) -----------------------------
+// back to the state NewPQIndex / NewIVFPQIndex leaves: untrained, no codes
+static int core_reset(PQCore &ix) {
+    if (ix.store.deleted && ix.store.cap > 0) CM_CUDA(cudaMemset(ix.store.deleted, 0, (size_t)ix.store.cap));
+    ix.store.n = 0;
+    ix.store.n_deleted_rows = 0;
+    ix.store.ids_host.clear();
+    ix.store.deleted_ids.clear();
+    if (ix.nlist > 0) {
+        CM_TRY(ix.coarse.reset());
+        for (auto &l : ix.lists) l.clear();
+        ix.list_of.clear();
+        ix.csr_dirty = true;
+    }
+    ix.trained = false;
+    return CM_OK;
+}
+
+// WriteTo of both index types: Flush; header; [nlist]; M, Nbits, Ksub, dsub; trained flag; [centroids]; codebooks
+// (size + data per sub-quantiser); then PQ: vector count, per vector (ID, code) in arrival order -- IVFPQ: list count,
+// per list (size, per vector ID + code); roaring blob.
+static int core_save(PQCore &ix, wire::Sink &s) {
+    const bool ivf = ix.nlist > 0;
+    CM_TRY(adc_flush(ix));
+    CM_TRY(wire::write_header(s, ivf ? "IVPQ" : "PQIX", ix.dim, ix.metric));
+    if (ivf) CM_WIRE_PUT(s.u32((uint32_t)ix.nlist), "nlist");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.M), "M");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.nbits), "Nbits");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.Ksub), "Ksub");
+    CM_WIRE_PUT(s.u32((uint32_t)ix.dsub), "dsub");
+    CM_WIRE_PUT(s.u8(ix.trained ? 1 : 0), "trained flag");
+    if (ix.trained) {
+        const size_t cb = (size_t)ix.Ksub * ix.dsub;
+        std::vector<float> cent(ivf ? (size_t)ix.nlist * ix.dim : 0), books((size_t)ix.M * cb);
+        CM_TRY(core_get_trained(ix, ivf ? cent.data() : nullptr, books.data()));
+        for (int l = 0; ivf && l < ix.nlist; l++) {
+            CM_WIRE_PUT(s.u32((uint32_t)ix.dim), "centroid size");
+            CM_WIRE_PUT(s.put(&cent[(size_t)l * ix.dim], (size_t)ix.dim * 4), "centroid data");
+        }
+        for (int m = 0; m < ix.M; m++) {
+            CM_WIRE_PUT(s.u32((uint32_t)cb), "codebook size");
+            CM_WIRE_PUT(s.put(&books[(size_t)m * cb], cb * 4), "codebook data");
+        }
+    }
+    const int64_t n = ix.store.n;
+    std::vector<uint8_t> codes((size_t)n * ix.M);
+    if (n > 0) CM_CUDA(cudaMemcpy(codes.data(), ix.store.codes, codes.size(), cudaMemcpyDeviceToHost));
+    const size_t per = 4 + (size_t)ix.M;
+    std::vector<uint8_t> rec;
+    auto put_rows = [&](const uint32_t *pos, int64_t first, int64_t m) {      // pos == NULL: positions first, first + 1, ...
+        rec.resize((size_t)m * per);
+        for (int64_t i = 0; i < m; i++) {
+            const int64_t at = pos ? (int64_t)pos[i] : first + i;
+            memcpy(&rec[(size_t)i * per], &ix.store.ids_host[(size_t)at], 4);
+            memcpy(&rec[(size_t)i * per + 4], &codes[(size_t)at * ix.M], (size_t)ix.M);
+        }
+        return s.put(rec.data(), rec.size());
+    };
+    if (!ivf) {
+        CM_WIRE_PUT(s.u32((uint32_t)n), "vector count");
+        CM_WIRE_PUT(put_rows(nullptr, 0, n), "vector codes");
+    } else {
+        CM_WIRE_PUT(s.u32((uint32_t)ix.lists.size()), "list count");
+        for (const std::vector<uint32_t> &L : ix.lists) {
+            CM_WIRE_PUT(s.u32((uint32_t)L.size()), "list size");
+            CM_WIRE_PUT(put_rows(L.data(), 0, (int64_t)L.size()), "list codes");
+        }
+    }
+    CM_WIRE_PUT(wire::write_empty_bitmap(s), "bitmap");
+    return CM_OK;
+}
+
+// ReadFrom of both index types: decode and validate everything, then replace the index state.
+static int core_load(PQCore &ix, wire::Source &s) {
+    const bool ivf = ix.nlist > 0;
+    CM_TRY(wire::read_header(s, ivf ? "IVPQ" : "PQIX", ix.dim, ix.metric));
+    uint32_t nlist = 0, M = 0, nbits = 0, Ksub = 0, dsub = 0;
+    uint8_t trained = 0;
+    if (ivf) CM_WIRE_GET(s.u32(&nlist), "nlist");
+    CM_WIRE_GET(s.u32(&M), "M");
+    CM_WIRE_GET(s.u32(&nbits), "Nbits");
+    CM_WIRE_GET(s.u32(&Ksub), "Ksub");
+    CM_WIRE_GET(s.u32(&dsub), "dsub");
+    if (ivf && (int64_t)nlist != ix.nlist) return fail(CM_ERR_INVALID_ARG, "parameter nlist mismatch: index has nlist=%d, serialized data has nlist=%u", ix.nlist, nlist);
+    if ((int64_t)M != ix.M) return fail(CM_ERR_INVALID_ARG, "parameter M mismatch: index has M=%d, serialized data has M=%u", ix.M, M);
+    if ((int64_t)nbits != ix.nbits) return fail(CM_ERR_INVALID_ARG, "parameter Nbits mismatch: index has Nbits=%d, serialized data has Nbits=%u", ix.nbits, nbits);
+    if ((int64_t)Ksub != ix.Ksub) return fail(CM_ERR_INVALID_ARG, "parameter Ksub mismatch: index has Ksub=%d, serialized data has Ksub=%u", ix.Ksub, Ksub);
+    if ((int64_t)dsub != ix.dsub) return fail(CM_ERR_INVALID_ARG, "parameter dsub mismatch: index has dsub=%d, serialized data has dsub=%u", ix.dsub, dsub);
+    CM_WIRE_GET(s.u8(&trained), "trained flag");
+    const size_t cb = (size_t)ix.Ksub * ix.dsub;
+    std::vector<float> cent, books;
+    if (trained == 1) {
+        if (ivf) {
+            cent.resize((size_t)ix.nlist * ix.dim);
+            for (int l = 0; l < ix.nlist; l++) {
+                uint32_t sz = 0;
+                CM_WIRE_GET(s.u32(&sz), "centroid size");
+                if ((int64_t)sz != ix.dim) return fail(CM_ERR_DIM_MISMATCH, "centroid %d has dimension %u, expected %d", l, sz, ix.dim);
+                CM_WIRE_GET(s.get(&cent[(size_t)l * ix.dim], (size_t)ix.dim * 4), "centroid data");
+            }
+        }
+        books.resize((size_t)ix.M * cb);
+        for (int m = 0; m < ix.M; m++) {
+            uint32_t sz = 0;
+            CM_WIRE_GET(s.u32(&sz), "codebook size");
+            if ((size_t)sz != cb) return fail(CM_ERR_INVALID_ARG, "codebook %d has %u values, expected %zu", m, sz, cb);
+            CM_WIRE_GET(s.get(&books[(size_t)m * cb], cb * 4), "codebook data");
+        }
+    }
+    std::vector<uint32_t> ids;
+    std::vector<int32_t> list_of;
+    std::vector<uint8_t> codes;
+    auto get_rows = [&](uint32_t count, int32_t list) {
+        const size_t at = ids.size();
+        ids.resize(at + count);
+        codes.resize((at + count) * (size_t)ix.M);
+        if (ivf) list_of.resize(at + count, list);
+        for (uint32_t i = 0; i < count; i++)
+            if (!s.u32(&ids[at + i]) || !s.get(&codes[(at + i) * (size_t)ix.M], (size_t)ix.M)) return false;
+        return true;
+    };
+    if (!ivf) {
+        uint32_t count = 0;
+        CM_WIRE_GET(s.u32(&count), "vector count");
+        CM_WIRE_GET(get_rows(count, 0), "vector codes");
+    } else {
+        uint32_t list_count = 0;
+        CM_WIRE_GET(s.u32(&list_count), "list count");
+        if (list_count > (uint32_t)ix.nlist) return fail(CM_ERR_INVALID_ARG, "serialized data has %u lists, index has nlist=%d", list_count, ix.nlist);
+        for (uint32_t l = 0; l < list_count; l++) {
+            uint32_t sz = 0;
+            CM_WIRE_GET(s.u32(&sz), "list size");
+            CM_WIRE_GET(get_rows(sz, (int32_t)l), "list codes");
+        }
+    }
+    std::vector<uint32_t> dead;
+    CM_TRY(wire::read_bitmap(s, &dead));
+    if (!ids.empty() && trained != 1) return fail(CM_ERR_NOT_TRAINED, "serialized data holds codes but no codebooks");
+    CM_TRY(core_reset(ix));
+    if (trained == 1) CM_TRY(core_set_trained(ix, ivf ? cent.data() : nullptr, books.data()));
+    if (!ids.empty()) CM_TRY(adc_load_codes(ix, ids.data(), codes.data(), ivf ? list_of.data() : nullptr, (int64_t)ids.size()));
+    for (uint32_t id : dead)
+        if (ix.store.remove(id) != CM_OK) ix.store.deleted_ids.insert(id);
+    return CM_OK;
+}
+
 static int core_search_host(PQCore &ix, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
                             uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts) {
     if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ix.nlist > 0 ? "index must be trained before searching" : "index not trained");
@@ -1074,5 +1221,30 @@ int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, in
     return cm::adc_search_device(h->ix, queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_pos_dev,
                                  out_counts_dev, (cudaStream_t)stream, false);
 }
+
+#define CM_WIRE_ABI(NAME, TYPE)                                                                                      \
+    int NAME##_save(TYPE *h, uint8_t *buf, int64_t cap, int64_t *bytes) {                                           \
+        if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");                                                 \
+        CM_CUDA(cudaSetDevice(h->ix.device));                                                                       \
+        return cm::wire::save_to_buffer([&](cm::wire::Sink &s) { return cm::core_save(h->ix, s); }, buf, cap, bytes); \
+    }                                                                                                               \
+    int NAME##_load(TYPE *h, const uint8_t *buf, int64_t len, int64_t *consumed) {                                  \
+        if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");                                                 \
+        CM_CUDA(cudaSetDevice(h->ix.device));                                                                       \
+        return cm::wire::load_from_buffer([&](cm::wire::Source &s) { return cm::core_load(h->ix, s); }, buf, len, consumed); \
+    }                                                                                                               \
+    int NAME##_save_file(TYPE *h, const char *path) {                                                               \
+        if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");                                                 \
+        CM_CUDA(cudaSetDevice(h->ix.device));                                                                       \
+        return cm::wire::save_to_file([&](cm::wire::Sink &s) { return cm::core_save(h->ix, s); }, path);            \
+    }                                                                                                               \
+    int NAME##_load_file(TYPE *h, const char *path) {                                                               \
+        if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");                                                 \
+        CM_CUDA(cudaSetDevice(h->ix.device));                                                                       \
+        return cm::wire::load_from_file([&](cm::wire::Source &s) { return cm::core_load(h->ix, s); }, path);        \
+    }
+CM_WIRE_ABI(cm_pq, cm_pq)
+CM_WIRE_ABI(cm_ivfpq, cm_ivfpq)
+#undef CM_WIRE_ABI
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 // Exactness is shard-local (every shard re-scores its candidates in reference order before the gather); a query a
 // shard could not answer on its tensor path (count -1) is redone on the exact path of every shard.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -29,6 +30,7 @@ struct cm_flat_sharded {
     std::vector<int> dev;
     std::vector<cm_flat *> shard;
     std::vector<cudaStream_t> st;          // one stream per shard, on its device
+    std::vector<char> direct;              // shard r's kernels read the queries from and write their lists into devices[0]'s memory (peer access)
     std::vector<cudaEvent_t> done;         // shard r's results are in the leader's gather buffer
     std::vector<cudaEvent_t> t_begin, t_searched;   // timing: shard r's stream before / after its local search
     cudaEvent_t t_merge0 = nullptr, t_merge1 = nullptr;   // leader: around the merge kernel
@@ -86,6 +88,7 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
     h->t_begin.resize((size_t)n_devices, nullptr);
     h->t_searched.resize((size_t)n_devices, nullptr);
     h->buf.resize((size_t)n_devices);
+    h->direct.assign((size_t)n_devices, 1);
     int rc = CM_OK;
     for (int r = 0; r < n_devices && rc == CM_OK; r++) {
         cudaSetDevice(devices[r]);
@@ -107,7 +110,10 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
                 e = cudaDeviceEnablePeerAccess(devices[r], 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = cm::fail(CM_ERR_CUDA, "peer access %d -> %d: %s", devices[0], devices[r], cudaGetErrorString(e));
                 cudaGetLastError();
-            }   // without peer access cudaMemcpyPeerAsync stages through the host: slower, still correct
+            } else {
+                h->direct[(size_t)r] = 0;   // no peer access: queries and lists move by cudaMemcpyPeerAsync (staged by the driver)
+            }
+            if (getenv("COMET_B200_SHARD_COPIES")) h->direct[(size_t)r] = 0;
         }
     }
     if (rc == CM_OK) {
@@ -315,12 +321,12 @@ static int sharded_search_impl(cm_flat_sharded *h, const float *q_lead_dev, int6
     for (int r = 0; r < W; r++) {
         cudaSetDevice(h->dev[(size_t)r]);
         cm_flat_sharded::Buf &b = h->buf[(size_t)r];
-        if (b.cap_q < nq * h->dim) {
+        if (!h->direct[(size_t)r] && b.cap_q < nq * h->dim) {
             cudaFree(b.q); b.q = nullptr;
             CM_CUDA(cudaMalloc(&b.q, (size_t)nq * h->dim * 4));
             b.cap_q = nq * h->dim;
         }
-        if (b.cap_o < nq * K) {
+        if (!h->direct[(size_t)r] && b.cap_o < nq * K) {
             cudaFree(b.ids); cudaFree(b.sc); cudaFree(b.cnt);
             b.ids = nullptr; b.sc = nullptr; b.cnt = nullptr;
             CM_CUDA(cudaMalloc(&b.ids, (size_t)nq * K * 4));
@@ -331,26 +337,34 @@ static int sharded_search_impl(cm_flat_sharded *h, const float *q_lead_dev, int6
         cudaStream_t s = h->st[(size_t)r];
         CM_CUDA(cudaStreamWaitEvent(s, h->start, 0));
         CM_CUDA(cudaEventRecord(h->t_begin[(size_t)r], s));
+        // With peer access the shard's kernels work on devices[0]'s memory themselves: the query preparation reads the
+        // query block over NVLink and the result emit writes this shard's [nq][K] lists straight into slot r of the
+        // gather buffers -- the exchange is part of the kernels, no copy sits between search and merge.
+        const bool direct = h->direct[(size_t)r] != 0;
+        const bool remote = h->dev[(size_t)r] != h->dev[0];
         const float *q_r = q_lead_dev;
-        if (h->dev[(size_t)r] != h->dev[0]) {
+        if (!direct) {
             CM_CUDA(cudaMemcpyPeerAsync(b.q, h->dev[(size_t)r], q_lead_dev, h->dev[0], (size_t)nq * h->dim * 4, s));
-            h->bytes_exchanged += nq * h->dim * 4;
             q_r = b.q;
         }
+        uint32_t *o_ids = direct ? h->g_ids + (size_t)r * nq * K : b.ids;
+        float *o_sc = direct ? h->g_sc + (size_t)r * nq * K : b.sc;
+        int64_t *o_cnt = direct ? h->g_cnt + (size_t)r * nq : b.cnt;
         const int64_t n_r = cm_flat_size(h->shard[(size_t)r]);
         if (n_r == 0) {
-            CM_CUDA(cudaMemsetAsync(b.cnt, 0, (size_t)nq * 8, s));
+            CM_TRY(cm::launch_fill_counts(o_cnt, nq, 0, s));
         } else {
             cm_search_params pr = *p;
             pr.k = std::min<int64_t>(K, n_r);          // a shard can contribute at most K rows to the global top-K
-            CM_TRY(cm_flat_search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, b.ids, b.sc, nullptr, b.cnt, (void *)s));
+            CM_TRY(cm_flat_search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, o_ids, o_sc, nullptr, o_cnt, (void *)s));
         }
         CM_CUDA(cudaEventRecord(h->t_searched[(size_t)r], s));
-        // this shard's lists go to slot r of the leader's gather buffers
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_ids + (size_t)r * nq * K, h->dev[0], b.ids, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_sc + (size_t)r * nq * K, h->dev[0], b.sc, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_cnt + (size_t)r * nq, h->dev[0], b.cnt, h->dev[(size_t)r], (size_t)nq * 8, s));
-        if (h->dev[(size_t)r] != h->dev[0]) h->bytes_exchanged += nq * K * 8 + nq * 8;
+        if (!direct) {       // this shard's lists go to slot r of the leader's gather buffers
+            CM_CUDA(cudaMemcpyPeerAsync(h->g_ids + (size_t)r * nq * K, h->dev[0], b.ids, h->dev[(size_t)r], (size_t)nq * K * 4, s));
+            CM_CUDA(cudaMemcpyPeerAsync(h->g_sc + (size_t)r * nq * K, h->dev[0], b.sc, h->dev[(size_t)r], (size_t)nq * K * 4, s));
+            CM_CUDA(cudaMemcpyPeerAsync(h->g_cnt + (size_t)r * nq, h->dev[0], b.cnt, h->dev[(size_t)r], (size_t)nq * 8, s));
+        }
+        if (remote) h->bytes_exchanged += nq * h->dim * 4 + nq * K * 8 + nq * 8;
         CM_CUDA(cudaEventRecord(h->done[(size_t)r], s));
     }
     cudaSetDevice(h->dev[0]);

@@ -119,12 +119,13 @@ int cm_flat_reserve(cm_flat *h, int64_t n_rows);
 /* n successive FlatIndex.Add calls (flat_index.go:169-189).  `rows` is preprocessed IN PLACE
  * (cosine normalises the caller's buffer) unless writeback == 0. */
 int cm_flat_add(cm_flat *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
-/* FlatIndex.ReadFrom (flat_index.go:488-614): restore STORED (already preprocessed) vectors as they are.  The
- * byte formats (FLAT / IVFX / PQIX / IVPQ / HNSW, magic + version 1) stay host code: the Go package's WriteTo /
- * ReadFrom keep working on its host mirror, and ReadFrom pushes the decoded state through the cm_*_load_* calls. */
+/* Restore STORED (already preprocessed) vectors as they are (appended; a unit vector is not normalised twice): the
+ * decoded-state half of FlatIndex.ReadFrom for hosts that parse the stream themselves.  cm_flat_load below takes
+ * the bytes. */
 int cm_flat_load_rows(cm_flat *h, const uint32_t *ids, const float *rows, int64_t n);
 /* rows already resident on the device (device pointer, row-major n x dim) */
 int cm_flat_add_device(cm_flat *h, const uint32_t *ids_host, const float *rows_dev, int64_t n, void *stream);
+int cm_flat_get_ids(const cm_flat *h, int64_t first, int64_t n, uint32_t *out);   /* node IDs by scan position */
 int cm_flat_remove(cm_flat *h, uint32_t id);                      /* flat_index.go:219-250 */
 int cm_flat_flush(cm_flat *h);                                    /* flat_index.go:266-299 */
 int64_t cm_flat_size(const cm_flat *h);                           /* len(idx.vectors), deleted included */
@@ -325,6 +326,11 @@ int64_t cm_hnsw_edge_count(const cm_hnsw *h);
 int cm_hnsw_export_graph(const cm_hnsw *h, int32_t *levels, int64_t *edge_off, uint32_t *edge_ids, uint32_t *entry_id,
                          int *max_level);
 int cm_hnsw_remove(cm_hnsw *h, uint32_t id);                         /* soft delete, hnsw_index.go:300-330 */
+/* HNSWIndex.Flush (hnsw_index.go:348-430): live nodes drop their edges to deleted nodes, a deleted entry point is
+ * replaced (a live node at maxLevel, else one of the highest level left -- maxLevel follows -- else the index is
+ * empty), deleted nodes are freed, the deleted set is cleared.  The reference picks the new entry point by walking a
+ * Go map, i.e. at random among the eligible nodes; this picks the earliest inserted eligible node. */
+int cm_hnsw_flush(cm_hnsw *h);
 /* nq independent searchSingleQuery calls (hnsw_index_search.go:248-354 + searchLayer hnsw_index.go:565-629);
  * p->ef_search as WithEfSearch.  out_stride >= min(k, ef, n).  out_work (optional, nq x 2): distance
  * evaluations and node expansions per query (the algorithmic-bytes figure of the roofline). */
@@ -333,6 +339,44 @@ int cm_hnsw_search(cm_hnsw *h, const float *queries, int64_t nq, int dim, const 
 int cm_hnsw_search_device(cm_hnsw *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
                           int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
                           int64_t *out_counts_dev, int64_t *work_dev, void *stream);
+
+/* ---- wire formats: WriteTo / ReadFrom of the five index types -------------------------------- */
+/* Byte for byte the reference's little-endian streams: magic ("FLAT" flat_index.go:366-470, "IVFX"
+ * ivf_index.go:468-610, "PQIX" pq_index.go:509-650, "IVPQ" ivfpq_index.go:544-700, "HNSW" hnsw_index.go:734-896),
+ * version 1, parameters, payload, roaring blob of the deleted set.
+ *   cm_*_save   = WriteTo: FLUSHES the index first (as the reference does), then serialises into `buf`.  buf == NULL
+ *                 is a size query (*bytes = exact size; the flush has happened).  cap too small ->
+ *                 CM_ERR_BUFFER_TOO_SMALL with *bytes = needed.
+ *   cm_*_load   = ReadFrom on a pre-constructed index with matching parameters (dimension, distance kind, nlist, M,
+ *                 Nbits, m, ef...: mismatches fail with the reference's messages).  The stream is decoded and validated
+ *                 completely before the index state is REPLACED.  *consumed = bytes read.  A non-empty deleted set in
+ *                 the stream (the reference never writes one) is honoured: those IDs come back soft-deleted.
+ *   cm_*_save_file / cm_*_load_file: the same on a file; a path ending in ".gz" is written gzip-compressed (the LSM
+ *                 layer's vector_%06d.bin.gz segments, storage_provider.go:163-166, storage.go:693-760); loading
+ *                 detects gzip by itself.
+ * HNSW: the reference writes nodes in Go map order (random); cm_hnsw_save writes them in insertion order. */
+int cm_flat_save(cm_flat *h, uint8_t *buf, int64_t cap, int64_t *bytes);
+int cm_flat_load(cm_flat *h, const uint8_t *buf, int64_t len, int64_t *consumed);
+int cm_flat_save_file(cm_flat *h, const char *path);
+int cm_flat_load_file(cm_flat *h, const char *path);
+int cm_ivf_save(cm_ivf *h, uint8_t *buf, int64_t cap, int64_t *bytes);
+int cm_ivf_load(cm_ivf *h, const uint8_t *buf, int64_t len, int64_t *consumed);
+int cm_ivf_save_file(cm_ivf *h, const char *path);
+int cm_ivf_load_file(cm_ivf *h, const char *path);
+int cm_pq_save(cm_pq *h, uint8_t *buf, int64_t cap, int64_t *bytes);
+int cm_pq_load(cm_pq *h, const uint8_t *buf, int64_t len, int64_t *consumed);
+int cm_pq_save_file(cm_pq *h, const char *path);
+int cm_pq_load_file(cm_pq *h, const char *path);
+int cm_ivfpq_save(cm_ivfpq *h, uint8_t *buf, int64_t cap, int64_t *bytes);
+int cm_ivfpq_load(cm_ivfpq *h, const uint8_t *buf, int64_t len, int64_t *consumed);
+int cm_ivfpq_save_file(cm_ivfpq *h, const char *path);
+int cm_ivfpq_load_file(cm_ivfpq *h, const char *path);
+int cm_hnsw_save(cm_hnsw *h, uint8_t *buf, int64_t cap, int64_t *bytes);
+int cm_hnsw_load(cm_hnsw *h, const uint8_t *buf, int64_t len, int64_t *consumed);
+int cm_hnsw_save_file(cm_hnsw *h, const char *path);
+int cm_hnsw_load_file(cm_hnsw *h, const char *path);
+/* the roaring portable-format decoder behind cm_*_load, exposed for its tests: IDs of `blob` into out_ids[cap] */
+int cm_debug_decode_roaring(const uint8_t *blob, int64_t len, uint32_t *out_ids, int64_t cap, int64_t *count);
 
 #ifdef __cplusplus
 }
