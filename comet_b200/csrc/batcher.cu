@@ -139,6 +139,14 @@ int cm_flat_batcher_search(cm_flat_batcher *b, const float *query, int dim, int6
         int64_t n = cm_flat_size(b->index), ke = (k <= 0 || k > n) ? n : k;
         if (out_stride < ke) return cm::fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)ke);
     }
+    if (cm_flat_metric(b->index) == CM_COSINE) {
+        // Distance.Preprocess fails on a zero query (distance.go:269-290) -- for THAT caller only: in the reference every
+        // Execute() is on its own, so a zero query must not take the rest of its batch down with it.  norm == 0 exactly
+        // when the float32 sum of squares is 0 (every term is >= 0), whatever the summation order or rounding mode.
+        float ss = 0.0f;
+        for (int j = 0; j < dim; j++) ss += query[j] * query[j];
+        if (ss == 0.0f) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector");
+    }
     BatchRequest r;
     r.query = query; r.k = k; r.threshold = threshold; r.out_ids = out_ids; r.out_scores = out_scores; r.out_count = out_count;
     r.stride = out_stride;

@@ -138,11 +138,12 @@ FlatIndex::~FlatIndex() {
 // the index (reference order) and, when writeback_host != nullptr, copied back preprocessed.
 int FlatIndex::add_from_device(const uint32_t *ids_host, const float *src_dev, int64_t n_add, float *writeback_host,
                                cudaStream_t st) {
+    WsScope ws(st);
     if (n_add <= 0) return CM_OK;
     CM_TRY(reserve(n + n_add));
     bool fma = rounding_mode() == CM_ROUND_FMA;
     int *flags = nullptr;
-    CM_TRY(ws_alloc((void **)&flags, (size_t)n_add * sizeof(int), st));
+    CM_TRY(ws.get(&flags, (size_t)n_add * sizeof(int)));
     const int pre_metric = raw_rows ? CM_L2 : metric;
     CM_TRY(launch_preprocess_rows(pre_metric, fma, src_dev, n_add, dim, dim, rows + (size_t)n * ld, ld, flags, st));
     int64_t good = n_add;
@@ -153,7 +154,6 @@ int FlatIndex::add_from_device(const uint32_t *ids_host, const float *src_dev, i
         for (int64_t i = 0; i < n_add; i++)
             if (hflags[(size_t)i]) { good = i; break; }
     }
-    ws_free(flags, st);
     if (good > 0) {
         std::vector<uint8_t> del((size_t)good, 0);
         bool any_del = false;
@@ -235,6 +235,7 @@ int FlatIndex::flush() {
 int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                              uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts,
                              cudaStream_t st, bool check_zero_queries) {
+    WsScope ws(st);
     cm_flat_stats stats{};
     int64_t launches0 = g_kernel_launches.load();
     if (nq <= 0) return CM_OK;
@@ -250,12 +251,11 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
             // query fails with ErrZeroVector on an empty index too
             float *qp0 = nullptr;
             int *qf0 = nullptr;
-            CM_TRY(ws_alloc((void **)&qp0, (size_t)nq * ld * 4, st));
-            CM_TRY(ws_alloc((void **)&qf0, (size_t)nq * sizeof(int), st));
+            CM_TRY(ws.get(&qp0, (size_t)nq * ld * 4));
+            CM_TRY(ws.get(&qf0, (size_t)nq * sizeof(int)));
             CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp0, ld, qf0, st));
             if (check_zero_queries) CM_CUDA(cudaMemcpyAsync(zero_flags_host(nq), qf0, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st));
             else CM_TRY(launch_mark_zero_queries(qf0, nq, out_counts, st));
-            ws_free(qp0, st); ws_free(qf0, st);
         }
         return CM_OK;
     }
@@ -268,8 +268,8 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
         std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
         std::sort(f.begin(), f.end());
         f.erase(std::unique(f.begin(), f.end()), f.end());
-        CM_TRY(ws_alloc((void **)&filt_dev, f.size() * 4, st));
-        CM_TRY(ws_alloc((void **)&skip_buf, (size_t)n, st));
+        CM_TRY(ws.get(&filt_dev, f.size() * 4));
+        CM_TRY(ws.get(&skip_buf, (size_t)n));
         CM_CUDA(cudaMemcpyAsync(filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
         CM_TRY(launch_build_skip(ids, deleted, n, filt_dev, (int64_t)f.size(), skip_buf, st));
         CM_CUDA(cudaStreamSynchronize(st));   // f goes out of scope
@@ -288,8 +288,8 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
     int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
     float *qp = nullptr;
     int *qflags = nullptr;
-    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
-    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
+    CM_TRY(ws.get(&qp, (size_t)nq_pad * ld * 4));
+    CM_TRY(ws.get(&qflags, (size_t)nq * sizeof(int)));
     int rc = CM_OK;
     if (path == CM_PATH_TENSOR) {
         rc = search_tensor(q_dev, qp, qflags, nq, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
@@ -306,7 +306,6 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
         // device entry point: nobody reads the flags on the host -- a zero query is reported as count -2
         CM_TRY(launch_mark_zero_queries(qflags, nq, out_counts, st));
     }
-    ws_free(qp, st); ws_free(qflags, st); ws_free(skip_buf, st); ws_free(filt_dev, st);
     stats.kernel_launches = g_kernel_launches.load() - launches0;
     {
         std::lock_guard<std::mutex> lk(stats_mu);
@@ -318,6 +317,7 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
 int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t k_eff, const uint8_t *skip,
                             float threshold, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                             int64_t *out_pos, int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
+    WsScope ws(st);
     if (k_eff > 4096) return search_exact_bigk(qp, nq, k_eff, skip, threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, stats);
     bool fma = rounding_mode() == CM_ROUND_FMA;
     ScanLaunch L;
@@ -326,8 +326,8 @@ int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t
     (void)nq_pad;
     uint64_t *pk = nullptr;
     int *pc = nullptr;
-    CM_TRY(ws_alloc((void **)&pk, (size_t)nq_run * L.grid * L.K * 8, st));
-    CM_TRY(ws_alloc((void **)&pc, (size_t)nq_run * L.grid * sizeof(int), st));
+    CM_TRY(ws.get(&pk, (size_t)nq_run * L.grid * L.K * 8));
+    CM_TRY(ws.get(&pc, (size_t)nq_run * L.grid * sizeof(int)));
     // big corpus: one pass (launch) per query group streams all rows; small table (fewer tiles than the
     // persistent grid): many query groups share one launch, otherwise most SMs would idle
     const int64_t n_tiles = (n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
@@ -341,7 +341,6 @@ int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t
     }
     CM_TRY(launch_merge_topk(pk, pc, (int)nq, L.grid, L.K, (int)k_eff, ids, out_stride, out_ids, out_scores, out_pos,
                              out_counts, st));
-    ws_free(pk, st); ws_free(pc, st);
     stats->path_used = CM_PATH_EXACT;
     stats->passes = passes;
     return CM_OK;

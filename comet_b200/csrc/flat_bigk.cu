@@ -51,7 +51,7 @@ __global__ void emit_sorted_kernel(const uint64_t *__restrict__ keys, long long 
     uint64_t key = keys[i];
     if (key == KEY_INF) return;
     uint32_t pos = key_pos(key);
-    out_ids[i] = row_ids[pos];
+    out_ids[i] = row_ids ? row_ids[pos] : pos;
     out_scores[i] = key_score(key);
     if (out_pos) out_pos[i] = pos;
 }
@@ -68,14 +68,15 @@ static void launch_all_keys(bool fma, const float *rows, int ld, int64_t n, cons
 int FlatIndex::search_exact_bigk(const float *qp, int64_t nq, int64_t k_eff, const uint8_t *skip, float threshold,
                                  int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                                  int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
+    WsScope ws(st);
     bool fma = rounding_mode() == CM_ROUND_FMA;
     uint64_t *keys = nullptr, *sorted = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, sorted, (int64_t)n, 0, 64, st);
-    CM_TRY(ws_alloc((void **)&keys, (size_t)n * 8, st));
-    CM_TRY(ws_alloc((void **)&sorted, (size_t)n * 8, st));
-    CM_TRY(ws_alloc(&tmp, tmp_bytes, st));
+    CM_TRY(ws.get(&keys, (size_t)n * 8));
+    CM_TRY(ws.get(&sorted, (size_t)n * 8));
+    CM_TRY(ws.get(&tmp, tmp_bytes));
     for (int64_t qi = 0; qi < nq; qi++) {
         const float *q = qp + (size_t)qi * ld;
         switch (metric) {
@@ -94,9 +95,44 @@ int FlatIndex::search_exact_bigk(const float *qp, int64_t nq, int64_t k_eff, con
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
-    ws_free(keys, st); ws_free(sorted, st); ws_free(tmp, st);
     stats->path_used = CM_PATH_EXACT;
     stats->passes = (int)nq;
+    return CM_OK;
+}
+
+// ---- merge of per-part candidate lists when K + Kp does not fit the shared-memory merge (k <= 0 / huge k on IVF, PQ,
+// IVFPQ: limiter.go:12-17 turns k <= 0 into "every candidate") ----------------------------------------------------------
+__global__ void part_keys_kernel(const uint64_t *__restrict__ part_keys, const int *__restrict__ part_counts, int parts, int Kp,
+                                 uint64_t *__restrict__ keys) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)parts * Kp) return;
+    int part = (int)(i / Kp), j = (int)(i % Kp);
+    keys[i] = j < part_counts[part] ? part_keys[i] : KEY_INF;
+}
+
+int merge_topk_bigk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int64_t K,
+                    const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                    int64_t *out_counts, cudaStream_t st) {
+    WsScope ws(st);
+    const int64_t total = (int64_t)parts * Kp;
+    uint64_t *keys = nullptr, *sorted = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, sorted, total, 0, 64, st);
+    CM_TRY(ws.get(&keys, (size_t)total * 8));
+    CM_TRY(ws.get(&sorted, (size_t)total * 8));
+    CM_TRY(ws.get(&tmp, tmp_bytes));
+    for (int q = 0; q < nq; q++) {
+        part_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part_keys + (size_t)q * total, part_counts + (size_t)q * parts,
+                                                                         parts, Kp, keys);
+        CM_CUDA(cudaGetLastError());
+        CM_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, sorted, total, 0, 64, st));
+        emit_sorted_kernel<<<(unsigned)((std::min<int64_t>(K, total) + 255) / 256), 256, 0, st>>>(
+            sorted, (long long)total, (long long)K, row_ids, out_ids + (size_t)q * out_stride, out_scores + (size_t)q * out_stride,
+            out_pos ? (long long *)out_pos + (size_t)q * out_stride : nullptr, (long long *)out_counts + q);
+        CM_CUDA(cudaGetLastError());
+        count_launch(5);
+    }
     return CM_OK;
 }
 
@@ -134,15 +170,16 @@ __global__ void merge_emit_kernel(const uint64_t *__restrict__ keys, long long t
 int merge_shards_bigk(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
                       int64_t in_stride, int64_t k, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                       int64_t *out_counts, cudaStream_t st) {
+    WsScope ws(st);
     const int64_t total = (int64_t)world * in_stride;
     if (total >= (1ll << 32)) return fail(CM_ERR_UNSUPPORTED, "%d shards x k=%lld too large for the shard merge", world, (long long)in_stride);
     uint64_t *keys = nullptr, *sorted = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, sorted, total, 0, 64, st);
-    CM_TRY(ws_alloc((void **)&keys, (size_t)total * 8, st));
-    CM_TRY(ws_alloc((void **)&sorted, (size_t)total * 8, st));
-    CM_TRY(ws_alloc(&tmp, tmp_bytes, st));
+    CM_TRY(ws.get(&keys, (size_t)total * 8));
+    CM_TRY(ws.get(&sorted, (size_t)total * 8));
+    CM_TRY(ws.get(&tmp, tmp_bytes));
     for (int64_t q = 0; q < nq; q++) {
         merge_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scores, (const long long *)counts, world, (long long)nq,
                                                                           (long long)q, (long long)in_stride, keys);
@@ -155,7 +192,6 @@ int merge_shards_bigk(const uint32_t *ids, const float *scores, const int64_t *c
         CM_CUDA(cudaGetLastError());
         count_launch(5);
     }
-    ws_free(keys, st); ws_free(sorted, st); ws_free(tmp, st);
     return CM_OK;
 }
 

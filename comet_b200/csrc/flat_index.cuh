@@ -17,6 +17,30 @@ int ws_alloc(void **p, size_t bytes, cudaStream_t s);
 namespace wire { struct Sink; struct Source; }
 void ws_free(void *p, cudaStream_t s);
 
+// Stream-ordered workspace of one call: everything taken through it goes back to the pool when the scope ends,
+// on every return path (an early CM_TRY return used to leak what had been allocated before it).
+struct WsScope {
+    cudaStream_t st;
+    std::vector<void *> owned;
+    explicit WsScope(cudaStream_t s) : st(s) {}
+    WsScope(const WsScope &) = delete;
+    WsScope &operator=(const WsScope &) = delete;
+    ~WsScope() {
+        for (void *p : owned) ws_free(p, st);
+    }
+    template <class T>
+    int get(T **p, size_t bytes) {
+        void *v = nullptr;
+        CM_TRY(ws_alloc(&v, bytes, st));
+        *p = static_cast<T *>(v);
+        owned.push_back(v);
+        return CM_OK;
+    }
+    void adopt(void *p) {           // a buffer a helper allocated with ws_alloc on the same stream
+        if (p) owned.push_back(p);
+    }
+};
+
 struct FlatIndex {
     int dim = 0, ld = 0, metric = 0, device = 0;
     int64_t n = 0, cap = 0;

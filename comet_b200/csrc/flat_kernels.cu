@@ -335,7 +335,11 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
     int C = next_pow2(K + Kp);
     if (C < 2048) C = 2048;
     size_t smem = (size_t)C * 8;
-    if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
+    if (smem > max_smem_optin()) {    // k <= 0 / huge k: one radix sort per query over the part lists (flat_bigk.cu)
+        if (pdl || overflow || stat_cnt) return fail(CM_ERR_UNSUPPORTED, "k=%d too large for the merge kernel", K);
+        return merge_topk_bigk(part_keys, part_counts, nq, parts, Kp, (int64_t)K, row_ids, out_stride, out_ids, out_scores, out_pos,
+                               out_counts, stream);
+    }
     CM_TRY(set_dyn_smem((const void *)merge_topk_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
     PdlLaunch L(dim3((unsigned)nq), dim3(MERGE_THREADS), smem, stream, 0, pdl);
@@ -551,15 +555,17 @@ int launch_fill_counts(int64_t *counts, int64_t nq, int64_t value, cudaStream_t 
 }
 
 // device entry points report a zero query under cosine (ErrZeroVector, distance.go:269-290) as count -2
-__global__ void mark_zero_queries_kernel(const int *__restrict__ flags, long long nq, long long *__restrict__ out_counts) {
+__global__ void mark_zero_queries_kernel(const int *flags, long long nq, long long *out_counts) {
+    pdl_wait();                 // a link of the step's programmatic-dependent-launch chain: behind the kernels that write the counts
+    pdl_trigger();
     long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (q < nq && flags[q]) out_counts[q] = -2;
 }
 int launch_mark_zero_queries(const int *flags, int64_t nq, int64_t *out_counts, cudaStream_t stream) {
     if (nq <= 0) return CM_OK;
-    mark_zero_queries_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(flags, (long long)nq, (long long *)out_counts);
+    PdlLaunch L(dim3((unsigned)((nq + 255) / 256)), dim3(256), 0, stream);
+    CM_CUDA(cudaLaunchKernelEx(&L.cfg, mark_zero_queries_kernel, flags, (long long)nq, (long long *)out_counts));
     count_launch();
-    CM_CUDA(cudaGetLastError());
     return CM_OK;
 }
 

@@ -851,6 +851,7 @@ bool FlatIndex::tensor_path_eligible(int64_t nq, int64_t k_eff, bool has_filter,
 int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t nq, int64_t k_eff, const uint8_t *skip,
                              float threshold, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
                              int64_t *out_counts, cudaStream_t st, cm_flat_stats *stats) {
+    WsScope ws(st);
     if (k_eff > RS_CAP / 2) return fail(CM_ERR_UNSUPPORTED, "tensor path supports k <= %d", RS_CAP / 2);
     CM_TRY(ensure_shadow(st));
     const int cg = tensor_cta_group;
@@ -956,7 +957,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
     float *h_masked = nullptr;
     if (use_ts && skip != nullptr) {
         const long long n_pad = (long long)T * TS_N;
-        CM_TRY(ws_alloc((void **)&h_masked, (size_t)n_pad * 4, st));
+        CM_TRY(ws.get(&h_masked, (size_t)n_pad * 4));
         masked_h_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(row_h, skip, (long long)n, n_pad, h_masked);
         count_launch();
         CM_CUDA(cudaGetLastError());
@@ -978,14 +979,14 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
         uint64_t *cand = nullptr, *keys2 = nullptr;
         int *ccnt = nullptr, *ovf = nullptr, *rcnt = nullptr, *kcnt = nullptr;
         uint64_t *rs = nullptr;   // survivor lists, ping-pong: [2][nq_pad][RS_CAP]
-        CM_TRY(ws_alloc((void **)&q16, (size_t)nq_pad * ldb * 2, st));
-        CM_TRY(ws_alloc((void **)&qn, (size_t)nq_pad * 8, st));
-        CM_TRY(ws_alloc((void **)&g, (size_t)nq_pad * 4, st));
-        CM_TRY(ws_alloc((void **)&cand, (size_t)nq_pad * n_reg * slots * 8, st));
-        CM_TRY(ws_alloc((void **)&ccnt, (size_t)nq_pad * (n_reg + 6) * 4, st));
+        CM_TRY(ws.get(&q16, (size_t)nq_pad * ldb * 2));
+        CM_TRY(ws.get(&qn, (size_t)nq_pad * 8));
+        CM_TRY(ws.get(&g, (size_t)nq_pad * 4));
+        CM_TRY(ws.get(&cand, (size_t)nq_pad * n_reg * slots * 8));
+        CM_TRY(ws.get(&ccnt, (size_t)nq_pad * (n_reg + 6) * 4));
         ovf = ccnt + (size_t)nq_pad * n_reg; rcnt = ovf + nq_pad; kcnt = rcnt + 2 * nq_pad;   // rcnt: [2][nq_pad]
-        CM_TRY(ws_alloc((void **)&rs, (size_t)2 * nq_pad * RS_CAP * 8, st));
-        CM_TRY(ws_alloc((void **)&keys2, (size_t)nq_pad * RS_CAP * 8, st));
+        CM_TRY(ws.get(&rs, (size_t)2 * nq_pad * RS_CAP * 8));
+        CM_TRY(ws.get(&keys2, (size_t)nq_pad * RS_CAP * 8));
         CUtensorMap tq;
         if (use_ts) {
             // one launch: Preprocess + padded fp32 copy + bf16 copy and norms + first bound + zeroed counters.
@@ -1113,10 +1114,7 @@ int FlatIndex::search_tensor(const float *q_raw, float *qp, int *qflags, int64_t
                                      out_scores + (size_t)q0 * out_stride, out_pos ? out_pos + (size_t)q0 * out_stride : nullptr,
                                      out_counts + q0, st, use_ts, ovf, rcnt + (size_t)last * nq_pad, rescored_dev));
         }
-        ws_free(q16, st); ws_free(qn, st); ws_free(g, st); ws_free(cand, st); ws_free(ccnt, st); ws_free(rs, st);
-        ws_free(keys2, st);
     }
-    ws_free(h_masked, st);
     CM_CUDA(cudaMemcpyAsync(staged_host, staged_dev, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (dbg_staged) {
         cudaStreamSynchronize(st);

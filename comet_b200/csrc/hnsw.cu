@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(32) hnsw_insert_kernel(GraphView G, long long 
 static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                               uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, int64_t *work,
                               cudaStream_t st, bool check_zero) {
+    WsScope ws(st);
     if (nq <= 0) return CM_OK;
     if (ix.n == 0 || ix.max_level == -1) {                                           // hnsw_index_search.go:258-260
         CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
@@ -559,8 +560,8 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
     const int ld = ix.ld;
     float *qp = nullptr;
     int *qflags = nullptr;
-    CM_TRY(ws_alloc((void **)&qp, (size_t)nq * ld * 4, st));
-    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
+    CM_TRY(ws.get(&qp, (size_t)nq * ld * 4));
+    CM_TRY(ws.get(&qflags, (size_t)nq * sizeof(int)));
     CM_TRY(launch_preprocess_rows(ix.metric, fma, q_dev, nq, ix.dim, ix.dim, qp, ld, qflags, st));
     if (check_zero && ix.metric == CM_COSINE) {
         std::vector<int> hf((size_t)nq);
@@ -568,7 +569,6 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
         CM_CUDA(cudaStreamSynchronize(st));
         for (int64_t i = 0; i < nq; i++)
             if (hf[(size_t)i]) {
-                ws_free(qp, st); ws_free(qflags, st);
                 return fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)i);
             }
     }
@@ -579,8 +579,8 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
         std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
         std::sort(f.begin(), f.end());
         f.erase(std::unique(f.begin(), f.end()), f.end());
-        CM_TRY(ws_alloc((void **)&filt_dev, f.size() * 4, st));
-        CM_TRY(ws_alloc((void **)&doc_skip, (size_t)ix.n, st));
+        CM_TRY(ws.get(&filt_dev, f.size() * 4));
+        CM_TRY(ws.get(&doc_skip, (size_t)ix.n));
         CM_CUDA(cudaMemcpyAsync(filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
         CM_TRY(launch_build_skip(ix.ids, nullptr, ix.n, filt_dev, (int64_t)f.size(), doc_skip, st));
         CM_CUDA(cudaStreamSynchronize(st));
@@ -593,8 +593,8 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (vis_words * 4 + (int64_t)cand_cap * 8)));
     uint32_t *visited = nullptr;
     HCand *heaps = nullptr;
-    CM_TRY(ws_alloc((void **)&visited, (size_t)qgroup * vis_words * 4, st));
-    CM_TRY(ws_alloc((void **)&heaps, (size_t)qgroup * cand_cap * sizeof(HCand), st));
+    CM_TRY(ws.get(&visited, (size_t)qgroup * vis_words * 4));
+    CM_TRY(ws.get(&heaps, (size_t)qgroup * cand_cap * sizeof(HCand)));
     GraphView G = ix.view();
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
@@ -619,7 +619,6 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
-    ws_free(qp, st); ws_free(qflags, st); ws_free(doc_skip, st); ws_free(filt_dev, st); ws_free(visited, st); ws_free(heaps, st);
     return CM_OK;
 }
 

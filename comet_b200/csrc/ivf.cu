@@ -257,6 +257,7 @@ static int launch_ivf_scan_m(bool fma, dim3 grid, size_t smem, cudaStream_t st, 
 static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                              uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
                              bool check_zero_queries) {
+    WsScope ws(st);
     if (nq <= 0) return CM_OK;
     if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");   // ivf_index_search.go:223
     int nprobes = p->nprobes;
@@ -270,14 +271,14 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
     if (k_eff <= 0 || k_eff > bound_c) k_eff = bound_c;    // sanitizeK against the most candidates any query can have
     if (out_stride < k_eff)
         return fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)k_eff);
-    if (k_eff > 16000) return fail(CM_ERR_UNSUPPORTED, "ivf search supports k <= 16000 (got %lld)", (long long)k_eff);
+    // k beyond the shared-memory merge (WithK(0) on long lists): launch_merge_topk falls back to a sort per query
 
     // 1. Distance.Preprocess on the queries (ivf_index_search.go:239), zero-padded block for the scans
     int64_t nq_pad = (nq + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
     float *qp = nullptr;
     int *qflags = nullptr;
-    CM_TRY(ws_alloc((void **)&qp, (size_t)nq_pad * ld * 4, st));
-    CM_TRY(ws_alloc((void **)&qflags, (size_t)nq * sizeof(int), st));
+    CM_TRY(ws.get(&qp, (size_t)nq_pad * ld * 4));
+    CM_TRY(ws.get(&qflags, (size_t)nq * sizeof(int)));
     if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
     CM_TRY(launch_preprocess_rows(ix.metric, fma, q_dev, nq, ix.dim, ix.dim, qp, ld, qflags, st));
     if (check_zero_queries && ix.metric == CM_COSINE) {
@@ -286,13 +287,11 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
         CM_CUDA(cudaStreamSynchronize(st));
         for (int64_t i = 0; i < nq; i++)
             if (hf[(size_t)i]) {
-                ws_free(qp, st); ws_free(qflags, st);
                 return fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)i);
             }
     }
     if (bound_c == 0 || k_eff == 0) {
         CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
-        ws_free(qp, st); ws_free(qflags, st);
         return CM_OK;
     }
 
@@ -300,11 +299,11 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
     uint32_t *c_ids = nullptr;
     float *c_sc = nullptr;
     long long *probe_list = nullptr, *probe_cnt = nullptr, *q_off = nullptr;
-    CM_TRY(ws_alloc((void **)&c_ids, (size_t)nq * nprobes * 4, st));
-    CM_TRY(ws_alloc((void **)&c_sc, (size_t)nq * nprobes * 4, st));
-    CM_TRY(ws_alloc((void **)&probe_list, (size_t)nq * nprobes * 8, st));
-    CM_TRY(ws_alloc((void **)&probe_cnt, (size_t)nq * 8, st));
-    CM_TRY(ws_alloc((void **)&q_off, (size_t)nq * (nprobes + 1) * 8, st));
+    CM_TRY(ws.get(&c_ids, (size_t)nq * nprobes * 4));
+    CM_TRY(ws.get(&c_sc, (size_t)nq * nprobes * 4));
+    CM_TRY(ws.get(&probe_list, (size_t)nq * nprobes * 8));
+    CM_TRY(ws.get(&probe_cnt, (size_t)nq * 8));
+    CM_TRY(ws.get(&q_off, (size_t)nq * (nprobes + 1) * 8));
     cm_flat_stats cst{};
     CM_TRY(ix.coarse.search_exact(qp, nq, nq_pad, nprobes, nullptr, 0.0f, nprobes, c_ids, c_sc, (int64_t *)probe_list,
                                   (int64_t *)probe_cnt, st, &cst));
@@ -322,8 +321,8 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
         std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
         std::sort(f.begin(), f.end());
         f.erase(std::unique(f.begin(), f.end()), f.end());
-        CM_TRY(ws_alloc((void **)&filt_dev, f.size() * 4, st));
-        CM_TRY(ws_alloc((void **)&skip_buf, (size_t)S.n, st));
+        CM_TRY(ws.get(&filt_dev, f.size() * 4));
+        CM_TRY(ws.get(&skip_buf, (size_t)S.n));
         CM_CUDA(cudaMemcpyAsync(filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
         CM_TRY(launch_build_skip(S.ids, S.deleted, S.n, filt_dev, (int64_t)f.size(), skip_buf, st));
         CM_CUDA(cudaStreamSynchronize(st));
@@ -338,8 +337,8 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (cap_c * 8)));
     uint64_t *keys = nullptr;
     int *kcnt = nullptr;
-    CM_TRY(ws_alloc((void **)&keys, (size_t)qgroup * cap_c * 8, st));
-    CM_TRY(ws_alloc((void **)&kcnt, (size_t)qgroup * n_chunks * 4, st));
+    CM_TRY(ws.get(&keys, (size_t)qgroup * cap_c * 8));
+    CM_TRY(ws.get(&kcnt, (size_t)qgroup * n_chunks * 4));
     size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
@@ -362,8 +361,6 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
-    ws_free(qp, st); ws_free(qflags, st); ws_free(c_ids, st); ws_free(c_sc, st); ws_free(probe_list, st); ws_free(probe_cnt, st);
-    ws_free(q_off, st); ws_free(skip_buf, st); ws_free(filt_dev, st); ws_free(keys, st); ws_free(kcnt, st);
     return CM_OK;
 }
 

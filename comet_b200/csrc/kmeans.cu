@@ -170,13 +170,14 @@ int kmeans_subspace(const float *x, int64_t n, int64_t ldx, int off, int d, int 
 
 // exact nearest-centroid assignment of n device rows ([n_pad][ld], n_pad multiple of 8) against `cent`
 int assign_nearest(FlatIndex &cent, const float *rows, int64_t n, long long *pos_out, cudaStream_t st) {
+    WsScope ws(st);
     const int64_t group = 32768;
     uint32_t *t_ids = nullptr;
     float *t_sc = nullptr;
     long long *t_cnt = nullptr;
-    CM_TRY(ws_alloc((void **)&t_ids, (size_t)std::min(group, n) * 4, st));
-    CM_TRY(ws_alloc((void **)&t_sc, (size_t)std::min(group, n) * 4, st));
-    CM_TRY(ws_alloc((void **)&t_cnt, (size_t)std::min(group, n) * 8, st));
+    CM_TRY(ws.get(&t_ids, (size_t)std::min(group, n) * 4));
+    CM_TRY(ws.get(&t_sc, (size_t)std::min(group, n) * 4));
+    CM_TRY(ws.get(&t_cnt, (size_t)std::min(group, n) * 8));
     for (int64_t i0 = 0; i0 < n; i0 += group) {
         int64_t m = std::min(group, n - i0);
         int64_t mpad = (m + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
@@ -184,11 +185,11 @@ int assign_nearest(FlatIndex &cent, const float *rows, int64_t n, long long *pos
         CM_TRY(cent.search_exact(rows + (size_t)i0 * cent.ld, m, mpad, 1, nullptr, 0.0f, 1, t_ids, t_sc, (int64_t *)(pos_out + i0),
                                  (int64_t *)t_cnt, st, &cst));
     }
-    ws_free(t_ids, st); ws_free(t_sc, st); ws_free(t_cnt, st);
     return CM_OK;
 }
 
 int kmeans_full(FlatIndex &cent, const float *rows, int64_t n, int k, int max_iter, long long *final_assign, cudaStream_t st) {
+    WsScope ws(st);
     if (n <= 0 || k <= 0) return fail(CM_ERR_INVALID_ARG, "k-means needs vectors and k > 0");
     if (k > n) k = (int)n;
     if (max_iter <= 0) max_iter = 20;
@@ -196,7 +197,7 @@ int kmeans_full(FlatIndex &cent, const float *rows, int64_t n, int k, int max_it
     KMeansWork W;
     CM_TRY(W.alloc(n, k, st));
     long long *pos = nullptr;
-    CM_TRY(ws_alloc((void **)&pos, (size_t)n * 8, st));
+    CM_TRY(ws.get(&pos, (size_t)n * 8));
     // centroid table: k raw rows in the FlatIndex (its TMA descriptor stays valid while rows are rewritten in place)
     cent.n = 0; cent.ids_host_mirror.clear();
     CM_TRY(cent.reserve(k));
@@ -227,7 +228,6 @@ int kmeans_full(FlatIndex &cent, const float *rows, int64_t n, int k, int max_it
         CM_CUDA(cudaGetLastError());
     }
     if (final_assign) CM_TRY(assign_nearest(cent, rows, n, final_assign, st));   // FindNearestCentroidIndex vs the FINAL centroids
-    ws_free(pos, st);
     W.release();
     return CM_OK;
 }
@@ -253,7 +253,7 @@ int launch_residuals(const float *rows, int64_t n, int d, int ld, const float *c
 int upload_training_rows(const float *rows_host, int64_t n, int dim, int ld, float **out, cudaStream_t st) {
     int64_t npad = (n + SCAN_MAX_QB - 1) / SCAN_MAX_QB * SCAN_MAX_QB;
     float *d = nullptr;
-    CM_TRY(ws_alloc((void **)&d, (size_t)npad * ld * 4, st));
+    CM_TRY(ws_alloc((void **)&d, (size_t)npad * ld * 4, st));       // ownership goes to the caller (*out)
     CM_CUDA(cudaMemsetAsync(d, 0, (size_t)npad * ld * 4, st));
     CM_CUDA(cudaMemcpy2DAsync(d, (size_t)ld * 4, rows_host, (size_t)dim * 4, (size_t)dim * 4, (size_t)n, cudaMemcpyHostToDevice, st));
     *out = d;

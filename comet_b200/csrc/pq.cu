@@ -35,6 +35,7 @@ namespace cm {
 
 static constexpr int ADC_THREADS = 256;
 static constexpr int ADC_CHUNK = 4096;      // fewest codes a CTA is given when a pair is sliced
+static constexpr int ADC_BIGK_PART = 3072;  // slice length of the big-k path: a multiple of every R * ADC_THREADS (256 .. 1024)
 
 struct CodeStore {
     int M = 0;
@@ -527,6 +528,7 @@ static int build_skip(CodeStore &S, const cm_search_params *p, const uint8_t **s
 static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                              uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
                              bool check_zero) {
+    WsScope ws(st);
     if (nq <= 0) return CM_OK;
     const bool ivf = ix.nlist > 0;
     if (!ix.trained) return fail(CM_ERR_NOT_TRAINED, ivf ? "index must be trained before searching" : "index not trained");
@@ -547,16 +549,18 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     if (k_eff <= 0 || k_eff > bound_c) k_eff = bound_c;
     if (out_stride < k_eff)
         return fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)k_eff);
-    if (k_eff > 8192) return fail(CM_ERR_UNSUPPORTED, "pq / ivfpq search supports k <= 8192 (got %lld)", (long long)k_eff);
+    // k beyond what a CTA can select in shared memory (WithK(0) on a large index): every CTA gets a slice of at most
+    // ADC_BIGK_PART codes and returns ALL of their keys; one radix sort per query orders them (flat_bigk.cu)
+    const bool bigk = k_eff > 8192;
     float *qp = nullptr;
     if (!ivf && S.n == 0) {      // pq_index_search.go:232: an empty index answers before Preprocess
         CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
         return CM_OK;
     }
     CM_TRY(prepare_queries(ix.metric, ix.dim, ix.ld, q_dev, nq, check_zero, &qp, st));
+    ws.adopt(qp);
     if (bound_c == 0 || k_eff == 0) {
         CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
-        ws_free(qp, st);
         return CM_OK;
     }
     bool fma = rounding_mode() == CM_ROUND_FMA;
@@ -566,11 +570,11 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     uint32_t *c_ids = nullptr;
     float *c_sc = nullptr;
     if (ivf) {
-        CM_TRY(ws_alloc((void **)&c_ids, (size_t)nq * nprobes * 4, st));
-        CM_TRY(ws_alloc((void **)&c_sc, (size_t)nq * nprobes * 4, st));
-        CM_TRY(ws_alloc((void **)&probe_list, (size_t)nq * nprobes * 8, st));
-        CM_TRY(ws_alloc((void **)&probe_cnt, (size_t)nq * 8, st));
-        CM_TRY(ws_alloc((void **)&q_off, (size_t)nq * (nprobes + 1) * 8, st));
+        CM_TRY(ws.get(&c_ids, (size_t)nq * nprobes * 4));
+        CM_TRY(ws.get(&c_sc, (size_t)nq * nprobes * 4));
+        CM_TRY(ws.get(&probe_list, (size_t)nq * nprobes * 8));
+        CM_TRY(ws.get(&probe_cnt, (size_t)nq * 8));
+        CM_TRY(ws.get(&q_off, (size_t)nq * (nprobes + 1) * 8));
         cm_flat_stats cst{};
         CM_TRY(ix.coarse.search_exact(qp, nq, nq_pad, nprobes, nullptr, 0.0f, nprobes, c_ids, c_sc, (int64_t *)probe_list,
                                       (int64_t *)probe_cnt, st, &cst));
@@ -581,9 +585,11 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     const uint8_t *skip = nullptr;
     uint8_t *skip_buf = nullptr;
     uint32_t *filt_dev = nullptr;
-    CM_TRY(build_skip(S, p, &skip, &skip_buf, &filt_dev, st));
+    const int rc_skip = build_skip(S, p, &skip, &skip_buf, &filt_dev, st);
+    ws.adopt(skip_buf); ws.adopt(filt_dev);
+    CM_TRY(rc_skip);
 
-    const int K = (int)k_eff;
+    const int K = bigk ? ADC_BIGK_PART : (int)k_eff;         // keys a CTA keeps
     // code bytes per row in 16-byte words -> kernel variant and rows per thread per round
     int MW = ((ix.M & 15) == 0 && (ix.M / 16 == 1 || ix.M / 16 == 2 || ix.M / 16 == 4 || ix.M / 16 == 6 || ix.M / 16 == 8)) ? ix.M / 16 : 0;
     if (const char *e = getenv("COMET_B200_ADC_GENERIC")) if (atoi(e)) MW = 0;
@@ -599,13 +605,14 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     int64_t n_slices = (8ll * sm_count() + nq * nprobes - 1) / (nq * nprobes);
     n_slices = std::max<int64_t>(1, std::min<int64_t>(n_slices, (max_len + ADC_CHUNK - 1) / ADC_CHUNK));
     if (const char *e = getenv("COMET_B200_ADC_SLICES")) n_slices = std::max<int64_t>(1, atoll(e));
+    if (bigk) n_slices = std::max<int64_t>(1, (max_len + ADC_BIGK_PART - 1) / ADC_BIGK_PART);
     const int64_t parts = (int64_t)nprobes * n_slices;              // per query
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 29) / (parts * K * 8)));
     if (qgroup * nprobes > 65535) qgroup = std::max<int64_t>(1, 65535 / nprobes);   // grid.y limit
     uint64_t *pk = nullptr;
     int *pc = nullptr;
-    CM_TRY(ws_alloc((void **)&pk, (size_t)qgroup * parts * K * 8, st));
-    CM_TRY(ws_alloc((void **)&pc, (size_t)qgroup * parts * 4, st));
+    CM_TRY(ws.get(&pk, (size_t)qgroup * parts * K * 8));
+    CM_TRY(ws.get(&pc, (size_t)qgroup * parts * 4));
     using AdcKernel = void (*)(const float *, int, int, int, int, int, int, const float *, const uint8_t *, long long,
                                const float *, int, const long long *, const long long *, const long long *, const uint32_t *,
                                int, const uint8_t *, float, int, int, int, uint64_t *, int *);
@@ -630,7 +637,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
             count_launch();
             CM_CUDA(cudaGetLastError());
         }
-        CM_TRY(launch_merge_topk(pk, pc, (int)m, (int)parts, K, K, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
+        CM_TRY(launch_merge_topk(pk, pc, (int)m, (int)parts, K, (int)k_eff, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
                                  out_scores + (size_t)q0 * out_stride, nullptr, out_counts + q0, st));
         adc_emit_kernel<<<(unsigned)m, 128, 0, st>>>(ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
                                                      ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
@@ -641,8 +648,6 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
-    ws_free(qp, st); ws_free(c_ids, st); ws_free(c_sc, st); ws_free(probe_list, st); ws_free(probe_cnt, st); ws_free(q_off, st);
-    ws_free(skip_buf, st); ws_free(filt_dev, st); ws_free(pk, st); ws_free(pc, st);
     return CM_OK;
 }
 

@@ -6,22 +6,76 @@
 // reference's result order (score, scan position) is (score, shard, rank within the shard's list) and the
 // per-shard top-K lists merge without ever looking at a row again (flat_index_search.go:277-291).
 //
-// One search = the path's ONE exchange step (there is no NCCL in it: a single process owns the devices, so the
-// exchange is peer-to-peer copies over NVLink ordered by CUDA events):
-//   leader stream: queries ready
-//   shard r stream: wait | copy queries leader -> r | cm_flat_search_device on shard r | copy [nq][K] ids, scores,
-//                   counts r -> leader's gather slot r | record
-//   leader stream: wait for every shard | merge_shards_kernel | (host variant: results to the caller)
+// One search = the path's ONE exchange step.  There is no NCCL in it: a single process owns the devices, so the
+// exchange runs over NVLink peer mappings, ordered by CUDA events:
+//   leader stream : queries ready (event `start`)
+//   shard r stream: wait(start) | cm_flat_search_device on shard r -- with peer access its query-preparation kernel READS
+//                   the query block from devices[0] and its result kernels WRITE the [nq][K] ids / scores / counts
+//                   straight into slot r of devices[0]'s gather buffers (no copy between search and merge; without
+//                   peer access the same bytes move by cudaMemcpyPeerAsync) | record(done[r])
+//   leader stream : wait(done[*]) | merge_shards_kernel | (host variant: results to the caller)
+// The shards are enqueued concurrently by one persistent worker thread each.
 // Exactness is shard-local (every shard re-scores its candidates in reference order before the gather); a query a
 // shard could not answer on its tensor path (count -1) is redone on the exact path of every shard.
 #include <algorithm>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
+
+
+// One persistent thread per shard: takes a job, runs it with the shard's device current, hands back status + message
+// (cm::fail writes a thread-local string, so the text has to travel with the status).
+struct ShardWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = true, stop = false;
+    int rc = CM_OK;
+    std::string msg;
+    explicit ShardWorker(int device) {
+        th = std::thread([this, device] {
+            cudaSetDevice(device);
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [&] { return has_job || stop; });
+                if (stop) return;
+                std::function<int()> f = std::move(job);
+                has_job = false;
+                lk.unlock();
+                int r = f();
+                std::string m = r == CM_OK ? std::string() : std::string(cm_last_error());
+                lk.lock();
+                rc = r; msg.swap(m); done = true;
+                cv.notify_all();
+            }
+        });
+    }
+    ~ShardWorker() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+    void post(std::function<int()> f) {
+        { std::lock_guard<std::mutex> lk(mu); job = std::move(f); has_job = true; done = false; }
+        cv.notify_all();
+    }
+    int wait(std::string *m) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+        if (m) *m = msg;
+        return rc;
+    }
+};
 
 struct cm_flat_sharded {
     int dim = 0, metric = 0;
@@ -47,6 +101,7 @@ struct cm_flat_sharded {
     int64_t cap_g = 0, cap_m = 0, cap_ql = 0, cap_gc = 0;
     int64_t bytes_exchanged = 0;           // peer bytes of the last search (queries out + lists back)
     std::mutex search_mu;                  // searches share the gather / merge buffers
+    std::vector<std::unique_ptr<ShardWorker>> workers;   // [W] (entry 0 unused: shard 0 is enqueued by the caller); empty = single-threaded
 };
 
 namespace cm {
@@ -124,12 +179,18 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
     }
     cudaSetDevice(prev);
     if (rc != CM_OK) { cm_flat_sharded_destroy(h); return rc; }
+    const char *thr = getenv("COMET_B200_SHARD_THREADS");
+    if (n_devices > 1 && !(thr && atoi(thr) == 0)) {
+        h->workers.resize((size_t)n_devices);
+        for (int r = 1; r < n_devices; r++) h->workers[(size_t)r].reset(new ShardWorker(devices[r]));
+    }
     *out = h;
     return CM_OK;
 }
 
 int cm_flat_sharded_destroy(cm_flat_sharded *h) {
     if (!h) return CM_OK;
+    h->workers.clear();            // joins the worker threads
     int prev = 0;
     cudaGetDevice(&prev);
     for (size_t r = 0; r < h->dev.size(); r++) {
@@ -295,6 +356,56 @@ int cm_flat_sharded_last_timing(cm_flat_sharded *h, double *search_ms_max, doubl
     return CM_OK;
 }
 
+// Everything shard r does for one search, enqueued on its stream (runs on the calling thread or on the shard's worker)
+static int shard_enqueue(cm_flat_sharded *h, int r, const float *q_lead_dev, int64_t nq, const cm_search_params *p, int64_t K) {
+    cudaSetDevice(h->dev[(size_t)r]);
+    cm_flat_sharded::Buf &b = h->buf[(size_t)r];
+    if (!h->direct[(size_t)r] && b.cap_q < nq * h->dim) {
+        cudaFree(b.q); b.q = nullptr;
+        CM_CUDA(cudaMalloc(&b.q, (size_t)nq * h->dim * 4));
+        b.cap_q = nq * h->dim;
+    }
+    if (!h->direct[(size_t)r] && b.cap_o < nq * K) {
+        cudaFree(b.ids); cudaFree(b.sc); cudaFree(b.cnt);
+        b.ids = nullptr; b.sc = nullptr; b.cnt = nullptr;
+        CM_CUDA(cudaMalloc(&b.ids, (size_t)nq * K * 4));
+        CM_CUDA(cudaMalloc(&b.sc, (size_t)nq * K * 4));
+        CM_CUDA(cudaMalloc(&b.cnt, (size_t)nq * 8));
+        b.cap_o = nq * K;
+    }
+    cudaStream_t s = h->st[(size_t)r];
+    CM_CUDA(cudaStreamWaitEvent(s, h->start, 0));
+    CM_CUDA(cudaEventRecord(h->t_begin[(size_t)r], s));
+    // With peer access the shard's kernels work on devices[0]'s memory themselves: the query preparation reads the
+    // query block over NVLink and the result emit writes this shard's [nq][K] lists straight into slot r of the
+    // gather buffers -- the exchange is part of the kernels, no copy sits between search and merge.
+    const bool direct = h->direct[(size_t)r] != 0;
+    const float *q_r = q_lead_dev;
+    if (!direct) {
+        CM_CUDA(cudaMemcpyPeerAsync(b.q, h->dev[(size_t)r], q_lead_dev, h->dev[0], (size_t)nq * h->dim * 4, s));
+        q_r = b.q;
+    }
+    uint32_t *o_ids = direct ? h->g_ids + (size_t)r * nq * K : b.ids;
+    float *o_sc = direct ? h->g_sc + (size_t)r * nq * K : b.sc;
+    int64_t *o_cnt = direct ? h->g_cnt + (size_t)r * nq : b.cnt;
+    const int64_t n_r = cm_flat_size(h->shard[(size_t)r]);
+    if (n_r == 0) {
+        CM_TRY(cm::launch_fill_counts(o_cnt, nq, 0, s));
+    } else {
+        cm_search_params pr = *p;
+        pr.k = std::min<int64_t>(K, n_r);          // a shard can contribute at most K rows to the global top-K
+        CM_TRY(cm_flat_search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, o_ids, o_sc, nullptr, o_cnt, (void *)s));
+    }
+    CM_CUDA(cudaEventRecord(h->t_searched[(size_t)r], s));
+    if (!direct) {       // this shard's lists go to slot r of the leader's gather buffers
+        CM_CUDA(cudaMemcpyPeerAsync(h->g_ids + (size_t)r * nq * K, h->dev[0], b.ids, h->dev[(size_t)r], (size_t)nq * K * 4, s));
+        CM_CUDA(cudaMemcpyPeerAsync(h->g_sc + (size_t)r * nq * K, h->dev[0], b.sc, h->dev[(size_t)r], (size_t)nq * K * 4, s));
+        CM_CUDA(cudaMemcpyPeerAsync(h->g_cnt + (size_t)r * nq, h->dev[0], b.cnt, h->dev[(size_t)r], (size_t)nq * 8, s));
+    }
+    CM_CUDA(cudaEventRecord(h->done[(size_t)r], s));
+    return CM_OK;
+}
+
 static int sharded_search_impl(cm_flat_sharded *h, const float *q_lead_dev, int64_t nq, const cm_search_params *p,
                                int64_t K, cudaStream_t lead) {
     // q_lead_dev: queries on the leader device, ready in `lead`'s order.  Leaves the merged result in h->m_*.
@@ -318,55 +429,20 @@ static int sharded_search_impl(cm_flat_sharded *h, const float *q_lead_dev, int6
         h->cap_m = nq * K;
     }
     CM_CUDA(cudaEventRecord(h->start, lead));
-    for (int r = 0; r < W; r++) {
-        cudaSetDevice(h->dev[(size_t)r]);
-        cm_flat_sharded::Buf &b = h->buf[(size_t)r];
-        if (!h->direct[(size_t)r] && b.cap_q < nq * h->dim) {
-            cudaFree(b.q); b.q = nullptr;
-            CM_CUDA(cudaMalloc(&b.q, (size_t)nq * h->dim * 4));
-            b.cap_q = nq * h->dim;
-        }
-        if (!h->direct[(size_t)r] && b.cap_o < nq * K) {
-            cudaFree(b.ids); cudaFree(b.sc); cudaFree(b.cnt);
-            b.ids = nullptr; b.sc = nullptr; b.cnt = nullptr;
-            CM_CUDA(cudaMalloc(&b.ids, (size_t)nq * K * 4));
-            CM_CUDA(cudaMalloc(&b.sc, (size_t)nq * K * 4));
-            CM_CUDA(cudaMalloc(&b.cnt, (size_t)nq * 8));
-            b.cap_o = nq * K;
-        }
-        cudaStream_t s = h->st[(size_t)r];
-        CM_CUDA(cudaStreamWaitEvent(s, h->start, 0));
-        CM_CUDA(cudaEventRecord(h->t_begin[(size_t)r], s));
-        // With peer access the shard's kernels work on devices[0]'s memory themselves: the query preparation reads the
-        // query block over NVLink and the result emit writes this shard's [nq][K] lists straight into slot r of the
-        // gather buffers -- the exchange is part of the kernels, no copy sits between search and merge.
-        const bool direct = h->direct[(size_t)r] != 0;
-        const bool remote = h->dev[(size_t)r] != h->dev[0];
-        const float *q_r = q_lead_dev;
-        if (!direct) {
-            CM_CUDA(cudaMemcpyPeerAsync(b.q, h->dev[(size_t)r], q_lead_dev, h->dev[0], (size_t)nq * h->dim * 4, s));
-            q_r = b.q;
-        }
-        uint32_t *o_ids = direct ? h->g_ids + (size_t)r * nq * K : b.ids;
-        float *o_sc = direct ? h->g_sc + (size_t)r * nq * K : b.sc;
-        int64_t *o_cnt = direct ? h->g_cnt + (size_t)r * nq : b.cnt;
-        const int64_t n_r = cm_flat_size(h->shard[(size_t)r]);
-        if (n_r == 0) {
-            CM_TRY(cm::launch_fill_counts(o_cnt, nq, 0, s));
-        } else {
-            cm_search_params pr = *p;
-            pr.k = std::min<int64_t>(K, n_r);          // a shard can contribute at most K rows to the global top-K
-            CM_TRY(cm_flat_search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, o_ids, o_sc, nullptr, o_cnt, (void *)s));
-        }
-        CM_CUDA(cudaEventRecord(h->t_searched[(size_t)r], s));
-        if (!direct) {       // this shard's lists go to slot r of the leader's gather buffers
-            CM_CUDA(cudaMemcpyPeerAsync(h->g_ids + (size_t)r * nq * K, h->dev[0], b.ids, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-            CM_CUDA(cudaMemcpyPeerAsync(h->g_sc + (size_t)r * nq * K, h->dev[0], b.sc, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-            CM_CUDA(cudaMemcpyPeerAsync(h->g_cnt + (size_t)r * nq, h->dev[0], b.cnt, h->dev[(size_t)r], (size_t)nq * 8, s));
-        }
-        if (remote) h->bytes_exchanged += nq * h->dim * 4 + nq * K * 8 + nq * 8;
-        CM_CUDA(cudaEventRecord(h->done[(size_t)r], s));
+    // The shards are enqueued concurrently: one persistent worker thread per shard beyond the first (a search is ~25
+    // launches per shard; one thread enqueueing 8 shards in turn would put 0.3 ms between the first and the last).
+    const bool threaded = W > 1 && h->workers.size() == (size_t)W;
+    for (int r = 1; r < W && threaded; r++) h->workers[(size_t)r]->post([=] { return shard_enqueue(h, r, q_lead_dev, nq, p, K); });
+    int rc = CM_OK;
+    for (int r = 0; r < (threaded ? 1 : W) && rc == CM_OK; r++) rc = shard_enqueue(h, r, q_lead_dev, nq, p, K);
+    for (int r = 1; r < W && threaded; r++) {
+        std::string msg;
+        const int rc_r = h->workers[(size_t)r]->wait(&msg);
+        if (rc_r != CM_OK && rc == CM_OK) rc = cm::fail(rc_r, "%s", msg.c_str());
     }
+    CM_TRY(rc);
+    for (int r = 0; r < W; r++)
+        if (h->dev[(size_t)r] != h->dev[0]) h->bytes_exchanged += nq * h->dim * 4 + nq * K * 8 + nq * 8;
     cudaSetDevice(h->dev[0]);
     for (int r = 0; r < W; r++) CM_CUDA(cudaStreamWaitEvent(lead, h->done[(size_t)r], 0));
     CM_CUDA(cudaEventRecord(h->t_merge0, lead));

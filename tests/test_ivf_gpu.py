@@ -92,3 +92,14 @@ def test_ivf_errors_and_small_reference_cases():
     with pytest.raises(capi.CometError) as e:
         g.search(np.zeros((1, 5), np.float32), k=1, nprobes=1)
     assert e.value.code == capi.ERR_DIM_MISMATCH
+
+
+def test_ivf_k_all_beyond_the_shared_memory_merge():
+    # WithK(0) = every candidate of the probed lists (limiter.go:12-17): 30,000 candidates per query here, far more
+    # than the shared-memory merge holds -- the sort fallback must give the same order, ties included
+    g, o, rng, x, lists = build_pair(30000, 16, 4, capi.L2SQ, 91, n_train=3000)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    q[0] = x[5]
+    check(g, o, q, 0, 4)
+    check(g, o, q, 20000, 3)
+    check(g, o, q[:1], 0, 2, threshold=20.0)

@@ -187,3 +187,17 @@ def test_adc_selection_under_heavy_ties():
     gi.add(ids, x.copy())
     check_ivfpq(gi, oi, q, 50, 2)
     check_ivfpq(gi, oi, q[:2], 3000, 1)
+
+
+def test_pq_and_ivfpq_k_all_beyond_the_per_cta_selection():
+    # WithK(0) on more codes than a CTA can select from (k > 8192): sliced scan returning every key + a sort per query;
+    # ADC scores tie massively (M = 4, 16 codewords), so this also checks tie order = candidate number
+    g, o, rng = pq_pair(20000, 16, capi.L2, 4, 4, 71)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    check_pq(g, o, q, 0)
+    check_pq(g, o, q[:2], 15000)
+    check_pq(g, o, q[:1], 0, threshold=12.0)
+    g, o, rng, lists = ivfpq_pair(26000, 16, capi.L2, 3, 4, 4, 72)
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    check_ivfpq(g, o, q, 0, 3)
+    check_ivfpq(g, o, q[:2], 12000, 2)
