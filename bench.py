@@ -627,6 +627,237 @@ def run_c5(args):
           "series": series})
     return 0
 
+
+# -------------------------------------------------------------------------------------------------
+# --workload c3 / c4: BASELINE.json configs[2] (IVFPQ 10M x 768, nlist 4096, nprobe 32, M 96, nbits 8, K 100) and
+# configs[3] (HNSW 1M x 768, M 16, efSearch 128, K 10) at their full sizes, one GPU.  Each line carries `value`
+# (device-resident queries), `e2e` (host API), `roofline` (the dominant kernel against the HBM peak in the algorithmic
+# bytes of SURVEY 8d), `cpu_baseline` (the oracle on the SAME index state, one query per host thread) and `parity`
+# (ids, score bits -- and for HNSW the work counters -- of those queries, bit-exact).
+# -------------------------------------------------------------------------------------------------
+def _oracle_queries_parallel(search_one, nq, cores):
+    """search_one(i) -> result; one query per host thread (ctypes drops the GIL inside the oracle)."""
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        res = list(ex.map(search_one, range(nq)))
+    return res, time.perf_counter() - t0
+
+
+def _device_leg(torch, fn_enqueue, steps, warmup):
+    for _ in range(max(3, warmup)):
+        fn_enqueue()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream()
+    e0.record(st)
+    for _ in range(steps):
+        fn_enqueue()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_c3(args):
+    import ctypes as C
+    import torch
+    from comet_b200 import capi
+    from oracle import oracle_py as O              # cpu_baseline + in-run parity
+    d, nq, k = DIM, BATCH, 100
+    n = args.rows if args.rows > 0 else 10_000_000
+    nlist, nprobe, M = 4096, 32, 96
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev); g.manual_seed(SEED)
+    # rows on a 32-dimensional linear manifold + small isotropic noise: one connected cloud, so the reference's
+    # deterministic k-means yields lists of comparable length (i.i.d. 768-d Gaussians have no cluster structure: hub
+    # lists and empty lists; DESIGN.md 6)
+    W3 = torch.randn((32, d), generator=g, device=dev)
+
+    def rows(m):
+        z = torch.randn((m, 32), generator=g, device=dev)
+        return (z @ W3 + 0.05 * torch.randn((m, d), generator=g, device=dev)).cpu().numpy()
+
+    ix = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
+    t0 = time.perf_counter(); ix.train(rows(nlist * 16)); t_train = time.perf_counter() - t0
+    lists = np.zeros(n, np.int32)
+    t_add = 0.0
+    slab = 500_000
+    for s0 in range(0, n, slab):
+        m = min(slab, n - s0)
+        x = rows(m)
+        t0 = time.perf_counter()
+        lists[s0:s0 + m] = ix.add(np.arange(s0 + 1, s0 + m + 1, dtype=np.uint32), x, writeback=False)
+        t_add += time.perf_counter() - t0
+        del x
+    q = rows(nq)
+    L = capi.lib()
+    qd = torch.from_numpy(q).to(dev)
+    o_ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+    o_sc = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((nq,), dtype=torch.int64, device=dev)
+    p, keep = capi.make_params(k=k, nprobes=nprobe)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def enqueue():
+        capi.check(L.cm_ivfpq_search_device(ix.h, capi.vp(qd.data_ptr()), nq, d, C.byref(p), k, capi.vp(o_ids.data_ptr()),
+                                            capi.vp(o_sc.data_ptr()), None, capi.vp(o_cnt.data_ptr()), capi.vp(stream)))
+    launches0 = L.cm_kernel_launches()
+    sampler = ClockSampler(0).start()
+    ms = _device_leg(torch, enqueue, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = (L.cm_kernel_launches() - launches0) * args.steps // (args.steps + max(3, args.warmup))
+    L.cm_profile_reset(); L.cm_profile_enable(1)
+    for _ in range(3):
+        enqueue()
+    torch.cuda.synchronize()
+    L.cm_profile_enable(0)
+    scan_ms, scan_n = capi.profile_get(capi.PROF_PQ_SCAN)
+    per = scan_ms / 3 * 1e-3                              # ADC scan time per step (all its launches)
+    scanned = L.cm_ivfpq_last_scanned(ix.h) / nq
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(e2e_steps):
+        gi, gs, gc = ix.search(q, k=k, nprobes=nprobe)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the oracle on the SAME trained state and codes (its ReadFrom-style loader)
+    cores = os.cpu_count() or 1
+    o = O.IVFPQ(d, capi.L2, nlist, M, 8)
+    o.set_trained(*ix.trained_state())
+    o.load_codes(np.arange(1, n + 1, dtype=np.uint32), ix.codes(), lists)
+    nchk = nq                                            # every query of the batch: parity and the CPU figure
+    res, dt = _oracle_queries_parallel(lambda i: o.search(q[i], k=k, nprobes=nprobe), nchk, cores)
+    ok_ids = all(np.array_equal(gi[i, :int(gc[i])], res[i][0]) for i in range(nchk))
+    ok_sc = all(np.array_equal(gs[i, :int(gc[i])].view(np.uint32), res[i][1].view(np.uint32)) for i in range(nchk))
+    hbm = measured_peaks()[0]
+    code_bytes = nq * scanned * M                       # SURVEY 8d: the code stream of the probed lists, M bytes per code
+    emit({"metric": "queries/sec (IVFPQ %dx768, nlist 4096, nprobe 32, M 96, nbits 8, K=100)" % n, "value": nq / (ms * 1e-3),
+          "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 codes)", "data": "synthetic",
+          "config": {"workload": "ivfpq_%dx768_nlist4096_nprobe32_m96_k100_b512" % n, "rows": n, "dim": d, "nlist": nlist, "nprobes": nprobe,
+                     "M": M, "nbits": 8, "k": k, "batch": nq, "data_shape": "32-d linear manifold + 0.05 noise in 768-d",
+                     "codes_scanned_per_query": scanned, "train_s": t_train, "add_s": t_add},
+          "clocks": clocks,
+          "e2e": {"value": nq / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": nq * d * 4,
+                  "d2h_bytes_per_step": nq * k * 8 + nq * 8, "steps": e2e_steps},
+          "gpu_launches": int(launches),
+          "roofline": {"kernel": "adc_scan_kernel (per-(query, probe) residual table in shared memory, list codes streamed)",
+                       "bound": "hbm", "achieved": code_bytes / per / 1e9, "peak": hbm, "unit": "GB/s", "frac": code_bytes / per / 1e9 / hbm,
+                       "traffic": None, "kernel_ms_per_step": per * 1e3, "launches_timed": scan_n,
+                       "note": "algorithmic bytes = codes scanned x M; the kernel is bound by shared-memory table lookups, not by this stream",
+                       "table_lookups_per_s": nq * scanned * M / per, "tables_built_per_s": nq * nprobe / per},
+          "cpu_baseline": {"value": nchk / dt, "unit": "queries/s", "cores": min(cores, nchk), "kind": "port",
+                           "sample": f"{nchk} of the {nq} queries on the same trained index and codes, one query per host thread, {dt:.1f} s"},
+          "parity": {"queries_checked": nchk, "ids_bit_exact": bool(ok_ids), "scores_bit_exact": bool(ok_sc)}})
+    return 0
+
+
+def run_c4(args):
+    import ctypes as C
+    import torch
+    from comet_b200 import capi
+    from oracle import oracle_py as O              # cpu_baseline + in-run parity
+    d, k, ef = DIM, 10, 128
+    n = args.rows if args.rows > 0 else 1_000_000
+    nq = args.batch if args.batch > 0 else BATCH
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev); g.manual_seed(SEED)
+    Wk = torch.randn((24, d), generator=g, device=dev)
+    x = (torch.randn((n, 24), generator=g, device=dev) @ Wk).cpu().numpy()
+    q = (torch.randn((nq, 24), generator=g, device=dev) @ Wk).cpu().numpy()
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    # graph: the exact 32-nearest-neighbour graph of the rows (built with the flat tensor path).  A graph built by the
+    # reference's own insertNode leaves 2M+1 nodes reachable (entry point never promoted, hnsw_index.go:266-284,
+    # 675-694; DESIGN.md 6), so the traversal kernel is measured on a graph that is actually explored.
+    flat = capi.FlatIndex(d, capi.L2)
+    flat.add(ids, x, writeback=False)
+    nbr = np.zeros((n, 32), np.uint32)
+    t0 = time.perf_counter()
+    for s0 in range(0, n, 16384):
+        gi, _, _ = flat.search(x[s0:s0 + 16384], k=33)
+        nbr[s0:s0 + 16384] = gi[:, 1:33]
+    t_knn = time.perf_counter() - t0
+    truth, _, _ = flat.search(q, k=k)
+    del flat
+    levels = np.zeros(n, np.int32)
+    off = np.arange(n + 1, dtype=np.int64) * 32
+    ix = capi.HNSWIndex(d, capi.L2, 16, 100, ef)
+    ix.load_graph(ids, x, levels, [(off, nbr.ravel())], 1, 0)
+    L = capi.lib()
+    qd = torch.from_numpy(q).to(dev)
+    o_ids = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+    o_sc = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.zeros((nq,), dtype=torch.int64, device=dev)
+    o_work = torch.zeros((nq, 2), dtype=torch.int64, device=dev)
+    p, keep = capi.make_params(k=k, ef_search=ef)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def enqueue():
+        capi.check(L.cm_hnsw_search_device(ix.h, capi.vp(qd.data_ptr()), nq, d, C.byref(p), k, capi.vp(o_ids.data_ptr()),
+                                           capi.vp(o_sc.data_ptr()), None, capi.vp(o_cnt.data_ptr()), capi.vp(o_work.data_ptr()),
+                                           capi.vp(stream)))
+    launches0 = L.cm_kernel_launches()
+    sampler = ClockSampler(0).start()
+    ms = _device_leg(torch, enqueue, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = (L.cm_kernel_launches() - launches0) * args.steps // (args.steps + max(3, args.warmup))
+    L.cm_profile_reset(); L.cm_profile_enable(1)
+    for _ in range(3):
+        enqueue()
+    torch.cuda.synchronize()
+    L.cm_profile_enable(0)
+    k_ms, k_n = capi.profile_get(capi.PROF_HNSW)
+    per = (k_ms / 3 * 1e-3) if k_n else ms * 1e-3        # traversal kernel time per step (all its launches)
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gi, gs, gc, work = ix.search(q, k=k, ef_search=ef, with_work=True)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    evals = float(work[:, 0].mean())
+    rec = float(np.mean([len(set(gi[i, :k].tolist()) & set(truth[i].tolist())) / k for i in range(nq)]))
+    cores = os.cpu_count() or 1
+    o = O.HNSW(d, capi.L2, 16, 100, ef)
+    o.load_graph(ids, x, levels, off, nbr.ravel(), 1, 0)
+    nchk = min(nq, 2048)                                 # parity on (up to) 2048 queries of the batch
+
+    def one(i):
+        r = o.search(q[i % nchk], k=k, ef_search=ef)
+        return r, O.HNSW.last_counters()
+    res, dt = _oracle_queries_parallel(one, nchk, cores)
+    reps = max(1, int(8.0 / max(dt, 1e-3)))              # CPU figure from ~8 s of work
+    if reps > 1:
+        _, dt_all = _oracle_queries_parallel(one, nchk * reps, cores)
+        cpu_qps = nchk * reps / dt_all
+    else:
+        dt_all, cpu_qps = dt, nchk / dt
+    ok_ids = all(np.array_equal(gi[i, :int(gc[i])], res[i][0][0]) for i in range(nchk))
+    ok_sc = all(np.array_equal(gs[i, :int(gc[i])].view(np.uint32), res[i][0][1].view(np.uint32)) for i in range(nchk))
+    ok_work = all((int(work[i, 0]), int(work[i, 1])) == tuple(res[i][1]) for i in range(nchk))
+    hbm = measured_peaks()[0]
+    row_bytes = nq * evals * (d * 4 + 4)                 # SURVEY 8d: one row (+ its id) per distance evaluation
+    emit({"metric": "queries/sec (HNSW %dx768, M 16, efSearch 128, K=10)" % n, "value": nq / (ms * 1e-3), "unit": "queries/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "hnsw_%dx768_m16_ef128_k10_b%d" % (n, nq), "rows": n, "dim": d, "degree": 32, "ef_search": ef, "k": k,
+                     "queries_in_flight": nq, "graph": "exact 32-NN graph of the rows, layer 0 only, loaded into the device and the oracle",
+                     "data_shape": "24-d linear manifold in 768-d", "knn_graph_build_s": t_knn,
+                     "distance_evaluations_per_query": evals, "expansions_per_query": float(work[:, 1].mean()),
+                     "recall_at_10_vs_flat": rec},
+          "clocks": clocks,
+          "e2e": {"value": nq / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": nq * d * 4,
+                  "d2h_bytes_per_step": nq * k * 8 + nq * 8 + nq * 16, "steps": e2e_steps},
+          "gpu_launches": int(launches),
+          "roofline": {"kernel": "hnsw_search_kernel (one warp per query, neighbour rows staged through shared memory)", "bound": "hbm",
+                       "achieved": row_bytes / per / 1e9, "peak": hbm, "unit": "GB/s", "frac": row_bytes / per / 1e9 / hbm, "traffic": None,
+                       "kernel_ms_per_step": per * 1e3, "launches_timed": k_n,
+                       "note": "algorithmic bytes = distance evaluations x (row + id); a dependent chain per query, throughput comes from queries in flight"},
+          "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": min(cores, nchk), "kind": "port",
+                           "sample": f"{nchk} of the {nq} queries on the same graph x {reps} rounds, one query per host thread, {dt_all:.1f} s"},
+          "parity": {"queries_checked": nchk, "ids_bit_exact": bool(ok_ids), "scores_bit_exact": bool(ok_sc),
+                     "work_counters_equal": bool(ok_work)}})
+    return 0
+
 # -------------------------------------------------------------------------------------------------
 # --workload c1 / b1: the single-query shapes (not the driver's bench line; parity-test configs measured
 # for DESIGN.md).  c1 = BASELINE.json configs[0], Flat L2Squared 10K x 128, K=10, one query per call: latency
@@ -708,8 +939,9 @@ def main():
     ap.add_argument("--no-rows-sharded", action="store_true", help="N > 1: skip the row-sharded leg (rows_sharded sub-record)")
     ap.add_argument("--sharding", default="auto", choices=["auto", "rows", "queries"])
     ap.add_argument("--rows", type=int, default=0, help="corpus rows (default 1M = BASELINE configs[1]); 12500000 = one 1/8 shard of the 100M x 768 config")
+    ap.add_argument("--batch", type=int, default=0, help="c4: queries in flight per call (default 512)")
     ap.add_argument("--metric-kind", default="cosine", choices=["cosine", "l2", "l2_squared"])
-    ap.add_argument("--workload", default="headline", choices=["headline", "c1", "b1", "c5"],
+    ap.add_argument("--workload", default="headline", choices=["headline", "c1", "b1", "c3", "c4", "c5"],
                     help="headline = the driver's bench line; c1 / b1 = single-query shapes (see run_single_query_shapes)")
     args = ap.parse_args()
     if args.rows > 0:
@@ -721,6 +953,10 @@ def main():
         return run_reference(args)
     if args.workload == "c5":
         return run_c5(args)
+    if args.workload == "c3":
+        return run_c3(args)
+    if args.workload == "c4":
+        return run_c4(args)
     if args.workload != "headline":
         return run_single_query_shapes(args)
     return run_ours(args)

@@ -417,6 +417,77 @@ int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// merge of per-shard results when the shards hold LISTS (IVF / IVFPQ list shards): the reference orders ties by the
+// candidate's number in its append loop over the probed lists (ivf_index_search.go:252-308), a number every shard
+// reports next to its scores (`gno`, unique per query across shards).  Order = (score, gno); the id of a winner is found
+// again by a binary search of its key in each shard's (sorted) list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) merge_keyed_shards_kernel(
+    const uint32_t *__restrict__ ids, const float *__restrict__ scores, const uint32_t *__restrict__ gno,
+    const long long *__restrict__ counts, int world, long long nq, long long in_stride, int K, int C, long long out_stride,
+    uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, long long *__restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);
+    __shared__ int cnt;
+    __shared__ uint64_t tau;
+    const CtaBarrier bar;
+    const int tid = threadIdx.x;
+    const long long q = blockIdx.x;
+    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+    __syncthreads();
+    long long bad = 0;
+    for (int r = 0; r < world; r++) bad = min(bad, counts[(size_t)r * nq + q]);
+    if (bad < 0) {
+        if (tid == 0) out_counts[q] = bad;
+        return;
+    }
+    for (int r = 0; r < world; r++) {
+        long long c = min(counts[(size_t)r * nq + q], in_stride);
+        const size_t base = ((size_t)r * nq + q) * in_stride;
+        for (int j = tid; j < c; j += MERGE_THREADS) buf[atomicAdd(&cnt, 1)] = make_key(scores[base + j], gno[base + j]);
+    }
+    compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
+    const int m = cnt;
+    for (int i = tid; i < m; i += MERGE_THREADS) {
+        const uint64_t key = buf[i];
+        uint32_t id = 0;
+        for (int r = 0; r < world; r++) {
+            const long long c = min(counts[(size_t)r * nq + q], in_stride);
+            const size_t base = ((size_t)r * nq + q) * in_stride;
+            long long lo = 0, hi = c;                 // first j with key(j) >= key
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if (make_key(scores[base + mid], gno[base + mid]) < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo < c && make_key(scores[base + lo], gno[base + lo]) == key) { id = ids[base + lo]; break; }
+        }
+        out_ids[(size_t)q * out_stride + i] = id;
+        out_scores[(size_t)q * out_stride + i] = key_score(key);
+    }
+    if (tid == 0) out_counts[q] = m;
+}
+
+int launch_merge_keyed_shards(const uint32_t *ids, const float *scores, const uint32_t *gno, const int64_t *counts, int world,
+                              int64_t nq, int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                              int64_t *out_counts, cudaStream_t stream) {
+    if (nq <= 0) return CM_OK;
+    int C = next_pow2((int)(world * in_stride));
+    if (C < 512) C = 512;
+    size_t smem = (size_t)C * 8;
+    if (smem > max_smem_optin())
+        return fail(CM_ERR_UNSUPPORTED, "%d list shards x k=%lld too large for the shard merge", world, (long long)in_stride);
+    CM_TRY(set_dyn_smem((const void *)merge_keyed_shards_kernel, smem));
+    ProfScope prof(CM_PROF_SELECT, stream);
+    merge_keyed_shards_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>(ids, scores, gno, (const long long *)counts, world,
+                                                                            (long long)nq, (long long)in_stride, K, C,
+                                                                            (long long)out_stride, out_ids, out_scores,
+                                                                            (long long *)out_counts);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    return CM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-row helpers
 // ------------------------------------------------------------------------------------------------
 // distance.go:244-264 PreprocessInPlace / :269-290 Preprocess.  One thread per row, sequential.

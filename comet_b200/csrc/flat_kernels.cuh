@@ -43,6 +43,11 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
 int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
                         int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                         int64_t *out_counts, cudaStream_t stream);
+// Merge of per-shard lists ordered by (score, gno): list shards of IVF / IVFPQ, gno = the candidate's number in the
+// reference's append loop over all probed lists (unique per query across shards)
+int launch_merge_keyed_shards(const uint32_t *ids, const float *scores, const uint32_t *gno, const int64_t *counts, int world,
+                              int64_t nq, int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
+                              int64_t *out_counts, cudaStream_t stream);
 // launch_merge_topk's fallback when K + Kp does not fit shared memory: one radix sort per query (flat_bigk.cu)
 int merge_topk_bigk(const uint64_t *part_keys, const int *part_counts, int nq, int parts, int Kp, int64_t K,
                     const uint32_t *row_ids, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,

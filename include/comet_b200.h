@@ -75,6 +75,7 @@ typedef struct cm_ivfpq cm_ivfpq;
 typedef struct cm_hnsw cm_hnsw;
 typedef struct cm_flat_batcher cm_flat_batcher;
 typedef struct cm_flat_sharded cm_flat_sharded;
+typedef struct cm_ivf_sharded cm_ivf_sharded;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 int cm_init(const int *device_ids, int n_devices); /* NULL/0: use the current device */
@@ -253,6 +254,42 @@ int cm_ivf_search(cm_ivf *h, const float *queries, int64_t nq, int dim, const cm
 int cm_ivf_search_device(cm_ivf *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
                          int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
                          int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
+
+/* ---- IVF list shards over the GPUs of one box, ONE host process ------------------------------------ */
+/* NewIVFIndex on a box with W GPUs: every shard (devices[r]) holds ALL centroids -- the coarse step is replicated -- and
+ * the inverted lists it owns (list l starts on shard l mod W; cm_ivf_sharded_rebalance reassigns greedily by length).
+ * A search scans, on every shard concurrently, the probed lists that shard holds; each shard returns its top-K together
+ * with every winner's number in the reference's append loop over ALL probed lists (ivf_index_search.go:252-268), computed
+ * from the replicated global list lengths; devices[0] merges by (score, that number): bit for bit the single index's
+ * answer, ties included.  Queries are read and lists written through NVLink peer mappings (no NCCL: one process).
+ * Searches on one handle are serialised; mutators need external exclusion.  k <= 0 ("all") is limited to
+ * W x k <= 28K entries per query. */
+int cm_ivf_sharded_create(int dim, int nlist, int metric, const int *devices, int n_devices, cm_ivf_sharded **out);
+int cm_ivf_sharded_destroy(cm_ivf_sharded *h);
+int cm_ivf_sharded_shards(const cm_ivf_sharded *h);
+int cm_ivf_sharded_set_centroids(cm_ivf_sharded *h, const float *centroids);      /* result of IVFIndex.Train, to every shard */
+int cm_ivf_sharded_train(cm_ivf_sharded *h, const float *rows, int64_t n);        /* IVFIndex.Train on devices[0] */
+int cm_ivf_sharded_get_centroids(const cm_ivf_sharded *h, float *out);
+int cm_ivf_sharded_trained(const cm_ivf_sharded *h);
+int64_t cm_ivf_sharded_size(const cm_ivf_sharded *h);
+int cm_ivf_sharded_shard_size(const cm_ivf_sharded *h, int shard, int64_t *rows);
+int cm_ivf_sharded_owner(const cm_ivf_sharded *h, int list);                      /* shard holding the list */
+int cm_ivf_sharded_default_nprobes(const cm_ivf_sharded *h);
+/* n successive IVFIndex.Add calls (ivf_index.go:258-283): preprocessing and list assignment once on devices[0], then
+ * every stored vector goes to the shard that owns its list */
+int cm_ivf_sharded_add(cm_ivf_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
+int cm_ivf_sharded_remove(cm_ivf_sharded *h, uint32_t id);
+int cm_ivf_sharded_flush(cm_ivf_sharded *h);
+/* greedy-by-length list assignment (longest list first onto the lightest shard); lists that change owner move whole */
+int cm_ivf_sharded_rebalance(cm_ivf_sharded *h);
+int cm_ivf_sharded_search(cm_ivf_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                          int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_counts);
+/* queries / outputs on devices[0]; never synchronises; a zero query under cosine is not detected on this entry point */
+int cm_ivf_sharded_search_device(cm_ivf_sharded *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                                 int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_counts_dev,
+                                 void *stream);
+/* vectors each shard scanned in the last host search, all queries together: per_shard[W] (balance of the assignment) */
+int cm_ivf_sharded_last_scanned(const cm_ivf_sharded *h, int64_t *per_shard);
 
 /* ---- pq_index.go / pq_index_search.go ------------------------------------------------------- */
 int cm_pq_create(int dim, int metric, int M, int nbits, cm_pq **out);   /* NewPQIndex pq_index.go:135 */
