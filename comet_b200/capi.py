@@ -161,6 +161,24 @@ SIGNATURES = {
     "cm_ivfpq_flush": (C.c_int, [vp]),
     "cm_ivfpq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
     "cm_ivfpq_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp, vp]),
+    "cm_ivfpq_sharded_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.POINTER(vp)]),
+    "cm_ivfpq_sharded_destroy": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_shards": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_set_trained": (C.c_int, [vp, f32p, f32p]),
+    "cm_ivfpq_sharded_train": (C.c_int, [vp, f32p, C.c_int64]),
+    "cm_ivfpq_sharded_get_trained": (C.c_int, [vp, f32p, f32p]),
+    "cm_ivfpq_sharded_trained": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_size": (C.c_int64, [vp]),
+    "cm_ivfpq_sharded_shard_size": (C.c_int, [vp, C.c_int, i64p]),
+    "cm_ivfpq_sharded_owner": (C.c_int, [vp, C.c_int]),
+    "cm_ivfpq_sharded_default_nprobes": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int, i32p]),
+    "cm_ivfpq_sharded_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_ivfpq_sharded_flush": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_rebalance": (C.c_int, [vp]),
+    "cm_ivfpq_sharded_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p]),
+    "cm_ivfpq_sharded_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp]),
+    "cm_ivfpq_sharded_last_scanned": (C.c_int, [vp, i64p]),
     "cm_hnsw_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "cm_hnsw_destroy": (C.c_int, [vp]),
     "cm_hnsw_size": (C.c_int64, [vp]),
@@ -789,6 +807,91 @@ class IVFPQIndex(_ADCIndex):
         if nprobes is None:
             nprobes = self.default_nprobes()
         return self._search(queries, k, threshold, nprobes, filter_ids, out_stride)
+
+
+class ShardedIVFPQIndex:
+    """Thin owner of a cm_ivfpq_sharded handle: one process, code lists spread over `devices`."""
+
+    def __init__(self, dim, metric, nlist, M, nbits, devices):
+        self.h = vp()
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        check(lib().cm_ivfpq_sharded_create(int(dim), int(metric), int(nlist), int(M), int(nbits), ptr(dv, i32p), len(dv),
+                                            C.byref(self.h)))
+        self.dim, self.metric, self.nlist, self.M, self.nbits, self.devices = dim, metric, nlist, M, nbits, list(devices)
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().cm_ivfpq_sharded_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(lib().cm_ivfpq_sharded_size(self.h))
+
+    def shard_size(self, r):
+        n = C.c_int64(0)
+        check(lib().cm_ivfpq_sharded_shard_size(self.h, int(r), C.byref(n)))
+        return n.value
+
+    def owner(self, l):
+        return int(lib().cm_ivfpq_sharded_owner(self.h, int(l)))
+
+    def set_trained(self, centroids, codebooks):
+        c, b = _f32(centroids), _f32(codebooks)
+        check(lib().cm_ivfpq_sharded_set_trained(self.h, ptr(c, f32p), ptr(b, f32p)))
+
+    def train(self, rows):
+        r = _f32(rows)
+        check(lib().cm_ivfpq_sharded_train(self.h, ptr(r, f32p), len(r)))
+
+    def trained_state(self):
+        ksub, dsub = 1 << self.nbits, self.dim // self.M
+        c = np.empty((self.nlist, self.dim), np.float32)
+        b = np.empty((self.M, ksub, dsub), np.float32)
+        check(lib().cm_ivfpq_sharded_get_trained(self.h, ptr(c, f32p), ptr(b, f32p)))
+        return c, b
+
+    def add(self, ids, rows, writeback=True):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        lists = np.full(len(ids), -1, np.int32)
+        check(lib().cm_ivfpq_sharded_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0, ptr(lists, i32p)))
+        return lists
+
+    def remove(self, id_):
+        check(lib().cm_ivfpq_sharded_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_ivfpq_sharded_flush(self.h))
+
+    def rebalance(self):
+        check(lib().cm_ivfpq_sharded_rebalance(self.h))
+
+    def default_nprobes(self):
+        return int(lib().cm_ivfpq_sharded_default_nprobes(self.h))
+
+    def search(self, queries, k=10, nprobes=None, threshold=0.0, filter_ids=None, out_stride=None):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        if nprobes is None:
+            nprobes = self.default_nprobes()
+        n = len(self)
+        stride = out_stride or max(1, n if (k <= 0 or k > n) else k)
+        ids = np.zeros((nq, stride), np.uint32)
+        sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, nprobes=nprobes, filter_ids=filter_ids)
+        check(lib().cm_ivfpq_sharded_search(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p), ptr(sc, f32p),
+                                            ptr(cnt, i64p)))
+        return ids, sc, cnt
+
+    def last_scanned(self):
+        out = np.zeros(len(self.devices), np.int64)
+        check(lib().cm_ivfpq_sharded_last_scanned(self.h, ptr(out, i64p)))
+        return out
 
 
 class HNSWIndex:

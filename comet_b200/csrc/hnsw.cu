@@ -603,7 +603,7 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
         ProfScope prof(CM_PROF_HNSW, st);
 #define CM_HNSW_LAUNCH(MM, F)                                                                                         \
     do {                                                                                                              \
-        CM_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<MM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CM_TRY(set_dyn_smem((const void *)hnsw_search_kernel<MM, F>, smem));                                               \
         hnsw_search_kernel<MM, F><<<blocks, HNSW_WARPS * 32, smem, st>>>(                                             \
             G, ix.entry_slot, ix.max_level, qp + (size_t)q0 * ld, (int)m, ef, (long long)p->k, p->threshold, doc_skip, visited, \
             vis_words, heaps, cand_cap, (long long)out_stride, out_ids + (size_t)q0 * out_stride,                     \
@@ -789,7 +789,7 @@ int cm_hnsw_add(cm_hnsw *h, const uint32_t *ids, float *rows, const int32_t *lev
         cm::GraphView G = ix.view();
 #define CM_HNSW_INS(MM, F)                                                                                            \
     do {                                                                                                              \
-        cudaFuncSetAttribute(cm::hnsw_insert_kernel<MM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        cm::set_dyn_smem((const void *)cm::hnsw_insert_kernel<MM, F>, smem);                                               \
         cm::hnsw_insert_kernel<MM, F><<<1, 32, smem, st>>>(G, (long long)ix.n, (int)good, ix.entry_slot, ix.max_level, ix.m, ix.efc, \
                                                            vis, cands, cand_cap, touched, tmp, status);               \
     } while (0)

@@ -31,7 +31,7 @@
 #include "flat_kernels.cuh"
 #include "kmeans.cuh"
 #include "select.cuh"
-#include "shard_worker.cuh"
+#include "list_shards.cuh"
 #include "wire.cuh"
 
 namespace cm {
@@ -260,7 +260,7 @@ static int launch_ivf_scan_m(bool fma, dim3 grid, size_t smem, cudaStream_t st, 
     smem = (size_t)ld * 4 + 2 * 128 * (size_t)(wide ? 256 : 128);
 #define CM_IVF_GO(F, C)                                                                                                   \
     do {                                                                                                                 \
-        CM_CUDA(cudaFuncSetAttribute(ivf_scan_kernel<METRIC, F, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CM_TRY(set_dyn_smem((const void *)ivf_scan_kernel<METRIC, F, C>, smem));                                               \
         ivf_scan_kernel<METRIC, F, C><<<grid, 128, smem, st>>>(rows, ld, queries, probe_list, q_off, list_off, members, nprobes, \
                                                                skip, threshold, cap_c, n_chunks, out_keys, out_cnt);     \
     } while (0)
@@ -822,37 +822,13 @@ int cm_ivf_load_file(cm_ivf *h, const char *path) {
 }
 
 // ================================================================================================
-// IVF list shards over the GPUs of one box, ONE host process: cm_ivf_sharded_*.
-//
-// Every shard is a complete cm_ivf with ALL centroids (the coarse step is replicated: nlist x dim floats) but only
-// the lists it owns.  A search runs on every shard concurrently: identical probe lists everywhere (the coarse scan is
-// deterministic), each shard scans the probed lists it holds and returns its top-K by (score, candidate number) TOGETHER
-// WITH each winner's number in the reference's append loop over ALL probed lists (ivf_index_search.go:252-268) -- computed
-// from the replicated global list lengths.  devices[0] merges the W lists by (score, global number): bit for bit the
-// single index's order, ties included.  Queries are read and lists written through NVLink peer mappings.
+// IVF list shards over the GPUs of one box, ONE host process: cm_ivf_sharded_*.  The search driver, the
+// global candidate numbering and the cross-shard merge are shared with IVFPQ: list_shards.cuh.
 // ================================================================================================
 struct cm_ivf_sharded {
-    int dim = 0, nlist = 0, metric = 0;
-    std::vector<int> dev;
+    cm::ListShards ls;
     std::vector<cm_ivf *> shard;
     cm_ivf *assigner = nullptr;             // devices[0]: centroids only; Add runs PreprocessInPlace + nearest centroid here
-    std::vector<int> owner;                 // [nlist] shard that holds the list
-    std::vector<long long> glob_len;        // [nlist] vectors in the list, deleted ones included (like len(idx.lists[l]))
-    std::vector<long long *> glob_len_dev;  // per shard: device copy of glob_len
-    bool len_dirty = true;
-    std::vector<cudaStream_t> st;
-    std::vector<cudaEvent_t> done;
-    std::vector<char> direct;
-    cudaEvent_t start = nullptr;
-    struct Buf { float *q = nullptr; uint32_t *ids = nullptr, *gno = nullptr; float *sc = nullptr; int64_t *cnt = nullptr; int64_t cap_q = 0, cap_o = 0; };
-    std::vector<Buf> buf;
-    uint32_t *g_ids = nullptr, *g_gno = nullptr, *m_ids = nullptr;
-    float *g_sc = nullptr, *m_sc = nullptr, *q_lead = nullptr;
-    int64_t *g_cnt = nullptr, *m_cnt = nullptr;
-    int64_t cap_g = 0, cap_m = 0, cap_ql = 0;
-    std::mutex search_mu;
-    std::vector<std::unique_ptr<ShardWorker>> workers;
-    std::vector<int64_t> last_scanned;      // per shard, last search
 };
 
 static int ivfs_clear_vectors(cm_ivf *h) {          // drop the vectors, keep the centroids
@@ -866,24 +842,13 @@ static int ivfs_clear_vectors(cm_ivf *h) {          // drop the vectors, keep th
 
 int cm_ivf_sharded_destroy(cm_ivf_sharded *h) {
     if (!h) return CM_OK;
-    h->workers.clear();
     int prev = 0;
     cudaGetDevice(&prev);
-    for (size_t r = 0; r < h->dev.size(); r++) {
-        cudaSetDevice(h->dev[r]);
-        if (r < h->st.size() && h->st[r]) { cudaStreamSynchronize(h->st[r]); cudaStreamDestroy(h->st[r]); }
-        if (r < h->done.size() && h->done[r]) cudaEventDestroy(h->done[r]);
-        if (r < h->glob_len_dev.size()) cudaFree(h->glob_len_dev[r]);
-        if (r < h->buf.size()) { cudaFree(h->buf[r].q); cudaFree(h->buf[r].ids); cudaFree(h->buf[r].gno); cudaFree(h->buf[r].sc); cudaFree(h->buf[r].cnt); }
-        if (r < h->shard.size() && h->shard[r]) cm_ivf_destroy(h->shard[r]);
-    }
-    if (!h->dev.empty()) {
-        cudaSetDevice(h->dev[0]);
-        if (h->assigner) cm_ivf_destroy(h->assigner);
-        if (h->start) cudaEventDestroy(h->start);
-        cudaFree(h->g_ids); cudaFree(h->g_gno); cudaFree(h->g_sc); cudaFree(h->g_cnt);
-        cudaFree(h->m_ids); cudaFree(h->m_sc); cudaFree(h->m_cnt); cudaFree(h->q_lead);
-    }
+    h->ls.workers.clear();
+    for (size_t r = 0; r < h->shard.size(); r++)
+        if (h->shard[r]) { cudaSetDevice(h->ls.dev[r]); cm_ivf_destroy(h->shard[r]); }
+    if (h->assigner) { cudaSetDevice(h->ls.dev[0]); cm_ivf_destroy(h->assigner); }
+    h->ls.destroy();
     cudaSetDevice(prev);
     delete h;
     return CM_OK;
@@ -892,66 +857,30 @@ int cm_ivf_sharded_destroy(cm_ivf_sharded *h) {
 int cm_ivf_sharded_create(int dim, int nlist, int metric, const int *devices, int n_devices, cm_ivf_sharded **out) {
     if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
-    if (!devices || n_devices <= 0 || n_devices > 64) return cm::fail(CM_ERR_INVALID_ARG, "need 1..64 devices");
-    CM_TRY(cm::ensure_device());
-    int n_dev = 0;
-    CM_CUDA(cudaGetDeviceCount(&n_dev));
-    for (int r = 0; r < n_devices; r++)
-        if (devices[r] < 0 || devices[r] >= n_dev) return cm::fail(CM_ERR_INVALID_ARG, "no CUDA device %d", devices[r]);
+    if (dim <= 0) return cm::fail(CM_ERR_INVALID_ARG, "dimension must be positive");
+    if (nlist <= 0) return cm::fail(CM_ERR_INVALID_ARG, "nlist must be positive");
+    if (metric < 0 || metric > 2) return cm::fail(CM_ERR_INVALID_ARG, "unknown distance kind");
+    cm_ivf_sharded *h = new cm_ivf_sharded();
+    int rc = h->ls.init(dim, nlist, metric, devices, n_devices);
+    if (rc != CM_OK) { delete h; return rc; }
     int prev = 0;
     cudaGetDevice(&prev);
-    cm_ivf_sharded *h = new cm_ivf_sharded();
-    h->dim = dim; h->nlist = nlist; h->metric = metric;
-    h->dev.assign(devices, devices + n_devices);
-    const size_t W = (size_t)n_devices;
-    h->shard.assign(W, nullptr); h->st.assign(W, nullptr); h->done.assign(W, nullptr); h->direct.assign(W, 1);
-    h->glob_len_dev.assign(W, nullptr); h->buf.resize(W); h->last_scanned.assign(W, 0);
-    int rc = CM_OK;
+    h->shard.assign((size_t)n_devices, nullptr);
     for (int r = 0; r < n_devices && rc == CM_OK; r++) {
         cudaSetDevice(devices[r]);
         rc = cm_ivf_create(dim, nlist, metric, &h->shard[(size_t)r]);
-        if (rc != CM_OK) break;
-        if (cudaStreamCreateWithFlags(&h->st[(size_t)r], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->done[(size_t)r], cudaEventDisableTiming) != cudaSuccess ||
-            cudaMalloc(&h->glob_len_dev[(size_t)r], (size_t)nlist * sizeof(long long)) != cudaSuccess)
-            rc = cm::fail(CM_ERR_CUDA, "stream / event / buffer creation on device %d failed", devices[r]);
-        if (rc == CM_OK && devices[r] != devices[0]) {
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, devices[r], devices[0]);
-            if (can) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = cm::fail(CM_ERR_CUDA, "peer access %d -> %d: %s", devices[r], devices[0], cudaGetErrorString(e));
-                cudaGetLastError();
-                cudaSetDevice(devices[0]);
-                e = cudaDeviceEnablePeerAccess(devices[r], 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = cm::fail(CM_ERR_CUDA, "peer access %d -> %d: %s", devices[0], devices[r], cudaGetErrorString(e));
-                cudaGetLastError();
-            } else {
-                h->direct[(size_t)r] = 0;
-            }
-            if (getenv("COMET_B200_SHARD_COPIES")) h->direct[(size_t)r] = 0;
-        }
     }
     if (rc == CM_OK) {
         cudaSetDevice(devices[0]);
         rc = cm_ivf_create(dim, nlist, metric, &h->assigner);
-        if (rc == CM_OK && cudaEventCreateWithFlags(&h->start, cudaEventDisableTiming) != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "event creation failed");
     }
     cudaSetDevice(prev);
     if (rc != CM_OK) { cm_ivf_sharded_destroy(h); return rc; }
-    h->owner.resize((size_t)nlist);
-    for (int l = 0; l < nlist; l++) h->owner[(size_t)l] = l % n_devices;     // until cm_ivf_sharded_rebalance looks at the lengths
-    h->glob_len.assign((size_t)nlist, 0);
-    const char *thr = getenv("COMET_B200_SHARD_THREADS");
-    if (n_devices > 1 && !(thr && atoi(thr) == 0)) {
-        h->workers.resize(W);
-        for (int r = 1; r < n_devices; r++) h->workers[(size_t)r].reset(new ShardWorker(devices[r]));
-    }
     *out = h;
     return CM_OK;
 }
 
-int cm_ivf_sharded_shards(const cm_ivf_sharded *h) { return h ? (int)h->dev.size() : 0; }
+int cm_ivf_sharded_shards(const cm_ivf_sharded *h) { return h ? h->ls.W() : 0; }
 int cm_ivf_sharded_trained(const cm_ivf_sharded *h) { return h && h->assigner && h->assigner->ix.trained ? 1 : 0; }
 int64_t cm_ivf_sharded_size(const cm_ivf_sharded *h) {
     int64_t n = 0;
@@ -959,9 +888,9 @@ int64_t cm_ivf_sharded_size(const cm_ivf_sharded *h) {
     return n;
 }
 int cm_ivf_sharded_default_nprobes(const cm_ivf_sharded *h) { return h ? cm_ivf_default_nprobes(h->assigner) : 0; }
-int cm_ivf_sharded_owner(const cm_ivf_sharded *h, int list) { return (h && list >= 0 && list < h->nlist) ? h->owner[(size_t)list] : -1; }
+int cm_ivf_sharded_owner(const cm_ivf_sharded *h, int list) { return (h && list >= 0 && list < h->ls.nlist) ? h->ls.owner[(size_t)list] : -1; }
 int cm_ivf_sharded_shard_size(const cm_ivf_sharded *h, int shard, int64_t *rows) {
-    if (!h || shard < 0 || shard >= (int)h->dev.size() || !rows) return cm::fail(CM_ERR_INVALID_ARG, "bad shard");
+    if (!h || shard < 0 || shard >= h->ls.W() || !rows) return cm::fail(CM_ERR_INVALID_ARG, "bad shard");
     *rows = cm_ivf_size(h->shard[(size_t)shard]);
     return CM_OK;
 }
@@ -983,7 +912,7 @@ int cm_ivf_sharded_train(cm_ivf_sharded *h, const float *rows, int64_t n) {     
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = cm_ivf_train(h->assigner, rows, n);
-    std::vector<float> c((size_t)h->nlist * h->dim);
+    std::vector<float> c((size_t)h->ls.nlist * h->ls.dim);
     if (rc == CM_OK) rc = cm_ivf_get_centroids(h->assigner, c.data());
     for (size_t r = 0; r < h->shard.size() && rc == CM_OK; r++) rc = cm_ivf_set_centroids(h->shard[r], c.data());
     cudaSetDevice(prev);
@@ -1002,42 +931,43 @@ int cm_ivf_sharded_add(cm_ivf_sharded *h, const uint32_t *ids, float *rows, int6
     if (n <= 0) return CM_OK;
     int prev = 0;
     cudaGetDevice(&prev);
-    const int W = (int)h->dev.size();
-    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)h->dim * 4));
+    cm::ListShards &ls = h->ls;
+    const int W = ls.W(), dim = ls.dim;
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)dim * 4));
     std::vector<float> stored;
     std::vector<int32_t> lists((size_t)std::min(slab, n));
     std::vector<std::vector<uint32_t>> sub_ids((size_t)W);
     std::vector<std::vector<int32_t>> sub_lists((size_t)W);
     std::vector<std::vector<float>> sub_rows((size_t)W);
     int rc = CM_OK, rc_zero = CM_OK;
+    std::string zero_msg;
     for (int64_t i0 = 0; i0 < n && rc == CM_OK && rc_zero == CM_OK; i0 += slab) {
         const int64_t m = std::min(slab, n - i0);
-        float *batch = rows + (size_t)i0 * h->dim;
-        if (!writeback) { stored.assign(batch, batch + (size_t)m * h->dim); batch = stored.data(); }
+        float *batch = rows + (size_t)i0 * dim;
+        if (!writeback) { stored.assign(batch, batch + (size_t)m * dim); batch = stored.data(); }
         int rc_a = cm_ivf_add(h->assigner, ids + i0, batch, m, 1, lists.data());      // rows come back preprocessed
         const int64_t good = cm_ivf_size(h->assigner);
-        if (rc_a == CM_ERR_ZERO_VECTOR) rc_zero = rc_a; else rc = rc_a;
-        std::string zero_msg = rc_zero != CM_OK ? std::string(cm_last_error()) : std::string();
+        if (rc_a == CM_ERR_ZERO_VECTOR) { rc_zero = rc_a; zero_msg = cm_last_error(); } else rc = rc_a;
         if (rc == CM_OK) rc = ivfs_clear_vectors(h->assigner);
         for (int r = 0; r < W; r++) { sub_ids[(size_t)r].clear(); sub_lists[(size_t)r].clear(); sub_rows[(size_t)r].clear(); }
         for (int64_t i = 0; i < good && rc == CM_OK; i++) {
             const int32_t l = lists[(size_t)i];
-            const int r = h->owner[(size_t)l];
+            const int r = ls.owner[(size_t)l];
             sub_ids[(size_t)r].push_back(ids[i0 + i]);
             sub_lists[(size_t)r].push_back(l);
-            sub_rows[(size_t)r].insert(sub_rows[(size_t)r].end(), batch + (size_t)i * h->dim, batch + (size_t)(i + 1) * h->dim);
-            h->glob_len[(size_t)l]++;
+            sub_rows[(size_t)r].insert(sub_rows[(size_t)r].end(), batch + (size_t)i * dim, batch + (size_t)(i + 1) * dim);
+            ls.glob_len[(size_t)l]++;
             if (out_lists) out_lists[i0 + i] = l;
         }
         for (int r = 0; r < W && rc == CM_OK; r++)
             if (!sub_ids[(size_t)r].empty())
                 rc = cm_ivf_load_lists(h->shard[(size_t)r], sub_ids[(size_t)r].data(), sub_rows[(size_t)r].data(), sub_lists[(size_t)r].data(),
                                        (int64_t)sub_ids[(size_t)r].size());
-        h->len_dirty = true;
-        if (rc == CM_OK && rc_zero != CM_OK) rc_zero = cm::fail(CM_ERR_ZERO_VECTOR, "%s", zero_msg.c_str());
+        ls.len_dirty = true;
     }
     cudaSetDevice(prev);
-    return rc != CM_OK ? rc : rc_zero;
+    if (rc != CM_OK) return rc;
+    return rc_zero == CM_OK ? CM_OK : cm::fail(CM_ERR_ZERO_VECTOR, "%s", zero_msg.c_str());
 }
 
 int cm_ivf_sharded_remove(cm_ivf_sharded *h, uint32_t id) {      // ivf_index.go:296-330: soft delete wherever the ID lives
@@ -1061,12 +991,12 @@ int cm_ivf_sharded_flush(cm_ivf_sharded *h) {                    // ivf_index.go
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = CM_OK;
-    std::fill(h->glob_len.begin(), h->glob_len.end(), 0);
+    std::fill(h->ls.glob_len.begin(), h->ls.glob_len.end(), 0);
     for (size_t r = 0; r < h->shard.size() && rc == CM_OK; r++) {
         rc = cm_ivf_flush(h->shard[r]);
-        for (int l = 0; l < h->nlist; l++) h->glob_len[(size_t)l] += (long long)h->shard[r]->ix.lists[(size_t)l].size();
+        for (int l = 0; l < h->ls.nlist; l++) h->ls.glob_len[(size_t)l] += (long long)h->shard[r]->ix.lists[(size_t)l].size();
     }
-    h->len_dirty = true;
+    h->ls.len_dirty = true;
     cudaSetDevice(prev);
     return rc;
 }
@@ -1075,46 +1005,40 @@ int cm_ivf_sharded_flush(cm_ivf_sharded *h) {                    // ivf_index.go
 // changed owner moves.  Ties in the reference's order are unaffected: a list moves whole, in its order.
 int cm_ivf_sharded_rebalance(cm_ivf_sharded *h) {
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
-    const int W = (int)h->dev.size();
-    std::vector<int> order((size_t)h->nlist);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->glob_len[(size_t)a] > h->glob_len[(size_t)b]; });
-    std::vector<long long> load((size_t)W, 0);
-    std::vector<int> want((size_t)h->nlist);
-    for (int l : order) {
-        int best = 0;
-        for (int r = 1; r < W; r++) if (load[(size_t)r] < load[(size_t)best]) best = r;
-        want[(size_t)l] = best;
-        load[(size_t)best] += h->glob_len[(size_t)l];
-    }
+    cm::ListShards &ls = h->ls;
+    const int W = ls.W(), dim = ls.dim;
+    const std::vector<int> want = ls.greedy_plan();
+    for (cm_ivf *s : h->shard)
+        if (!s->ix.store.deleted_ids.empty()) return cm::fail(CM_ERR_UNSUPPORTED, "flush before rebalancing");
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = CM_OK;
-    // collect the movers per source shard, append them to their targets, then drop them at the source
+    // movers per source shard are appended to their targets, then the source keeps what stays
     for (int r = 0; r < W && rc == CM_OK; r++) {
         cm::IVFIndex &ix = h->shard[(size_t)r]->ix;
         std::vector<std::vector<int64_t>> pos_to((size_t)W);
-        for (int l = 0; l < h->nlist; l++)
-            if (h->owner[(size_t)l] == r && want[(size_t)l] != r)
+        for (int l = 0; l < ls.nlist; l++)
+            if (ls.owner[(size_t)l] == r && want[(size_t)l] != r)
                 for (uint32_t p : ix.lists[(size_t)l]) pos_to[(size_t)want[(size_t)l]].push_back((int64_t)p);
         bool any = false;
         for (int t = 0; t < W && rc == CM_OK; t++) {
             std::vector<int64_t> &pos = pos_to[(size_t)t];
             if (pos.empty()) continue;
             any = true;
-            if (!ix.store.deleted_ids.empty()) { rc = cm::fail(CM_ERR_UNSUPPORTED, "flush before rebalancing"); break; }
-            std::vector<float> rows(pos.size() * (size_t)h->dim);
+            std::vector<float> rows(pos.size() * (size_t)dim);
             std::vector<uint32_t> ids(pos.size());
             std::vector<int32_t> lo(pos.size());
             rc = cm_ivf_get_rows(h->shard[(size_t)r], pos.data(), (int64_t)pos.size(), rows.data());
             for (size_t i = 0; i < pos.size(); i++) { ids[i] = ix.store.ids_host_mirror[(size_t)pos[i]]; lo[i] = ix.list_of[(size_t)pos[i]]; }
             if (rc == CM_OK) rc = cm_ivf_load_lists(h->shard[(size_t)t], ids.data(), rows.data(), lo.data(), (int64_t)pos.size());
         }
-        if (any && rc == CM_OK) {        // drop the moved vectors at the source: soft-delete by position is not available, so rebuild the rest
+        if (any && rc == CM_OK) {
             std::vector<int64_t> keep;
-            for (int64_t i = 0; i < ix.store.n; i++)
-                if (want[(size_t)ix.list_of[(size_t)i]] == r || h->owner[(size_t)ix.list_of[(size_t)i]] != r) keep.push_back(i);
-            std::vector<float> rows(keep.size() * (size_t)h->dim);
+            for (int64_t i = 0; i < ix.store.n; i++) {
+                const int l = ix.list_of[(size_t)i];
+                if (!(ls.owner[(size_t)l] == r && want[(size_t)l] != r)) keep.push_back(i);      // everything that is not leaving
+            }
+            std::vector<float> rows(keep.size() * (size_t)dim);
             std::vector<uint32_t> ids(keep.size());
             std::vector<int32_t> lo(keep.size());
             if (!keep.empty()) rc = cm_ivf_get_rows(h->shard[(size_t)r], keep.data(), (int64_t)keep.size(), rows.data());
@@ -1123,110 +1047,16 @@ int cm_ivf_sharded_rebalance(cm_ivf_sharded *h) {
             if (rc == CM_OK && !keep.empty()) rc = cm_ivf_load_lists(h->shard[(size_t)r], ids.data(), rows.data(), lo.data(), (int64_t)keep.size());
         }
     }
-    if (rc == CM_OK) h->owner = want;
+    if (rc == CM_OK) ls.owner = want;
     cudaSetDevice(prev);
     return rc;
 }
 
-static int ivfs_shard_enqueue(cm_ivf_sharded *h, int r, const float *q_lead_dev, int64_t nq, const cm_search_params *p, int64_t K) {
-    cudaSetDevice(h->dev[(size_t)r]);
-    cm_ivf_sharded::Buf &b = h->buf[(size_t)r];
-    const bool direct = h->direct[(size_t)r] != 0;
-    if (!direct && b.cap_q < nq * h->dim) {
-        cudaFree(b.q); b.q = nullptr;
-        CM_CUDA(cudaMalloc(&b.q, (size_t)nq * h->dim * 4));
-        b.cap_q = nq * h->dim;
-    }
-    if (!direct && b.cap_o < nq * K) {
-        cudaFree(b.ids); cudaFree(b.gno); cudaFree(b.sc); cudaFree(b.cnt);
-        b.ids = b.gno = nullptr; b.sc = nullptr; b.cnt = nullptr;
-        CM_CUDA(cudaMalloc(&b.ids, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&b.gno, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&b.sc, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&b.cnt, (size_t)nq * 8));
-        b.cap_o = nq * K;
-    }
-    cudaStream_t s = h->st[(size_t)r];
-    CM_CUDA(cudaStreamWaitEvent(s, h->start, 0));
-    const float *q_r = q_lead_dev;
-    if (!direct) {
-        CM_CUDA(cudaMemcpyPeerAsync(b.q, h->dev[(size_t)r], q_lead_dev, h->dev[0], (size_t)nq * h->dim * 4, s));
-        q_r = b.q;
-    }
-    const size_t slot = (size_t)r * nq * K;
-    uint32_t *o_ids = direct ? h->g_ids + slot : b.ids, *o_gno = direct ? h->g_gno + slot : b.gno;
-    float *o_sc = direct ? h->g_sc + slot : b.sc;
-    int64_t *o_cnt = direct ? h->g_cnt + (size_t)r * nq : b.cnt;
-    cm_search_params pr = *p;
-    pr.k = K;                 // clamped to what this shard can hold inside
-    CM_TRY(cm::ivf_search_device(h->shard[(size_t)r]->ix, q_r, nq, &pr, K, o_ids, o_sc, nullptr, o_cnt, s, false,
-                                 h->glob_len_dev[(size_t)r], o_gno));
-    if (!direct) {
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_ids + slot, h->dev[0], b.ids, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_gno + slot, h->dev[0], b.gno, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_sc + slot, h->dev[0], b.sc, h->dev[(size_t)r], (size_t)nq * K * 4, s));
-        CM_CUDA(cudaMemcpyPeerAsync(h->g_cnt + (size_t)r * nq, h->dev[0], b.cnt, h->dev[(size_t)r], (size_t)nq * 8, s));
-    }
-    CM_CUDA(cudaEventRecord(h->done[(size_t)r], s));
-    return CM_OK;
-}
-
-// effective k of a sharded search: sanitizeK against the most candidates nprobes lists can hold (global lengths)
-static int64_t ivfs_effective_k(const cm_ivf_sharded *h, const cm_search_params *p, int *nprobes_out) {
-    int nprobes = p->nprobes;
-    if (nprobes <= 0 || nprobes > h->nlist) nprobes = h->nlist;
-    std::vector<long long> len = h->glob_len;
-    std::sort(len.begin(), len.end(), std::greater<long long>());
-    int64_t bound = 0;
-    for (int i = 0; i < nprobes; i++) bound += len[(size_t)i];
-    if (nprobes_out) *nprobes_out = nprobes;
-    return (p->k <= 0 || p->k > bound) ? bound : p->k;
-}
-
-static int ivfs_search_impl(cm_ivf_sharded *h, const float *q_lead_dev, int64_t nq, const cm_search_params *p, int64_t K,
-                            cudaStream_t lead) {
-    const int W = (int)h->dev.size();
-    if ((size_t)W * (size_t)K * 8 > cm::max_smem_optin())
-        return cm::fail(CM_ERR_UNSUPPORTED, "%d list shards x k=%lld too large for the shard merge", W, (long long)K);
-    if (h->len_dirty) {
-        for (int r = 0; r < W; r++) {
-            cudaSetDevice(h->dev[(size_t)r]);
-            CM_CUDA(cudaMemcpy(h->glob_len_dev[(size_t)r], h->glob_len.data(), (size_t)h->nlist * sizeof(long long), cudaMemcpyHostToDevice));
-        }
-        h->len_dirty = false;
-    }
-    cudaSetDevice(h->dev[0]);
-    if (h->cap_g < (int64_t)W * nq * K) {
-        cudaFree(h->g_ids); cudaFree(h->g_gno); cudaFree(h->g_sc); cudaFree(h->g_cnt);
-        h->g_ids = h->g_gno = nullptr; h->g_sc = nullptr; h->g_cnt = nullptr;
-        CM_CUDA(cudaMalloc(&h->g_ids, (size_t)W * nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->g_gno, (size_t)W * nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->g_sc, (size_t)W * nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->g_cnt, (size_t)W * nq * 8));
-        h->cap_g = (int64_t)W * nq * K;
-    }
-    if (h->cap_m < nq * K) {
-        cudaFree(h->m_ids); cudaFree(h->m_sc); cudaFree(h->m_cnt);
-        h->m_ids = nullptr; h->m_sc = nullptr; h->m_cnt = nullptr;
-        CM_CUDA(cudaMalloc(&h->m_ids, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->m_sc, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->m_cnt, (size_t)nq * 8));
-        h->cap_m = nq * K;
-    }
-    CM_CUDA(cudaEventRecord(h->start, lead));
-    const bool threaded = W > 1 && h->workers.size() == (size_t)W;
-    for (int r = 1; r < W && threaded; r++) h->workers[(size_t)r]->post([=] { return ivfs_shard_enqueue(h, r, q_lead_dev, nq, p, K); });
-    int rc = CM_OK;
-    for (int r = 0; r < (threaded ? 1 : W) && rc == CM_OK; r++) rc = ivfs_shard_enqueue(h, r, q_lead_dev, nq, p, K);
-    for (int r = 1; r < W && threaded; r++) {
-        std::string msg;
-        const int rc_r = h->workers[(size_t)r]->wait(&msg);
-        if (rc_r != CM_OK && rc == CM_OK) rc = cm::fail(rc_r, "%s", msg.c_str());
-    }
-    CM_TRY(rc);
-    cudaSetDevice(h->dev[0]);
-    for (int r = 0; r < W; r++) CM_CUDA(cudaStreamWaitEvent(lead, h->done[(size_t)r], 0));
-    return cm::launch_merge_keyed_shards(h->g_ids, h->g_sc, h->g_gno, h->g_cnt, W, nq, K, (int)K, K, h->m_ids, h->m_sc, h->m_cnt, lead);
+static cm::ListShards::ShardSearch ivfs_search_fn(cm_ivf_sharded *h) {
+    return [h](int r, const float *q, int64_t nq, const cm_search_params *p, int64_t K, uint32_t *o_ids, float *o_sc, int64_t *o_cnt,
+               cudaStream_t s, const long long *glob_len, uint32_t *o_gno) {
+        return cm::ivf_search_device(h->shard[(size_t)r]->ix, q, nq, p, K, o_ids, o_sc, nullptr, o_cnt, s, false, glob_len, o_gno);
+    };
 }
 
 // queries / outputs on devices[0], enqueued on `stream`; never synchronises.  A zero query under cosine is NOT detected
@@ -1237,29 +1067,10 @@ int cm_ivf_sharded_search_device(cm_ivf_sharded *h, const float *queries_dev, in
     if (!h || !p || (nq > 0 && (!queries_dev || !out_ids_dev || !out_scores_dev || !out_counts_dev)))
         return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     if (!cm_ivf_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
-    if (dim != h->dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->dim, dim);
+    if (dim != h->ls.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ls.dim, dim);
     if (nq <= 0) return CM_OK;
-    std::lock_guard<std::mutex> lk(h->search_mu);
-    const int64_t K = ivfs_effective_k(h, p, nullptr);
-    if (out_stride < K) return cm::fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)K);
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaStream_t lead = (cudaStream_t)stream;
-    int rc = CM_OK;
-    cudaSetDevice(h->dev[0]);
-    if (K == 0) {
-        rc = cm::launch_fill_counts(out_counts_dev, nq, 0, lead);
-    } else {
-        rc = ivfs_search_impl(h, queries_dev, nq, p, K, lead);
-        if (rc == CM_OK) {
-            cudaSetDevice(h->dev[0]);
-            cudaMemcpy2DAsync(out_ids_dev, (size_t)out_stride * 4, h->m_ids, (size_t)K * 4, (size_t)K * 4, (size_t)nq, cudaMemcpyDeviceToDevice, lead);
-            cudaMemcpy2DAsync(out_scores_dev, (size_t)out_stride * 4, h->m_sc, (size_t)K * 4, (size_t)K * 4, (size_t)nq, cudaMemcpyDeviceToDevice, lead);
-            cudaMemcpyAsync(out_counts_dev, h->m_cnt, (size_t)nq * 8, cudaMemcpyDeviceToDevice, lead);
-        }
-    }
-    cudaSetDevice(prev);
-    return rc;
+    return h->ls.search_device(ivfs_search_fn(h), queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_counts_dev,
+                               (cudaStream_t)stream);
 }
 
 // nq independent searchSingleQuery calls (ivf_index_search.go:217-322) against the whole list-sharded index
@@ -1268,41 +1079,12 @@ int cm_ivf_sharded_search(cm_ivf_sharded *h, const float *queries, int64_t nq, i
     if (!h || !p || (nq > 0 && (!queries || !out_ids || !out_scores || !out_counts)))
         return cm::fail(CM_ERR_INVALID_ARG, "null argument");
     if (!cm_ivf_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
-    if (dim != h->dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->dim, dim);
+    if (dim != h->ls.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ls.dim, dim);
     if (nq <= 0) return CM_OK;
-    if (h->metric == CM_COSINE)                      // Distance.Preprocess fails on a zero query (distance.go:269-290)
-        for (int64_t q = 0; q < nq; q++) {
-            float ss = 0.0f;
-            for (int j = 0; j < dim; j++) ss += queries[(size_t)q * dim + j] * queries[(size_t)q * dim + j];
-            if (ss == 0.0f) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)q);
-        }
-    std::lock_guard<std::mutex> lk(h->search_mu);
-    const int64_t K = ivfs_effective_k(h, p, nullptr);
-    if (out_stride < K) return cm::fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)K);
-    if (K == 0) { memset(out_counts, 0, (size_t)nq * 8); return CM_OK; }
+    int rc = h->ls.search_host(ivfs_search_fn(h), queries, nq, p, out_stride, out_ids, out_scores, out_counts);
     int prev = 0;
     cudaGetDevice(&prev);
-    cudaSetDevice(h->dev[0]);
-    cudaStream_t lead = h->st[0];
-    int rc = CM_OK;
-    if (h->cap_ql < nq * dim) {
-        cudaFree(h->q_lead); h->q_lead = nullptr;
-        if (cudaMalloc(&h->q_lead, (size_t)nq * dim * 4) != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "query buffer allocation failed");
-        else h->cap_ql = nq * dim;
-    }
-    if (rc == CM_OK) {
-        cudaMemcpyAsync(h->q_lead, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, lead);
-        rc = ivfs_search_impl(h, h->q_lead, nq, p, K, lead);
-    }
-    if (rc == CM_OK) {
-        cudaSetDevice(h->dev[0]);
-        cudaMemcpy2DAsync(out_ids, (size_t)out_stride * 4, h->m_ids, (size_t)K * 4, (size_t)K * 4, (size_t)nq, cudaMemcpyDeviceToHost, lead);
-        cudaMemcpy2DAsync(out_scores, (size_t)out_stride * 4, h->m_sc, (size_t)K * 4, (size_t)K * 4, (size_t)nq, cudaMemcpyDeviceToHost, lead);
-        cudaMemcpyAsync(out_counts, h->m_cnt, (size_t)nq * 8, cudaMemcpyDeviceToHost, lead);
-        cudaError_t e = cudaStreamSynchronize(lead);
-        if (e != cudaSuccess) rc = cm::fail(CM_ERR_CUDA, "sharded ivf search: %s", cudaGetErrorString(e));
-    }
-    for (size_t r = 0; r < h->shard.size(); r++) h->last_scanned[r] = cm_ivf_last_scanned(h->shard[r]);
+    for (size_t r = 0; r < h->shard.size(); r++) h->ls.last_scanned[r] = cm_ivf_last_scanned(h->shard[r]);
     cudaSetDevice(prev);
     return rc;
 }
@@ -1310,7 +1092,7 @@ int cm_ivf_sharded_search(cm_ivf_sharded *h, const float *queries, int64_t nq, i
 // vectors each shard scanned in the last host search (all queries): the balance of the list assignment
 int cm_ivf_sharded_last_scanned(const cm_ivf_sharded *h, int64_t *per_shard) {
     if (!h || !per_shard) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
-    for (size_t r = 0; r < h->shard.size(); r++) per_shard[r] = h->last_scanned[r];
+    for (size_t r = 0; r < h->shard.size(); r++) per_shard[r] = h->ls.last_scanned[r];
     return CM_OK;
 }
 

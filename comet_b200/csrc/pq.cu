@@ -22,12 +22,14 @@
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <string>
 #include <unordered_set>
 #include <vector>
 
 #include "flat_index.cuh"
 #include "flat_kernels.cuh"
 #include "kmeans.cuh"
+#include "list_shards.cuh"
 #include "select.cuh"
 #include "wire.cuh"
 
@@ -448,11 +450,13 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     if (tid == 0) part_counts[part] = mcount;
 }
 
-// candidate numbers of the final lists -> store positions and ids
+// candidate numbers of the final lists -> store positions and ids; for list shards (cm_ivfpq_sharded_*) also the
+// candidate's number in the reference's append loop over ALL probed lists, from the global list lengths
 __global__ void adc_emit_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
                                 const long long *__restrict__ list_off, const uint32_t *__restrict__ members, int nprobes,
                                 const uint32_t *__restrict__ row_ids, long long out_stride, uint32_t *__restrict__ out_ids,
-                                long long *__restrict__ out_pos, const long long *__restrict__ out_counts) {
+                                long long *__restrict__ out_pos, const long long *__restrict__ out_counts,
+                                const long long *__restrict__ glob_len, uint32_t *__restrict__ out_gno) {
     const int q = blockIdx.x;
     const long long m = out_counts[q];
     for (long long i = threadIdx.x; i < m; i += blockDim.x) {
@@ -461,13 +465,18 @@ __global__ void adc_emit_kernel(const long long *__restrict__ probe_list, const 
         uint32_t pos;
         if (members) {
             const long long *qo = q_off + (size_t)q * (nprobes + 1);
+            const long long *pl = probe_list + (size_t)q * nprobes;
             int lo = 0, hi = nprobes;
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
                 if (qo[mid] <= c) lo = mid; else hi = mid;
             }
-            long long l = probe_list[(size_t)q * nprobes + lo];
-            pos = members[list_off[l] + (c - qo[lo])];
+            pos = members[list_off[pl[lo]] + (c - qo[lo])];
+            if (out_gno) {
+                long long before = 0;
+                for (int j = 0; j < lo; j++) before += glob_len[pl[j]];
+                out_gno[o] = (uint32_t)(before + (c - qo[lo]));
+            }
         } else {
             pos = (uint32_t)c;
         }
@@ -527,7 +536,7 @@ static int build_skip(CodeStore &S, const cm_search_params *p, const uint8_t **s
 // nq independent searchSingleQuery calls (PQ when ix.nlist == 0, else IVFPQ)
 static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,
                              uint32_t *out_ids, float *out_scores, int64_t *out_pos, int64_t *out_counts, cudaStream_t st,
-                             bool check_zero) {
+                             bool check_zero, const long long *glob_len = nullptr, uint32_t *out_gno = nullptr) {
     WsScope ws(st);
     if (nq <= 0) return CM_OK;
     const bool ivf = ix.nlist > 0;
@@ -560,7 +569,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     CM_TRY(prepare_queries(ix.metric, ix.dim, ix.ld, q_dev, nq, check_zero, &qp, st));
     ws.adopt(qp);
     if (bound_c == 0 || k_eff == 0) {
-        CM_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)nq * sizeof(int64_t), st));
+        CM_TRY(launch_fill_counts(out_counts, nq, 0, st));       // a kernel: the counts may live on a peer device (list shards)
         return CM_OK;
     }
     bool fma = rounding_mode() == CM_ROUND_FMA;
@@ -622,7 +631,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         CM_ADC_CASE(0) CM_ADC_CASE(1) CM_ADC_CASE(2) CM_ADC_CASE(4) CM_ADC_CASE(6) CM_ADC_CASE(8)
     }
 #undef CM_ADC_CASE
-    CM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CM_TRY(set_dyn_smem((const void *)kern, smem));      // only ever grows: concurrent searches ask for different sizes
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
         CM_CUDA(cudaMemsetAsync(pc, 0, (size_t)m * parts * 4, st));
@@ -644,7 +653,8 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
                                                      ivf ? ix.members : nullptr, nprobes, S.ids, (long long)out_stride,
                                                      out_ids + (size_t)q0 * out_stride,
                                                      out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,
-                                                     (const long long *)(out_counts + q0));
+                                                     (const long long *)(out_counts + q0), glob_len,
+                                                     out_gno ? out_gno + (size_t)q0 * out_stride : nullptr);
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
@@ -1251,5 +1261,296 @@ int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, in
 CM_WIRE_ABI(cm_pq, cm_pq)
 CM_WIRE_ABI(cm_ivfpq, cm_ivfpq)
 #undef CM_WIRE_ABI
+
+// ================================================================================================
+// IVFPQ list shards over the GPUs of one box, ONE host process: cm_ivfpq_sharded_*.  Every shard holds the
+// centroids and the residual codebooks (replicated: they are small) and the code lists it owns; Add encodes once on
+// devices[0] and routes the codes.  Search driver, global candidate numbers and merge: list_shards.cuh.
+// ================================================================================================
+struct cm_ivfpq_sharded {
+    cm::ListShards ls;
+    int M = 0, nbits = 0;
+    std::vector<cm_ivfpq *> shard;
+    cm_ivfpq *assigner = nullptr;          // devices[0]: trained state only; Add preprocesses, assigns and encodes here
+};
+
+static int ivfpqs_clear_vectors(cm::PQCore &ix) {          // drop the codes, keep the trained state
+    if (ix.store.deleted && ix.store.cap > 0) CM_CUDA(cudaMemset(ix.store.deleted, 0, (size_t)ix.store.cap));
+    ix.store.n = 0;
+    ix.store.n_deleted_rows = 0;
+    ix.store.ids_host.clear();
+    ix.store.deleted_ids.clear();
+    for (auto &l : ix.lists) l.clear();
+    ix.list_of.clear();
+    ix.csr_dirty = true;
+    return CM_OK;
+}
+
+int cm_ivfpq_sharded_destroy(cm_ivfpq_sharded *h) {
+    if (!h) return CM_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    h->ls.workers.clear();
+    for (size_t r = 0; r < h->shard.size(); r++)
+        if (h->shard[r]) { cudaSetDevice(h->ls.dev[r]); cm_ivfpq_destroy(h->shard[r]); }
+    if (h->assigner) { cudaSetDevice(h->ls.dev[0]); cm_ivfpq_destroy(h->assigner); }
+    h->ls.destroy();
+    cudaSetDevice(prev);
+    delete h;
+    return CM_OK;
+}
+
+int cm_ivfpq_sharded_create(int dim, int metric, int nlist, int M, int nbits, const int *devices, int n_devices,
+                            cm_ivfpq_sharded **out) {
+    if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices <= 0) return cm::fail(CM_ERR_INVALID_ARG, "need 1..64 devices");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cm_ivfpq_sharded *h = new cm_ivfpq_sharded();
+    h->M = M; h->nbits = nbits;
+    // the first shard validates the parameters (NewIVFPQIndex, ivfpq_index.go:114-160) before anything else is set up
+    h->shard.assign((size_t)n_devices, nullptr);
+    int rc = CM_OK;
+    for (int r = 0; r < n_devices && rc == CM_OK; r++) {
+        if (cudaSetDevice(devices[r]) != cudaSuccess) { rc = cm::fail(CM_ERR_INVALID_ARG, "no CUDA device %d", devices[r]); break; }
+        rc = cm_ivfpq_create(dim, metric, nlist, M, nbits, &h->shard[(size_t)r]);
+    }
+    if (rc == CM_OK) {
+        cudaSetDevice(devices[0]);
+        rc = cm_ivfpq_create(dim, metric, nlist, M, nbits, &h->assigner);
+    }
+    if (rc == CM_OK) rc = h->ls.init(dim, nlist, metric, devices, n_devices);
+    cudaSetDevice(prev);
+    if (rc != CM_OK) {
+        std::string msg = cm_last_error();
+        if (h->ls.dev.empty()) {          // init never ran: free the shards by hand
+            for (size_t r = 0; r < h->shard.size(); r++) if (h->shard[r]) { cudaSetDevice(devices[r]); cm_ivfpq_destroy(h->shard[r]); }
+            if (h->assigner) { cudaSetDevice(devices[0]); cm_ivfpq_destroy(h->assigner); }
+            cudaSetDevice(prev);
+            delete h;
+        } else {
+            cm_ivfpq_sharded_destroy(h);
+        }
+        return cm::fail(rc, "%s", msg.c_str());
+    }
+    *out = h;
+    return CM_OK;
+}
+
+int cm_ivfpq_sharded_shards(const cm_ivfpq_sharded *h) { return h ? h->ls.W() : 0; }
+int cm_ivfpq_sharded_trained(const cm_ivfpq_sharded *h) { return h && h->assigner && h->assigner->ix.trained ? 1 : 0; }
+int64_t cm_ivfpq_sharded_size(const cm_ivfpq_sharded *h) {
+    int64_t n = 0;
+    if (h) for (cm_ivfpq *s : h->shard) n += cm_ivfpq_size(s);
+    return n;
+}
+int cm_ivfpq_sharded_default_nprobes(const cm_ivfpq_sharded *h) { return h ? cm_ivfpq_default_nprobes(h->assigner) : 0; }
+int cm_ivfpq_sharded_owner(const cm_ivfpq_sharded *h, int list) { return (h && list >= 0 && list < h->ls.nlist) ? h->ls.owner[(size_t)list] : -1; }
+int cm_ivfpq_sharded_shard_size(const cm_ivfpq_sharded *h, int shard, int64_t *rows) {
+    if (!h || shard < 0 || shard >= h->ls.W() || !rows) return cm::fail(CM_ERR_INVALID_ARG, "bad shard");
+    *rows = cm_ivfpq_size(h->shard[(size_t)shard]);
+    return CM_OK;
+}
+
+int cm_ivfpq_sharded_set_trained(cm_ivfpq_sharded *h, const float *centroids, const float *codebooks) {
+    if (!h || !centroids || !codebooks) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (cm_ivfpq_sharded_size(h) > 0) return cm::fail(CM_ERR_INVALID_ARG, "cannot replace the trained state of a non-empty index");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = cm_ivfpq_set_trained(h->assigner, centroids, codebooks);
+    for (size_t r = 0; r < h->shard.size() && rc == CM_OK; r++) rc = cm_ivfpq_set_trained(h->shard[r], centroids, codebooks);
+    cudaSetDevice(prev);
+    return rc;
+}
+int cm_ivfpq_sharded_get_trained(const cm_ivfpq_sharded *h, float *centroids, float *codebooks) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    return cm_ivfpq_get_trained(h->assigner, centroids, codebooks);
+}
+int cm_ivfpq_sharded_train(cm_ivfpq_sharded *h, const float *rows, int64_t n) {     // IVFPQIndex.Train (ivfpq_index.go:180-259) on devices[0]
+    if (!h || (n > 0 && !rows)) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (cm_ivfpq_sharded_size(h) > 0) return cm::fail(CM_ERR_UNSUPPORTED, "retraining a non-empty index is not supported");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = cm_ivfpq_train(h->assigner, rows, n);
+    const cm::PQCore &a = h->assigner->ix;
+    std::vector<float> cent((size_t)a.nlist * a.dim), books((size_t)a.M * a.Ksub * a.dsub);
+    if (rc == CM_OK) rc = cm_ivfpq_get_trained(h->assigner, cent.data(), books.data());
+    for (size_t r = 0; r < h->shard.size() && rc == CM_OK; r++) rc = cm_ivfpq_set_trained(h->shard[r], cent.data(), books.data());
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// n successive IVFPQIndex.Add calls (ivfpq_index.go:279-319): preprocess, nearest centroid, residual, encode -- once, on
+// devices[0]; every (id, code) then goes to the shard that owns its list, lists keep arrival order.
+int cm_ivfpq_sharded_add(cm_ivfpq_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists) {
+    if (!h || (n > 0 && (!ids || !rows))) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!cm_ivfpq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before adding");
+    if (n <= 0) return CM_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cm::ListShards &ls = h->ls;
+    const int W = ls.W(), dim = ls.dim, M = h->M;
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)dim * 4));
+    std::vector<int32_t> lists((size_t)std::min(slab, n));
+    std::vector<uint8_t> codes;
+    std::vector<std::vector<uint32_t>> sub_ids((size_t)W);
+    std::vector<std::vector<int32_t>> sub_lists((size_t)W);
+    std::vector<std::vector<uint8_t>> sub_codes((size_t)W);
+    int rc = CM_OK, rc_zero = CM_OK;
+    std::string zero_msg;
+    for (int64_t i0 = 0; i0 < n && rc == CM_OK && rc_zero == CM_OK; i0 += slab) {
+        const int64_t m = std::min(slab, n - i0);
+        int rc_a = cm_ivfpq_add(h->assigner, ids + i0, rows + (size_t)i0 * dim, m, writeback, lists.data());
+        const int64_t good = cm_ivfpq_size(h->assigner);
+        if (rc_a == CM_ERR_ZERO_VECTOR) { rc_zero = rc_a; zero_msg = cm_last_error(); } else rc = rc_a;
+        codes.resize((size_t)std::max<int64_t>(good, 1) * M);
+        if (rc == CM_OK && good > 0) rc = cm_ivfpq_get_codes(h->assigner, 0, good, codes.data());
+        if (rc == CM_OK) rc = ivfpqs_clear_vectors(h->assigner->ix);
+        for (int r = 0; r < W; r++) { sub_ids[(size_t)r].clear(); sub_lists[(size_t)r].clear(); sub_codes[(size_t)r].clear(); }
+        for (int64_t i = 0; i < good && rc == CM_OK; i++) {
+            const int32_t l = lists[(size_t)i];
+            const int r = ls.owner[(size_t)l];
+            sub_ids[(size_t)r].push_back(ids[i0 + i]);
+            sub_lists[(size_t)r].push_back(l);
+            sub_codes[(size_t)r].insert(sub_codes[(size_t)r].end(), codes.begin() + (size_t)i * M, codes.begin() + (size_t)(i + 1) * M);
+            ls.glob_len[(size_t)l]++;
+            if (out_lists) out_lists[i0 + i] = l;
+        }
+        for (int r = 0; r < W && rc == CM_OK; r++)
+            if (!sub_ids[(size_t)r].empty())
+                rc = cm_ivfpq_load_codes(h->shard[(size_t)r], sub_ids[(size_t)r].data(), sub_codes[(size_t)r].data(), sub_lists[(size_t)r].data(),
+                                         (int64_t)sub_ids[(size_t)r].size());
+        ls.len_dirty = true;
+    }
+    cudaSetDevice(prev);
+    if (rc != CM_OK) return rc;
+    return rc_zero == CM_OK ? CM_OK : cm::fail(CM_ERR_ZERO_VECTOR, "%s", zero_msg.c_str());
+}
+
+int cm_ivfpq_sharded_remove(cm_ivfpq_sharded *h, uint32_t id) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    bool found = false, already = false;
+    for (cm_ivfpq *s : h->shard) {
+        int rc = cm_ivfpq_remove(s, id);
+        if (rc == CM_OK) found = true;
+        else if (rc == CM_ERR_NOT_FOUND && strstr(cm_last_error(), "already")) already = true;
+        else if (rc != CM_ERR_NOT_FOUND) { cudaSetDevice(prev); return rc; }
+    }
+    cudaSetDevice(prev);
+    if (found) return CM_OK;
+    return cm::fail(CM_ERR_NOT_FOUND, already ? "vector with ID %u already deleted" : "vector with ID %u not found", id);
+}
+
+int cm_ivfpq_sharded_flush(cm_ivfpq_sharded *h) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = CM_OK;
+    std::fill(h->ls.glob_len.begin(), h->ls.glob_len.end(), 0);
+    for (size_t r = 0; r < h->shard.size() && rc == CM_OK; r++) {
+        rc = cm_ivfpq_flush(h->shard[r]);
+        for (int l = 0; l < h->ls.nlist; l++) h->ls.glob_len[(size_t)l] += (long long)h->shard[r]->ix.lists[(size_t)l].size();
+    }
+    h->ls.len_dirty = true;
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// greedy-by-length list assignment; lists that change owner move whole (codes and ids), in their order
+int cm_ivfpq_sharded_rebalance(cm_ivfpq_sharded *h) {
+    if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
+    cm::ListShards &ls = h->ls;
+    const int W = ls.W(), M = h->M;
+    const std::vector<int> want = ls.greedy_plan();
+    for (cm_ivfpq *s : h->shard)
+        if (!s->ix.store.deleted_ids.empty()) return cm::fail(CM_ERR_UNSUPPORTED, "flush before rebalancing");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = CM_OK;
+    for (int r = 0; r < W && rc == CM_OK; r++) {
+        cm::PQCore &ix = h->shard[(size_t)r]->ix;
+        const int64_t n = ix.store.n;
+        bool any = false;
+        for (int l = 0; l < ls.nlist && !any; l++) any = ls.owner[(size_t)l] == r && want[(size_t)l] != r && !ix.lists[(size_t)l].empty();
+        if (!any) continue;
+        std::vector<uint8_t> all((size_t)n * M);
+        rc = cm_ivfpq_get_codes(h->shard[(size_t)r], 0, n, all.data());
+        if (rc != CM_OK) break;
+        const std::vector<uint32_t> ids_all = ix.store.ids_host;
+        const std::vector<int32_t> lo_all = ix.list_of;
+        const std::vector<std::vector<uint32_t>> lists_all = ix.lists;
+        // target t receives the positions of the lists moving to it (list by list, each in its order); r keeps the rest
+        for (int t = 0; t < W && rc == CM_OK; t++) {
+            std::vector<uint32_t> ids;
+            std::vector<int32_t> lo;
+            std::vector<uint8_t> codes;
+            if (t == r) {
+                for (int64_t i = 0; i < n; i++) {
+                    const int l = lo_all[(size_t)i];
+                    if (ls.owner[(size_t)l] == r && want[(size_t)l] != r) continue;
+                    ids.push_back(ids_all[(size_t)i]); lo.push_back(l);
+                    codes.insert(codes.end(), all.begin() + (size_t)i * M, all.begin() + (size_t)(i + 1) * M);
+                }
+                rc = ivfpqs_clear_vectors(ix);
+            } else {
+                for (int l = 0; l < ls.nlist; l++)
+                    if (ls.owner[(size_t)l] == r && want[(size_t)l] == t)
+                        for (uint32_t pos : lists_all[(size_t)l]) {
+                            ids.push_back(ids_all[pos]); lo.push_back(l);
+                            codes.insert(codes.end(), all.begin() + (size_t)pos * M, all.begin() + (size_t)(pos + 1) * M);
+                        }
+            }
+            if (rc == CM_OK && !ids.empty())
+                rc = cm_ivfpq_load_codes(h->shard[(size_t)t], ids.data(), codes.data(), lo.data(), (int64_t)ids.size());
+        }
+    }
+    if (rc == CM_OK) ls.owner = want;
+    cudaSetDevice(prev);
+    return rc;
+}
+
+static cm::ListShards::ShardSearch ivfpqs_search_fn(cm_ivfpq_sharded *h) {
+    return [h](int r, const float *q, int64_t nq, const cm_search_params *p, int64_t K, uint32_t *o_ids, float *o_sc, int64_t *o_cnt,
+               cudaStream_t s, const long long *glob_len, uint32_t *o_gno) {
+        return cm::adc_search_device(h->shard[(size_t)r]->ix, q, nq, p, K, o_ids, o_sc, nullptr, o_cnt, s, false, glob_len, o_gno);
+    };
+}
+
+int cm_ivfpq_sharded_search_device(cm_ivfpq_sharded *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                                   int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_counts_dev,
+                                   void *stream) {
+    if (!h || !p || (nq > 0 && (!queries_dev || !out_ids_dev || !out_scores_dev || !out_counts_dev)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!cm_ivfpq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
+    if (dim != h->ls.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ls.dim, dim);
+    if (nq <= 0) return CM_OK;
+    return h->ls.search_device(ivfpqs_search_fn(h), queries_dev, nq, p, out_stride, out_ids_dev, out_scores_dev, out_counts_dev,
+                               (cudaStream_t)stream);
+}
+
+// nq independent searchSingleQuery calls (ivfpq_index_search.go:231-390) against the whole list-sharded index
+int cm_ivfpq_sharded_search(cm_ivfpq_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                            int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_counts) {
+    if (!h || !p || (nq > 0 && (!queries || !out_ids || !out_scores || !out_counts)))
+        return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (!cm_ivfpq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before searching");
+    if (dim != h->ls.dim) return cm::fail(CM_ERR_DIM_MISMATCH, "query dimension mismatch: expected %d, got %d", h->ls.dim, dim);
+    if (nq <= 0) return CM_OK;
+    int rc = h->ls.search_host(ivfpqs_search_fn(h), queries, nq, p, out_stride, out_ids, out_scores, out_counts);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (size_t r = 0; r < h->shard.size(); r++) h->ls.last_scanned[r] = cm_ivfpq_last_scanned(h->shard[r]);
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int cm_ivfpq_sharded_last_scanned(const cm_ivfpq_sharded *h, int64_t *per_shard) {
+    if (!h || !per_shard) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    for (size_t r = 0; r < h->shard.size(); r++) per_shard[r] = h->ls.last_scanned[r];
+    return CM_OK;
+}
 
 }  // extern "C"

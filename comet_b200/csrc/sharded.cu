@@ -49,7 +49,7 @@ struct cm_flat_sharded {
     // per-search buffers, grown on demand (shard side: on its device; gather side: on the leader)
     struct Buf {
         float *q = nullptr; uint32_t *ids = nullptr; float *sc = nullptr; int64_t *cnt = nullptr;
-        int64_t cap_q = 0, cap_o = 0;
+        int64_t cap_q = 0, cap_o = 0, cap_n = 0;
     };
     std::vector<Buf> buf;
     uint32_t *g_ids = nullptr; float *g_sc = nullptr; int64_t *g_cnt = nullptr;      // [W][nq][K], [W][nq]
@@ -322,12 +322,18 @@ static int shard_enqueue(cm_flat_sharded *h, int r, const float *q_lead_dev, int
         b.cap_q = nq * h->dim;
     }
     if (!h->direct[(size_t)r] && b.cap_o < nq * K) {
-        cudaFree(b.ids); cudaFree(b.sc); cudaFree(b.cnt);
-        b.ids = nullptr; b.sc = nullptr; b.cnt = nullptr;
+        cudaFree(b.ids); cudaFree(b.sc);
+        b.ids = nullptr; b.sc = nullptr;
+        b.cap_o = 0;
         CM_CUDA(cudaMalloc(&b.ids, (size_t)nq * K * 4));
         CM_CUDA(cudaMalloc(&b.sc, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&b.cnt, (size_t)nq * 8));
         b.cap_o = nq * K;
+    }
+    if (!h->direct[(size_t)r] && b.cap_n < nq) {
+        cudaFree(b.cnt); b.cnt = nullptr;
+        b.cap_n = 0;
+        CM_CUDA(cudaMalloc(&b.cnt, (size_t)nq * 8));
+        b.cap_n = nq;
     }
     cudaStream_t s = h->st[(size_t)r];
     CM_CUDA(cudaStreamWaitEvent(s, h->start, 0));
@@ -368,21 +374,29 @@ static int sharded_search_impl(cm_flat_sharded *h, const float *q_lead_dev, int6
     const int W = (int)h->dev.size();
     h->bytes_exchanged = 0;
     cudaSetDevice(h->dev[0]);
-    CM_TRY(cm::grow((void **)&h->g_ids, &h->cap_g, (int64_t)W * nq * K, 8));       // ids + scores share the element count
-    if (!h->g_sc || h->cap_gc < (int64_t)W * nq * K) {
-        cudaFree(h->g_sc); h->g_sc = nullptr;
+    if (h->cap_g < (int64_t)W * nq * K) {
+        cudaFree(h->g_ids); cudaFree(h->g_sc);
+        h->g_ids = nullptr; h->g_sc = nullptr;
+        h->cap_g = 0;
+        CM_CUDA(cudaMalloc(&h->g_ids, (size_t)W * nq * K * 4));
         CM_CUDA(cudaMalloc(&h->g_sc, (size_t)W * nq * K * 4));
-        cudaFree(h->g_cnt); h->g_cnt = nullptr;
-        CM_CUDA(cudaMalloc(&h->g_cnt, (size_t)W * nq * 8));
-        h->cap_gc = (int64_t)W * nq * K;
+        h->cap_g = (int64_t)W * nq * K;
     }
     if (h->cap_m < nq * K) {
-        cudaFree(h->m_ids); cudaFree(h->m_sc); cudaFree(h->m_cnt);
-        h->m_ids = nullptr; h->m_sc = nullptr; h->m_cnt = nullptr;
+        cudaFree(h->m_ids); cudaFree(h->m_sc);
+        h->m_ids = nullptr; h->m_sc = nullptr;
+        h->cap_m = 0;
         CM_CUDA(cudaMalloc(&h->m_ids, (size_t)nq * K * 4));
         CM_CUDA(cudaMalloc(&h->m_sc, (size_t)nq * K * 4));
-        CM_CUDA(cudaMalloc(&h->m_cnt, (size_t)nq * 8));
         h->cap_m = nq * K;
+    }
+    if (h->cap_gc < nq) {                 // the per-query counts grow with the batch, whatever K is
+        cudaFree(h->g_cnt); cudaFree(h->m_cnt);
+        h->g_cnt = nullptr; h->m_cnt = nullptr;
+        h->cap_gc = 0;
+        CM_CUDA(cudaMalloc(&h->g_cnt, (size_t)W * nq * 8));
+        CM_CUDA(cudaMalloc(&h->m_cnt, (size_t)nq * 8));
+        h->cap_gc = nq;
     }
     CM_CUDA(cudaEventRecord(h->start, lead));
     // The shards are enqueued concurrently: one persistent worker thread per shard beyond the first (a search is ~25

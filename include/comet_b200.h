@@ -76,6 +76,7 @@ typedef struct cm_hnsw cm_hnsw;
 typedef struct cm_flat_batcher cm_flat_batcher;
 typedef struct cm_flat_sharded cm_flat_sharded;
 typedef struct cm_ivf_sharded cm_ivf_sharded;
+typedef struct cm_ivfpq_sharded cm_ivfpq_sharded;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
 int cm_init(const int *device_ids, int n_devices); /* NULL/0: use the current device */
@@ -339,6 +340,33 @@ int cm_ivfpq_search(cm_ivfpq *h, const float *queries, int64_t nq, int dim, cons
 int cm_ivfpq_search_device(cm_ivfpq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
                            int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev,
                            int64_t *out_pos_dev, int64_t *out_counts_dev, void *stream);
+
+/* ---- IVFPQ list shards over the GPUs of one box, ONE host process ------------------------------------ */
+/* Same layout and merge as cm_ivf_sharded_* (global candidate numbers from the replicated list lengths,
+ * ivfpq_index_search.go:263-322); centroids and residual codebooks are replicated, Add encodes once on devices[0] and
+ * routes (id, code) to the shard that owns the list. */
+int cm_ivfpq_sharded_create(int dim, int metric, int nlist, int M, int nbits, const int *devices, int n_devices,
+                            cm_ivfpq_sharded **out);
+int cm_ivfpq_sharded_destroy(cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_shards(const cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_set_trained(cm_ivfpq_sharded *h, const float *centroids, const float *codebooks);
+int cm_ivfpq_sharded_train(cm_ivfpq_sharded *h, const float *rows, int64_t n);
+int cm_ivfpq_sharded_get_trained(const cm_ivfpq_sharded *h, float *centroids, float *codebooks);
+int cm_ivfpq_sharded_trained(const cm_ivfpq_sharded *h);
+int64_t cm_ivfpq_sharded_size(const cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_shard_size(const cm_ivfpq_sharded *h, int shard, int64_t *rows);
+int cm_ivfpq_sharded_owner(const cm_ivfpq_sharded *h, int list);
+int cm_ivfpq_sharded_default_nprobes(const cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_add(cm_ivfpq_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
+int cm_ivfpq_sharded_remove(cm_ivfpq_sharded *h, uint32_t id);
+int cm_ivfpq_sharded_flush(cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_rebalance(cm_ivfpq_sharded *h);
+int cm_ivfpq_sharded_search(cm_ivfpq_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
+                            int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_counts);
+int cm_ivfpq_sharded_search_device(cm_ivfpq_sharded *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                                   int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_counts_dev,
+                                   void *stream);
+int cm_ivfpq_sharded_last_scanned(const cm_ivfpq_sharded *h, int64_t *per_shard);
 
 /* ---- hnsw_index.go / hnsw_index_search.go --------------------------------------------------- */
 int cm_hnsw_create(int dim, int metric, int m, int ef_construction, int ef_search, cm_hnsw **out);   /* NewHNSWIndex hnsw_index.go:172 */

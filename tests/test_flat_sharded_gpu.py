@@ -48,6 +48,7 @@ def test_sharded_small_exact_path_with_ties_across_shards(metric):
     _check(g, o, q, 1)
     _check(g, o, q, 1500)                                # k larger than a shard
     _check(g, o, q[:1], 0)                               # k <= 0: everything, in order
+    _check(g, o, q, 5)                                   # a larger batch with a smaller k after it: per-query buffers regrow
 
 
 def test_sharded_duplicate_rows_everywhere():

@@ -130,3 +130,71 @@ def test_list_shards_errors():
     with pytest.raises(capi.CometError) as e:
         g.search(np.ones((1, d + 1), np.float32), k=3)
     assert e.value.code == capi.ERR_DIM_MISMATCH
+
+
+# ---- IVFPQ list shards ---------------------------------------------------------------------------------------------
+def build_pq(n, d, nlist, M, nbits, metric, seed, shards):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32) + (0.2 if metric == capi.COSINE else 0.0)
+    x[n // 2] = x[3]                              # identical rows -> identical codes in the same list; ADC scores tie anyway
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    o = O.IVFPQ(d, metric, nlist, M, nbits)
+    o.train(x[:max(nlist * 10, (1 << nbits) * 2, 800)].copy())
+    g = capi.ShardedIVFPQIndex(d, metric, nlist, M, nbits, _devices(shards))
+    g.set_trained(o.centroids(), o.codebooks())
+    o.add(ids, x.copy())
+    lists = g.add(ids, x.copy())
+    return g, o, rng, x, lists
+
+
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_ivfpq_list_shards_match_the_single_index(metric):
+    g, o, rng, x, lists = build_pq(7000, 32, 18, 8, 4, metric, 200 + metric, 4)     # 16 codewords: heavy score ties
+    ol = o.lists()
+    for l in range(18):
+        assert np.array_equal((np.nonzero(lists == l)[0] + 1).astype(np.uint32), ol[l][0])
+    assert len(g) == 7000 and sum(g.shard_size(r) for r in range(4)) == 7000
+    q = rng.standard_normal((8, 32)).astype(np.float32)
+    q[0] = x[3]
+    for nprobes in (1, 4, 18):
+        check(g, o, q, 10, nprobes)
+    check(g, o, q, 200, 6)
+    check(g, o, q[:3], 0, 2)
+    check(g, o, q[:3], 50, 5, filter_ids=np.arange(2, 7000, 4, dtype=np.uint32))
+    for dead in (5, 3500, 6999):
+        g.remove(dead)
+        o.remove(dead)
+    check(g, o, q, 30, 6)
+    g.flush()
+    o.flush()
+    check(g, o, q, 30, 6)
+    g.rebalance()
+    assert sum(g.shard_size(r) for r in range(4)) == 6997
+    check(g, o, q, 30, 6)
+    check(g, o, q, 30, 18)
+    more = np.arange(9001, 9201, dtype=np.uint32)
+    xm = rng.standard_normal((200, 32)).astype(np.float32) + (0.2 if metric == capi.COSINE else 0.0)
+    g.add(more, xm.copy())
+    o.add(more, xm.copy())
+    check(g, o, q, 30, 7)
+    g.search(q, k=10, nprobes=7)
+    assert g.last_scanned().sum() > 0
+
+
+def test_ivfpq_list_shards_train_on_device_and_errors():
+    rng = np.random.default_rng(5)
+    d = 16
+    x = rng.standard_normal((1500, d)).astype(np.float32)
+    g = capi.ShardedIVFPQIndex(d, capi.L2, 6, 4, 4, _devices(3))
+    with pytest.raises(capi.CometError) as e:
+        g.search(x[:2], k=3)
+    assert e.value.code == capi.ERR_NOT_TRAINED
+    g.train(x.copy())
+    o = O.IVFPQ(d, capi.L2, 6, 4, 4)
+    o.set_trained(*g.trained_state())
+    ids = np.arange(1, 1501, dtype=np.uint32)
+    g.add(ids, x.copy())
+    o.add(ids, x.copy())
+    check(g, o, x[7:12].copy(), 15, 3)
+    with pytest.raises(capi.CometError):
+        capi.ShardedIVFPQIndex(d, capi.L2, 6, 5, 4, _devices(2))       # dim not divisible by M
