@@ -138,27 +138,48 @@ struct PQCore {
     uint32_t *members = nullptr;
     long long *list_off = nullptr;
     int64_t members_cap = 0;
-    uint8_t *codes_by_list = nullptr;   // [n][M] codes in CSR (list) order: a probed list is one contiguous stream
+    uint8_t *codes_by_list = nullptr;   // the codes again, list by list: a probed list is one contiguous stream.  M % 16 == 0: every
+                                        // list starts on a 32-row boundary (tile_off) and each 32-row tile is stored word-major,
+                                        // [M/16][32 rows][16 bytes], so a warp's 16-byte loads of 32 rows are one 512-byte run
+    long long *tile_off = nullptr;      // [nlist+1] padded row offset of every list in codes_by_list (multiples of 32); M % 16 == 0 only
+    int64_t tiled_rows = 0;             // rows of codes_by_list including the padding
+    float *codebooks_t = nullptr;       // dsub == 8: [M][2][Ksub] float4 -- the table build reads a codeword half per lane, coalesced
+    bool cbt_dirty = true;
     bool csr_dirty = true;
     std::vector<int64_t> sizes_desc;
     std::mutex csr_mu;
     unsigned long long *scanned_total = nullptr;   // device: codes scanned by the last IVFPQ search (all queries)
 
-    ~PQCore() { cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); cudaFree(codes_by_list); }
+    ~PQCore() {
+        cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); cudaFree(codes_by_list);
+        cudaFree(tile_off); cudaFree(codebooks_t);
+    }
+    bool tiled() const { return (M & 15) == 0; }
+    int sync_codebooks_t(cudaStream_t st);
     int lut_entries() const { return Ksub < 256 ? Ksub : 256; }
     int sync_csr(cudaStream_t st);
 };
 
-// codes_by_list[i] = codes[members[i]]: 16 bytes per thread when M is a multiple of 16
+// codes_by_list from the store: CSR entry i (list l, j-th member) -> 16-byte word k of its code
+//   M % 16 == 0: tiled -- row p = tile_off[l] + j, word k at ((p / 32) * 32 * M) + k * 512 + (p % 32) * 16
+//   else       : linear, codes_by_list[i] = codes[members[i]]
 __global__ void gather_codes_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ members, long long n,
-                                    int M, uint8_t *__restrict__ out) {
+                                    int M, const long long *__restrict__ list_off, const long long *__restrict__ tile_off, int nlist,
+                                    uint8_t *__restrict__ out) {
     if ((M & 15) == 0) {
         const int w = M / 16;
         long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
         if (t >= n * w) return;
         long long i = t / w;
         int k = (int)(t - i * w);
-        reinterpret_cast<uint4 *>(out)[t] = __ldg(reinterpret_cast<const uint4 *>(codes + (size_t)members[i] * M) + k);
+        int lo = 0, hi = nlist;                    // list of CSR entry i: largest l with list_off[l] <= i
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (list_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        const long long p = tile_off[lo] + (i - list_off[lo]);
+        const size_t dst = (size_t)(p >> 5) * 32 * M + (size_t)k * 512 + (size_t)(p & 31) * 16;
+        *reinterpret_cast<uint4 *>(out + dst) = __ldg(reinterpret_cast<const uint4 *>(codes + (size_t)members[i] * M) + k);
     } else {
         long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
         if (t >= n * M) return;
@@ -167,35 +188,66 @@ __global__ void gather_codes_kernel(const uint8_t *__restrict__ codes, const uin
     }
 }
 
+// codebooks [M][Ksub][8] -> [M][2][Ksub] float4
+__global__ void transpose_codebooks_kernel(const float4 *__restrict__ cb, int M, int Ksub, float4 *__restrict__ out) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)M * Ksub * 2) return;
+    const int h = (int)(t & 1);
+    const long long mc = t >> 1;                   // m * Ksub + c
+    const long long m = mc / Ksub, c = mc - m * Ksub;
+    out[(m * 2 + h) * Ksub + c] = cb[t];
+}
+
+int PQCore::sync_codebooks_t(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(csr_mu);
+    if (!cbt_dirty || dsub != 8 || !codebooks) return CM_OK;
+    if (!codebooks_t) CM_CUDA(cudaMalloc(&codebooks_t, (size_t)M * Ksub * 8 * 4));
+    const long long work = (long long)M * Ksub * 2;
+    transpose_codebooks_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(codebooks), M, Ksub,
+                                                                              reinterpret_cast<float4 *>(codebooks_t));
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    CM_CUDA(cudaStreamSynchronize(st));
+    cbt_dirty = false;
+    return CM_OK;
+}
+
 int PQCore::sync_csr(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(csr_mu);
     if (!csr_dirty || nlist == 0) return CM_OK;
     int64_t n = store.n;
-    if (n > members_cap || !members) {
-        cudaFree(members);
-        cudaFree(codes_by_list);
-        codes_by_list = nullptr;
-        members_cap = std::max<int64_t>(n + n / 2, 1024);
-        CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
-        CM_CUDA(cudaMalloc(&codes_by_list, (size_t)members_cap * M));
-    }
-    if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
     std::vector<uint32_t> flat;
     flat.reserve((size_t)n);
-    std::vector<long long> off((size_t)nlist + 1, 0);
+    std::vector<long long> off((size_t)nlist + 1, 0), toff((size_t)nlist + 1, 0);
     sizes_desc.assign((size_t)nlist, 0);
     for (int l = 0; l < nlist; l++) {
         off[(size_t)l] = (long long)flat.size();
         flat.insert(flat.end(), lists[(size_t)l].begin(), lists[(size_t)l].end());
         sizes_desc[(size_t)l] = (int64_t)lists[(size_t)l].size();
+        toff[(size_t)l + 1] = toff[(size_t)l] + (((long long)lists[(size_t)l].size() + 31) & ~31ll);
     }
     off[(size_t)nlist] = (long long)flat.size();
+    const int64_t rows_needed = tiled() ? std::max<int64_t>(toff[(size_t)nlist], 32) : n;
+    if (n > members_cap || !members || rows_needed > tiled_rows || !codes_by_list) {
+        cudaFree(members);
+        cudaFree(codes_by_list);
+        codes_by_list = nullptr;
+        members_cap = std::max<int64_t>(n + n / 2, 1024);
+        tiled_rows = std::max<int64_t>(rows_needed + rows_needed / 2, 1024);
+        CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
+        CM_CUDA(cudaMalloc(&codes_by_list, (size_t)tiled_rows * M));
+    }
+    if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
+    if (!tile_off) CM_CUDA(cudaMalloc(&tile_off, (size_t)(nlist + 1) * sizeof(long long)));
     std::sort(sizes_desc.begin(), sizes_desc.end(), std::greater<int64_t>());
     if (!flat.empty()) CM_CUDA(cudaMemcpyAsync(members, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(list_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(tile_off, toff.data(), toff.size() * 8, cudaMemcpyHostToDevice, st));
     if (n > 0) {
-        const long long work = (M & 15) == 0 ? (long long)n * (M / 16) : (long long)n * M;
-        gather_codes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, codes_by_list);
+        if (tiled()) CM_CUDA(cudaMemsetAsync(codes_by_list, 0, (size_t)rows_needed * M, st));     // the padding rows are read (never emitted)
+        const long long work = tiled() ? (long long)n * (M / 16) : (long long)n * M;
+        gather_codes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, list_off, tile_off, nlist,
+                                                                            codes_by_list);
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
@@ -260,7 +312,8 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
     const long long *__restrict__ q_off, const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
     int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C, int n_slices,
-    uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    uint64_t *__restrict__ part_keys, int *__restrict__ part_counts, const long long *__restrict__ tile_off,
+    const float4 *__restrict__ codebooks_t) {
     constexpr int R = AdcRows<MW>::R;
     constexpr int T = ADC_THREADS;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -305,15 +358,18 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     if (dsub == 8 && lut_n == T) {
         // thread = table column c, four sub-quantisers in flight (independent chains); the residual
         // piece is a shared-memory broadcast, the codebook row a coalesced 32-byte load
-        const float4 *cb4 = reinterpret_cast<const float4 *>(codebooks) + (size_t)tid * 2;
+        // codeword halves: [m][h][c] float4 in the transposed copy (a warp's load is one 512-byte run; from the reference
+        // layout [m][c][8] the same two loads touch twice the lines)
+        const float4 *cb4 = codebooks_t ? codebooks_t + tid : reinterpret_cast<const float4 *>(codebooks) + (size_t)tid * 2;
         const size_t m_stride4 = (size_t)Ksub * 2;
+        const size_t h_stride4 = codebooks_t ? (size_t)Ksub : 1;
         int m = 0;
         for (; m + 4 <= M; m += 4) {
             float4 a[4], b[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 a[u] = __ldg(cb4 + (size_t)(m + u) * m_stride4);
-                b[u] = __ldg(cb4 + (size_t)(m + u) * m_stride4 + 1);
+                b[u] = __ldg(cb4 + (size_t)(m + u) * m_stride4 + h_stride4);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -328,7 +384,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
             }
         }
         for (; m < M; m++) {
-            const float4 a = __ldg(cb4 + (size_t)m * m_stride4), b = __ldg(cb4 + (size_t)m * m_stride4 + 1);
+            const float4 a = __ldg(cb4 + (size_t)m * m_stride4), b = __ldg(cb4 + (size_t)m * m_stride4 + h_stride4);
             const float4 r0 = *reinterpret_cast<const float4 *>(res + m * 8);
             const float4 r1 = *reinterpret_cast<const float4 *>(res + m * 8 + 4);
             float d = 0.0f;
@@ -368,7 +424,10 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     if (keep_end > limit) keep_end = K;
     // the pair's code rows are one contiguous stream: the store itself (PQ) or the list's slice of the
     // list-ordered copy (IVFPQ; `codes` then points at codes_by_list)
-    const uint8_t *rows = codes + (mem ? (size_t)list_off[list] * M : 0);
+    // tiled (tile_off != nullptr): the list starts at padded row tile_off[list]; row j, 16-byte word w sits at
+    // (j / 32) * 32 * M + w * 512 + (j % 32) * 16 -- c0 and the round size are multiples of 32, so j % 32 is the lane
+    const uint8_t *rows = codes + (mem ? (size_t)(tile_off ? tile_off[list] : list_off[list]) * M : 0);
+    const int lane = tid & 31;
     for (long long base = c0; base < c1; base += (long long)R * T) {
         bool live[R];
         float dist[R];
@@ -378,16 +437,20 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
             for (int r = 0; r < R; r++) {
                 const long long j = base + (long long)r * T + tid;
                 live[r] = j < c1;
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(rows + (size_t)(live[r] ? j : c0) * M);
+                const long long js = live[r] ? j : c0 + lane;          // dead rows re-read the slice's first tile: never emitted
+                const uint4 *c4 = tile_off ? reinterpret_cast<const uint4 *>(rows + (size_t)(js >> 5) * 32 * M) + lane
+                                           : reinterpret_cast<const uint4 *>(rows + (size_t)js * M);
+                const int wstride = tile_off ? 32 : 1;
 #pragma unroll
                 for (int w = 0; w < MW; w++) {
-                    uint4 v = __ldg(c4 + w);           // dead rows re-read row c0: harmless, never emitted
+                    uint4 v = __ldg(c4 + w * wstride);
                     wd[r][w * 4 + 0] = v.x; wd[r][w * 4 + 1] = v.y; wd[r][w * 4 + 2] = v.z; wd[r][w * 4 + 3] = v.w;
                 }
             }
             // next round's rows towards L2 while this round computes (one 128-byte line per 128 bytes of rows)
             {
-                const long long nb = (base + (long long)R * T) * M, ne = min(c1, base + 2ll * R * T) * M;
+                const long long c1p = tile_off ? ((c1 + 31) & ~31ll) : c1;
+                const long long nb = (base + (long long)R * T) * M, ne = min(c1p, base + 2ll * R * T) * M;
                 for (long long o = nb + (long long)tid * 128; o < ne; o += (long long)T * 128) prefetch_l2(rows + o);
             }
             float sum[R];
@@ -410,10 +473,16 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
             for (int r = 0; r < R; r++) {
                 const long long j = base + (long long)r * T + tid;
                 live[r] = j < c1;
-                const uint8_t *code = rows + (size_t)(live[r] ? j : c0) * M;
                 float sum = 0.0f;
-                if (live[r])
-                    for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+                if (live[r]) {
+                    if (tile_off) {      // tiled store, byte-wise walk: byte m of row j is in word m / 16 of its tile
+                        const uint8_t *tile = rows + (size_t)(j >> 5) * 32 * M + (size_t)(j & 31) * 16;
+                        for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + tile[(size_t)(m >> 4) * 512 + (m & 15)]]);
+                    } else {
+                        const uint8_t *code = rows + (size_t)j * M;
+                        for (int m = 0; m < M; m++) sum = __fadd_rn(sum, lut[m * lut_n + code[m]]);
+                    }
+                }
                 dist[r] = __fsqrt_rn(sum);
             }
         }
@@ -548,6 +617,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         if (nprobes <= 0 || nprobes > ix.nlist) nprobes = ix.nlist;
         CM_TRY(ix.sync_csr(st));
     }
+    CM_TRY(ix.sync_codebooks_t(st));
     int64_t bound_c = S.n, max_len = S.n;
     if (ivf) {
         bound_c = 0;
@@ -620,11 +690,11 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     if (qgroup * nprobes > 65535) qgroup = std::max<int64_t>(1, 65535 / nprobes);   // grid.y limit
     uint64_t *pk = nullptr;
     int *pc = nullptr;
-    CM_TRY(ws.get(&pk, (size_t)qgroup * parts * K * 8));
-    CM_TRY(ws.get(&pc, (size_t)qgroup * parts * 4));
     using AdcKernel = void (*)(const float *, int, int, int, int, int, int, const float *, const uint8_t *, long long,
                                const float *, int, const long long *, const long long *, const long long *, const uint32_t *,
-                               int, const uint8_t *, float, int, int, int, uint64_t *, int *);
+                               int, const uint8_t *, float, int, int, int, uint64_t *, int *, const long long *, const float4 *);
+    CM_TRY(ws.get(&pk, (size_t)qgroup * parts * K * 8));
+    CM_TRY(ws.get(&pc, (size_t)qgroup * parts * 4));
     AdcKernel kern = nullptr;
 #define CM_ADC_CASE(W) case W: kern = fma ? adc_scan_kernel<true, W> : adc_scan_kernel<false, W>; break;
     switch (MW) {
@@ -642,7 +712,9 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
                                                   ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
                                                   ix.coarse.ld, ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
                                                   ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off,
-                                                  ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, (int)n_slices, pk, pc);
+                                                  ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, (int)n_slices, pk, pc,
+                                                  (ivf && ix.tiled()) ? ix.tile_off : nullptr,
+                                                  ix.dsub == 8 ? reinterpret_cast<const float4 *>(ix.codebooks_t) : nullptr);
             count_launch();
             CM_CUDA(cudaGetLastError());
         }
@@ -844,6 +916,7 @@ static int core_set_trained(PQCore &ix, const float *centroids, const float *cod
         CM_TRY(rc);
     }
     ix.trained = true;
+    ix.cbt_dirty = true;
     return CM_OK;
 }
 
@@ -877,7 +950,7 @@ static int core_train(PQCore &ix, const float *rows, int64_t n) {
     cudaError_t e = cudaStreamSynchronize(st);
     release_stream(st);
     if (rc == CM_OK && e != cudaSuccess) rc = fail(CM_ERR_CUDA, "train: %s", cudaGetErrorString(e));
-    if (rc == CM_OK) ix.trained = true;
+    if (rc == CM_OK) { ix.trained = true; ix.cbt_dirty = true; }
     return rc;
 }
 
