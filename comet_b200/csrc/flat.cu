@@ -130,6 +130,7 @@ int FlatIndex::reserve(int64_t want) {
 FlatIndex::~FlatIndex() {
     cudaFree(rows); cudaFree(ids); cudaFree(deleted);
     cudaFree(staged_dev);
+    cudaFree(id_sorted); cudaFree(pos_sorted);
     cudaFreeHost(staged_host);
     free_shadow();
 }
@@ -228,6 +229,7 @@ int FlatIndex::flush() {
     n_deleted_rows = 0;
     deleted_ids.clear();
     shadow_rows = 0;
+    sorted_n = -1;
     return CM_OK;
 }
 
@@ -260,28 +262,36 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
         return CM_OK;
     }
 
-    // 1. soft deletes + document filter -> per-row skip mask (flat_index_search.go:255-263)
+    // 1. soft deletes + document filter (flat_index_search.go:255-263): the caller's IDs are sorted on the device
+    //    (flat_filter.cu); a selective filter becomes an explicit candidate list, any other a per-row skip mask
     const uint8_t *skip = nullptr;
     uint8_t *skip_buf = nullptr;
     uint32_t *filt_dev = nullptr;
-    if (p->filter_ids && p->nfilter > 0) {
-        std::vector<uint32_t> f(p->filter_ids, p->filter_ids + p->nfilter);
-        std::sort(f.begin(), f.end());
-        f.erase(std::unique(f.begin(), f.end()), f.end());
-        CM_TRY(ws.get(&filt_dev, f.size() * 4));
-        CM_TRY(ws.get(&skip_buf, (size_t)n));
-        CM_CUDA(cudaMemcpyAsync(filt_dev, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
-        CM_TRY(launch_build_skip(ids, deleted, n, filt_dev, (int64_t)f.size(), skip_buf, st));
-        CM_CUDA(cudaStreamSynchronize(st));   // f goes out of scope
-        skip = skip_buf;
+    const bool has_filter = p->filter_ids && p->nfilter > 0;
+    bool gather = false;
+    if (has_filter) {
+        CM_TRY(ws.get(&filt_dev, (size_t)p->nfilter * 4));
+        CM_TRY(upload_filter_ids(p->filter_ids, p->nfilter, filt_dev, st));
+        CM_TRY(sort_u32_device(filt_dev, p->nfilter, ws, st));
+        gather = p->nfilter <= n / 16 && k_eff <= 4096;
+        if (const char *e = getenv("COMET_B200_FILTER_GATHER")) gather = atoi(e) != 0 && k_eff <= 4096;
+        if (!gather) {
+            CM_TRY(ws.get(&skip_buf, (size_t)n));
+            CM_TRY(launch_build_skip(ids, deleted, n, filt_dev, p->nfilter, skip_buf, st));
+            skip = skip_buf;
+        }
     } else if (n_deleted_rows > 0) {
         skip = deleted;
     }
 
     // 2. pick the pipeline
     int path = p->path;
-    if (path == CM_PATH_AUTO)
-        path = tensor_path_eligible(nq, k_eff, p->filter_ids && p->nfilter > 0, p->threshold) ? CM_PATH_TENSOR : CM_PATH_EXACT;
+    if (path == CM_PATH_AUTO) {
+        // a filter (or a deleted set) that leaves under half of the rows may leave the candidate pass short of k survivors
+        // in its first samples: it would detect that and the host would redo the query exactly -- right, but slower
+        const bool sparse = (has_filter && p->nfilter < n / 2) || n_deleted_rows > n / 2;
+        path = tensor_path_eligible(nq, k_eff, sparse, p->threshold) ? CM_PATH_TENSOR : CM_PATH_EXACT;
+    }
 
     // 3. Distance.Preprocess on every query (flat_index_search.go:236) into a zero-padded [nq_pad][ld] block (the
     //    tensor path folds it into its own query-preparation kernel), then the search proper
@@ -291,7 +301,22 @@ int FlatIndex::search_device(const float *q_dev, int64_t nq, const cm_search_par
     CM_TRY(ws.get(&qp, (size_t)nq_pad * ld * 4));
     CM_TRY(ws.get(&qflags, (size_t)nq * sizeof(int)));
     int rc = CM_OK;
-    if (path == CM_PATH_TENSOR) {
+    if (gather) {
+        // selective filter: look the IDs up, score exactly those rows (no pass over the corpus)
+        if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
+        CM_TRY(launch_preprocess_rows(metric, fma, q_dev, nq, dim, dim, qp, ld, qflags, st));
+        CM_TRY(ensure_id_sort(st));
+        const int64_t cap = std::max<int64_t>(128, (int64_t)p->nfilter * max_id_run);
+        uint32_t *cand_pos = nullptr;
+        int *cand_cnt = nullptr;
+        CM_TRY(ws.get(&cand_pos, (size_t)cap * 4));
+        CM_TRY(ws.get(&cand_cnt, sizeof(int)));
+        CM_TRY(filter_candidates(filt_dev, p->nfilter, cand_pos, cap, cand_cnt, ws, st));
+        rc = gather_scan_topk(*this, qp, nq, cand_pos, cand_cnt, cap, p->threshold, k_eff, out_stride, out_ids, out_scores, out_pos,
+                              out_counts, st);
+        stats.path_used = CM_PATH_EXACT;
+        stats.passes = 0;
+    } else if (path == CM_PATH_TENSOR) {
         rc = search_tensor(q_dev, qp, qflags, nq, k_eff, skip, p->threshold, out_stride, out_ids, out_scores, out_pos, out_counts, st, &stats);
     } else {
         if (nq_pad > nq) CM_CUDA(cudaMemsetAsync(qp + (size_t)nq * ld, 0, (size_t)(nq_pad - nq) * ld * 4, st));
@@ -378,6 +403,7 @@ int FlatIndex::reset() {
     ids_host_mirror.clear();
     deleted_ids.clear();
     shadow_rows = 0;
+    sorted_n = -1;
     return CM_OK;
 }
 

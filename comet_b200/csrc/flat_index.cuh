@@ -41,6 +41,15 @@ struct WsScope {
     }
 };
 
+struct FlatIndex;
+// flat_filter.cu
+int upload_filter_ids(const uint32_t *ids, int64_t nf, uint32_t *dst_dev, cudaStream_t st);
+int sort_u32_device(uint32_t *keys, int64_t n, WsScope &ws, cudaStream_t st);
+// ivf.cu: top-k over an explicit candidate list (ascending scan positions, count on the device, at most `cap`)
+int gather_scan_topk(FlatIndex &S, const float *qp, int64_t nq, const uint32_t *cand_pos, const int *cand_cnt_dev, int64_t cap,
+                     float threshold, int64_t k_eff, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                     int64_t *out_counts, cudaStream_t st);
+
 struct FlatIndex {
     int dim = 0, ld = 0, metric = 0, device = 0;
     int64_t n = 0, cap = 0;
@@ -65,6 +74,11 @@ struct FlatIndex {
     CUtensorMap tmap_bf16;                  // box 64 x 128 rows (both operands staged in shared memory)
     CUtensorMap tmap_bf16_ts;               // box 64 x 32 rows (query-resident pass, flat_gemm_ts.cu)
 
+    // document filters (flat_filter.cu): node IDs sorted with their scan positions, rebuilt lazily after Add / Flush
+    uint32_t *id_sorted = nullptr, *pos_sorted = nullptr;
+    int64_t sorted_n = -1, sorted_cap = 0;
+    int max_id_run = 1;                     // most rows that share one node ID (Add does not reject repeated IDs)
+
     std::mutex stats_mu;
     cm_flat_stats last_stats{};
     unsigned long long *rescored_dev = nullptr;   // device: candidates re-scored by the last tensor-path search (all queries)
@@ -81,6 +95,9 @@ struct FlatIndex {
     int reset();
     int load_stored_rows(const uint32_t *ids_host, const float *rows_host, int64_t n_add);
     int read_rows(int64_t first, int64_t m, float *out) const;
+    int ensure_id_sort(cudaStream_t st);
+    int filter_candidates(const uint32_t *filt_sorted, int64_t nf, uint32_t *cand_pos, int64_t cap, int *cand_cnt, WsScope &ws,
+                          cudaStream_t st);
     int save(wire::Sink &s);       // FlatIndex.WriteTo
     int load(wire::Source &s);     // FlatIndex.ReadFrom
     int search_device(const float *q_dev, int64_t nq, const cm_search_params *p, int64_t out_stride,

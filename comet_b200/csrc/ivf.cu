@@ -384,6 +384,66 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
     return CM_OK;
 }
 
+// ---- top-k over an explicit candidate list (selective document filters of the flat index, flat_filter.cu) ---------------
+// The list scan with ONE "list" shared by every query: candidate c is scan position cand_pos[c] (ascending), so the key
+// order (score, candidate number) is the flat search's (score, position).
+__global__ void gather_view_kernel(const int *__restrict__ cand_cnt, long long cap, long long nq, long long *__restrict__ probe_list,
+                                   long long *__restrict__ q_off, long long *__restrict__ list_off) {
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long m = min((long long)*cand_cnt, cap);
+    if (q == 0) { list_off[0] = 0; list_off[1] = m; }
+    if (q < nq) { probe_list[q] = 0; q_off[2 * q] = 0; q_off[2 * q + 1] = m; }
+}
+
+int gather_scan_topk(FlatIndex &S, const float *qp, int64_t nq, const uint32_t *cand_pos, const int *cand_cnt_dev, int64_t cap,
+                     float threshold, int64_t k_eff, int64_t out_stride, uint32_t *out_ids, float *out_scores, int64_t *out_pos,
+                     int64_t *out_counts, cudaStream_t st) {
+    WsScope ws(st);
+    if (nq <= 0) return CM_OK;
+    const int ld = S.ld;
+    const bool fma = rounding_mode() == CM_ROUND_FMA;
+    if (k_eff > cap) k_eff = cap;
+    if (k_eff <= 0) return launch_fill_counts(out_counts, nq, 0, st);
+    long long *probe_list = nullptr, *q_off = nullptr, *list_off = nullptr;
+    CM_TRY(ws.get(&probe_list, (size_t)nq * 8));
+    CM_TRY(ws.get(&q_off, (size_t)nq * 16));
+    CM_TRY(ws.get(&list_off, 16));
+    gather_view_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cand_cnt_dev, (long long)cap, (long long)nq, probe_list, q_off, list_off);
+    count_launch();
+    CM_CUDA(cudaGetLastError());
+    const int n_chunks = (int)((cap + 127) / 128);
+    const long long cap_c = (long long)n_chunks * 128;
+    int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (cap_c * 8)));
+    qgroup = std::min<int64_t>(qgroup, 65535);
+    uint64_t *keys = nullptr;
+    int *kcnt = nullptr;
+    CM_TRY(ws.get(&keys, (size_t)qgroup * cap_c * 8));
+    CM_TRY(ws.get(&kcnt, (size_t)qgroup * n_chunks * 4));
+    size_t smem = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
+        const int64_t m = std::min(qgroup, nq - q0);
+        CM_CUDA(cudaMemsetAsync(kcnt, 0, (size_t)m * n_chunks * 4, st));
+        dim3 grid((unsigned)n_chunks, (unsigned)m);
+        const float *qq = qp + (size_t)q0 * ld;
+        const long long *pl = probe_list + q0, *qo = q_off + 2 * q0;
+        ProfScope prof(CM_PROF_IVF_SCAN, st);
+        switch (S.metric) {
+        case CM_L2: CM_TRY(launch_ivf_scan_m<CM_L2>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, list_off, cand_pos, 1, nullptr, threshold, cap_c, n_chunks, keys, kcnt)); break;
+        case CM_L2SQ: CM_TRY(launch_ivf_scan_m<CM_L2SQ>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, list_off, cand_pos, 1, nullptr, threshold, cap_c, n_chunks, keys, kcnt)); break;
+        default: CM_TRY(launch_ivf_scan_m<CM_COSINE>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, list_off, cand_pos, 1, nullptr, threshold, cap_c, n_chunks, keys, kcnt)); break;
+        }
+        CM_TRY(launch_merge_topk(keys, kcnt, (int)m, n_chunks, 128, (int)k_eff, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
+                                 out_scores + (size_t)q0 * out_stride, nullptr, out_counts + q0, st));
+        ivf_emit_kernel<<<(unsigned)m, 128, 0, st>>>(pl, qo, list_off, cand_pos, 1, S.ids, (long long)out_stride,
+                                                     out_ids + (size_t)q0 * out_stride,
+                                                     out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,
+                                                     (const long long *)(out_counts + q0), nullptr, nullptr);
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
+    return CM_OK;
+}
+
 }  // namespace cm
 
 // ------------------------------------------------------------------------------------------------

@@ -99,13 +99,63 @@ def test_tensor_path_ties_fall_back_to_exact():
         assert_same_results(ids_g[i], sc_g[i], cnt_g[i], oi[i, :oc[i]], os_[i, :oc[i]], what=f"query {i}")
 
 
-def test_auto_path_picks_tensor_for_large_batches():
+def test_auto_path_policy():
+    # CM_PATH_AUTO (measured in tools/nq_sweep.py): the candidate pass at every batch size once the index has 65,536
+    # rows -- one query included -- the exact scan below that, for k > 256 and under filters that leave few rows
     g, o, rng = make_pair(66_000, 64, capi.COSINE, 21, 2)
     q = rng.standard_normal((64, 64)).astype(np.float32)
-    g.search(q, k=10)
-    assert g.last_stats()["path_used"] == capi.PATH_TENSOR
-    g.search(q[:8], k=10)
+    for nq in (64, 8, 1):
+        ids_g, sc_g, cnt_g = g.search(q[:nq], k=10)
+        assert g.last_stats()["path_used"] == capi.PATH_TENSOR
+        oi, os_, oc = o.search_batch(q[:nq], 10)
+        for i in range(nq):
+            assert_same_results(ids_g[i], sc_g[i], cnt_g[i], oi[i, :oc[i]], os_[i, :oc[i]], what=f"nq {nq} query {i}")
+    g.search(q[:8], k=300)
     assert g.last_stats()["path_used"] == capi.PATH_EXACT
+    small, _, _ = make_pair(20_000, 64, capi.COSINE, 22, 2)
+    small.search(q, k=10)
+    assert small.last_stats()["path_used"] == capi.PATH_EXACT
+
+
+def test_document_filters_on_the_device():
+    # WithDocumentIDs (flat_index_search.go:255-263): selective filters are looked up and only their rows are scored;
+    # the others become a skip mask -- under the exact scan or, when they keep at least half of the rows, the tensor path
+    g, o, rng = make_pair(70_000, 48, capi.L2, 23, 2)
+    n = 70_000
+    q = rng.standard_normal((9, 48)).astype(np.float32)
+    ids_all = np.arange(1, n + 1, dtype=np.uint32)
+    for dead in (10, 11, 50_000):
+        g.remove(dead)
+        o.remove(dead)
+
+    def both(filt, k, **kw):
+        gi, gs, gc = g.search(q, k=k, filter_ids=filt, **kw)
+        for i in range(len(q)):
+            oi, os_ = o.search(q[i], k=k, filter_ids=filt, **kw)
+            assert_same_results(gi[i], gs[i], gc[i], oi, os_, what=f"query {i}")
+        return g.last_stats()
+
+    sel = rng.choice(ids_all, 300, replace=False)
+    sel = np.concatenate([sel, sel[:20], np.array([10, 11, 999_999, 0], np.uint32)]).astype(np.uint32)   # repeats, deleted, unknown
+    st = both(sel, 25)
+    assert st["passes"] == 0                               # no pass over the corpus
+    both(sel, 1000)                                        # k beyond the filtered rows: everything that passes, in order
+    both(sel, 25, threshold=float(np.sort(((g.get_rows(np.arange(2000)) - q[0]) ** 2).sum(1))[5]) ** 0.5 + 3.0)
+    both(np.array([10, 11], np.uint32), 5)                 # only deleted rows: nothing
+    both(ids_all[::16].copy(), 40)                         # 1/16 of the rows: still the gather path
+    st = both(ids_all[::3].copy(), 40)                     # a third: skip mask + exact scan
+    assert st["path_used"] == capi.PATH_EXACT and st["passes"] > 0
+    st = both(np.delete(ids_all, np.arange(0, n, 5)), 40)  # four fifths: skip mask folded into the candidate pass
+    assert st["path_used"] == capi.PATH_TENSOR and st["fallback_queries"] == 0
+    # node IDs may repeat (Add does not reject them): a filter ID selects every row that carries it
+    x2 = rng.standard_normal((3, 48)).astype(np.float32)
+    dup = np.array([sel[0], sel[0], sel[1]], np.uint32)
+    g.add(dup, x2.copy())
+    o.add(dup, x2.copy())
+    both(sel, 25)
+    g.flush()
+    o.flush()
+    both(sel, 25)
 
 
 def test_tensor_path_select_shapes_and_candidate_count(monkeypatch):
