@@ -195,6 +195,10 @@ SIGNATURES = {
                                         vp, vp, vp, vp]),
     "cm_flat_get_ids": (C.c_int, [vp, C.c_int64, C.c_int64, u32p]),
     "cm_hnsw_flush": (C.c_int, [vp]),
+    "cm_ivf_get_ids": (C.c_int, [vp, C.c_int64, C.c_int64, u32p]),
+    "cm_pq_get_ids": (C.c_int, [vp, C.c_int64, C.c_int64, u32p]),
+    "cm_ivfpq_get_ids": (C.c_int, [vp, C.c_int64, C.c_int64, u32p]),
+    "cm_hnsw_get_nodes": (C.c_int, [vp, C.c_int64, C.c_int64, u32p, f32p]),
     "cm_debug_decode_roaring": (C.c_int, [u8p, C.c_int64, u32p, C.c_int64, i64p]),
     "cm_flat_save": (C.c_int, [vp, u8p, C.c_int64, i64p]),
     "cm_flat_load": (C.c_int, [vp, u8p, C.c_int64, i64p]),

@@ -876,6 +876,18 @@ int cm_hnsw_export_graph(const cm_hnsw *h, int32_t *levels, int64_t *edge_off, u
     return CM_OK;
 }
 
+// node IDs and STORED vectors by slot (insertion order): what a host mirror needs after cm_hnsw_load
+int cm_hnsw_get_nodes(const cm_hnsw *h, int64_t first, int64_t n, uint32_t *ids_out, float *rows_out) {
+    if (!h || first < 0 || n < 0 || first + n > h->ix.n) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n == 0) return CM_OK;
+    CM_CUDA(cudaSetDevice(h->ix.device));
+    if (ids_out) CM_CUDA(cudaMemcpy(ids_out, h->ix.ids + first, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (rows_out)
+        CM_CUDA(cudaMemcpy2D(rows_out, (size_t)h->ix.dim * 4, h->ix.rows + (size_t)first * h->ix.ld, (size_t)h->ix.ld * 4,
+                             (size_t)h->ix.dim * 4, (size_t)n, cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+
 int cm_hnsw_remove(cm_hnsw *h, uint32_t id) {     // hnsw_index.go:300-330 soft delete
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
     CM_CUDA(cudaSetDevice(h->ix.device));

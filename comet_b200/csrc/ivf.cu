@@ -650,6 +650,13 @@ int cm_ivf_load_lists(cm_ivf *h, const uint32_t *ids, const float *rows, const i
     return rc;
 }
 
+// node IDs by store position (with cm_ivf_get_rows: what a host mirror needs after cm_ivf_load)
+int cm_ivf_get_ids(const cm_ivf *h, int64_t first, int64_t n, uint32_t *out) {
+    if (!h || first < 0 || n < 0 || first + n > h->ix.store.n || (n > 0 && !out)) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n > 0) memcpy(out, h->ix.store.ids_host_mirror.data() + first, (size_t)n * 4);
+    return CM_OK;
+}
+
 int cm_ivf_remove(cm_ivf *h, uint32_t id) {     // ivf_index.go:296-330 soft delete
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
     CM_CUDA(cudaSetDevice(h->ix.device));

@@ -1197,6 +1197,11 @@ int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out) {
     CM_CUDA(cudaMemcpy(out, h->ix.store.codes + (size_t)first * h->ix.M, (size_t)n * h->ix.M, cudaMemcpyDeviceToHost));
     return CM_OK;
 }
+int cm_pq_get_ids(const cm_pq *h, int64_t first, int64_t n, uint32_t *out) {       // node IDs by store position
+    if (!h || first < 0 || n < 0 || first + n > h->ix.store.n || (n > 0 && !out)) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n > 0) memcpy(out, h->ix.store.ids_host.data() + first, (size_t)n * 4);
+    return CM_OK;
+}
 int cm_pq_remove(cm_pq *h, uint32_t id) {
     if (!h) return cm::fail(CM_ERR_INVALID_ARG, "null handle");
     CM_CUDA(cudaSetDevice(h->ix.device));
@@ -1273,6 +1278,11 @@ int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out
     if (n <= 0) return CM_OK;
     CM_CUDA(cudaSetDevice(h->ix.device));
     CM_CUDA(cudaMemcpy(out, h->ix.store.codes + (size_t)first * h->ix.M, (size_t)n * h->ix.M, cudaMemcpyDeviceToHost));
+    return CM_OK;
+}
+int cm_ivfpq_get_ids(const cm_ivfpq *h, int64_t first, int64_t n, uint32_t *out) {   // node IDs by store position
+    if (!h || first < 0 || n < 0 || first + n > h->ix.store.n || (n > 0 && !out)) return cm::fail(CM_ERR_INVALID_ARG, "bad range");
+    if (n > 0) memcpy(out, h->ix.store.ids_host.data() + first, (size_t)n * 4);
     return CM_OK;
 }
 int64_t cm_ivfpq_last_scanned(const cm_ivfpq *h) {

@@ -22,7 +22,10 @@
 #include <cmath>
 #include <cstdint>
 #include <functional>
+#include <istream>
+#include <iterator>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -184,7 +187,8 @@ private:
     friend class VectorIndex;
 };
 
-// index.go:32-63 (io.WriterTo / io.ReaderFrom are not part of the search path: out of scope)
+// index.go:32-63, io.WriterTo / io.ReaderFrom included: WriteTo / ReadFrom move the reference's byte formats
+// (FLAT / IVFX / PQIX / IVPQ / HNSW) through cm_*_save / cm_*_load
 class VectorIndex {
 public:
     virtual ~VectorIndex() = default;
@@ -198,9 +202,37 @@ public:
     virtual VectorIndexKind Kind() const = 0;
     virtual bool Trained() const = 0;
     size_t Len() const { return nodes_.size(); }
+    // WriteTo (e.g. flat_index.go:366-470): flushes, then writes the reference's stream; returns the bytes written
+    int64_t WriteTo(std::ostream &w) {
+        Flush();
+        int64_t need = 0;
+        saveBytes(nullptr, 0, &need);
+        std::vector<uint8_t> buf((size_t)std::max<int64_t>(need, 1));
+        check(saveBytes(buf.data(), need, &need));
+        w.write(reinterpret_cast<const char *>(buf.data()), (std::streamsize)need);
+        if (!w) throw Error(CM_ERR_INVALID_ARG, "failed to write index data");
+        return need;
+    }
+    // ReadFrom (e.g. flat_index.go:488-614) on a pre-constructed index with matching parameters: replaces its state
+    int64_t ReadFrom(std::istream &r) {
+        std::vector<uint8_t> buf((std::istreambuf_iterator<char>(r)), std::istreambuf_iterator<char>());
+        int64_t used = 0;
+        check(loadBytes(buf.data(), (int64_t)buf.size(), &used));
+        nodes_.clear(); by_id_.clear(); deleted_.clear();
+        rebuildMirror();
+        return used;
+    }
 
 protected:
     friend class VectorSearch;
+    virtual int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) = 0;
+    virtual int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) = 0;
+    virtual void rebuildMirror() = 0;             // host nodes (ID + stored vector where the index keeps one) from the device state
+    void mirrorFrom(const std::vector<uint32_t> &ids, const std::vector<float> *rows) {
+        for (size_t i = 0; i < ids.size(); i++)
+            remember(NewVectorNodeWithID(ids[i], rows ? std::vector<float>(rows->begin() + (long)(i * (size_t)dim_), rows->begin() + (long)((i + 1) * (size_t)dim_))
+                                                      : std::vector<float>()));
+    }
     VectorIndex(int dim, comet::DistanceKind kind) : dim_(dim), kind_(kind) {}
     // nq searchSingleQuery calls in ONE device batch: flat row-major queries -> ids/scores/counts [nq][stride]
     virtual void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride,
@@ -318,9 +350,56 @@ protected:
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_flat_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data()));
     }
+    int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) override { return cm_flat_save(h_, buf, cap, bytes); }
+    int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) override { return cm_flat_load(h_, buf, len, used); }
+    void rebuildMirror() override {
+        const int64_t n = cm_flat_size(h_);
+        std::vector<uint32_t> ids((size_t)n);
+        std::vector<float> rows((size_t)n * dim_);
+        std::vector<int64_t> pos((size_t)n);
+        for (int64_t i = 0; i < n; i++) pos[(size_t)i] = i;
+        if (n > 0) { check(cm_flat_get_ids(h_, 0, n, ids.data())); check(cm_flat_get_rows(h_, pos.data(), n, rows.data())); }
+        mirrorFrom(ids, &rows);
+    }
     cm_flat *h_ = nullptr;
 };
 inline std::unique_ptr<FlatIndex> NewFlatIndex(int dim, DistanceKind kind) { return std::make_unique<FlatIndex>(dim, kind); }   // flat_index.go:118
+
+// The same index row-sharded over the GPUs of the box (cm_flat_sharded_*: one process drives every device; NVLink peer
+// mappings carry queries and per-shard top-K lists; one merge kernel).  Same API, same answers; WriteTo / ReadFrom are
+// not offered on this variant (save each segment from a single-GPU index).
+class ShardedFlatIndex : public VectorIndex {
+public:
+    ShardedFlatIndex(int dim, comet::DistanceKind kind, const std::vector<int> &devices, int64_t rowsPerShard) : VectorIndex(dim, kind) {
+        check(cm_flat_sharded_create(dim, (int)kind, devices.data(), (int)devices.size(), rowsPerShard, &h_));
+    }
+    ~ShardedFlatIndex() override { cm_flat_sharded_destroy(h_); }
+    void Train(const std::vector<VectorNode> &) override {}
+    void Add(VectorNode v) override {
+        checkDim(v);
+        uint32_t id = v.ID();
+        check(cm_flat_sharded_add(h_, &id, v.Vector().data(), 1, 1));
+        remember(v);
+    }
+    void Remove(const VectorNode &v) override { check(cm_flat_sharded_remove(h_, v.ID())); deleted_.insert(v.ID()); }
+    void Flush() override { check(cm_flat_sharded_flush(h_)); forget(deleted_); deleted_.clear(); }
+    VectorIndexKind Kind() const override { return "flat"; }
+    bool Trained() const override { return true; }
+    int Shards() const { return cm_flat_sharded_shards(h_); }
+
+protected:
+    void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
+                     std::vector<float> &scores, std::vector<int64_t> &counts) override {
+        check(cm_flat_sharded_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), counts.data()));
+    }
+    int saveBytes(uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    int loadBytes(const uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    void rebuildMirror() override {}
+    cm_flat_sharded *h_ = nullptr;
+};
+inline std::unique_ptr<ShardedFlatIndex> NewShardedFlatIndex(int dim, DistanceKind kind, const std::vector<int> &devices, int64_t rowsPerShard) {
+    return std::make_unique<ShardedFlatIndex>(dim, kind, devices, rowsPerShard);
+}
 
 // ---- IVFIndex (ivf_index.go) -------------------------------------------------------------------
 class IVFIndex : public VectorIndex {
@@ -350,6 +429,17 @@ protected:
     void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_ivf_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data()));
+    }
+    int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) override { return cm_ivf_save(h_, buf, cap, bytes); }
+    int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) override { return cm_ivf_load(h_, buf, len, used); }
+    void rebuildMirror() override {
+        const int64_t n = cm_ivf_size(h_);
+        std::vector<uint32_t> ids((size_t)n);
+        std::vector<float> rows((size_t)n * dim_);
+        std::vector<int64_t> pos((size_t)n);
+        for (int64_t i = 0; i < n; i++) pos[(size_t)i] = i;
+        if (n > 0) { check(cm_ivf_get_ids(h_, 0, n, ids.data())); check(cm_ivf_get_rows(h_, pos.data(), n, rows.data())); }
+        mirrorFrom(ids, &rows);
     }
     int nlist_;
     cm_ivf *h_ = nullptr;
@@ -383,6 +473,14 @@ protected:
     void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_pq_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data()));
+    }
+    int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) override { return cm_pq_save(h_, buf, cap, bytes); }
+    int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) override { return cm_pq_load(h_, buf, len, used); }
+    void rebuildMirror() override {                      // PQIndex.ReadFrom keeps IDs only: NewVectorNodeWithID(id, nil), pq_index.go:815
+        const int64_t n = cm_pq_size(h_);
+        std::vector<uint32_t> ids((size_t)n);
+        if (n > 0) check(cm_pq_get_ids(h_, 0, n, ids.data()));
+        mirrorFrom(ids, nullptr);
     }
     cm_pq *h_ = nullptr;
 };
@@ -420,6 +518,14 @@ protected:
     void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_ivfpq_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data()));
+    }
+    int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) override { return cm_ivfpq_save(h_, buf, cap, bytes); }
+    int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) override { return cm_ivfpq_load(h_, buf, len, used); }
+    void rebuildMirror() override {
+        const int64_t n = cm_ivfpq_size(h_);
+        std::vector<uint32_t> ids((size_t)n);
+        if (n > 0) check(cm_ivfpq_get_ids(h_, 0, n, ids.data()));
+        mirrorFrom(ids, nullptr);
     }
     cm_ivfpq *h_ = nullptr;
 };
@@ -459,7 +565,9 @@ public:
         for (const auto &n : nodes) remember(n);
     }
     void Remove(const VectorNode &v) override { check(cm_hnsw_remove(h_, v.ID())); deleted_.insert(v.ID()); }
-    void Flush() override {}
+    // hnsw_index.go:348-430: edges to deleted nodes go, a deleted entry point is replaced, deleted nodes are freed
+    void Flush() override { check(cm_hnsw_flush(h_)); forget(deleted_); deleted_.clear(); }
+    int MaxLevel() const { return cm_hnsw_max_level(h_); }
     VectorIndexKind Kind() const override { return "hnsw"; }
     bool Trained() const override { return true; }
 
@@ -468,6 +576,15 @@ protected:
     void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
                      std::vector<float> &scores, std::vector<int64_t> &counts) override {
         check(cm_hnsw_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), nullptr, counts.data(), nullptr));
+    }
+    int saveBytes(uint8_t *buf, int64_t cap, int64_t *bytes) override { return cm_hnsw_save(h_, buf, cap, bytes); }
+    int loadBytes(const uint8_t *buf, int64_t len, int64_t *used) override { return cm_hnsw_load(h_, buf, len, used); }
+    void rebuildMirror() override {
+        const int64_t n = cm_hnsw_size(h_);
+        std::vector<uint32_t> ids((size_t)n);
+        std::vector<float> rows((size_t)n * dim_);
+        if (n > 0) check(cm_hnsw_get_nodes(h_, 0, n, ids.data(), rows.data()));
+        mirrorFrom(ids, &rows);
     }
     int randomLevel() {
         int m = m_ > 0 ? m_ : 16, level = 0;

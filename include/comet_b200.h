@@ -247,6 +247,7 @@ int cm_ivf_load_lists(cm_ivf *h, const uint32_t *ids, const float *rows, const i
 int cm_ivf_remove(cm_ivf *h, uint32_t id);                          /* ivf_index.go:296-330 */
 int cm_ivf_flush(cm_ivf *h);                                        /* ivf_index.go:342-390 */
 int cm_ivf_get_rows(const cm_ivf *h, const int64_t *positions, int64_t n, float *out);
+int cm_ivf_get_ids(const cm_ivf *h, int64_t first, int64_t n, uint32_t *out);   /* node IDs by store position */
 /* nq independent searchSingleQuery calls (ivf_index_search.go:217-322); p->nprobes as WithNProbes.
  * out_stride >= min(k, B) where B = the most candidates nprobes lists can hold (k <= 0: B itself). */
 int cm_ivf_search(cm_ivf *h, const float *queries, int64_t nq, int dim, const cm_search_params *p,
@@ -305,6 +306,7 @@ int64_t cm_pq_size(const cm_pq *h);
 /* n successive PQIndex.Add calls (pq_index.go:262-292): PreprocessInPlace + encode (pq_index.go:439-473) */
 int cm_pq_add(cm_pq *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
 int cm_pq_get_codes(const cm_pq *h, int64_t first, int64_t n, uint8_t *out);   /* idx.codes[first:first+n] */
+int cm_pq_get_ids(const cm_pq *h, int64_t first, int64_t n, uint32_t *out);     /* node IDs by store position */
 int cm_pq_load_codes(cm_pq *h, const uint32_t *ids, const uint8_t *codes, int64_t n);   /* PQIndex.ReadFrom pq_index.go:652-846 */
 int cm_pq_remove(cm_pq *h, uint32_t id);
 int cm_pq_flush(cm_pq *h);
@@ -329,6 +331,7 @@ int cm_ivfpq_default_nprobes(const cm_ivfpq *h);                        /* ivfpq
 /* n successive IVFPQIndex.Add calls (ivfpq_index.go:279-319): preprocess, nearest centroid, residual, encode */
 int cm_ivfpq_add(cm_ivfpq *h, const uint32_t *ids, float *rows, int64_t n, int writeback, int32_t *out_lists);
 int cm_ivfpq_get_codes(const cm_ivfpq *h, int64_t first, int64_t n, uint8_t *out);   /* codes in arrival order */
+int cm_ivfpq_get_ids(const cm_ivfpq *h, int64_t first, int64_t n, uint32_t *out);
 int cm_ivfpq_load_codes(cm_ivfpq *h, const uint32_t *ids, const uint8_t *codes, const int32_t *list_of, int64_t n);
 int64_t cm_ivfpq_last_scanned(const cm_ivfpq *h);                    /* codes scanned by the last search */
 int cm_ivfpq_remove(cm_ivfpq *h, uint32_t id);
@@ -390,6 +393,8 @@ int cm_hnsw_max_level(const cm_hnsw *h);
 int64_t cm_hnsw_edge_count(const cm_hnsw *h);
 int cm_hnsw_export_graph(const cm_hnsw *h, int32_t *levels, int64_t *edge_off, uint32_t *edge_ids, uint32_t *entry_id,
                          int *max_level);
+/* node IDs and STORED vectors by slot (insertion order); either output may be NULL */
+int cm_hnsw_get_nodes(const cm_hnsw *h, int64_t first, int64_t n, uint32_t *ids_out, float *rows_out);
 int cm_hnsw_remove(cm_hnsw *h, uint32_t id);                         /* soft delete, hnsw_index.go:300-330 */
 /* HNSWIndex.Flush (hnsw_index.go:348-430): live nodes drop their edges to deleted nodes, a deleted entry point is
  * replaced (a live node at maxLevel, else one of the highest level left -- maxLevel follows -- else the index is

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <sstream>
 #include <iostream>
 
 #include "comet.hpp"
@@ -126,6 +127,79 @@ static void test_hnsw() {
     EXPECT(throws([&] { idx->NewSearch()->WithQuery({{1, 2}}).Execute(); }, "query dimension mismatch: expected 4, got 2"));
 }
 
+
+static void test_serialisation_flush_and_shards() {
+    // flat_index_test.go / ivf_index_test.go ... "WriteTo and ReadFrom" round trips: a restored index answers like the saved one
+    std::vector<VectorNode> nodes;
+    for (int i = 0; i < 300; i++)
+        nodes.push_back(NewVectorNodeWithID((uint32_t)(i + 1), {(float)(i % 17), (float)(i % 5) * 0.5f, (float)(i / 30), 1.0f + (float)(i % 3)}));
+    auto same = [](const std::vector<VectorResult> &a, const std::vector<VectorResult> &b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); i++)
+            if (a[i].GetId() != b[i].GetId() || a[i].Score != b[i].Score) return false;
+        return true;
+    };
+    const std::vector<float> q = {3.0f, 1.0f, 4.0f, 2.0f};
+    {
+        auto a = NewFlatIndex(4, Cosine);
+        for (auto &n : nodes) a->Add(n);
+        a->Remove(nodes[5]);
+        std::stringstream ss;
+        int64_t wrote = a->WriteTo(ss);
+        EXPECT(wrote == (int64_t)ss.str().size() && a->Len() == 299);          // WriteTo flushes (flat_index.go:367-370)
+        EXPECT(ss.str().compare(0, 4, "FLAT") == 0);
+        auto b = NewFlatIndex(4, Cosine);
+        EXPECT(b->ReadFrom(ss) == wrote && b->Len() == 299);
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(7).Execute(), b->NewSearch()->WithQuery({q}).WithK(7).Execute()));
+        EXPECT(b->NewSearch()->WithQuery({q}).WithK(1).Execute()[0].Node.Vector().size() == 4);    // the mirror holds the stored vectors
+        std::stringstream again(ss.str());
+        EXPECT(throws([&] { NewFlatIndex(5, Cosine)->ReadFrom(again); }, "dimension mismatch: index has dim=5, serialized data has dim=4"));
+    }
+    {
+        auto a = NewIVFPQIndex(4, Euclidean, 3, 2, 4);
+        a->Train(nodes);
+        for (auto &n : nodes) a->Add(n);
+        std::stringstream ss;
+        a->WriteTo(ss);
+        EXPECT(ss.str().compare(0, 4, "IVPQ") == 0);
+        auto b = NewIVFPQIndex(4, Euclidean, 3, 2, 4);
+        b->ReadFrom(ss);
+        EXPECT(b->Trained() && b->Len() == 300);
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(9).WithNProbes(2).Execute(), b->NewSearch()->WithQuery({q}).WithK(9).WithNProbes(2).Execute()));
+    }
+    {
+        // HNSWIndex.Flush (hnsw_index.go:348-430): removed nodes disappear for good, the entry point is replaced
+        auto a = NewHNSWIndex(4, Euclidean, 4, 20, 20);
+        a->SetLevelSeed(11);
+        for (auto &n : nodes) a->Add(n);
+        a->Remove(nodes[0]);                                    // the first node inserted is the entry point
+        a->Remove(nodes[1]);
+        a->Flush();
+        EXPECT(a->Len() == 298);
+        auto r = a->NewSearch()->WithQuery({nodes[40].Vector()}).WithK(3).Execute();
+        EXPECT(!r.empty() && r[0].GetId() != 1 && r[0].GetId() != 2);
+        EXPECT(throws([&] { a->Remove(nodes[0]); }));
+        std::stringstream ss;
+        a->WriteTo(ss);
+        auto b = NewHNSWIndex(4, Euclidean, 4, 20, 20);
+        b->ReadFrom(ss);
+        EXPECT(b->Len() == 298 && b->MaxLevel() == a->MaxLevel());
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(5).Execute(), b->NewSearch()->WithQuery({q}).WithK(5).Execute()));
+    }
+    {
+        // the row-sharded flat index answers like the single one (three shards on the visible device)
+        auto a = NewFlatIndex(4, Euclidean);
+        auto s = NewShardedFlatIndex(4, Euclidean, {0, 0, 0}, 120);
+        for (auto &n : nodes) { a->Add(n); s->Add(n); }
+        EXPECT(s->Shards() == 3 && s->Len() == 300);
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(25).Execute(), s->NewSearch()->WithQuery({q}).WithK(25).Execute()));
+        a->Remove(nodes[7]); s->Remove(nodes[7]);
+        a->Flush(); s->Flush();
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(25).Execute(), s->NewSearch()->WithQuery({q}).WithK(25).Execute()));
+        EXPECT(throws([&] { s->Add(NewVectorNodeWithID(999, {1, 2, 3})); }, "vector dimension mismatch: expected 4, got 3"));
+    }
+}
+
 int main(int argc, char **argv) {
     bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
     test_limiter_and_aggregation();
@@ -136,6 +210,7 @@ int main(int argc, char **argv) {
         test_flat();
         test_trained_indexes();
         test_hnsw();
+        test_serialisation_flush_and_shards();
     }
     std::printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
     return failures ? 1 : 0;
