@@ -190,7 +190,7 @@ __device__ __forceinline__ float row_distance_rw(const float *row, const float *
 // needed row with 16-byte cp.async (a quarter-warp per row: coalesced, two steps in flight) and each lane then walks
 // its own row's piece.  The per-lane `row_distance` walk keeps only 64 bytes per lane in flight and re-fetches lines
 // through L1 when many warps share an SM.  Must be called by all 32 lanes; rows must not be written by this kernel.
-template <int METRIC, bool FMA>
+template <int METRIC, bool FMA, int NS>
 __device__ __forceinline__ float warp_row_distances(const float *__restrict__ rows, int ld, uint32_t nb, bool need,
                                                     const float *__restrict__ q_s, uint8_t *stage, int lane) {
     const uint32_t mask = __ballot_sync(0xffffffffu, need);
@@ -210,25 +210,27 @@ __device__ __forceinline__ float warp_row_distances(const float *__restrict__ ro
     }
     const int n_ch = ld / 32;
     const uint32_t stage_u = smem_u32(stage);
+    // NS - 1 steps (4 KB each: 128 bytes of every needed row) in flight: an expansion is a chain of ld / 32 dependent
+    // steps, each an HBM round trip, and with few queries per SM nothing else hides that latency.  Every iteration
+    // commits exactly one (possibly empty) group so the wait below is the same constant throughout.
     auto issue = [&](int c) {
-        const uint32_t base = stage_u + (uint32_t)(c & 1) * 4096u;
+        if (c < n_ch) {
+            const uint32_t base = stage_u + (uint32_t)(c % NS) * 4096u;
 #pragma unroll
-        for (int p = 0; p < 8; p++)
-            if (cp[p]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[p]), "l"(src[p] + c * 32) : "memory");
+            for (int p = 0; p < 8; p++)
+                if (cp[p]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[p]), "l"(src[p] + c * 32) : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue(0);
+#pragma unroll
+    for (int c = 0; c < NS - 1; c++) issue(c);
     float acc = 0.0f;
     for (int c = 0; c < n_ch; c++) {
-        if (c + 1 < n_ch) {
-            issue(c + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+        issue(c + NS - 1);                       // into the slot the previous iteration finished reading
+        asm volatile("cp.async.wait_group %0;" ::"n"(NS - 1) : "memory");
         __syncwarp();
         if (need) {
-            const uint8_t *sp = stage + (size_t)(c & 1) * 4096 + lane * 128;
+            const uint8_t *sp = stage + (size_t)(c % NS) * 4096 + lane * 128;
             const float *qc = q_s + c * 32;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -242,6 +244,7 @@ __device__ __forceinline__ float warp_row_distances(const float *__restrict__ ro
         }
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     return metric_finish<METRIC>(acc);
 }
 
@@ -252,13 +255,15 @@ struct WarpScratch {
     float *nb_d;       // [32]
     uint32_t *nb_slot; // [32]
     uint32_t *nb_new;  // [32]
-    uint8_t *stage;    // [2][32 rows][128 B] row pieces of one expansion's neighbours (16-byte pieces XOR-swizzled)
+    uint8_t *stage;    // [stages][32 rows][128 B] row pieces of one expansion's neighbours (16-byte pieces XOR-swizzled)
 };
-static constexpr int HNSW_STAGE_BYTES = 2 * 32 * 128;
+static constexpr int HNSW_STAGE_STEP = 32 * 128;       // one step: 128 bytes of 32 rows
 __host__ __device__ inline size_t warp_scratch_head(int ld, int ef) {
     return (((size_t)ld * 4 + (size_t)(ef + 1) * sizeof(HCand) + 32 * 12) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t warp_scratch_bytes(int ld, int ef) { return warp_scratch_head(ld, ef) + HNSW_STAGE_BYTES; }
+__host__ __device__ inline size_t warp_scratch_bytes(int ld, int ef, int stages = 2) {
+    return warp_scratch_head(ld, ef) + (size_t)stages * HNSW_STAGE_STEP;
+}
 __device__ __forceinline__ WarpScratch carve(uint8_t *base, int ld, int ef) {
     WarpScratch w;
     w.q_s = reinterpret_cast<float *>(base);
@@ -310,7 +315,7 @@ __device__ __forceinline__ void greedy_descend(const GraphView &G, const float *
 // searchLayer(query, entry, ef, layer), hnsw_index.go:565-629.  Leaves the results ASCENDING in `sorted`
 // (= the cands buffer, whose heap is dead by then) and returns their number, or -1 on candidate-heap overflow.
 // touched (optional): every slot whose visited bit was set is appended, so the caller can clear the bits.
-template <int METRIC, bool FMA, bool STAGED>
+template <int METRIC, bool FMA, bool STAGED, int NS = 2>
 __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratch &W, long long entry, int ef, int layer,
                                             uint32_t *vis, HCand *cands, int cand_cap, uint32_t *touched, int *n_touched,
                                             long long &evals, long long &expansions, int lane) {
@@ -361,7 +366,7 @@ __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratc
                 }
                 if (!STAGED && isnew) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, W.q_s, G.ld);
             }
-            if (STAGED) d = warp_row_distances<METRIC, FMA>(G.rows, G.ld, nb, isnew != 0u, W.q_s, W.stage, lane);
+            if (STAGED) d = warp_row_distances<METRIC, FMA, NS>(G.rows, G.ld, nb, isnew != 0u, W.q_s, W.stage, lane);
             W.nb_d[lane] = d; W.nb_slot[lane] = nb; W.nb_new[lane] = isnew;
             evals += __popc(__ballot_sync(0xffffffffu, isnew != 0u));
             __syncwarp();
@@ -394,7 +399,7 @@ __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratc
     return n;
 }
 
-template <int METRIC, bool FMA>
+template <int METRIC, bool FMA, int NS>
 __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
     GraphView G, long long entry_slot, int max_level, const float *__restrict__ queries, int nq, int ef, long long k_req,
     float threshold, const uint8_t *__restrict__ doc_skip, uint32_t *__restrict__ visited, long long vis_words,
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * HNSW_WARPS + warp;
     if (q >= nq) return;
-    WarpScratch W = carve(smem + (size_t)warp * warp_scratch_bytes(G.ld, ef), G.ld, ef);
+    WarpScratch W = carve(smem + (size_t)warp * warp_scratch_bytes(G.ld, ef, NS), G.ld, ef);
     for (int j = lane; j < G.ld; j += 32) W.q_s[j] = queries[(size_t)q * G.ld + j];
     __syncwarp();
     HCand *cands = cand_heaps + (size_t)q * cand_cap;
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(
     greedy_descend<METRIC, FMA>(G, W.q_s, max_level, 0, curr, curr_dist, evals, lane);
 
     // phase 2: searchLayer(query, curr, ef, 0)
-    int n = search_layer<METRIC, FMA, true>(G, W, curr, ef, 0, vis, cands, cand_cap, nullptr, nullptr, evals, expansions, lane);
+    int n = search_layer<METRIC, FMA, true, NS>(G, W, curr, ef, 0, vis, cands, cand_cap, nullptr, nullptr, evals, expansions, lane);
 
     // results: post-filter (hnsw_index_search.go:321-335), already ascending, first k
     if (lane == 0) {
@@ -587,7 +592,12 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
     }
     const long long vis_words = (ix.n + 31) / 32;
     const int cand_cap = (int)std::min<int64_t>(ix.n + 1, (int64_t)16 * ef + 4096);
-    size_t smem = warp_scratch_bytes(ld, ef) * HNSW_WARPS;
+    // Row-staging depth per query warp: few queries per SM -> deep (the traversal is a chain of HBM round trips, only
+    // more bytes in flight per warp hide them), many -> shallow (resident warps hide them, shared memory is the limit)
+    int stages = nq <= (int64_t)sm_count() * 4 ? 8 : (nq <= (int64_t)sm_count() * 12 ? 4 : 2);
+    if (const char *e = getenv("COMET_B200_HNSW_STAGES")) { int v = atoi(e); stages = v >= 8 ? 8 : (v >= 4 ? 4 : 2); }
+    while (stages > 2 && warp_scratch_bytes(ld, ef, stages) * HNSW_WARPS > max_smem_optin()) stages /= 2;
+    size_t smem = warp_scratch_bytes(ld, ef, stages) * HNSW_WARPS;
     if (smem > max_smem_optin()) return fail(CM_ERR_UNSUPPORTED, "efSearch %d with dim %d does not fit shared memory", ef, ix.dim);
     // queries in groups so that the visited bitmaps stay bounded (<= 1 GiB)
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (vis_words * 4 + (int64_t)cand_cap * 8)));
@@ -601,20 +611,27 @@ static int hnsw_search_device(HNSWIndex &ix, const float *q_dev, int64_t nq, con
         CM_CUDA(cudaMemsetAsync(visited, 0, (size_t)m * vis_words * 4, st));
         unsigned blocks = (unsigned)((m + HNSW_WARPS - 1) / HNSW_WARPS);
         ProfScope prof(CM_PROF_HNSW, st);
-#define CM_HNSW_LAUNCH(MM, F)                                                                                         \
+#define CM_HNSW_LAUNCH_NS(MM, F, NS)                                                                                  \
     do {                                                                                                              \
-        CM_TRY(set_dyn_smem((const void *)hnsw_search_kernel<MM, F>, smem));                                               \
-        hnsw_search_kernel<MM, F><<<blocks, HNSW_WARPS * 32, smem, st>>>(                                             \
+        CM_TRY(set_dyn_smem((const void *)hnsw_search_kernel<MM, F, NS>, smem));                                      \
+        hnsw_search_kernel<MM, F, NS><<<blocks, HNSW_WARPS * 32, smem, st>>>(                                         \
             G, ix.entry_slot, ix.max_level, qp + (size_t)q0 * ld, (int)m, ef, (long long)p->k, p->threshold, doc_skip, visited, \
             vis_words, heaps, cand_cap, (long long)out_stride, out_ids + (size_t)q0 * out_stride,                     \
             out_scores + (size_t)q0 * out_stride, out_pos ? (long long *)out_pos + (size_t)q0 * out_stride : nullptr,  \
             (long long *)out_counts + q0, work ? (long long *)work + (size_t)q0 * 2 : nullptr);                       \
+    } while (0)
+#define CM_HNSW_LAUNCH(MM, F)                                                                                         \
+    do {                                                                                                              \
+        if (stages == 8) CM_HNSW_LAUNCH_NS(MM, F, 8);                                                                 \
+        else if (stages == 4) CM_HNSW_LAUNCH_NS(MM, F, 4);                                                            \
+        else CM_HNSW_LAUNCH_NS(MM, F, 2);                                                                             \
     } while (0)
         switch (ix.metric) {
         case CM_L2: if (fma) CM_HNSW_LAUNCH(CM_L2, true); else CM_HNSW_LAUNCH(CM_L2, false); break;
         case CM_L2SQ: if (fma) CM_HNSW_LAUNCH(CM_L2SQ, true); else CM_HNSW_LAUNCH(CM_L2SQ, false); break;
         default: if (fma) CM_HNSW_LAUNCH(CM_COSINE, true); else CM_HNSW_LAUNCH(CM_COSINE, false); break;
         }
+#undef CM_HNSW_LAUNCH_NS
 #undef CM_HNSW_LAUNCH
         count_launch();
         CM_CUDA(cudaGetLastError());
