@@ -71,4 +71,28 @@ for s in range(n):
 h = capi.HNSWIndex(d, capi.L2, 4, 20, 16)
 h.load_graph(ids[:n], x[:n], levels, [(l0_off, l0), (l1_off, np.asarray(l1, np.uint32))], 1, 1)
 h.search(q[:9], k=5)
+# round 2: row shards / list shards (one process, shards sharing the device), device filters, big-k fallbacks, wire formats,
+# HNSW flush
+sf = capi.ShardedFlatIndex(d, capi.L2SQ, [0, 0, 0], 6000)
+sf.add(ids, x.copy()); sf.search(q[:9], k=10); sf.search(q[:2], k=0); sf.remove(7); sf.flush(); sf.search(q, k=10)
+si = capi.ShardedIVFIndex(d, 16, capi.L2, [0, 0])
+si.train(x[:2000].copy()); si.add(ids[:5000], x[:5000].copy()); si.search(q[:9], k=10, nprobes=4); si.rebalance(); si.search(q[:9], k=10, nprobes=4)
+sp = capi.ShardedIVFPQIndex(d, capi.L2, 8, 8, 4, [0, 0])
+sp.train(x[:2000].copy()); sp.add(ids[:5000], x[:5000].copy()); sp.search(q[:9], k=10, nprobes=3); sp.rebalance(); sp.search(q[:9], k=10, nprobes=3)
+f = capi.FlatIndex(d, capi.L2)
+f.add(ids, x.copy())
+f.search(q[:9], k=10, filter_ids=ids[:300])                 # selective: candidate list
+f.search(q[:9], k=10, filter_ids=ids[::3].copy())           # skip mask, exact scan
+f.search(q, k=10, filter_ids=ids[::3].copy(), path=capi.PATH_TENSOR)
+iv.search(q[:2], k=0, nprobes=16); pq.search(q[:2], k=0); ip.search(q[:2], k=0, nprobes=8)
+for kind, ix, mk in (("flat", f, lambda: capi.FlatIndex(d, capi.L2)), ("ivf", iv, lambda: capi.IVFIndex(d, 16, capi.L2)),
+                     ("pq", pq, lambda: capi.PQIndex(d, capi.L2, 8, 4)), ("ivfpq", ip, lambda: capi.IVFPQIndex(d, capi.L2, 8, 8, 4))):
+    blob = capi.save_bytes(kind, ix.h)
+    other = mk()
+    capi.load_bytes(kind, other.h, blob)
+    other.search(q[:3], k=5)
+hb.remove(int(ids[0])); hb.remove(int(ids[3])); hb.flush(); hb.search(q[:4], k=5)
+blob = capi.save_bytes("hnsw", hb.h)
+hb2 = capi.HNSWIndex(d, capi.L2, 4, 20, 16)
+capi.load_bytes("hnsw", hb2.h, blob); hb2.search(q[:4], k=5)
 print("sanitize smoke done")
