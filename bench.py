@@ -8,9 +8,12 @@ GPU per step; synthetic N(0,1) data, random-init (there is no dataset to downloa
 
 One "step" = one device batch: every query of the batch is searched against the whole corpus
 (nq independent searchSingleQuery calls, flat_index_search.go:221-294) and its K best (id, score)
-pairs are produced.  N > 1 (under torchrun): the corpus is row-sharded over the ranks, every rank
-searches the global batch (512 x N queries) against its shard, per-shard top-K lists are
-all-gathered over NCCL and merged -- per-GPU work is constant, so `scaling` is "weak".
+pairs are produced.  N > 1 (under torchrun): the 1M x 768 corpus fits every GPU, so queries are the
+independent units -- every rank answers its own 512 queries against a replica, no data-path collective,
+per-GPU work constant ("weak").  The same line carries `rows_sharded`: the north-star layout (rows sharded
+over the N GPUs, one exchange step) through the library's single-process sharded index, driven by rank 0.
+`--sharding rows` runs the per-process variant (NCCL all-gather of per-shard top-K + device merge).
+`--workload c1 / b1 / c3 / c4 / c5`: BASELINE.json's other configurations (c5 = 100M x 768 over 8 GPUs).
 
 `value`  : queries/s with queries already resident in HBM (CUDA events on the launching stream).
 `e2e`    : queries/s through cm_flat_search with HOST buffers (pinned): H2D of the queries and D2H

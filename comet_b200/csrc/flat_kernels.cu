@@ -355,62 +355,77 @@ int launch_merge_topk(const uint64_t *part_keys, const int *part_counts, int nq,
 // returns its own sorted top-K; the global order (score, scan position) is (score, shard, rank in
 // the shard's list), so the merge needs nothing but the gathered lists.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MERGE_THREADS) merge_shards_kernel(
+// Every gathered entry finds its own place: its rank in the union is its rank in its own (sorted) list plus, for every
+// other shard, the number of that shard's entries that order before it -- a binary search per shard on the ordered score
+// bits, ties going to the lower shard.  No selection, no sort, no atomics; W x K threads-worth of independent work.
+static constexpr int MERGE_RANK_THREADS = 256;
+__global__ void __launch_bounds__(MERGE_RANK_THREADS) merge_shards_kernel(
     const uint32_t *__restrict__ ids, const float *__restrict__ scores, const long long *__restrict__ counts, int world,
-    long long nq, long long in_stride, int K, int C, long long out_stride, uint32_t *__restrict__ out_ids,
+    long long nq, long long in_stride, int K, long long out_stride, uint32_t *__restrict__ out_ids,
     float *__restrict__ out_scores, long long *__restrict__ out_counts) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);
-    __shared__ int cnt;
-    __shared__ uint64_t tau;
-    const CtaBarrier bar;
+    uint32_t *ord = reinterpret_cast<uint32_t *>(smem);                 // [world][in_stride] ordered score bits
+    __shared__ int cnt_s[64];
+    __shared__ long long bad_s;
     const int tid = threadIdx.x;
     const long long q = blockIdx.x;
-    if (tid == 0) { cnt = 0; tau = KEY_INF; }
-    __syncthreads();
     // A shard that could not answer a query (tensor-path candidate overflow: count -1, see cm_flat_search_device)
-    // makes the merged answer unknown too: the -1 is passed on, never silently treated as an empty list.
-    if (counts) {
-        long long bad = 0;          // -2 (zero query under cosine: every non-empty shard says so) wins over -1
-        for (int r = 0; r < world; r++) bad = min(bad, counts[(size_t)r * nq + q]);
-        if (bad < 0) {
-            if (tid == 0 && out_counts) out_counts[q] = bad;
-            return;
+    // makes the merged answer unknown too: the -1 is passed on, never silently treated as an empty list;
+    // -2 (zero query under cosine: every non-empty shard says so) wins over -1.
+    if (tid == 0) {
+        long long bad = 0, total = 0;
+        for (int r = 0; r < world; r++) {
+            long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
+            bad = min(bad, c);
+            c = max(0ll, min(c, in_stride));
+            cnt_s[r] = (int)c;
+            total += c;
+        }
+        bad_s = bad;
+        if (out_counts) out_counts[q] = bad < 0 ? bad : min((long long)K, total);
+    }
+    __syncthreads();
+    if (bad_s < 0) return;
+    const long long n_all = (long long)world * in_stride;
+    for (long long e = tid; e < n_all; e += MERGE_RANK_THREADS) {
+        const int r = (int)(e / in_stride), j = (int)(e - (long long)r * in_stride);
+        if (j < cnt_s[r]) ord[e] = float_to_ordered(scores[((size_t)r * nq + q) * in_stride + j]);
+    }
+    __syncthreads();
+    for (long long e = tid; e < n_all; e += MERGE_RANK_THREADS) {
+        const int r = (int)(e / in_stride), j = (int)(e - (long long)r * in_stride);
+        if (j >= cnt_s[r]) continue;
+        const uint32_t mine = ord[e];
+        long long rank = j;
+        for (int r2 = 0; r2 < world && rank < K; r2++) {
+            if (r2 == r) continue;
+            const uint32_t *o2 = ord + (size_t)r2 * in_stride;
+            int lo = 0, hi = cnt_s[r2];
+            if (r2 < r) { while (lo < hi) { int mid = (lo + hi) >> 1; if (o2[mid] <= mine) lo = mid + 1; else hi = mid; } }   // ties: lower shard first
+            else        { while (lo < hi) { int mid = (lo + hi) >> 1; if (o2[mid] < mine) lo = mid + 1; else hi = mid; } }
+            rank += lo;
+        }
+        if (rank < K) {
+            const size_t src = ((size_t)r * nq + q) * in_stride + j;
+            out_ids[(size_t)q * out_stride + rank] = ids[src];
+            out_scores[(size_t)q * out_stride + rank] = scores[src];
         }
     }
-    for (int r = 0; r < world; r++) {
-        long long c = counts ? counts[(size_t)r * nq + q] : in_stride;
-        if (c > in_stride) c = in_stride;
-        const float *sc = scores + ((size_t)r * nq + q) * in_stride;
-        for (int j = tid; j < c; j += MERGE_THREADS) buf[atomicAdd(&cnt, 1)] = make_key(sc[j], (uint32_t)(r * in_stride + j));
-    }
-    compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
-    int m = cnt;
-    for (int i = tid; i < m; i += MERGE_THREADS) {
-        uint64_t key = buf[i];
-        uint32_t src = key_pos(key);
-        uint32_t r = src / (uint32_t)in_stride, j = src % (uint32_t)in_stride;
-        out_ids[(size_t)q * out_stride + i] = ids[((size_t)r * nq + q) * in_stride + j];
-        out_scores[(size_t)q * out_stride + i] = key_score(key);
-    }
-    if (tid == 0 && out_counts) out_counts[q] = m;
 }
 
 int launch_merge_shards(const uint32_t *ids, const float *scores, const int64_t *counts, int world, int64_t nq,
                         int64_t in_stride, int K, int64_t out_stride, uint32_t *out_ids, float *out_scores,
                         int64_t *out_counts, cudaStream_t stream) {
     if (nq <= 0) return CM_OK;
-    int C = next_pow2((int)(world * in_stride));
-    if (C < 512) C = 512;
-    size_t smem = (size_t)C * 8;
-    if (smem > max_smem_optin())    // k <= 0 / huge k: one radix sort per query over the gathered lists (flat_bigk.cu)
+    size_t smem = (size_t)world * in_stride * 4;
+    if (smem + 1024 > max_smem_optin() || world > 64)    // k <= 0 / huge k: one radix sort per query over the gathered lists (flat_bigk.cu)
         return merge_shards_bigk(ids, scores, counts, world, nq, in_stride, (int64_t)K, out_stride, out_ids, out_scores, out_counts, stream);
     CM_TRY(set_dyn_smem((const void *)merge_shards_kernel, smem));
     ProfScope prof(CM_PROF_SELECT, stream);
-    merge_shards_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>(ids, scores, (const long long *)counts, world,
-                                                                      (long long)nq, (long long)in_stride, K, C,
-                                                                      (long long)out_stride, out_ids, out_scores,
-                                                                      (long long *)out_counts);
+    merge_shards_kernel<<<(unsigned)nq, MERGE_RANK_THREADS, smem, stream>>>(ids, scores, (const long long *)counts, world,
+                                                                           (long long)nq, (long long)in_stride, K,
+                                                                           (long long)out_stride, out_ids, out_scores,
+                                                                           (long long *)out_counts);
     count_launch();
     CM_CUDA(cudaGetLastError());
     return CM_OK;

@@ -9,7 +9,7 @@ import shutil
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "gpurun_out", "final")
+SRC = os.path.join(ROOT, "gpurun_out", "final")       # r01; later rounds: gpurun_out/<tag>final (set in main)
 DST = os.path.join(ROOT, "profiles")
 
 
@@ -47,7 +47,10 @@ def table(ls):
 
 
 def main():
+    global SRC
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if tag != "r01":
+        SRC = os.path.join(ROOT, "gpurun_out", tag + "final")
     os.makedirs(DST, exist_ok=True)
 
     def cp(src, dst):
@@ -65,7 +68,12 @@ def main():
                  ("idx_1m.json", "bench_indexes_1Mx768.json"), ("c3.json", "bench_c3_ivfpq_10Mx768.json"),
                  ("c4.json", "bench_c4_hnsw_1Mx768.json"), ("pytest.log", "pytest_gpu.log"),
                  ("summary_tensor.md", "ncu_full_tensor_path.md"), ("summary_scan.md", "ncu_full_exact_scan.md"),
-                 ("summary_adc.md", "ncu_full_adc_scan.md")]:
+                 ("summary_adc.md", "ncu_full_adc_scan.md"),
+                 # round 2
+                 ("bench_n1_l2.json", "bench_n1_l2.json"), ("bench_c3.json", "bench_c3.json"), ("bench_c4.json", "bench_c4.json"),
+                 ("bench_c4_b8192.json", "bench_c4_b8192.json"), ("bench_c5_one_shard.json", "bench_c5_one_shard_12.5Mx768_l2.json"),
+                 ("launches_tensor_path_l2.csv", "launches_tensor_path_l2.csv"), ("memcheck.log", "memcheck_all_paths.log"),
+                 ("racecheck.log", "racecheck_all_paths.log"), ("gpu.txt", "gpu.txt")]:
         cp(s, d)
     # per-step launch tables
     md = []
@@ -75,7 +83,8 @@ def main():
         md.append("## Tensor path: the launches of one step (512 queries x 1M x 768, K=100)\n")
         md.append("`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3 "
                   "--no-cpu-baseline`; serialised, cold-cache durations: compare shares, not absolutes.\n")
-        md.append(table(step_table(ls, "preprocess_rows")))
+        first = "prep_queries" if any("prep_queries" in l[0] for l in ls) else "preprocess_rows"
+        md.append(table(step_table(ls, first)))
     p = os.path.join(SRC, "launches_exact_scan.csv")
     if os.path.exists(p):
         ls = [l for l in launches(p) if "flat_scan" in l[0]]
@@ -105,7 +114,7 @@ def main():
                 vals.append(rd + float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u])
                 rd = None
         return vals
-    g = dram("summary_tensor.md", "flat_gemm_kernel")
+    g = dram("summary_tensor.md", "flat_gemm_ts_kernel") or dram("summary_tensor.md", "flat_gemm_kernel")
     if g:
         traffic["flat_gemm_kernel_per_step_bytes"] = int(sum(g[-3:]))
         traffic["flat_gemm_kernel_launches"] = [int(x) for x in g]
