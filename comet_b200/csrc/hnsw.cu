@@ -152,6 +152,29 @@ __device__ __forceinline__ HCand h_pop(HCand *a, int &n) {
     return a[last];
 }
 
+// heap.Push of Go's container/heap by the whole warp, same result as the serial h_push: sift-up compares the NEW element
+// with its successive parents and stops at the first one it is not less than -- so every ancestor on the path to the
+// root is loaded by its own lane at once, a ballot finds how far the element climbs, the ancestors below that point move
+// down one level and the element lands.  One round of loads instead of a dependent chain of log2(n) (lane 0 replaying the
+// heaps serially was most of an expansion's time).  Must be called by all 32 lanes with identical arguments.
+template <bool IS_MAX>
+__device__ __forceinline__ void h_push_warp(HCand *a, int &n, HCand c, int lane) {
+    const int j = n;
+    const int D = 31 - __clz(j + 1);                      // ancestors of index j: ((j + 1) >> l) - 1, l = 1 .. D
+    HCand anc{0.0f, 0u};
+    bool lt = false;
+    if (lane >= 1 && lane <= D) {
+        anc = a[((j + 1) >> lane) - 1];
+        lt = IS_MAX ? (c.d > anc.d) : (c.d < anc.d);      // less(new, ancestor)
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, lt);
+    const int up = __ffs(~(m >> 1)) - 1;                  // leading run of "less than the parent": levels climbed
+    if (lane >= 1 && lane <= up) a[((j + 1) >> (lane - 1)) - 1] = anc;
+    if (lane == 0) a[((j + 1) >> up) - 1] = c;
+    __syncwarp();
+    n = j + 1;
+}
+
 // Distance.Calculate(a = vector in shared memory, b = row) by ONE lane in the reference's order
 template <int METRIC, bool FMA>
 __device__ __forceinline__ float row_distance(const float *__restrict__ row, const float *__restrict__ q_s, int ld) {
@@ -319,15 +342,15 @@ template <int METRIC, bool FMA, bool STAGED, int NS = 2>
 __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratch &W, long long entry, int ef, int layer,
                                             uint32_t *vis, HCand *cands, int cand_cap, uint32_t *touched, int *n_touched,
                                             long long &evals, long long &expansions, int lane) {
-    int n_c = 0, n_r = 0;
+    int n_c = 0, n_r = 0;                 // identical on every lane: pushes are warp-cooperative, pops run on lane 0
     bool overflow = false;
     if (G.deleted[entry] == 0) {
-        if (lane == 0) {
-            float d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)entry * G.ld, W.q_s, G.ld);
-            HCand c{d, (uint32_t)entry};
-            h_push<false>(cands, n_c, c);
-            h_push<true>(W.res, n_r, c);
-        }
+        float d = 0.0f;
+        if (lane == 0) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)entry * G.ld, W.q_s, G.ld);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        const HCand c{d, (uint32_t)entry};
+        h_push_warp<false>(cands, n_c, c, lane);
+        h_push_warp<true>(W.res, n_r, c, lane);
         evals++;
     }
     if (lane == 0) {
@@ -338,30 +361,44 @@ __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratc
     for (;;) {
         uint32_t cur_slot = 0;
         int go = 0;
-        if (lane == 0 && n_c > 0) {
-            HCand cur = h_pop<false>(cands, n_c);
-            if (!(n_r >= ef && cur.d > W.res[0].d)) { go = 1; cur_slot = cur.slot; }
+        if (n_c > 0) {
+            if (lane == 0) {
+                int nn = n_c;
+                HCand cur = h_pop<false>(cands, nn);
+                if (!(n_r >= ef && cur.d > W.res[0].d)) { go = 1; cur_slot = cur.slot; }
+            }
+            n_c--;
         }
         go = __shfl_sync(0xffffffffu, go, 0);
         if (!go) break;
         cur_slot = __shfl_sync(0xffffffffu, cur_slot, 0);
         expansions++;
-        int deg = 0;
-        const uint32_t *E = nullptr;
-        if (layer <= G.levels[cur_slot]) {                          // layer < len(node.Edges)
+        int deg = 0, width = 0;
+        uint32_t *E = nullptr;
+        if (layer == 0 || layer <= G.levels[cur_slot]) {            // layer < len(node.Edges); every node has layer 0
             int *degp;
             E = G.edges(cur_slot, layer, &degp);
-            deg = *degp;
+            width = layer == 0 ? G.E0 : G.EU;                       // the adjacency row is that wide whatever its degree:
+            deg = *degp;                                            // degree and neighbours are fetched together below
         }
-        for (int b = 0; b < deg; b += 32) {
+        for (int b = 0; b < width; b += 32) {
             int j = b + lane;
             uint32_t nb = 0, isnew = 0;
             float d = 0.0f;
+            const uint32_t nb_raw = j < width ? E[j] : 0u;
+            if (b >= deg) break;                                    // uniform: deg is the same on every lane
             if (j < deg) {
-                nb = E[j];
-                if (G.deleted[nb] == 0) {
-                    uint32_t bit = 1u << (nb & 31);
-                    uint32_t old = atomicOr(&vis[nb >> 5], bit);
+                nb = nb_raw;
+                const uint32_t bit = 1u << (nb & 31);
+                if (STAGED) {
+                    // search: the deleted flag and the visited bit travel together; marking a deleted node visited changes
+                    // nothing (it is skipped whenever it is met) and the insertion path, which records what it touched, keeps
+                    // the reference's order of tests
+                    const uint8_t del = G.deleted[nb];
+                    const uint32_t old = atomicOr(&vis[nb >> 5], bit);
+                    isnew = del == 0 && (old & bit) == 0u;
+                } else if (G.deleted[nb] == 0) {
+                    const uint32_t old = atomicOr(&vis[nb >> 5], bit);
                     isnew = (old & bit) == 0u;
                 }
                 if (!STAGED && isnew) d = row_distance_rw<METRIC, FMA>(G.rows + (size_t)nb * G.ld, W.q_s, G.ld);
@@ -370,29 +407,33 @@ __device__ __forceinline__ int search_layer(const GraphView &G, const WarpScratc
             W.nb_d[lane] = d; W.nb_slot[lane] = nb; W.nb_new[lane] = isnew;
             evals += __popc(__ballot_sync(0xffffffffu, isnew != 0u));
             __syncwarp();
-            if (lane == 0) {
-                int cnt = min(32, deg - b);
-                for (int t = 0; t < cnt; t++) {
-                    if (!W.nb_new[t]) continue;
-                    if (touched) touched[(*n_touched)++] = W.nb_slot[t];
-                    float dt = W.nb_d[t];
-                    if (n_r < ef || dt < W.res[0].d) {
-                        HCand c{dt, W.nb_slot[t]};
-                        if (n_c >= cand_cap) { overflow = true; break; }
-                        h_push<false>(cands, n_c, c);
-                        h_push<true>(W.res, n_r, c);
-                        if (n_r > ef) (void)h_pop<true>(W.res, n_r);
+            const int cnt = min(32, deg - b);
+            for (int t = 0; t < cnt; t++) {                         // every lane walks the neighbours in order
+                if (!W.nb_new[t]) continue;
+                if (touched && lane == 0) touched[(*n_touched)++] = W.nb_slot[t];
+                const float dt = W.nb_d[t];
+                if (n_r < ef || dt < W.res[0].d) {
+                    const HCand c{dt, W.nb_slot[t]};
+                    if (n_c >= cand_cap) { overflow = true; break; }
+                    h_push_warp<false>(cands, n_c, c, lane);
+                    h_push_warp<true>(W.res, n_r, c, lane);
+                    if (n_r > ef) {
+                        if (lane == 0) { int nn = n_r; (void)h_pop<true>(W.res, nn); }
+                        n_r--;
+                        __syncwarp();
                     }
                 }
             }
             __syncwarp();
+            if (overflow) break;
         }
-        if (__shfl_sync(0xffffffffu, (int)overflow, 0)) break;
+        if (overflow) break;
     }
     int n = -1;
     if (lane == 0 && !overflow) {
         n = n_r;
-        for (int i = n - 1; i >= 0; i--) cands[i] = h_pop<true>(W.res, n_r);     // :622-626 ascending
+        int nn = n_r;
+        for (int i = n - 1; i >= 0; i--) cands[i] = h_pop<true>(W.res, nn);      // :622-626 ascending
     }
     n = __shfl_sync(0xffffffffu, n, 0);
     __syncwarp();
