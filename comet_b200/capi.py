@@ -161,6 +161,19 @@ SIGNATURES = {
     "cm_ivfpq_flush": (C.c_int, [vp]),
     "cm_ivfpq_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p, i64p]),
     "cm_ivfpq_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp, vp]),
+    "cm_pq_sharded_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_int64, C.POINTER(vp)]),
+    "cm_pq_sharded_destroy": (C.c_int, [vp]),
+    "cm_pq_sharded_shards": (C.c_int, [vp]),
+    "cm_pq_sharded_size": (C.c_int64, [vp]),
+    "cm_pq_sharded_trained": (C.c_int, [vp]),
+    "cm_pq_sharded_train": (C.c_int, [vp, f32p, C.c_int64]),
+    "cm_pq_sharded_set_codebooks": (C.c_int, [vp, f32p]),
+    "cm_pq_sharded_get_codebooks": (C.c_int, [vp, f32p]),
+    "cm_pq_sharded_add": (C.c_int, [vp, u32p, f32p, C.c_int64, C.c_int]),
+    "cm_pq_sharded_remove": (C.c_int, [vp, C.c_uint32]),
+    "cm_pq_sharded_flush": (C.c_int, [vp]),
+    "cm_pq_sharded_search": (C.c_int, [vp, f32p, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, u32p, f32p, i64p]),
+    "cm_pq_sharded_search_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.POINTER(SearchParams), C.c_int64, vp, vp, vp, vp]),
     "cm_ivfpq_sharded_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.POINTER(vp)]),
     "cm_ivfpq_sharded_destroy": (C.c_int, [vp]),
     "cm_ivfpq_sharded_shards": (C.c_int, [vp]),
@@ -811,6 +824,65 @@ class IVFPQIndex(_ADCIndex):
         if nprobes is None:
             nprobes = self.default_nprobes()
         return self._search(queries, k, threshold, nprobes, filter_ids, out_stride)
+
+
+class ShardedPQIndex:
+    """Thin owner of a cm_pq_sharded handle: one process, code rows sharded over `devices`."""
+
+    def __init__(self, dim, metric, M, nbits, devices, rows_per_shard):
+        self.h = vp()
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        check(lib().cm_pq_sharded_create(int(dim), int(metric), int(M), int(nbits), ptr(dv, i32p), len(dv), int(rows_per_shard),
+                                         C.byref(self.h)))
+        self.dim, self.metric, self.M, self.nbits, self.devices = dim, metric, M, nbits, list(devices)
+
+    def __del__(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().cm_pq_sharded_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(lib().cm_pq_sharded_size(self.h))
+
+    def train(self, rows):
+        r = _f32(rows)
+        check(lib().cm_pq_sharded_train(self.h, ptr(r, f32p), len(r)))
+
+    def set_codebooks(self, cb):
+        c = _f32(cb)
+        check(lib().cm_pq_sharded_set_codebooks(self.h, ptr(c, f32p)))
+
+    def codebooks(self):
+        out = np.empty((self.M, 1 << self.nbits, self.dim // self.M), np.float32)
+        check(lib().cm_pq_sharded_get_codebooks(self.h, ptr(out, f32p)))
+        return out
+
+    def add(self, ids, rows, writeback=True):
+        ids = _u32(np.atleast_1d(ids))
+        if not (isinstance(rows, np.ndarray) and rows.dtype == np.float32 and rows.flags.c_contiguous):
+            rows = _f32(rows)
+        rows2 = rows.reshape(len(ids), self.dim)
+        check(lib().cm_pq_sharded_add(self.h, ptr(ids, u32p), ptr(rows2, f32p), len(ids), 1 if writeback else 0))
+
+    def remove(self, id_):
+        check(lib().cm_pq_sharded_remove(self.h, int(id_)))
+
+    def flush(self):
+        check(lib().cm_pq_sharded_flush(self.h))
+
+    def search(self, queries, k=10, threshold=0.0, filter_ids=None):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq, d = q.shape
+        n = len(self)
+        stride = max(1, n if (k <= 0 or k > n) else k)
+        ids = np.zeros((nq, stride), np.uint32)
+        sc = np.zeros((nq, stride), np.float32)
+        cnt = np.zeros(nq, np.int64)
+        p, keep = make_params(k=k, threshold=threshold, filter_ids=filter_ids)
+        check(lib().cm_pq_sharded_search(self.h, ptr(q, f32p), nq, d, C.byref(p), stride, ptr(ids, u32p), ptr(sc, f32p), ptr(cnt, i64p)))
+        return ids, sc, cnt
 
 
 class ShardedIVFPQIndex:

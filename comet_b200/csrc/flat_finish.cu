@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 2) ts_select_kernel(
                     if (lane >= o) inc += t;
                 }
                 int before = inc - sum;
+                __syncwarp();            // every lane has read s_rank before the one that owns the bucket rewrites it
                 if (r > before && r <= inc) {
                     int rr = r - before, bb = 0;
                     for (; bb < 7; bb++) {

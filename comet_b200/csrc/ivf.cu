@@ -1015,7 +1015,7 @@ int cm_ivf_sharded_add(cm_ivf_sharded *h, const uint32_t *ids, float *rows, int6
         int rc_a = cm_ivf_add(h->assigner, ids + i0, batch, m, 1, lists.data());      // rows come back preprocessed
         const int64_t good = cm_ivf_size(h->assigner);
         if (rc_a == CM_ERR_ZERO_VECTOR) { rc_zero = rc_a; zero_msg = cm_last_error(); } else rc = rc_a;
-        if (rc == CM_OK) rc = ivfs_clear_vectors(h->assigner);
+        if (rc == CM_OK) { cudaSetDevice(ls.dev[0]); rc = ivfs_clear_vectors(h->assigner); }
         for (int r = 0; r < W; r++) { sub_ids[(size_t)r].clear(); sub_lists[(size_t)r].clear(); sub_rows[(size_t)r].clear(); }
         for (int64_t i = 0; i < good && rc == CM_OK; i++) {
             const int32_t l = lists[(size_t)i];
@@ -1110,7 +1110,7 @@ int cm_ivf_sharded_rebalance(cm_ivf_sharded *h) {
             std::vector<int32_t> lo(keep.size());
             if (!keep.empty()) rc = cm_ivf_get_rows(h->shard[(size_t)r], keep.data(), (int64_t)keep.size(), rows.data());
             for (size_t i = 0; i < keep.size(); i++) { ids[i] = ix.store.ids_host_mirror[(size_t)keep[i]]; lo[i] = ix.list_of[(size_t)keep[i]]; }
-            if (rc == CM_OK) rc = ivfs_clear_vectors(h->shard[(size_t)r]);
+            if (rc == CM_OK) { cudaSetDevice(ls.dev[(size_t)r]); rc = ivfs_clear_vectors(h->shard[(size_t)r]); }
             if (rc == CM_OK && !keep.empty()) rc = cm_ivf_load_lists(h->shard[(size_t)r], ids.data(), rows.data(), lo.data(), (int64_t)keep.size());
         }
     }

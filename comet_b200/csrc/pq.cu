@@ -1489,7 +1489,7 @@ int cm_ivfpq_sharded_add(cm_ivfpq_sharded *h, const uint32_t *ids, float *rows, 
         if (rc_a == CM_ERR_ZERO_VECTOR) { rc_zero = rc_a; zero_msg = cm_last_error(); } else rc = rc_a;
         codes.resize((size_t)std::max<int64_t>(good, 1) * M);
         if (rc == CM_OK && good > 0) rc = cm_ivfpq_get_codes(h->assigner, 0, good, codes.data());
-        if (rc == CM_OK) rc = ivfpqs_clear_vectors(h->assigner->ix);
+        if (rc == CM_OK) { cudaSetDevice(ls.dev[0]); rc = ivfpqs_clear_vectors(h->assigner->ix); }
         for (int r = 0; r < W; r++) { sub_ids[(size_t)r].clear(); sub_lists[(size_t)r].clear(); sub_codes[(size_t)r].clear(); }
         for (int64_t i = 0; i < good && rc == CM_OK; i++) {
             const int32_t l = lists[(size_t)i];
@@ -1577,6 +1577,7 @@ int cm_ivfpq_sharded_rebalance(cm_ivfpq_sharded *h) {
                     ids.push_back(ids_all[(size_t)i]); lo.push_back(l);
                     codes.insert(codes.end(), all.begin() + (size_t)i * M, all.begin() + (size_t)(i + 1) * M);
                 }
+                cudaSetDevice(ls.dev[(size_t)r]);          // the shard's own device: its buffers are not mapped on the others
                 rc = ivfpqs_clear_vectors(ix);
             } else {
                 for (int l = 0; l < ls.nlist; l++)

@@ -33,12 +33,45 @@
 #include "shard_worker.cuh"
 
 
+// what a row shard has to offer: FlatIndex and PQIndex shard the same way (the candidate number of a result IS its store
+// position, so (score, shard, rank within the shard's list) is the single index's order for both)
+struct ShardOps {
+    int64_t (*size)(const void *);
+    int (*add)(void *, const uint32_t *, float *, int64_t, int);
+    int (*remove)(void *, uint32_t);
+    int (*flush)(void *);
+    int (*search_device)(void *, const float *, int64_t, int, const cm_search_params *, int64_t, uint32_t *, float *, int64_t *, void *);
+    int (*destroy)(void *);
+};
+static const ShardOps FLAT_OPS = {
+    [](const void *h) { return cm_flat_size((const cm_flat *)h); },
+    [](void *h, const uint32_t *ids, float *rows, int64_t n, int wb) { return cm_flat_add((cm_flat *)h, ids, rows, n, wb); },
+    [](void *h, uint32_t id) { return cm_flat_remove((cm_flat *)h, id); },
+    [](void *h) { return cm_flat_flush((cm_flat *)h); },
+    [](void *h, const float *q, int64_t nq, int dim, const cm_search_params *p, int64_t stride, uint32_t *ids, float *sc, int64_t *cnt, void *st) {
+        return cm_flat_search_device((cm_flat *)h, q, nq, dim, p, stride, ids, sc, nullptr, cnt, st);
+    },
+    [](void *h) { return cm_flat_destroy((cm_flat *)h); },
+};
+static const ShardOps PQ_OPS = {
+    [](const void *h) { return cm_pq_size((const cm_pq *)h); },
+    [](void *h, const uint32_t *ids, float *rows, int64_t n, int wb) { return cm_pq_add((cm_pq *)h, ids, rows, n, wb); },
+    [](void *h, uint32_t id) { return cm_pq_remove((cm_pq *)h, id); },
+    [](void *h) { return cm_pq_flush((cm_pq *)h); },
+    [](void *h, const float *q, int64_t nq, int dim, const cm_search_params *p, int64_t stride, uint32_t *ids, float *sc, int64_t *cnt, void *st) {
+        return cm_pq_search_device((cm_pq *)h, q, nq, dim, p, stride, ids, sc, nullptr, cnt, st);
+    },
+    [](void *h) { return cm_pq_destroy((cm_pq *)h); },
+};
+
 struct cm_flat_sharded {
     int dim = 0, metric = 0;
     int64_t rows_per_shard = 0, n = 0;
     int cur = 0;                           // shard that receives the next Add (scan order = shard order)
+    const ShardOps *ops = &FLAT_OPS;
+    int64_t pq_cb_floats = 0;              // PQ shards: floats of the codebooks (M x Ksub x dsub = 2^nbits x dim)
     std::vector<int> dev;
-    std::vector<cm_flat *> shard;
+    std::vector<void *> shard;             // cm_flat * or cm_pq * (see ops)
     std::vector<cudaStream_t> st;          // one stream per shard, on its device
     std::vector<char> direct;              // shard r's kernels read the queries from and write their lists into devices[0]'s memory (peer access)
     std::vector<cudaEvent_t> done;         // shard r's results are in the leader's gather buffer
@@ -75,8 +108,8 @@ static int grow(void **p, int64_t *cap, int64_t want, size_t elem) {
 
 extern "C" {
 
-int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_devices, int64_t rows_per_shard,
-                           cm_flat_sharded **out) {
+static int row_shards_create(int dim, int metric, const int *devices, int n_devices, int64_t rows_per_shard, const ShardOps *ops,
+                             const std::function<int(void **)> &make_shard, cm_flat_sharded **out) {
     if (!out) return cm::fail(CM_ERR_INVALID_ARG, "out is NULL");
     *out = nullptr;
     if (dim <= 0) return cm::fail(CM_ERR_INVALID_ARG, "dimension must be positive");
@@ -91,7 +124,7 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
     int prev = 0;
     cudaGetDevice(&prev);
     cm_flat_sharded *h = new cm_flat_sharded();
-    h->dim = dim; h->metric = metric; h->rows_per_shard = rows_per_shard;
+    h->dim = dim; h->metric = metric; h->rows_per_shard = rows_per_shard; h->ops = ops;
     h->dev.assign(devices, devices + n_devices);
     h->shard.resize((size_t)n_devices, nullptr);
     h->st.resize((size_t)n_devices, nullptr);
@@ -103,7 +136,7 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
     int rc = CM_OK;
     for (int r = 0; r < n_devices && rc == CM_OK; r++) {
         cudaSetDevice(devices[r]);
-        rc = cm_flat_create(dim, metric, &h->shard[(size_t)r]);
+        rc = make_shard(&h->shard[(size_t)r]);
         if (rc != CM_OK) break;
         if (cudaStreamCreateWithFlags(&h->st[(size_t)r], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&h->done[(size_t)r]) != cudaSuccess || cudaEventCreate(&h->t_begin[(size_t)r]) != cudaSuccess ||
@@ -144,6 +177,12 @@ int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_device
     return CM_OK;
 }
 
+int cm_flat_sharded_create(int dim, int metric, const int *devices, int n_devices, int64_t rows_per_shard,
+                           cm_flat_sharded **out) {
+    return row_shards_create(dim, metric, devices, n_devices, rows_per_shard, &FLAT_OPS,
+                             [=](void **sh) { return cm_flat_create(dim, metric, (cm_flat **)sh); }, out);
+}
+
 int cm_flat_sharded_destroy(cm_flat_sharded *h) {
     if (!h) return CM_OK;
     h->workers.clear();            // joins the worker threads
@@ -156,7 +195,7 @@ int cm_flat_sharded_destroy(cm_flat_sharded *h) {
         if (h->t_begin[r]) cudaEventDestroy(h->t_begin[r]);
         if (h->t_searched[r]) cudaEventDestroy(h->t_searched[r]);
         cudaFree(h->buf[r].q); cudaFree(h->buf[r].ids); cudaFree(h->buf[r].sc); cudaFree(h->buf[r].cnt);
-        if (h->shard[r]) cm_flat_destroy(h->shard[r]);
+        if (h->shard[r]) h->ops->destroy(h->shard[r]);
     }
     if (!h->dev.empty()) {
         cudaSetDevice(h->dev[0]);
@@ -178,7 +217,7 @@ int64_t cm_flat_sharded_last_exchange_bytes(const cm_flat_sharded *h) { return h
 // Rows go to shard `cur` until it holds rows_per_shard rows, then to the next one: scan order == (shard, position
 // within the shard), also after a Flush has shortened earlier shards.
 static int sharded_room(cm_flat_sharded *h) {
-    while (h->cur < (int)h->dev.size() && cm_flat_size(h->shard[(size_t)h->cur]) >= h->rows_per_shard) h->cur++;
+    while (h->cur < (int)h->dev.size() && h->ops->size(h->shard[(size_t)h->cur]) >= h->rows_per_shard) h->cur++;
     return h->cur < (int)h->dev.size() ? CM_OK
                                        : cm::fail(CM_ERR_UNSUPPORTED, "sharded index is full: %lld rows in %d shards of %lld",
                                                   (long long)h->n, (int)h->dev.size(), (long long)h->rows_per_shard);
@@ -194,12 +233,12 @@ int cm_flat_sharded_add(cm_flat_sharded *h, const uint32_t *ids, float *rows, in
     while (done < n && rc == CM_OK) {
         rc = sharded_room(h);
         if (rc != CM_OK) break;
-        cm_flat *sh = h->shard[(size_t)h->cur];
-        const int64_t before = cm_flat_size(sh);
+        void *sh = h->shard[(size_t)h->cur];
+        const int64_t before = h->ops->size(sh);
         const int64_t m = std::min(h->rows_per_shard - before, n - done);
         cudaSetDevice(h->dev[(size_t)h->cur]);
-        rc = cm_flat_add(sh, ids + done, rows + (size_t)done * h->dim, m, writeback);
-        const int64_t added = cm_flat_size(sh) - before;     // a zero vector under cosine stops the batch at that row
+        rc = h->ops->add(sh, ids + done, rows + (size_t)done * h->dim, m, writeback);
+        const int64_t added = h->ops->size(sh) - before;     // a zero vector under cosine stops the batch at that row
         h->n += added;
         done += added;
     }
@@ -212,12 +251,13 @@ int cm_flat_sharded_add(cm_flat_sharded *h, const uint32_t *ids, float *rows, in
 int cm_flat_sharded_add_device(cm_flat_sharded *h, int r, const uint32_t *ids_host, const float *rows_dev, int64_t n,
                                void *stream) {
     if (!h || r < 0 || r >= (int)h->dev.size()) return cm::fail(CM_ERR_INVALID_ARG, "bad shard");
-    const int64_t have = cm_flat_size(h->shard[(size_t)r]);
+    if (h->ops != &FLAT_OPS) return cm::fail(CM_ERR_UNSUPPORTED, "device-resident rows are a FlatIndex entry point");
+    const int64_t have = cm_flat_size((cm_flat *)h->shard[(size_t)r]);
     if (have + n > h->rows_per_shard) return cm::fail(CM_ERR_UNSUPPORTED, "shard %d would exceed its %lld rows", r, (long long)h->rows_per_shard);
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(h->dev[(size_t)r]);
-    int rc = cm_flat_add_device(h->shard[(size_t)r], ids_host, rows_dev, n, stream);
+    int rc = cm_flat_add_device((cm_flat *)h->shard[(size_t)r], ids_host, rows_dev, n, stream);
     cudaSetDevice(prev);
     if (rc == CM_OK) h->n += n;
     return rc;
@@ -231,7 +271,7 @@ int cm_flat_sharded_reserve(cm_flat_sharded *h, int64_t n_rows) {
     for (size_t r = 0; r < h->dev.size() && rc == CM_OK && n_rows > 0; r++) {
         const int64_t m = std::min(n_rows, h->rows_per_shard);
         cudaSetDevice(h->dev[r]);
-        rc = cm_flat_reserve(h->shard[r], m);
+        if (h->ops == &FLAT_OPS) rc = cm_flat_reserve((cm_flat *)h->shard[r], m);
         n_rows -= m;
     }
     cudaSetDevice(prev);
@@ -245,7 +285,7 @@ int cm_flat_sharded_remove(cm_flat_sharded *h, uint32_t id) {
     cudaGetDevice(&prev);
     int rc = CM_ERR_NOT_FOUND;
     for (size_t r = 0; r < h->dev.size(); r++) {
-        rc = cm_flat_remove(h->shard[r], id);
+        rc = h->ops->remove(h->shard[r], id);
         if (rc != CM_ERR_NOT_FOUND) break;
     }
     cudaSetDevice(prev);
@@ -260,8 +300,8 @@ int cm_flat_sharded_flush(cm_flat_sharded *h) {
     int rc = CM_OK;
     int64_t total = 0;
     for (size_t r = 0; r < h->dev.size() && rc == CM_OK; r++) {
-        rc = cm_flat_flush(h->shard[r]);
-        total += cm_flat_size(h->shard[r]);
+        rc = h->ops->flush(h->shard[r]);
+        total += h->ops->size(h->shard[r]);
     }
     if (rc == CM_OK) h->n = total;
     cudaSetDevice(prev);
@@ -270,7 +310,7 @@ int cm_flat_sharded_flush(cm_flat_sharded *h) {
 
 int cm_flat_sharded_shard_size(const cm_flat_sharded *h, int r, int64_t *rows) {
     if (!h || r < 0 || r >= (int)h->dev.size() || !rows) return cm::fail(CM_ERR_INVALID_ARG, "bad shard");
-    *rows = cm_flat_size(h->shard[(size_t)r]);
+    *rows = h->ops->size(h->shard[(size_t)r]);
     return CM_OK;
 }
 
@@ -280,7 +320,7 @@ int cm_flat_sharded_last_stats(const cm_flat_sharded *h, cm_flat_stats *out) {
     memset(out, 0, sizeof(*out));
     for (size_t r = 0; r < h->dev.size(); r++) {
         cm_flat_stats s;
-        if (cm_flat_last_stats(h->shard[r], &s) != CM_OK) continue;
+        if (h->ops != &FLAT_OPS || cm_flat_last_stats((cm_flat *)h->shard[r], &s) != CM_OK) continue;
         out->path_used = std::max(out->path_used, s.path_used);
         out->passes = std::max(out->passes, s.passes);
         out->candidates += s.candidates;
@@ -350,13 +390,13 @@ static int shard_enqueue(cm_flat_sharded *h, int r, const float *q_lead_dev, int
     uint32_t *o_ids = direct ? h->g_ids + (size_t)r * nq * K : b.ids;
     float *o_sc = direct ? h->g_sc + (size_t)r * nq * K : b.sc;
     int64_t *o_cnt = direct ? h->g_cnt + (size_t)r * nq : b.cnt;
-    const int64_t n_r = cm_flat_size(h->shard[(size_t)r]);
+    const int64_t n_r = h->ops->size(h->shard[(size_t)r]);
     if (n_r == 0) {
         CM_TRY(cm::launch_fill_counts(o_cnt, nq, 0, s));
     } else {
         cm_search_params pr = *p;
         pr.k = std::min<int64_t>(K, n_r);          // a shard can contribute at most K rows to the global top-K
-        CM_TRY(cm_flat_search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, o_ids, o_sc, nullptr, o_cnt, (void *)s));
+        CM_TRY(h->ops->search_device(h->shard[(size_t)r], q_r, nq, h->dim, &pr, K, o_ids, o_sc, o_cnt, (void *)s));
     }
     CM_CUDA(cudaEventRecord(h->t_searched[(size_t)r], s));
     if (!direct) {       // this shard's lists go to slot r of the leader's gather buffers
@@ -442,8 +482,7 @@ int cm_flat_sharded_search_device(cm_flat_sharded *h, const float *queries_dev, 
     int rc = CM_OK;
     if (K == 0) {
         // empty index: shard 0 (on devices[0]) answers like an empty FlatIndex
-        rc = cm_flat_search_device(h->shard[0], queries_dev, nq, dim, p, out_stride, out_ids_dev, out_scores_dev, nullptr,
-                                   out_counts_dev, stream);
+        rc = h->ops->search_device(h->shard[0], queries_dev, nq, dim, p, out_stride, out_ids_dev, out_scores_dev, out_counts_dev, stream);
     } else {
         rc = sharded_search_impl(h, queries_dev, nq, p, K, lead);
         if (rc == CM_OK) {
@@ -465,8 +504,10 @@ int cm_flat_sharded_search(cm_flat_sharded *h, const float *queries, int64_t nq,
     if (nq <= 0) return CM_OK;
     const int64_t K = sharded_k(h, p->k);
     if (out_stride < K) return cm::fail(CM_ERR_BUFFER_TOO_SMALL, "out_stride %lld < effective k %lld", (long long)out_stride, (long long)K);
-    if (K == 0)          // empty index: shard 0 answers like an empty FlatIndex (a zero query under cosine still fails)
-        return cm_flat_search(h->shard[0], queries, nq, dim, p, out_stride, out_ids, out_scores, nullptr, out_counts);
+    if (K == 0) {        // empty index: shard 0 answers like an empty index of its kind (FlatIndex: a zero query under cosine still fails)
+        if (h->ops == &FLAT_OPS) return cm_flat_search((cm_flat *)h->shard[0], queries, nq, dim, p, out_stride, out_ids, out_scores, nullptr, out_counts);
+        return cm_pq_search((cm_pq *)h->shard[0], queries, nq, dim, p, out_stride, out_ids, out_scores, nullptr, out_counts);
+    }
     std::unique_lock<std::mutex> lk(h->search_mu);
     int prev = 0;
     cudaGetDevice(&prev);
@@ -513,6 +554,76 @@ int cm_flat_sharded_search(cm_flat_sharded *h, const float *queries, int64_t nq,
         }
     }
     return CM_OK;
+}
+
+// ---- PQIndex row shards: the same driver over cm_pq shards (codebooks replicated: they are M x Ksub x dsub floats) ------
+int cm_pq_sharded_create(int dim, int metric, int M, int nbits, const int *devices, int n_devices, int64_t rows_per_shard,
+                         cm_pq_sharded **out) {
+    int rc = row_shards_create(dim, metric, devices, n_devices, rows_per_shard, &PQ_OPS,
+                               [=](void **sh) { return cm_pq_create(dim, metric, M, nbits, (cm_pq **)sh); }, (cm_flat_sharded **)out);
+    if (rc == CM_OK) (*(cm_flat_sharded **)out)->pq_cb_floats = ((int64_t)1 << nbits) * dim;
+    return rc;
+}
+int cm_pq_sharded_destroy(cm_pq_sharded *h) { return cm_flat_sharded_destroy((cm_flat_sharded *)h); }
+int cm_pq_sharded_shards(const cm_pq_sharded *h) { return cm_flat_sharded_shards((const cm_flat_sharded *)h); }
+int64_t cm_pq_sharded_size(const cm_pq_sharded *h) { return cm_flat_sharded_size((const cm_flat_sharded *)h); }
+int cm_pq_sharded_trained(const cm_pq_sharded *h) {
+    const cm_flat_sharded *s = (const cm_flat_sharded *)h;
+    return s && !s->shard.empty() && cm_pq_trained((const cm_pq *)s->shard[0]);
+}
+// PQIndex.Train (pq_index.go:193-247) on devices[0]; the codebooks then go to every shard
+int cm_pq_sharded_train(cm_pq_sharded *h, const float *rows, int64_t n) {
+    cm_flat_sharded *s = (cm_flat_sharded *)h;
+    if (!s || (n > 0 && !rows)) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    if (s->n > 0) return cm::fail(CM_ERR_UNSUPPORTED, "retraining a non-empty index is not supported");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cm_pq *lead = (cm_pq *)s->shard[0];
+    int rc = cm_pq_train(lead, rows, n);
+    std::vector<float> cb((size_t)s->pq_cb_floats);
+    if (rc == CM_OK) rc = cm_pq_get_codebooks(lead, cb.data());
+    for (size_t r = 1; r < s->shard.size() && rc == CM_OK; r++) rc = cm_pq_set_codebooks((cm_pq *)s->shard[r], cb.data());
+    cudaSetDevice(prev);
+    return rc;
+}
+int cm_pq_sharded_set_codebooks(cm_pq_sharded *h, const float *codebooks) {
+    cm_flat_sharded *s = (cm_flat_sharded *)h;
+    if (!s || !codebooks) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = CM_OK;
+    for (size_t r = 0; r < s->shard.size() && rc == CM_OK; r++) rc = cm_pq_set_codebooks((cm_pq *)s->shard[r], codebooks);
+    cudaSetDevice(prev);
+    return rc;
+}
+int cm_pq_sharded_get_codebooks(const cm_pq_sharded *h, float *out) {
+    const cm_flat_sharded *s = (const cm_flat_sharded *)h;
+    if (!s || !out) return cm::fail(CM_ERR_INVALID_ARG, "null argument");
+    return cm_pq_get_codebooks((const cm_pq *)s->shard[0], out);
+}
+int cm_pq_sharded_add(cm_pq_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback) {
+    if (!cm_pq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index must be trained before adding vectors");
+    return cm_flat_sharded_add((cm_flat_sharded *)h, ids, rows, n, writeback);
+}
+int cm_pq_sharded_remove(cm_pq_sharded *h, uint32_t id) { return cm_flat_sharded_remove((cm_flat_sharded *)h, id); }
+int cm_pq_sharded_flush(cm_pq_sharded *h) { return cm_flat_sharded_flush((cm_flat_sharded *)h); }
+int cm_pq_sharded_search(cm_pq_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                         uint32_t *out_ids, float *out_scores, int64_t *out_counts) {
+    if (!cm_pq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index not trained");
+    const cm_flat_sharded *s = (const cm_flat_sharded *)h;
+    if (s->metric == CM_COSINE && queries && dim == s->dim && s->n > 0)      // Distance.Preprocess fails on a zero query (distance.go:269-290);
+        for (int64_t q = 0; q < nq; q++) {                                    // an empty PQ index answers before it (pq_index_search.go:232)
+            float ss = 0.0f;
+            for (int j = 0; j < dim; j++) ss += queries[(size_t)q * dim + j] * queries[(size_t)q * dim + j];
+            if (ss == 0.0f) return cm::fail(CM_ERR_ZERO_VECTOR, "cannot normalize zero vector (query %lld)", (long long)q);
+        }
+    return cm_flat_sharded_search((cm_flat_sharded *)h, queries, nq, dim, p, out_stride, out_ids, out_scores, out_counts);
+}
+int cm_pq_sharded_search_device(cm_pq_sharded *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                                int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_counts_dev, void *stream) {
+    if (!cm_pq_sharded_trained(h)) return cm::fail(CM_ERR_NOT_TRAINED, "index not trained");
+    return cm_flat_sharded_search_device((cm_flat_sharded *)h, queries_dev, nq, dim, p, out_stride, out_ids_dev, out_scores_dev,
+                                         out_counts_dev, stream);
 }
 
 }  // extern "C"

@@ -76,6 +76,7 @@ typedef struct cm_hnsw cm_hnsw;
 typedef struct cm_flat_batcher cm_flat_batcher;
 typedef struct cm_flat_sharded cm_flat_sharded;
 typedef struct cm_ivf_sharded cm_ivf_sharded;
+typedef struct cm_pq_sharded cm_pq_sharded;
 typedef struct cm_ivfpq_sharded cm_ivfpq_sharded;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
@@ -316,6 +317,27 @@ int cm_pq_search(cm_pq *h, const float *queries, int64_t nq, int dim, const cm_s
 int cm_pq_search_device(cm_pq *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
                         int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_pos_dev,
                         int64_t *out_counts_dev, void *stream);
+
+/* ---- PQIndex row shards over the GPUs of one box, ONE host process ---------------------------------- */
+/* PQ shards by rows exactly like flat (the candidate number of a PQ result IS its store position, so the per-shard lists
+ * merge by (score, shard, rank) into the single index's order -- ADC scores tie constantly); the codebooks are replicated.
+ * Same exchange as cm_flat_sharded_*: queries read and lists written through NVLink peer mappings, one merge kernel. */
+int cm_pq_sharded_create(int dim, int metric, int M, int nbits, const int *devices, int n_devices, int64_t rows_per_shard,
+                         cm_pq_sharded **out);
+int cm_pq_sharded_destroy(cm_pq_sharded *h);
+int cm_pq_sharded_shards(const cm_pq_sharded *h);
+int64_t cm_pq_sharded_size(const cm_pq_sharded *h);
+int cm_pq_sharded_trained(const cm_pq_sharded *h);
+int cm_pq_sharded_train(cm_pq_sharded *h, const float *rows, int64_t n);            /* PQIndex.Train on devices[0], then replicated */
+int cm_pq_sharded_set_codebooks(cm_pq_sharded *h, const float *codebooks);
+int cm_pq_sharded_get_codebooks(const cm_pq_sharded *h, float *out);
+int cm_pq_sharded_add(cm_pq_sharded *h, const uint32_t *ids, float *rows, int64_t n, int writeback);
+int cm_pq_sharded_remove(cm_pq_sharded *h, uint32_t id);
+int cm_pq_sharded_flush(cm_pq_sharded *h);
+int cm_pq_sharded_search(cm_pq_sharded *h, const float *queries, int64_t nq, int dim, const cm_search_params *p, int64_t out_stride,
+                         uint32_t *out_ids, float *out_scores, int64_t *out_counts);
+int cm_pq_sharded_search_device(cm_pq_sharded *h, const float *queries_dev, int64_t nq, int dim, const cm_search_params *p,
+                                int64_t out_stride, uint32_t *out_ids_dev, float *out_scores_dev, int64_t *out_counts_dev, void *stream);
 
 /* ---- ivfpq_index.go / ivfpq_index_search.go ------------------------------------------------- */
 int cm_ivfpq_create(int dim, int metric, int nlist, int M, int nbits, cm_ivfpq **out);   /* NewIVFPQIndex ivfpq_index.go:114 */

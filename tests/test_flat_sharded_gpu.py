@@ -181,3 +181,51 @@ def test_sharded_device_entry_point_reports_exchange_bytes():
         assert_same_results(o_ids[i, :k].cpu().numpy().view(np.uint32), o_sc[i, :k].cpu().numpy(), int(o_cnt[i]), oi, os_)
     remote = sum(1 for r in devs if r != devs[0])
     assert g.exchange_bytes() == remote * (nq * d * 4 + nq * k * 8 + nq * 8)
+
+
+# ---- PQIndex row shards (cm_pq_sharded_*) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_pq_row_shards_match_the_single_index(metric):
+    rng = np.random.default_rng(40 + metric)
+    n, d, M, nbits, per = 5000, 32, 8, 4, 1300            # 16 codewords per sub-quantiser: ADC scores tie constantly
+    x = rng.standard_normal((n, d)).astype(np.float32) + (0.2 if metric == capi.COSINE else 0.0)
+    x[10] = x[4000]
+    q = rng.standard_normal((7, d)).astype(np.float32)
+    q[0] = x[10]
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    o = O.PQ(d, metric, M, nbits)
+    o.train(x[:800].copy())
+    g = capi.ShardedPQIndex(d, metric, M, nbits, _devices(4), per)
+    with pytest.raises(capi.CometError) as e:
+        g.add(ids[:5], x[:5].copy())
+    assert e.value.code == capi.ERR_NOT_TRAINED
+    g.set_codebooks(o.codebooks())
+    o.add(ids, x.copy())
+    g.add(ids, x.copy())
+    assert len(g) == n
+    _check(g, o, q, 10)
+    _check(g, o, q, 300)
+    _check(g, o, q[:2], 0)
+    _check(g, o, q[:3], 40, filter_ids=np.arange(2, n, 3, dtype=np.uint32))
+    for dead in (11, 1300, 1301, 4999):
+        g.remove(dead)
+        o.remove(dead)
+    _check(g, o, q, 25)
+    g.flush()
+    o.flush()
+    assert len(g) == n - 4
+    _check(g, o, q, 25)
+    # trained on the device: codebooks equal on every shard, answers equal to a single device-trained index
+    g2 = capi.ShardedPQIndex(d, metric, M, nbits, _devices(3), 2000)
+    g2.train(x[:800].copy())
+    o2 = O.PQ(d, metric, M, nbits)
+    o2.set_codebooks(g2.codebooks())
+    g2.add(ids, x.copy())
+    o2.add(ids, x.copy())
+    _check(g2, o2, q, 15)
+    if metric == capi.COSINE:
+        qz = q[:2].copy()
+        qz[1] = 0
+        with pytest.raises(capi.CometError) as e:
+            g2.search(qz, k=3)
+        assert e.value.code == capi.ERR_ZERO_VECTOR
