@@ -37,6 +37,7 @@ namespace cm {
 
 static constexpr int ADC_THREADS = 256;
 static constexpr int ADC_CHUNK = 4096;      // fewest codes a CTA is given when a pair is sliced
+static constexpr int ADC_RING_RUNS = 2;     // independent row pipelines per warp of the ring scan
 static constexpr int ADC_BIGK_PART = 3072;  // slice length of the big-k path: a multiple of every R * ADC_THREADS (256 .. 1024)
 
 struct CodeStore {
@@ -142,8 +143,15 @@ struct PQCore {
                                         // list starts on a 32-row boundary (tile_off) and each 32-row tile is stored word-major,
                                         // [M/16][32 rows][16 bytes], so a warp's 16-byte loads of 32 rows are one 512-byte run
     long long *tile_off = nullptr;      // [nlist+1] padded row offset of every list in codes_by_list (multiples of 32); M % 16 == 0 only
+                                        // (ring layout: the list's first pipeline step)
     int64_t tiled_rows = 0;             // rows of codes_by_list including the padding
+    int64_t cbl_bytes = 0;              // bytes allocated for codes_by_list
     float *codebooks_t = nullptr;       // dsub == 8: [M][2][Ksub] float4 -- the table build reads a codeword half per lane, coalesced
+    // Ring layout (adc_ring_kernel; 8-bit codes, M = 32 * PER): lane l of a warp owns sub-quantisers PER*l .. PER*l+PER-1.
+    // codes_by_list holds, per list, one 128-byte line per pipeline step t: lane l's 4 bytes = the PER code bytes of row t - l
+    // (16-byte groups of four steps: [(t / 4)][lane][t % 4][4 bytes]); codebooks_r [c][j][dsub / 4][lane] float4.
+    bool ring_layout = false;           // what codes_by_list currently holds
+    float *codebooks_r = nullptr;
     bool cbt_dirty = true;
     bool csr_dirty = true;
     std::vector<int64_t> sizes_desc;
@@ -152,9 +160,18 @@ struct PQCore {
 
     ~PQCore() {
         cudaFree(codebooks); cudaFree(members); cudaFree(list_off); cudaFree(scanned_total); cudaFree(codes_by_list);
-        cudaFree(tile_off); cudaFree(codebooks_t);
+        cudaFree(tile_off); cudaFree(codebooks_t); cudaFree(codebooks_r);
     }
     bool tiled() const { return (M & 15) == 0; }
+    static bool ring_combo(int per, int d4) {       // adc_ring_kernel instantiations
+        return (per == 1 && (d4 == 2 || d4 == 6)) || (per == 2 && d4 >= 1 && d4 <= 3) || (per == 3 && (d4 == 1 || d4 == 2)) ||
+               (per == 4 && (d4 == 1 || d4 == 2));
+    }
+    bool ring_wanted() const {
+        if (nlist <= 0 || Ksub != 256 || (M & 31) != 0 || (dsub & 3) != 0 || !ring_combo(M / 32, dsub / 4)) return false;
+        if (const char *e = getenv("COMET_B200_ADC_RING")) return atoi(e) != 0;
+        return true;
+    }
     int sync_codebooks_t(cudaStream_t st);
     int lut_entries() const { return Ksub < 256 ? Ksub : 256; }
     int sync_csr(cudaStream_t st);
@@ -198,9 +215,58 @@ __global__ void transpose_codebooks_kernel(const float4 *__restrict__ cb, int M,
     out[(m * 2 + h) * Ksub + c] = cb[t];
 }
 
+// ring layout of the codes: CSR entry i (list lo, row r), lane l -> the PER code bytes of sub-quantisers PER*l.. at step r + l
+__global__ void gather_codes_ring_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ members, long long n,
+                                         int M, int per, const long long *__restrict__ list_off,
+                                         const long long *__restrict__ step_off, int nlist, uint8_t *__restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n * 32) return;
+    const long long i = t >> 5;
+    const int l = (int)(t & 31);
+    int lo = 0, hi = nlist;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (list_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const long long st = step_off[lo] + (i - list_off[lo]) + l;
+    const uint8_t *src = codes + (size_t)members[i] * M + (size_t)per * l;
+    uint32_t w = 0;
+    for (int j = 0; j < per; j++) w |= (uint32_t)src[j] << (8 * j);
+    *reinterpret_cast<uint32_t *>(out + ((size_t)(st >> 2) * 32 + l) * 16 + (size_t)(st & 3) * 4) = w;
+}
+
+// codebooks [M][256][dsub] -> [c][j][dsub / 4][lane] float4 with m = per * lane + j
+__global__ void ring_codebooks_kernel(const float4 *__restrict__ cb, int per, int d4n, float4 *__restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = 256ll * per * d4n * 32;
+    if (t >= total) return;
+    const int l = (int)(t & 31);
+    long long u = t >> 5;
+    const int d4 = (int)(u % d4n); u /= d4n;
+    const int j = (int)(u % per);
+    const long long c = u / per;
+    const long long m = (long long)per * l + j;
+    out[t] = cb[(m * 256 + c) * d4n + d4];
+}
+
 int PQCore::sync_codebooks_t(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(csr_mu);
-    if (!cbt_dirty || dsub != 8 || !codebooks) return CM_OK;
+    if (!codebooks) return CM_OK;
+    const bool need_r = ring_wanted();
+    if (!cbt_dirty && (!need_r || codebooks_r)) return CM_OK;
+    if (need_r || codebooks_r) {
+        if (!codebooks_r) CM_CUDA(cudaMalloc(&codebooks_r, (size_t)M * Ksub * dsub * 4));
+        const long long work = (long long)M * Ksub * (dsub / 4);
+        ring_codebooks_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(codebooks), M / 32, dsub / 4,
+                                                                             reinterpret_cast<float4 *>(codebooks_r));
+        count_launch();
+        CM_CUDA(cudaGetLastError());
+    }
+    if (dsub != 8) {
+        CM_CUDA(cudaStreamSynchronize(st));
+        cbt_dirty = false;
+        return CM_OK;
+    }
     if (!codebooks_t) CM_CUDA(cudaMalloc(&codebooks_t, (size_t)M * Ksub * 8 * 4));
     const long long work = (long long)M * Ksub * 2;
     transpose_codebooks_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(codebooks), M, Ksub,
@@ -214,7 +280,8 @@ int PQCore::sync_codebooks_t(cudaStream_t st) {
 
 int PQCore::sync_csr(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(csr_mu);
-    if (!csr_dirty || nlist == 0) return CM_OK;
+    const bool ring = ring_wanted();
+    if ((!csr_dirty && ring == ring_layout) || nlist == 0) return CM_OK;
     int64_t n = store.n;
     std::vector<uint32_t> flat;
     flat.reserve((size_t)n);
@@ -224,18 +291,22 @@ int PQCore::sync_csr(cudaStream_t st) {
         off[(size_t)l] = (long long)flat.size();
         flat.insert(flat.end(), lists[(size_t)l].begin(), lists[(size_t)l].end());
         sizes_desc[(size_t)l] = (int64_t)lists[(size_t)l].size();
-        toff[(size_t)l + 1] = toff[(size_t)l] + (((long long)lists[(size_t)l].size() + 31) & ~31ll);
+        // tiled: whole 32-row tiles; ring: len + 31 pipeline steps (row r reaches lane 31 at step r + 31), whole 32-step chunks
+        const long long len = (long long)lists[(size_t)l].size();
+        toff[(size_t)l + 1] = toff[(size_t)l] + (ring ? ((len + 32 + 31) & ~31ll) : ((len + 31) & ~31ll));
     }
     off[(size_t)nlist] = (long long)flat.size();
-    const int64_t rows_needed = tiled() ? std::max<int64_t>(toff[(size_t)nlist], 32) : n;
-    if (n > members_cap || !members || rows_needed > tiled_rows || !codes_by_list) {
+    const int64_t rows_needed = (tiled() || ring) ? std::max<int64_t>(toff[(size_t)nlist], 32) : n;
+    const int64_t row_bytes = ring ? 128 : M;
+    if (n > members_cap || !members || rows_needed * row_bytes > cbl_bytes || !codes_by_list) {
         cudaFree(members);
         cudaFree(codes_by_list);
         codes_by_list = nullptr;
         members_cap = std::max<int64_t>(n + n / 2, 1024);
         tiled_rows = std::max<int64_t>(rows_needed + rows_needed / 2, 1024);
+        cbl_bytes = tiled_rows * row_bytes;
         CM_CUDA(cudaMalloc(&members, (size_t)members_cap * sizeof(uint32_t)));
-        CM_CUDA(cudaMalloc(&codes_by_list, (size_t)tiled_rows * M));
+        CM_CUDA(cudaMalloc(&codes_by_list, (size_t)cbl_bytes));
     }
     if (!list_off) CM_CUDA(cudaMalloc(&list_off, (size_t)(nlist + 1) * sizeof(long long)));
     if (!tile_off) CM_CUDA(cudaMalloc(&tile_off, (size_t)(nlist + 1) * sizeof(long long)));
@@ -244,15 +315,23 @@ int PQCore::sync_csr(cudaStream_t st) {
     CM_CUDA(cudaMemcpyAsync(list_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(tile_off, toff.data(), toff.size() * 8, cudaMemcpyHostToDevice, st));
     if (n > 0) {
-        if (tiled()) CM_CUDA(cudaMemsetAsync(codes_by_list, 0, (size_t)rows_needed * M, st));     // the padding rows are read (never emitted)
-        const long long work = tiled() ? (long long)n * (M / 16) : (long long)n * M;
-        gather_codes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, list_off, tile_off, nlist,
-                                                                            codes_by_list);
+        // the padding rows / steps are read (never emitted)
+        if (tiled() || ring) CM_CUDA(cudaMemsetAsync(codes_by_list, 0, (size_t)rows_needed * row_bytes, st));
+        if (ring) {
+            const long long work = (long long)n * 32;
+            gather_codes_ring_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, M / 32, list_off,
+                                                                                     tile_off, nlist, codes_by_list);
+        } else {
+            const long long work = tiled() ? (long long)n * (M / 16) : (long long)n * M;
+            gather_codes_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, members, (long long)n, M, list_off, tile_off, nlist,
+                                                                                codes_by_list);
+        }
         count_launch();
         CM_CUDA(cudaGetLastError());
     }
     CM_CUDA(cudaStreamSynchronize(st));
     csr_dirty = false;
+    ring_layout = ring;
     return CM_OK;
 }
 
@@ -519,6 +598,219 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
     if (tid == 0) part_counts[part] = mcount;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ADC scan, ring form (IVFPQ, 8-bit codes, M = 32 * PER).  The row-per-lane scan above pays ~4 shared-memory
+// wavefronts per table read: 32 lanes, 32 random banks.  Here a LANE owns sub-quantisers (PER*lane ..
+// PER*lane+PER-1) and their table rows live in bank `lane` only (lut[(j*256 + c)*32 + lane]), so every
+// table read of a warp is one conflict-free wavefront.  A row's sum must still be the reference's
+// sequential m = 0..M-1 chain (pq_index_search.go:300-311), so the rows flow through the lanes as a
+// pipeline: at step t lane l takes the partial sum lane l-1 produced at step t-1 (one shuffle), adds
+// its PER table values in order, and lane 31 holds the finished sum of row t - 31.  The codes are stored
+// pre-skewed for this (PQCore::ring_layout): step t is one 128-byte line, lane l's word = its bytes of
+// row t - l.  Each warp walks a contiguous run of the slice's rows (32 steps of fill, then one row per
+// step); lane 31's sums are staged in shared memory and selected 32 at a time by the whole warp.
+// The table build: lane = owner of the sub-quantisers, warp = table column, residual in registers,
+// codewords from the ring copy of the codebooks (512-byte coalesced runs), stores conflict-free.
+// ------------------------------------------------------------------------------------------------
+// one table read of the ring scan: byte j of the packed code word selects the row; lut_lane = this lane's bank
+// (table row (j, c) at lut_lane + j * 32 KB + c * 128 bytes)
+__device__ __forceinline__ float ring_lut_read(const float *lut_lane, uint32_t word, int j) {
+    uint32_t c;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(c) : "r"(word), "r"(0x4440u | (uint32_t)j));
+    return *reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(lut_lane) + (size_t)j * 32768u + (c << 7));
+}
+
+template <bool FMA, int PER, int D4>
+__global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
+    const float *__restrict__ queries, int ld, const float4 *__restrict__ cbr, const uint8_t *__restrict__ ring,
+    const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
+    const long long *__restrict__ q_off, const long long *__restrict__ list_off, const long long *__restrict__ step_off,
+    const uint32_t *__restrict__ members, int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C,
+    int n_slices, uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    constexpr int T = ADC_THREADS, NW = T / 32, DS = D4 * 4, S = ADC_RING_RUNS;
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *lut = reinterpret_cast<float *>(smem);                         // [PER][256][32 lanes]
+    float *stage = lut + PER * 256 * 32;                                  // [NW][S][32] finished sums of a chunk
+    uint64_t *buf = reinterpret_cast<uint64_t *>(stage + NW * S * 32);    // [C]
+    __shared__ int cnt;
+    __shared__ uint64_t tau;
+    __shared__ int sel_hist[256];
+    __shared__ uint32_t sel_red[4];
+    const CtaBarrier bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long pair = blockIdx.y;
+    const int q = (int)(pair / nprobes), pr = (int)(pair % nprobes);
+    const long long list = probe_list[pair];
+    const long long len = list_off[list + 1] - list_off[list];
+    const uint32_t *mem = members + list_off[list];
+    const long long order0 = q_off[(size_t)q * (nprobes + 1) + pr];
+    long long per = (len + n_slices - 1) / n_slices;
+    per = (per + T * S - 1) / (T * S) * (T * S);
+    const long long c0 = (long long)blockIdx.x * per;
+    const size_t part = (size_t)pair * n_slices + blockIdx.x;
+    if (c0 >= len) return;                                                // part_counts was zeroed by the host
+    const long long c1 = min(len, c0 + per);
+    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+
+    // this warp's rows of the slice: S runs [a_s, b_s) of equal length (whole chunks of 32), walked as S
+    // independent pipelines -- a pipeline step is a dependent shuffle -> add chain, two of them interleave
+    long long pw = (c1 - c0 + NW * S - 1) / (NW * S);
+    pw = (pw + 31) & ~31ll;                   // rows per run
+    const int nchunks = (int)(pw >> 5) + 1;   // 31 steps of fill, then a row per step
+    const uint4 *lines = reinterpret_cast<const uint4 *>(ring + (size_t)step_off[list] * 128) + lane;
+    const long long gmax = (len + 31) >> 2;   // last 4-step group of the list that holds codes
+    long long ra[S], rb[S], G[S];
+    uint4 cw[S][4];
+#pragma unroll
+    for (int st = 0; st < S; st++) {
+        ra[st] = c0 + ((long long)warp * S + st) * pw;
+        rb[st] = min(c1, ra[st] + pw);
+        G[st] = ra[st] >> 2;
+        // the first code lines are requested before the table build: their latency hides under it
+#pragma unroll
+        for (int u = 0; u < 4; u++) cw[st][u] = __ldg(lines + min(G[st] + u, gmax) * 32);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {         // and the rest of the run's first two chunks towards L2
+            const long long o = (G[st] + 8 * u) * 512 + lane * 128;
+            if (o < (gmax + 1) * 512) prefetch_l2(reinterpret_cast<const uint8_t *>(lines - lane) + o);
+        }
+    }
+
+    // ---- table: this lane's residual pieces (ivfpq_index_search.go:285-296), then 256 / NW columns per warp ----
+    {
+        float res[PER][DS];
+        const float *qv = queries + (size_t)q * ld + (size_t)lane * PER * DS;
+        const float *cv = centroids + (size_t)list * cld + (size_t)lane * PER * DS;
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+#pragma unroll
+            for (int d = 0; d < DS; d++) res[j][d] = __fsub_rn(__ldg(qv + j * DS + d), __ldg(cv + j * DS + d));
+        constexpr int U = 4;                                              // columns in flight
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            for (int cg = 0; cg < 256 / NW; cg += U) {
+                float4 a[U][D4];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int c = warp + NW * (cg + u);
+#pragma unroll
+                    for (int d4 = 0; d4 < D4; d4++) a[u][d4] = __ldg(cbr + ((size_t)(c * PER + j) * D4 + d4) * 32 + lane);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int c = warp + NW * (cg + u);
+                    float d = 0.0f;
+#pragma unroll
+                    for (int d4 = 0; d4 < D4; d4++) {
+                        d = l2_step<FMA>(d, res[j][4 * d4 + 0], a[u][d4].x);
+                        d = l2_step<FMA>(d, res[j][4 * d4 + 1], a[u][d4].y);
+                        d = l2_step<FMA>(d, res[j][4 * d4 + 2], a[u][d4].z);
+                        d = l2_step<FMA>(d, res[j][4 * d4 + 3], a[u][d4].w);
+                    }
+                    lut[(j * 256 + c) * 32 + lane] = d;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int round_keys = T * S;             // a round (one chunk of every run) appends at most this many keys
+    const int limit = C - round_keys;
+    // keys a mid-stream compaction may leave: barely more than K, so that the bound it sets lets the rest of a list
+    // through rarely (a bin boundary of the radix select's second pass nearly always falls inside the margin)
+    const int keep_mid = min(K + (limit - K) / 2, K + max(16, K / 8));
+    const float *lut_s = lut + lane;          // this lane's bank
+    float sum_in[S];                          // the partial sum this lane produced at the previous step
+#pragma unroll
+    for (int st = 0; st < S; st++) sum_in[st] = 0.0f;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int rounds_left = C / round_keys;
+    const uint8_t *list_bytes = ring + (size_t)step_off[list] * 128;
+    const long long list_end = (gmax + 1) * 512;
+    for (int ch = 0; ch < nchunks; ch++) {
+        // the chunk after next towards L2 (a chunk of a run is 32 lines of 128 bytes: one per lane); the register ring
+        // below then only has to cover an L2 hit
+#pragma unroll
+        for (int st = 0; st < S; st++) {
+            const long long o = (G[st] + 16) * 512 + lane * 128;
+            if (o < list_end) prefetch_l2(list_bytes + o);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            uint32_t wd[S][4];
+#pragma unroll
+            for (int st = 0; st < S; st++) {
+                const uint4 w4 = cw[st][g & 3];
+                cw[st][g & 3] = __ldg(lines + min(G[st] + g + 4, gmax) * 32);
+                wd[st][0] = w4.x; wd[st][1] = w4.y; wd[st][2] = w4.z; wd[st][3] = w4.w;
+            }
+            float o[S][4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+#pragma unroll
+                for (int st = 0; st < S; st++) {
+                    float in = __shfl_up_sync(0xffffffffu, sum_in[st], 1);
+                    if (lane == 0) in = 0.0f;
+                    float acc = in;
+#pragma unroll
+                    for (int j = 0; j < PER; j++) acc = __fadd_rn(acc, ring_lut_read(lut_s, wd[st][e], j));
+                    sum_in[st] = acc;
+                    o[st][e] = acc;
+                }
+            }
+            if (lane == 31) {
+#pragma unroll
+                for (int st = 0; st < S; st++)
+                    reinterpret_cast<float4 *>(stage + (warp * S + st) * 32)[g] = make_float4(o[st][0], o[st][1], o[st][2], o[st][3]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int st = 0; st < S; st++) {
+            G[st] += 8;
+            const float sum = stage[(warp * S + st) * 32 + lane];
+            // lane i holds the row that left the pipeline at step a + 32 ch + i: row a + 32 ch + i - 31
+            const long long j = ra[st] + 32ll * ch + lane - 31;
+            bool ok = j >= ra[st] && j < rb[st];
+            const float dist = __fsqrt_rn(sum);
+            if (ok && skip != nullptr && skip[mem[j]]) ok = false;
+            if (ok && threshold > 0.0f && dist > threshold) ok = false;
+            uint64_t key = 0;
+            if (ok) {
+                key = make_key(dist, (uint32_t)(order0 + j));
+                ok = key < tau;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (bal != 0u) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&cnt, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (ok) buf[slot0 + __popc(bal & lt_mask)] = key;
+            }
+        }
+        __syncwarp();
+        if (--rounds_left == 0) {             // the buffer may not hold another round: look at the fill together
+            __syncthreads();
+            int fill = cnt;
+            __syncthreads();
+            if (fill > limit) {
+                if (!compact_select(buf, C, K, keep_mid, &cnt, &tau, tid, T, sel_hist, sel_red))
+                    compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+                fill = cnt;
+                __syncthreads();
+            }
+            rounds_left = max(1, (C - fill) / round_keys);
+        }
+    }
+    // the CTA's answer: exactly the K smallest, in any order (merge_topk_kernel / merge_topk_bigk order them); only
+    // score ties across the K-th place need the sort
+    if (!compact_select(buf, C, K, K, &cnt, &tau, tid, T, sel_hist, sel_red)) compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+    const int mcount = cnt;
+    uint64_t *dst = part_keys + part * K;
+    for (int i = tid; i < mcount; i += T) dst[i] = buf[i];
+    if (tid == 0) part_counts[part] = mcount;
+}
+
 // candidate numbers of the final lists -> store positions and ids; for list shards (cm_ivfpq_sharded_*) also the
 // candidate's number in the reference's append loop over ALL probed lists, from the global list lengths
 __global__ void adc_emit_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ q_off,
@@ -673,10 +965,12 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     int MW = ((ix.M & 15) == 0 && (ix.M / 16 == 1 || ix.M / 16 == 2 || ix.M / 16 == 4 || ix.M / 16 == 6 || ix.M / 16 == 8)) ? ix.M / 16 : 0;
     if (const char *e = getenv("COMET_B200_ADC_GENERIC")) if (atoi(e)) MW = 0;
     const int R = MW == 0 ? 1 : (MW <= 4 ? 4 : (MW <= 6 ? 3 : 2));
-    int C = next_pow2(K + R * ADC_THREADS);         // a round's appends always fit above a compacted buffer
+    const bool ring = ivf && ix.ring_layout;         // codes_by_list is in the ring layout: adc_ring_kernel
+    int C = next_pow2(K + (ring ? ADC_RING_RUNS : R) * ADC_THREADS);         // a round's appends always fit above a compacted buffer
     if (C < 1024) C = 1024;
     const int lut_n = ix.lut_entries();
     size_t smem = (size_t)ix.M * lut_n * 4 + (size_t)((ix.dim + 3) & ~3) * 4 + (size_t)C * 8;
+    if (ring) smem = (size_t)ix.M * 256 * 4 + (size_t)(ADC_THREADS / 32) * ADC_RING_RUNS * 32 * 4 + (size_t)C * 8;
     if (smem > max_smem_optin())
         return fail(CM_ERR_UNSUPPORTED, "M=%d x %d table entries + k=%d do not fit shared memory", ix.M, lut_n, K);
     // slices per pair: enough CTAs for a few waves (two CTAs per SM), but never so many that a CTA
@@ -701,13 +995,31 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         CM_ADC_CASE(0) CM_ADC_CASE(1) CM_ADC_CASE(2) CM_ADC_CASE(4) CM_ADC_CASE(6) CM_ADC_CASE(8)
     }
 #undef CM_ADC_CASE
-    CM_TRY(set_dyn_smem((const void *)kern, smem));      // only ever grows: concurrent searches ask for different sizes
+    using RingKernel = void (*)(const float *, int, const float4 *, const uint8_t *, const float *, int, const long long *,
+                                const long long *, const long long *, const long long *, const uint32_t *, int, const uint8_t *,
+                                float, int, int, int, uint64_t *, int *);
+    RingKernel rkern = nullptr;
+    if (ring) {
+        const int per = ix.M / 32, d4 = ix.dsub / 4;
+#define CM_RING_CASE(P, D) if (per == P && d4 == D) rkern = fma ? adc_ring_kernel<true, P, D> : adc_ring_kernel<false, P, D>;
+        CM_RING_CASE(1, 2) CM_RING_CASE(1, 6) CM_RING_CASE(2, 1) CM_RING_CASE(2, 2) CM_RING_CASE(2, 3)
+        CM_RING_CASE(3, 1) CM_RING_CASE(3, 2) CM_RING_CASE(4, 1) CM_RING_CASE(4, 2)
+#undef CM_RING_CASE
+        if (!rkern) return fail(CM_ERR_UNSUPPORTED, "ring layout without a kernel for M=%d dsub=%d", ix.M, ix.dsub);
+    }
+    CM_TRY(set_dyn_smem(ring ? (const void *)rkern : (const void *)kern, smem));      // only ever grows: concurrent searches ask for different sizes
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
         CM_CUDA(cudaMemsetAsync(pc, 0, (size_t)m * parts * 4, st));
         dim3 grid((unsigned)n_slices, (unsigned)(m * nprobes));
         {
             ProfScope prof(CM_PROF_PQ_SCAN, st);
+            if (ring)
+                rkern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, reinterpret_cast<const float4 *>(ix.codebooks_r),
+                                                       ix.codes_by_list, ix.coarse.rows, ix.coarse.ld, probe_list + (size_t)q0 * nprobes,
+                                                       q_off + (size_t)q0 * (nprobes + 1), ix.list_off, ix.tile_off, ix.members, nprobes,
+                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc);
+            else
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
                                                   ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
                                                   ix.coarse.ld, ivf ? probe_list + (size_t)q0 * nprobes : nullptr,

@@ -201,3 +201,64 @@ def test_pq_and_ivfpq_k_all_beyond_the_per_cta_selection():
     q = rng.standard_normal((3, 16)).astype(np.float32)
     check_ivfpq(g, o, q, 0, 3)
     check_ivfpq(g, o, q[:2], 12000, 2)
+
+
+# The IVFPQ scan has a second form for 8-bit codes with M = 32 * PER ("ring": a lane owns PER sub-quantisers, the rows
+# flow through the lanes; codes stored pre-skewed per list).  Every instantiated (PER, dsub / 4) pair, short / ragged /
+# empty lists, lists long enough for several rounds and compactions, slices, threshold, filter, k = all -- against
+# the oracle, and against the row-per-lane form on the same index (COMET_B200_ADC_RING=0 rebuilds the by-list copy).
+@pytest.mark.parametrize("d,M", [(256, 32), (768, 32), (256, 64), (512, 64), (768, 64), (384, 96), (768, 96), (512, 128),
+                                 (1024, 128)])
+def test_ivfpq_ring_scan_every_variant(d, M, monkeypatch):
+    g, o, rng, lists = ivfpq_pair(7000, d, capi.L2, 5, M, 8, 300 + M + d)
+    sizes = np.bincount(lists, minlength=5)
+    assert sizes.max() > 1300            # more than one buffer of candidates per pair: compaction runs
+    q = rng.standard_normal((6, d)).astype(np.float32)
+    check_ivfpq(g, o, q, 100, 5)
+    check_ivfpq(g, o, q[:3], 10, 2)
+    check_ivfpq(g, o, q[:2], 0, 3)
+    check_ivfpq(g, o, q[:2], 500, 5, threshold=float(np.sqrt(2 * d) * 0.97))
+    check_ivfpq(g, o, q[:2], 64, 5, filter_ids=np.arange(3, 7000, 7, dtype=np.uint32))
+    for slices in ("2", "5"):
+        monkeypatch.setenv("COMET_B200_ADC_SLICES", slices)
+        check_ivfpq(g, o, q[:3], 100, 5)
+    monkeypatch.delenv("COMET_B200_ADC_SLICES")
+    ring = g.search(q, k=100, nprobes=5)
+    monkeypatch.setenv("COMET_B200_ADC_RING", "0")
+    rows = g.search(q, k=100, nprobes=5)
+    monkeypatch.delenv("COMET_B200_ADC_RING")
+    for a, b in zip(ring, rows):
+        assert np.array_equal(a, b)
+    again = g.search(q, k=100, nprobes=5)
+    for a, b in zip(ring, again):
+        assert np.array_equal(a, b)
+
+
+def test_ivfpq_ring_scan_ragged_lists_and_updates():
+    # tiny and empty lists (fewer rows than the 32-lane pipeline is deep), delete / flush / add between searches
+    d, M, nlist = 768, 96, 40
+    g, o, rng, lists = ivfpq_pair(900, d, capi.COSINE, nlist, M, 8, 41)
+    sizes = np.bincount(lists, minlength=nlist)
+    assert sizes.min() < 31
+    q = rng.standard_normal((9, d)).astype(np.float32) + np.float32(0.2)
+    check_ivfpq(g, o, q, 100, 40)
+    check_ivfpq(g, o, q, 7, 1)
+    for i in range(2, 900, 4):
+        g.remove(i)
+        o.remove(i)
+    check_ivfpq(g, o, q, 100, 12)
+    g.flush()
+    o.flush()
+    check_ivfpq(g, o, q, 100, 12)
+    x2 = rng.standard_normal((333, d)).astype(np.float32) + np.float32(0.2)
+    ids2 = np.arange(5000, 5333, dtype=np.uint32)
+    g.add(ids2, x2.copy())
+    o.add(ids2, x2.copy())
+    check_ivfpq(g, o, q, 0, 40)
+
+
+def test_ivfpq_ring_scan_k_all_beyond_the_per_cta_selection():
+    g, o, rng, lists = ivfpq_pair(30000, 256, capi.L2, 2, 64, 8, 73)
+    q = rng.standard_normal((2, 256)).astype(np.float32)
+    check_ivfpq(g, o, q, 0, 2)
+    check_ivfpq(g, o, q[:1], 12000, 1)

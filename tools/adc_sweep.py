@@ -41,7 +41,7 @@ def main():
     ref = None
     out = {}
     for cfg in args.configs.split(";"):
-        for k in ("COMET_B200_ADC_SLICES", "COMET_B200_ADC_GENERIC"):
+        for k in ("COMET_B200_ADC_SLICES", "COMET_B200_ADC_GENERIC", "COMET_B200_ADC_RING"):
             os.environ.pop(k, None)
         for kv in cfg.split(","):
             if kv:
