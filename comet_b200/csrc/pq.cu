@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
     const long long *__restrict__ q_off, const long long *__restrict__ list_off, const long long *__restrict__ step_off,
     const uint32_t *__restrict__ members, int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C,
-    int n_slices, uint64_t *__restrict__ part_keys, int *__restrict__ part_counts) {
+    int n_slices, uint64_t *__restrict__ part_keys, int *__restrict__ part_counts, unsigned long long *q_tau) {
     constexpr int T = ADC_THREADS, NW = T / 32, DS = D4 * 4, S = ADC_RING_RUNS;
     extern __shared__ __align__(16) uint8_t smem[];
     float *lut = reinterpret_cast<float *>(smem);                         // [PER][256][32 lanes]
@@ -650,41 +650,52 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     const size_t part = (size_t)pair * n_slices + blockIdx.x;
     if (c0 >= len) return;                                                // part_counts was zeroed by the host
     const long long c1 = min(len, c0 + per);
-    if (tid == 0) { cnt = 0; tau = KEY_INF; }
+    if (tid == 0) {                                                       // the bound the query's earlier CTAs found, if any
+        cnt = 0;
+        tau = q_tau != nullptr ? (uint64_t)*reinterpret_cast<volatile unsigned long long *>(q_tau + q) : KEY_INF;
+    }
 
     // this warp's rows of the slice: S runs [a_s, b_s) of equal length (whole chunks of 32), walked as S
     // independent pipelines -- a pipeline step is a dependent shuffle -> add chain, two of them interleave
     long long pw = (c1 - c0 + NW * S - 1) / (NW * S);
     pw = (pw + 31) & ~31ll;                   // rows per run
     const int nchunks = (int)(pw >> 5) + 1;   // 31 steps of fill, then a row per step
-    const uint4 *lines = reinterpret_cast<const uint4 *>(ring + (size_t)step_off[list] * 128) + lane;
-    const long long gmax = (len + 31) >> 2;   // last 4-step group of the list that holds codes
-    long long ra[S], rb[S], G[S];
+    const uint8_t *list_bytes = ring + (size_t)step_off[list] * 128;
+    const uint4 *lines = reinterpret_cast<const uint4 *>(list_bytes) + lane;
+    const int gmax = (int)((len + 31) >> 2);  // last 4-step group of the list that holds codes (512 bytes a group)
+    long long ra[S], rb[S];
+    int G[S];
     uint4 cw[S][4];
 #pragma unroll
     for (int st = 0; st < S; st++) {
         ra[st] = c0 + ((long long)warp * S + st) * pw;
         rb[st] = min(c1, ra[st] + pw);
-        G[st] = ra[st] >> 2;
+        G[st] = (int)min(ra[st] >> 2, (long long)gmax);
         // the first code lines are requested before the table build: their latency hides under it
 #pragma unroll
-        for (int u = 0; u < 4; u++) cw[st][u] = __ldg(lines + min(G[st] + u, gmax) * 32);
+        for (int u = 0; u < 4; u++) cw[st][u] = __ldg(lines + (size_t)min(G[st] + u, gmax) * 32);
 #pragma unroll
         for (int u = 0; u < 2; u++) {         // and the rest of the run's first two chunks towards L2
-            const long long o = (G[st] + 8 * u) * 512 + lane * 128;
-            if (o < (gmax + 1) * 512) prefetch_l2(reinterpret_cast<const uint8_t *>(lines - lane) + o);
+            const int line = (G[st] + 8 * u) * 4 + lane;
+            if (line < (gmax + 1) * 4) prefetch_l2(list_bytes + (size_t)line * 128);
         }
     }
 
     // ---- table: this lane's residual pieces (ivfpq_index_search.go:285-296), then 256 / NW columns per warp ----
     {
+        // the residual, fetched once per CTA (coalesced) and handed to the lanes through the candidate buffer's space
+        float *res_s = reinterpret_cast<float *>(buf);
+        for (int i = tid; i < 32 * PER * DS; i += T)
+            res_s[i] = __fsub_rn(__ldg(queries + (size_t)q * ld + i), __ldg(centroids + (size_t)list * cld + i));
+        __syncthreads();
         float res[PER][DS];
-        const float *qv = queries + (size_t)q * ld + (size_t)lane * PER * DS;
-        const float *cv = centroids + (size_t)list * cld + (size_t)lane * PER * DS;
 #pragma unroll
         for (int j = 0; j < PER; j++)
 #pragma unroll
-            for (int d = 0; d < DS; d++) res[j][d] = __fsub_rn(__ldg(qv + j * DS + d), __ldg(cv + j * DS + d));
+            for (int d4 = 0; d4 < D4; d4++) {
+                const float4 v = *reinterpret_cast<const float4 *>(res_s + (lane * PER + j) * DS + 4 * d4);
+                res[j][4 * d4 + 0] = v.x; res[j][4 * d4 + 1] = v.y; res[j][4 * d4 + 2] = v.z; res[j][4 * d4 + 3] = v.w;
+            }
         constexpr int U = 4;                                              // columns in flight
 #pragma unroll
         for (int j = 0; j < PER; j++) {
@@ -725,15 +736,13 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     for (int st = 0; st < S; st++) sum_in[st] = 0.0f;
     const uint32_t lt_mask = (1u << lane) - 1u;
     int rounds_left = C / round_keys;
-    const uint8_t *list_bytes = ring + (size_t)step_off[list] * 128;
-    const long long list_end = (gmax + 1) * 512;
     for (int ch = 0; ch < nchunks; ch++) {
         // the chunk after next towards L2 (a chunk of a run is 32 lines of 128 bytes: one per lane); the register ring
         // below then only has to cover an L2 hit
 #pragma unroll
         for (int st = 0; st < S; st++) {
-            const long long o = (G[st] + 16) * 512 + lane * 128;
-            if (o < list_end) prefetch_l2(list_bytes + o);
+            const int line = (G[st] + 16) * 4 + lane;
+            if (line < (gmax + 1) * 4) prefetch_l2(list_bytes + (size_t)line * 128);
         }
 #pragma unroll
         for (int g = 0; g < 8; g++) {
@@ -741,7 +750,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
 #pragma unroll
             for (int st = 0; st < S; st++) {
                 const uint4 w4 = cw[st][g & 3];
-                cw[st][g & 3] = __ldg(lines + min(G[st] + g + 4, gmax) * 32);
+                cw[st][g & 3] = __ldg(lines + (size_t)min(G[st] + g + 4, gmax) * 32);
                 wd[st][0] = w4.x; wd[st][1] = w4.y; wd[st][2] = w4.z; wd[st][3] = w4.w;
             }
             float o[S][4];
@@ -789,7 +798,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
             }
         }
         __syncwarp();
-        if (--rounds_left == 0) {             // the buffer may not hold another round: look at the fill together
+        if (ch + 1 < nchunks && --rounds_left == 0) {   // the buffer may not hold another round: look at the fill together
             __syncthreads();
             int fill = cnt;
             __syncthreads();
@@ -797,6 +806,13 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
                 if (!compact_select(buf, C, K, keep_mid, &cnt, &tau, tid, T, sel_hist, sel_red))
                     compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
                 fill = cnt;
+                // K of this CTA's keys are under tau: no key at or above it is among the query's K best, in any list.
+                // The CTAs of a query share the smallest such bound (the far lists then append next to nothing).
+                if (q_tau != nullptr && tid == 0) atomicMin(q_tau + q, (unsigned long long)tau);
+                __syncthreads();
+            }
+            if (q_tau != nullptr) {
+                if (tid == 0) tau = min(tau, (uint64_t)*reinterpret_cast<volatile unsigned long long *>(q_tau + q));
                 __syncthreads();
             }
             rounds_left = max(1, (C - fill) / round_keys);
@@ -997,7 +1013,9 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
 #undef CM_ADC_CASE
     using RingKernel = void (*)(const float *, int, const float4 *, const uint8_t *, const float *, int, const long long *,
                                 const long long *, const long long *, const long long *, const uint32_t *, int, const uint8_t *,
-                                float, int, int, int, uint64_t *, int *);
+                                float, int, int, int, uint64_t *, int *, unsigned long long *);
+    unsigned long long *q_tau = nullptr;      // per query: the smallest K-th-key bound any of its CTAs has found
+    if (ring && !bigk) CM_TRY(ws.get(&q_tau, (size_t)std::min(qgroup, nq) * 8));
     RingKernel rkern = nullptr;
     if (ring) {
         const int per = ix.M / 32, d4 = ix.dsub / 4;
@@ -1014,11 +1032,12 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
         dim3 grid((unsigned)n_slices, (unsigned)(m * nprobes));
         {
             ProfScope prof(CM_PROF_PQ_SCAN, st);
+            if (ring && q_tau) CM_CUDA(cudaMemsetAsync(q_tau, 0xff, (size_t)m * 8, st));
             if (ring)
                 rkern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, reinterpret_cast<const float4 *>(ix.codebooks_r),
                                                        ix.codes_by_list, ix.coarse.rows, ix.coarse.ld, probe_list + (size_t)q0 * nprobes,
                                                        q_off + (size_t)q0 * (nprobes + 1), ix.list_off, ix.tile_off, ix.members, nprobes,
-                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc);
+                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc, q_tau);
             else
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
                                                   ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
