@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     const float *__restrict__ centroids, int cld, const long long *__restrict__ probe_list,
     const long long *__restrict__ q_off, const long long *__restrict__ list_off, const long long *__restrict__ step_off,
     const uint32_t *__restrict__ members, int nprobes, const uint8_t *__restrict__ skip, float threshold, int K, int C,
-    int n_slices, uint64_t *__restrict__ part_keys, int *__restrict__ part_counts, unsigned long long *q_tau) {
+    int n_slices, uint64_t *__restrict__ part_keys, int *__restrict__ part_counts, unsigned long long *q_tau, int nq) {
     constexpr int T = ADC_THREADS, NW = T / 32, DS = D4 * 4, S = ADC_RING_RUNS;
     extern __shared__ __align__(16) uint8_t smem[];
     float *lut = reinterpret_cast<float *>(smem);                         // [PER][256][32 lanes]
@@ -638,8 +638,10 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     __shared__ uint32_t sel_red[4];
     const CtaBarrier bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long pair = blockIdx.y;
-    const int q = (int)(pair / nprobes), pr = (int)(pair % nprobes);
+    // CTAs run probe-major: every query's nearest list first.  By the time the far lists of a query are scanned, q_tau
+    // holds the K-th key of a near one and next to nothing of a far list gets past it.
+    const int q = (int)(blockIdx.y % nq), pr = (int)(blockIdx.y / nq);
+    const long long pair = (long long)q * nprobes + pr;
     const long long list = probe_list[pair];
     const long long len = list_off[list + 1] - list_off[list];
     const uint32_t *mem = members + list_off[list];
@@ -735,8 +737,10 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
 #pragma unroll
     for (int st = 0; st < S; st++) sum_in[st] = 0.0f;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    int rounds_left = C / round_keys;
     for (int ch = 0; ch < nchunks; ch++) {
+        // the bound the query's other CTAs have found so far (one broadcast load, used when the chunk is selected)
+        uint64_t tau_q = KEY_INF;
+        if (q_tau != nullptr) tau_q = *reinterpret_cast<volatile unsigned long long *>(q_tau + q);
         // the chunk after next towards L2 (a chunk of a run is 32 lines of 128 bytes: one per lane); the register ring
         // below then only has to cover an L2 hit
 #pragma unroll
@@ -774,6 +778,8 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
             }
         }
         __syncwarp();
+        const uint64_t bound = min((uint64_t)tau, tau_q);
+        bool full = false;                    // did an append of this warp end above the compaction mark?
 #pragma unroll
         for (int st = 0; st < S; st++) {
             G[st] += 8;
@@ -787,7 +793,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
             uint64_t key = 0;
             if (ok) {
                 key = make_key(dist, (uint32_t)(order0 + j));
-                ok = key < tau;
+                ok = key < bound;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, ok);
             if (bal != 0u) {
@@ -795,33 +801,24 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
                 if (lane == 0) slot0 = atomicAdd(&cnt, __popc(bal));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 if (ok) buf[slot0 + __popc(bal & lt_mask)] = key;
+                full |= slot0 + __popc(bal) > limit;
             }
         }
         __syncwarp();
-        if (ch + 1 < nchunks && --rounds_left == 0) {   // the buffer may not hold another round: look at the fill together
-            __syncthreads();
-            int fill = cnt;
-            __syncthreads();
-            if (fill > limit) {
-                if (!compact_select(buf, C, K, keep_mid, &cnt, &tau, tid, T, sel_hist, sel_red))
-                    compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
-                fill = cnt;
-                // K of this CTA's keys are under tau: no key at or above it is among the query's K best, in any list.
-                // The CTAs of a query share the smallest such bound (the far lists then append next to nothing).
-                if (q_tau != nullptr && tid == 0) atomicMin(q_tau + q, (unsigned long long)tau);
-                __syncthreads();
-            }
-            if (q_tau != nullptr) {
-                if (tid == 0) tau = min(tau, (uint64_t)*reinterpret_cast<volatile unsigned long long *>(q_tau + q));
-                __syncthreads();
-            }
-            rounds_left = max(1, (C - fill) / round_keys);
+        // one barrier per round: the warp whose append ended highest saw the final fill, so the OR is exact.  Above the
+        // mark the buffer may not hold another round (round_keys appends at most): compact, and tell the query's other CTAs
+        if (ch + 1 < nchunks && __syncthreads_or(full)) {
+            if (!compact_select(buf, C, K, keep_mid, &cnt, &tau, tid, T, sel_hist, sel_red))
+                compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
+            // K of this CTA's keys are under tau: no key at or above it is among the query's K best, in any list
+            if (q_tau != nullptr && tid == 0) atomicMin(q_tau + q, (unsigned long long)tau);
         }
     }
     // the CTA's answer: exactly the K smallest, in any order (merge_topk_kernel / merge_topk_bigk order them); only
     // score ties across the K-th place need the sort
     if (!compact_select(buf, C, K, K, &cnt, &tau, tid, T, sel_hist, sel_red)) compact_topk(buf, C, K, &cnt, &tau, tid, T, bar);
     const int mcount = cnt;
+    if (q_tau != nullptr && tid == 0 && mcount >= K) atomicMin(q_tau + q, (unsigned long long)tau);
     uint64_t *dst = part_keys + part * K;
     for (int i = tid; i < mcount; i += T) dst[i] = buf[i];
     if (tid == 0) part_counts[part] = mcount;
@@ -1013,7 +1010,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
 #undef CM_ADC_CASE
     using RingKernel = void (*)(const float *, int, const float4 *, const uint8_t *, const float *, int, const long long *,
                                 const long long *, const long long *, const long long *, const uint32_t *, int, const uint8_t *,
-                                float, int, int, int, uint64_t *, int *, unsigned long long *);
+                                float, int, int, int, uint64_t *, int *, unsigned long long *, int);
     unsigned long long *q_tau = nullptr;      // per query: the smallest K-th-key bound any of its CTAs has found
     if (ring && !bigk) CM_TRY(ws.get(&q_tau, (size_t)std::min(qgroup, nq) * 8));
     RingKernel rkern = nullptr;
@@ -1037,7 +1034,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
                 rkern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, reinterpret_cast<const float4 *>(ix.codebooks_r),
                                                        ix.codes_by_list, ix.coarse.rows, ix.coarse.ld, probe_list + (size_t)q0 * nprobes,
                                                        q_off + (size_t)q0 * (nprobes + 1), ix.list_off, ix.tile_off, ix.members, nprobes,
-                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc, q_tau);
+                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc, q_tau, (int)m);
             else
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
                                                   ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
