@@ -349,15 +349,19 @@ int FlatIndex::search_exact(const float *qp, int64_t nq, int64_t nq_pad, int64_t
     CM_TRY(plan_scan(metric, fma, (int)std::min<int64_t>(nq, SCAN_MAX_QB), ld, n, (int)k_eff, &L));
     int64_t nq_run = (nq + L.qb - 1) / L.qb * L.qb;   // <= nq_pad
     (void)nq_pad;
-    uint64_t *pk = nullptr;
-    int *pc = nullptr;
-    CM_TRY(ws.get(&pk, (size_t)nq_run * L.grid * L.K * 8));
-    CM_TRY(ws.get(&pc, (size_t)nq_run * L.grid * sizeof(int)));
     // big corpus: one pass (launch) per query group streams all rows; small table (fewer tiles than the
     // persistent grid): many query groups share one launch, otherwise most SMs would idle
     const int64_t n_tiles = (n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int64_t n_groups = nq_run / L.qb;
     const int64_t per_launch = n_tiles >= 2 * (int64_t)sm_count() ? 1 : std::min<int64_t>(n_groups, 32768);
+    // ... and with many groups in the launch a group gets only as many CTAs as keeps the launch at about one wave: a
+    // CTA that fetches its 8 queries for a single 128-row tile spends its time on the fetch and on the 32-way merge
+    // behind it (IVF / IVFPQ coarse step: 512 queries x 4096 centroids went from 2048 one-tile CTAs to 256 of 8 tiles)
+    if (per_launch > 1) L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(L.grid, L.slots / std::min(per_launch, n_groups)));
+    uint64_t *pk = nullptr;
+    int *pc = nullptr;
+    CM_TRY(ws.get(&pk, (size_t)nq_run * L.grid * L.K * 8));
+    CM_TRY(ws.get(&pc, (size_t)nq_run * L.grid * sizeof(int)));
     int passes = 0;
     for (int64_t g0 = 0; g0 < n_groups; g0 += per_launch, passes++) {
         int64_t q0 = g0 * L.qb;

@@ -217,6 +217,7 @@ int plan_scan(int metric, bool fma, int nq, int ld, int64_t n_rows, int K, ScanL
     if (stages < 3) return fail(CM_ERR_UNSUPPORTED, "k=%d with dim pad %d does not fit the scan kernel's shared memory", K, ld);
     int64_t n_tiles = (n_rows + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     int grid = sm_count() * ctas_per_sm;
+    out->slots = grid;
     if (grid > n_tiles) grid = (int)(n_tiles > 0 ? n_tiles : 1);
     out->metric = metric; out->fma = fma; out->qb = qb; out->stages = stages; out->grid = grid;
     out->K = K; out->C = C; out->smem = scan_smem_bytes(qb, ld, stages, C);

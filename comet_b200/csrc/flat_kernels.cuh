@@ -18,6 +18,7 @@ struct ScanLaunch {
     int qb;            // queries per pass (1,2,4,8)
     int stages;        // TMA ring depth
     int grid;          // persistent CTAs
+    int slots;         // CTAs of this footprint the device holds at once
     int K, C;          // keep K, buffer capacity C (pow2, C >= K + SCAN_TILE_ROWS)
     size_t smem;
 };

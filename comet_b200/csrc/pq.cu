@@ -383,6 +383,10 @@ template <int MW> struct AdcRows { static constexpr int R = MW == 0 ? 1 : (MW <=
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// one thread asks for `bytes` (a multiple of 16) contiguous bytes to be brought into L2
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <bool FMA, int MW>
 __global__ void __launch_bounds__(ADC_THREADS, 2) adc_scan_kernel(
@@ -676,10 +680,10 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
         // the first code lines are requested before the table build: their latency hides under it
 #pragma unroll
         for (int u = 0; u < 4; u++) cw[st][u] = __ldg(lines + (size_t)min(G[st] + u, gmax) * 32);
-#pragma unroll
-        for (int u = 0; u < 2; u++) {         // and the rest of the run's first two chunks towards L2
-            const int line = (G[st] + 8 * u) * 4 + lane;
-            if (line < (gmax + 1) * 4) prefetch_l2(list_bytes + (size_t)line * 128);
+        // and the run's first two chunks (4 KB each) towards L2
+        {
+            const int g1 = min(G[st] + 16, gmax + 1);
+            if (lane == 0 && g1 > G[st]) prefetch_l2_bulk(list_bytes + (size_t)G[st] * 512, (uint32_t)(g1 - G[st]) * 512u);
         }
     }
 
@@ -741,12 +745,12 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
         // the bound the query's other CTAs have found so far (one broadcast load, used when the chunk is selected)
         uint64_t tau_q = KEY_INF;
         if (q_tau != nullptr) tau_q = *reinterpret_cast<volatile unsigned long long *>(q_tau + q);
-        // the chunk after next towards L2 (a chunk of a run is 32 lines of 128 bytes: one per lane); the register ring
-        // below then only has to cover an L2 hit
+        // the chunk after next towards L2 (4 KB per run, one bulk prefetch): the register ring below then only has to
+        // cover an L2 hit
 #pragma unroll
         for (int st = 0; st < S; st++) {
-            const int line = (G[st] + 16) * 4 + lane;
-            if (line < (gmax + 1) * 4) prefetch_l2(list_bytes + (size_t)line * 128);
+            const int g0 = G[st] + 16, g1 = min(g0 + 8, gmax + 1);
+            if (lane == 0 && g1 > g0) prefetch_l2_bulk(list_bytes + (size_t)g0 * 512, (uint32_t)(g1 - g0) * 512u);
         }
 #pragma unroll
         for (int g = 0; g < 8; g++) {

@@ -58,8 +58,11 @@ def main():
         dt = (time.perf_counter() - t0) / 5
         L.cm_profile_enable(0)
         ms, cnt = capi.profile_get(capi.PROF_PQ_SCAN)
+        coarse_ms = capi.profile_get(capi.PROF_FLAT_SCAN)[0] / 5
+        select_ms = capi.profile_get(capi.PROF_SELECT)[0] / 5
         scanned = L.cm_ivfpq_last_scanned(ix.h) / args.nq
         out[cfg] = {"ms_per_batch": dt * 1e3, "qps": args.nq / dt, "adc_ms_per_batch": ms / 5, "launches_per_batch": cnt / 5,
+                    "coarse_scan_ms": coarse_ms, "merges_ms": select_ms,
                     "lookups_per_s": args.nq * scanned * M / (ms / 5 * 1e-3), "same_bits_as_first": same}
         print(cfg, json.dumps(out[cfg]), flush=True)
     print(json.dumps(out))
