@@ -744,10 +744,10 @@ def run_c3(args):
           "e2e": {"value": nq / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": nq * d * 4,
                   "d2h_bytes_per_step": nq * k * 8 + nq * 8, "steps": e2e_steps},
           "gpu_launches": int(launches),
-          "roofline": {"kernel": "adc_scan_kernel (per-(query, probe) residual table in shared memory, list codes streamed)",
+          "roofline": {"kernel": "adc_ring_kernel (per-(query, probe) residual table in shared memory, one bank per lane; list codes streamed pre-skewed)",
                        "bound": "hbm", "achieved": code_bytes / per / 1e9, "peak": hbm, "unit": "GB/s", "frac": code_bytes / per / 1e9 / hbm,
                        "traffic": None, "kernel_ms_per_step": per * 1e3, "launches_timed": scan_n,
-                       "note": "algorithmic bytes = codes scanned x M; the kernel is bound by shared-memory table lookups, not by this stream",
+                       "note": "algorithmic bytes = codes scanned x M; the kernel is bound by the SM load/store data pipe (table reads, shuffles, codeword loads: 71 % busy in profiles/r02_ncu_full_adc_ring.md), not by this stream",
                        "table_lookups_per_s": nq * scanned * M / per, "tables_built_per_s": nq * nprobe / per},
           "cpu_baseline": {"value": nchk / dt, "unit": "queries/s", "cores": min(cores, nchk), "kind": "port",
                            "sample": f"{nchk} of the {nq} queries on the same trained index and codes, one query per host thread, {dt:.1f} s"},

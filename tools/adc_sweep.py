@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from comet_b200 import capi  # noqa: E402
 
+if os.environ.get("COMET_B200_SO"):          # A/B runs: another build of the library
+    capi.SO_PATH = os.environ["COMET_B200_SO"]
+
 
 def main():
     import torch
