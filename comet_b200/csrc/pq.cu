@@ -168,7 +168,7 @@ struct PQCore {
                (per == 4 && (d4 == 1 || d4 == 2));
     }
     bool ring_wanted() const {
-        if (nlist <= 0 || Ksub != 256 || (M & 31) != 0 || (dsub & 3) != 0 || !ring_combo(M / 32, dsub / 4)) return false;
+        if (Ksub != 256 || (M & 31) != 0 || (dsub & 3) != 0 || !ring_combo(M / 32, dsub / 4)) return false;
         if (const char *e = getenv("COMET_B200_ADC_RING")) return atoi(e) != 0;
         return true;
     }
@@ -229,7 +229,7 @@ __global__ void gather_codes_ring_kernel(const uint8_t *__restrict__ codes, cons
         if (list_off[mid] <= i) lo = mid; else hi = mid;
     }
     const long long st = step_off[lo] + (i - list_off[lo]) + l;
-    const uint8_t *src = codes + (size_t)members[i] * M + (size_t)per * l;
+    const uint8_t *src = codes + (size_t)(members ? members[i] : (uint32_t)i) * M + (size_t)per * l;
     uint32_t w = 0;
     for (int j = 0; j < per; j++) w |= (uint32_t)src[j] << (8 * j);
     *reinterpret_cast<uint32_t *>(out + ((size_t)(st >> 2) * 32 + l) * 16 + (size_t)(st & 3) * 4) = w;
@@ -281,7 +281,34 @@ int PQCore::sync_codebooks_t(cudaStream_t st) {
 int PQCore::sync_csr(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(csr_mu);
     const bool ring = ring_wanted();
-    if ((!csr_dirty && ring == ring_layout) || nlist == 0) return CM_OK;
+    if (!csr_dirty && ring == ring_layout) return CM_OK;
+    if (nlist == 0) {
+        // PQ: the store is one list.  Ring form: a pre-skewed copy of all codes (positions = candidate numbers)
+        if (ring && store.n > 0) {
+            const long long steps = ((long long)store.n + 32 + 31) & ~31ll;
+            if (steps * 128 > cbl_bytes || !codes_by_list) {
+                cudaFree(codes_by_list);
+                codes_by_list = nullptr;
+                cbl_bytes = (steps + steps / 2) * 128;
+                CM_CUDA(cudaMalloc(&codes_by_list, (size_t)cbl_bytes));
+            }
+            if (!list_off) CM_CUDA(cudaMalloc(&list_off, 2 * sizeof(long long)));
+            if (!tile_off) CM_CUDA(cudaMalloc(&tile_off, 2 * sizeof(long long)));
+            const long long off[2] = {0, (long long)store.n}, toff[2] = {0, steps};
+            CM_CUDA(cudaMemcpyAsync(list_off, off, sizeof(off), cudaMemcpyHostToDevice, st));
+            CM_CUDA(cudaMemcpyAsync(tile_off, toff, sizeof(toff), cudaMemcpyHostToDevice, st));
+            CM_CUDA(cudaMemsetAsync(codes_by_list, 0, (size_t)steps * 128, st));
+            const long long work = (long long)store.n * 32;
+            gather_codes_ring_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(store.codes, nullptr, (long long)store.n, M, M / 32,
+                                                                                     list_off, tile_off, 1, codes_by_list);
+            count_launch();
+            CM_CUDA(cudaGetLastError());
+            CM_CUDA(cudaStreamSynchronize(st));      // off / toff live on this stack
+        }
+        csr_dirty = false;
+        ring_layout = ring && store.n > 0;
+        return CM_OK;
+    }
     int64_t n = store.n;
     std::vector<uint32_t> flat;
     flat.reserve((size_t)n);
@@ -646,10 +673,11 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
     // holds the K-th key of a near one and next to nothing of a far list gets past it.
     const int q = (int)(blockIdx.y % nq), pr = (int)(blockIdx.y / nq);
     const long long pair = (long long)q * nprobes + pr;
-    const long long list = probe_list[pair];
+    // PQ (members == nullptr): one list, the store itself; candidate number = position
+    const long long list = members ? probe_list[pair] : 0;
     const long long len = list_off[list + 1] - list_off[list];
-    const uint32_t *mem = members + list_off[list];
-    const long long order0 = q_off[(size_t)q * (nprobes + 1) + pr];
+    const uint32_t *mem = members ? members + list_off[list] : nullptr;
+    const long long order0 = members ? q_off[(size_t)q * (nprobes + 1) + pr] : 0;
     long long per = (len + n_slices - 1) / n_slices;
     per = (per + T * S - 1) / (T * S) * (T * S);
     const long long c0 = (long long)blockIdx.x * per;
@@ -692,7 +720,8 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
         // the residual, fetched once per CTA (coalesced) and handed to the lanes through the candidate buffer's space
         float *res_s = reinterpret_cast<float *>(buf);
         for (int i = tid; i < 32 * PER * DS; i += T)
-            res_s[i] = __fsub_rn(__ldg(queries + (size_t)q * ld + i), __ldg(centroids + (size_t)list * cld + i));
+            res_s[i] = centroids ? __fsub_rn(__ldg(queries + (size_t)q * ld + i), __ldg(centroids + (size_t)list * cld + i))
+                                 : __ldg(queries + (size_t)q * ld + i);
         __syncthreads();
         float res[PER][DS];
 #pragma unroll
@@ -792,7 +821,7 @@ __global__ void __launch_bounds__(ADC_THREADS, 2) adc_ring_kernel(
             const long long j = ra[st] + 32ll * ch + lane - 31;
             bool ok = j >= ra[st] && j < rb[st];
             const float dist = __fsqrt_rn(sum);
-            if (ok && skip != nullptr && skip[mem[j]]) ok = false;
+            if (ok && skip != nullptr && skip[mem ? mem[j] : (uint32_t)j]) ok = false;
             if (ok && threshold > 0.0f && dist > threshold) ok = false;
             uint64_t key = 0;
             if (ok) {
@@ -924,8 +953,8 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     if (ivf) {
         nprobes = p->nprobes;
         if (nprobes <= 0 || nprobes > ix.nlist) nprobes = ix.nlist;
-        CM_TRY(ix.sync_csr(st));
     }
+    CM_TRY(ix.sync_csr(st));
     CM_TRY(ix.sync_codebooks_t(st));
     int64_t bound_c = S.n, max_len = S.n;
     if (ivf) {
@@ -982,7 +1011,7 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
     int MW = ((ix.M & 15) == 0 && (ix.M / 16 == 1 || ix.M / 16 == 2 || ix.M / 16 == 4 || ix.M / 16 == 6 || ix.M / 16 == 8)) ? ix.M / 16 : 0;
     if (const char *e = getenv("COMET_B200_ADC_GENERIC")) if (atoi(e)) MW = 0;
     const int R = MW == 0 ? 1 : (MW <= 4 ? 4 : (MW <= 6 ? 3 : 2));
-    const bool ring = ivf && ix.ring_layout;         // codes_by_list is in the ring layout: adc_ring_kernel
+    const bool ring = ix.ring_layout;                // codes_by_list is in the ring layout: adc_ring_kernel
     int C = next_pow2(K + (ring ? ADC_RING_RUNS : R) * ADC_THREADS);         // a round's appends always fit above a compacted buffer
     if (C < 1024) C = 1024;
     const int lut_n = ix.lut_entries();
@@ -1036,9 +1065,11 @@ static int adc_search_device(PQCore &ix, const float *q_dev, int64_t nq, const c
             if (ring && q_tau) CM_CUDA(cudaMemsetAsync(q_tau, 0xff, (size_t)m * 8, st));
             if (ring)
                 rkern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, reinterpret_cast<const float4 *>(ix.codebooks_r),
-                                                       ix.codes_by_list, ix.coarse.rows, ix.coarse.ld, probe_list + (size_t)q0 * nprobes,
-                                                       q_off + (size_t)q0 * (nprobes + 1), ix.list_off, ix.tile_off, ix.members, nprobes,
-                                                       skip, p->threshold, K, C, (int)n_slices, pk, pc, q_tau, (int)m);
+                                                       ix.codes_by_list, ivf ? ix.coarse.rows : nullptr, ix.coarse.ld,
+                                                       ivf ? probe_list + (size_t)q0 * nprobes : nullptr,
+                                                       ivf ? q_off + (size_t)q0 * (nprobes + 1) : nullptr, ix.list_off, ix.tile_off,
+                                                       ivf ? ix.members : nullptr, nprobes, skip, p->threshold, K, C, (int)n_slices, pk, pc,
+                                                       q_tau, (int)m);
             else
             kern<<<grid, ADC_THREADS, smem, st>>>(qp + (size_t)q0 * ix.ld, ix.ld, ix.dim, ix.M, ix.Ksub, ix.dsub, lut_n,
                                                   ix.codebooks, ivf ? ix.codes_by_list : S.codes, (long long)S.n, ivf ? ix.coarse.rows : nullptr,
@@ -1132,6 +1163,7 @@ static int adc_add(PQCore &ix, const uint32_t *ids, float *rows, int64_t n, int 
         if (ivf) cudaMemcpyAsync(hpos.data(), a_pos, (size_t)good * 8, cudaMemcpyDeviceToHost, st);
         int64_t n_before = ix.store.n;
         rc = ix.store.commit(ids + i0, good, st);      // synchronises the stream
+        ix.csr_dirty = true;
         if (rc != CM_OK) break;
         if (ivf) {
             for (int64_t i = 0; i < good; i++) {
@@ -1169,6 +1201,7 @@ static int adc_load_codes(PQCore &ix, const uint32_t *ids, const uint8_t *codes,
         if (e != cudaSuccess) rc = fail(CM_ERR_CUDA, "load_codes: %s", cudaGetErrorString(e));
     }
     if (rc == CM_OK) rc = ix.store.commit(ids, n, st);
+    ix.csr_dirty = true;
     if (rc == CM_OK && ivf) {
         for (int64_t i = 0; i < n; i++) {
             ix.lists[(size_t)list_of[i]].push_back((uint32_t)(n_before + i));
@@ -1186,6 +1219,7 @@ static int adc_flush(PQCore &ix) {
     std::vector<int64_t> new_pos;
     int64_t n_old = ix.store.n;
     CM_TRY(ix.store.flush(&new_pos));
+    ix.csr_dirty = true;
     if (ix.nlist > 0) {
         std::vector<int32_t> nlo((size_t)ix.store.n);
         for (auto &l : ix.lists) {
@@ -1300,6 +1334,7 @@ static int core_get_trained(const PQCore &ix, float *centroids, float *codebooks
 static int core_reset(PQCore &ix) {
     if (ix.store.deleted && ix.store.cap > 0) CM_CUDA(cudaMemset(ix.store.deleted, 0, (size_t)ix.store.cap));
     ix.store.n = 0;
+    ix.csr_dirty = true;
     ix.store.n_deleted_rows = 0;
     ix.store.ids_host.clear();
     ix.store.deleted_ids.clear();
@@ -1692,6 +1727,7 @@ struct cm_ivfpq_sharded {
 static int ivfpqs_clear_vectors(cm::PQCore &ix) {          // drop the codes, keep the trained state
     if (ix.store.deleted && ix.store.cap > 0) CM_CUDA(cudaMemset(ix.store.deleted, 0, (size_t)ix.store.cap));
     ix.store.n = 0;
+    ix.csr_dirty = true;
     ix.store.n_deleted_rows = 0;
     ix.store.ids_host.clear();
     ix.store.deleted_ids.clear();

@@ -262,3 +262,36 @@ def test_ivfpq_ring_scan_k_all_beyond_the_per_cta_selection():
     q = rng.standard_normal((2, 256)).astype(np.float32)
     check_ivfpq(g, o, q, 0, 2)
     check_ivfpq(g, o, q[:1], 12000, 1)
+
+
+@pytest.mark.parametrize("d,M", [(256, 32), (512, 64), (768, 96), (1024, 128)])
+def test_pq_ring_scan(d, M, monkeypatch):
+    # the plain PQ index keeps a pre-skewed copy of its store for the same scan: slices of one long list, threshold,
+    # filter, delete / flush / add in between, and the row-per-lane form on the same index
+    g, o, rng = pq_pair(21000, d, capi.L2, M, 8, 500 + M)
+    q = rng.standard_normal((5, d)).astype(np.float32)
+    check_pq(g, o, q, 100)
+    check_pq(g, o, q[:2], 0)
+    check_pq(g, o, q[:2], 300, threshold=float(np.sqrt(2 * d) * 0.97))
+    check_pq(g, o, q[:2], 64, filter_ids=np.arange(3, 21000, 7, dtype=np.uint32))
+    for slices in ("1", "3"):
+        monkeypatch.setenv("COMET_B200_ADC_SLICES", slices)
+        check_pq(g, o, q[:3], 100)
+    monkeypatch.delenv("COMET_B200_ADC_SLICES")
+    ring = g.search(q, k=100)
+    monkeypatch.setenv("COMET_B200_ADC_RING", "0")
+    rows = g.search(q, k=100)
+    monkeypatch.delenv("COMET_B200_ADC_RING")
+    for a, b in zip(ring, rows):
+        assert np.array_equal(a, b)
+    for i in range(2, 6000, 5):
+        g.remove(i)
+        o.remove(i)
+    check_pq(g, o, q, 100)
+    g.flush()
+    o.flush()
+    x2 = rng.standard_normal((700, d)).astype(np.float32)
+    ids2 = np.arange(50000, 50700, dtype=np.uint32)
+    g.add(ids2, x2.copy())
+    o.add(ids2, x2.copy())
+    check_pq(g, o, q, 100)

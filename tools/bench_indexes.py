@@ -163,9 +163,17 @@ def main():
         pq = capi.PQIndex(d, capi.L2, M, 8)
         t0 = time.perf_counter(); pq.train(x[:20000].copy()); t_train = time.perf_counter() - t0
         t0 = time.perf_counter(); pq.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+        r_ring = pq.search(q[:128], k=100)
         dt = timed(lambda: pq.search(q[:128], k=100), reps=3)
+        os.environ["COMET_B200_ADC_RING"] = "0"          # the row-per-lane form on the same index
+        r_rows = pq.search(q[:128], k=100)
+        dt_rows = timed(lambda: pq.search(q[:128], k=100), reps=3)
+        os.environ.pop("COMET_B200_ADC_RING")
+        same = all(np.array_equal(a, b) for a, b in zip(r_ring, r_rows))
         out["pq"] = {"n": n, "dim": d, "M": M, "nbits": 8, "k": 100, "train_s": t_train, "add_s": t_add, "qps_host_api": 128 / dt,
-                     "ms_per_batch_128q": dt * 1e3, "lookups_per_s": 128 * n * M / dt, "code_GBps": 128 * n * M / dt / 1e9}
+                     "ms_per_batch_128q": dt * 1e3, "lookups_per_s": 128 * n * M / dt, "code_GBps": 128 * n * M / dt / 1e9,
+                     "row_per_lane_form": {"ms_per_batch_128q": dt_rows * 1e3, "lookups_per_s": 128 * n * M / dt_rows,
+                                           "same_results": bool(same)}}
         del pq
     if "ivfpq" in only:
         ivfpq = capi.IVFPQIndex(d, capi.L2, nlist, M, 8)
