@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--nlist", type=int, default=4096)
     ap.add_argument("--nq", type=int, default=512)
     ap.add_argument("--configs", default=";SLICES=2")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart() before the timed searches (ncu --profile-from-start off)")
     args = ap.parse_args()
     d, M, nprobe = 768, 96, 32
     dev = torch.device("cuda", 0)
@@ -54,6 +55,8 @@ def main():
         if ref is None:
             ref = r
         same = bool(np.array_equal(r[0], ref[0]) and np.array_equal(r[1].view(np.uint32), ref[1].view(np.uint32)))
+        if args.cuda_profiler:
+            torch.cuda.cudart().cudaProfilerStart()
         L.cm_profile_reset(); L.cm_profile_enable(1)
         t0 = time.perf_counter()
         for _ in range(5):
