@@ -168,6 +168,7 @@ __device__ __forceinline__ void h_push_warp(HCand *a, int &n, HCand c, int lane)
         lt = IS_MAX ? (c.d > anc.d) : (c.d < anc.d);      // less(new, ancestor)
     }
     const unsigned m = __ballot_sync(0xffffffffu, lt);
+    __syncwarp();                                         // every ancestor is read before any slot is rewritten
     const int up = __ffs(~(m >> 1)) - 1;                  // leading run of "less than the parent": levels climbed
     if (lane >= 1 && lane <= up) a[((j + 1) >> (lane - 1)) - 1] = anc;
     if (lane == 0) a[((j + 1) >> up) - 1] = c;

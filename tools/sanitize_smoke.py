@@ -40,6 +40,11 @@ for (d2, M2, n2) in ((64, 16, 6000), (768, 96, 2600)):
     ip2 = capi.IVFPQIndex(d2, capi.L2, 2, M2, 8)
     ip2.train(x2[:600].copy()); ip2.add(ids2, x2.copy()); ip2.search(q2, k=20, nprobes=2)
     ip2.remove(3); ip2.search(q2[:2], k=20, nprobes=1); ip2.flush(); ip2.search(q2[:2], k=20, nprobes=2)
+    # M = 96 takes the ring form of the scan (lane-owned table banks, pre-skewed codes); the row-per-lane form again
+    os.environ["COMET_B200_ADC_RING"] = "0"
+    pq2.search(q2, k=20); ip2.search(q2, k=20, nprobes=2)
+    os.environ.pop("COMET_B200_ADC_RING")
+    ip2.search(q2, k=300, nprobes=2); ip2.search(q2[:2], k=0, nprobes=2)
 # tensor path with 256-byte re-score pieces (row pitch a multiple of 64 floats) and both select launch shapes
 x3 = rng.standard_normal((17000, 128)).astype(np.float32)
 f3 = capi.FlatIndex(128, capi.L2)
