@@ -150,6 +150,21 @@ def test_ragged_shapes(dim, n):
     check_queries(g, o, q, 0)        # WithK(0) -> everything
 
 
+@pytest.mark.parametrize("metric", [capi.L2, capi.COSINE])
+def test_small_table_many_query_groups(metric):
+    # the shape of an IVF / IVFPQ coarse step: a table of a few dozen 128-row tiles scanned for hundreds of queries in ONE
+    # launch; a query group then gets only a few CTAs (one wave for the launch), each walking several tiles
+    rng = np.random.default_rng(4096 + metric)
+    x = rng.standard_normal((3001, 48)).astype(np.float32) + np.float32(0.1)
+    x[1500:1530] = x[10]                      # ties across tiles
+    g, o = build_pair(x, metric)
+    q = rng.standard_normal((603, 48)).astype(np.float32) + np.float32(0.1)
+    ids, sc, cnt = g.search(q, k=32, path=capi.PATH_EXACT)
+    for i in range(0, 603, 7):
+        oi, os_ = o.search(q[i], k=32)
+        assert_same_results(ids[i], sc[i], cnt[i], oi, os_, what=f"query {i}")
+
+
 @pytest.mark.parametrize("k", [1, 100, 1000, 4096])
 def test_k_sweep(k):
     rng = np.random.default_rng(k)
