@@ -357,11 +357,15 @@ def run_ours(args):
             ach = flops / per / 1e12
             capped = bool(clocks) and ("sw_power_cap" in clocks["reasons"] or (
                 clocks["sm_mhz"] and clocks["sm_max_mhz"] and clocks["sm_mhz"] < 0.9 * clocks["sm_max_mhz"]))
+            # a power-cap flag sampled while the clock stayed at its maximum is not the sustained regime: a pass that
+            # beats the sustained cuBLAS figure is measured against the burst one (the fraction never flatters itself)
+            if capped and ach > tf_sus:
+                capped = False
             peak = tf_sus if capped else tf_burst
             roof = {"kernel": "flat_gemm_ts_kernel (tcgen05 bf16, queries resident in tensor memory, %d launches per step)" % (gemm_n // n_prof),
                     "bound": "tensor", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak,
-                    "regime": "sustained (power cap / low clock seen in this run)" if capped else "burst (no power cap, clock >= 90 % of max in this run)",
+                    "regime": "sustained (power cap / low clock seen in this run)" if capped else "burst (clock >= 90 % of max in this run, or faster than the sustained cuBLAS figure)",
                     "frac_of_burst": ach / tf_burst, "frac_of_sustained": ach / tf_sus,
                     "traffic": measured_traffic("flat_gemm_kernel_per_step_bytes") if (world == 1 and N_ROWS == 1_000_000) else None,
                     "traffic_note": "DRAM bytes of the candidate-pass launches of one step, ncu capture in profiles/; algorithmic = %d (bf16 shadow once)" % (shard * DIM * 2),
