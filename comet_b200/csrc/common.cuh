@@ -97,6 +97,31 @@ __device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// (A packed add behind a packed multiply is NOT usable on this path: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with explicit .rn and --fmad=false, which would fuse the two roundings the reference performs separately.)
+__device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// four metric_step<METRIC, false> on elements j..j+3 of one query: the element-wise part packed (two IEEE round-to-nearest
+// operations per instruction), the accumulation four sequential scalar adds -- the reference's order
+// (distance.go:114-121, 158-165, 201-216)
+template <int METRIC>
+__device__ __forceinline__ float metric_step4_unfused(float acc, const float4 &q, const float4 &x) {
+    uint64_t a01 = pk2(q.x, q.y), a23 = pk2(q.z, q.w), b01 = pk2(x.x, x.y), b23 = pk2(x.z, x.w);
+    if (METRIC != CM_COSINE) {
+        a01 = sub2_rn(a01, b01); a23 = sub2_rn(a23, b23);
+        b01 = a01; b23 = a23;
+    }
+    float p0, p1, p2, p3;
+    unpk2(mul2_rn(a01, b01), p0, p1);
+    unpk2(mul2_rn(a23, b23), p2, p3);
+    acc = __fadd_rn(acc, p0);
+    acc = __fadd_rn(acc, p1);
+    acc = __fadd_rn(acc, p2);
+    return __fadd_rn(acc, p3);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------

@@ -219,6 +219,184 @@ __global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__
     if (tid == 0) out_cnt[(size_t)q * n_chunks + blockIdx.x] = s_cnt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// List-major scan (batches).  The query-major kernel above streams every probed list once per query that
+// probes it (16 times at 512 queries x 32 probes over 1024 lists) and sits on the DRAM roofline doing so.
+// Here the (query, probe) pairs are grouped by list and a CTA takes 128 rows of a list for up to IVF_QB
+// pairs at once: the rows are gathered once per block of pairs (the blocks of a list follow each other
+// in the grid, so the second one finds them in L2), each thread walks its row for all the block's
+// queries in the reference's order.  A pair's candidates keep their numbers q_off[query][probe] + j
+// (ivf_index_search.go:252-268, the tie-break key); its keys go to the parts
+// tile_off[query][probe] + tile of the query, 128 slots each, which merge_topk_kernel reads as before.
+// ------------------------------------------------------------------------------------------------
+static constexpr int IVF_QB = 8;
+
+// per query: tile_off[q][p] = number of 128-row tiles of probes 0..p-1; per list: pairs probing it
+__global__ void ivf_group_count_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ list_off,
+                                       int nprobes, int nq, long long *__restrict__ tile_off, int *__restrict__ list_cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    long long acc = 0;
+    for (int p = 0; p < nprobes; p++) {
+        tile_off[(size_t)q * (nprobes + 1) + p] = acc;
+        const long long l = probe_list[(size_t)q * nprobes + p];
+        acc += (list_off[l + 1] - list_off[l] + 127) >> 7;
+        atomicAdd(&list_cnt[l], 1);
+    }
+    tile_off[(size_t)q * (nprobes + 1) + nprobes] = acc;
+}
+
+// one CTA: pair_off[l] = pairs of lists < l, blk_off[l] = blocks of IVF_QB pairs of lists < l; cursors start at pair_off
+__global__ void ivf_group_scan_kernel(const int *__restrict__ list_cnt, int nlist, int *__restrict__ pair_off,
+                                      int *__restrict__ blk_off, int *__restrict__ cursor) {
+    __shared__ int carry_p, carry_b;
+    __shared__ int wp[32], wb[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry_p = 0; carry_b = 0; }
+    __syncthreads();
+    for (int l0 = 0; l0 <= nlist; l0 += 1024) {
+        const int l = l0 + tid;
+        const int c = l < nlist ? list_cnt[l] : 0;
+        int ip = c, ib = (c + IVF_QB - 1) / IVF_QB;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tp = __shfl_up_sync(0xffffffffu, ip, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ip += tp; ib += tb; }
+        }
+        if (lane == 31) { wp[warp] = ip; wb[warp] = ib; }
+        __syncthreads();
+        int bp = carry_p, bb = carry_b;
+        for (int w = 0; w < warp; w++) { bp += wp[w]; bb += wb[w]; }
+        if (l <= nlist) {
+            const int ep = bp + ip - c, eb = bb + ib - (c + IVF_QB - 1) / IVF_QB;     // exclusive
+            pair_off[l] = ep; blk_off[l] = eb;
+            if (l < nlist) cursor[l] = ep;
+        }
+        __syncthreads();
+        if (tid == 1023) { carry_p = bp + ip; carry_b = bb + ib; }
+        __syncthreads();
+    }
+}
+
+__global__ void ivf_group_scatter_kernel(const long long *__restrict__ probe_list, long long n_pairs, int *__restrict__ cursor,
+                                         int *__restrict__ pairs_sorted) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    pairs_sorted[atomicAdd(&cursor[probe_list[i]], 1)] = (int)i;
+}
+
+template <int METRIC, bool FMA>
+__global__ void __launch_bounds__(128) ivf_scan_lists_kernel(
+    const float *__restrict__ rows, int ld, const float *__restrict__ queries, const long long *__restrict__ q_off,
+    const long long *__restrict__ tile_off, const long long *__restrict__ list_off, const uint32_t *__restrict__ members,
+    int nprobes, int nlist, const int *__restrict__ pair_off, const int *__restrict__ blk_off,
+    const int *__restrict__ pairs_sorted, const uint8_t *__restrict__ skip, float threshold, long long parts_per_q,
+    uint64_t *__restrict__ out_keys, int *__restrict__ out_cnt) {
+    constexpr int CH = 32, PCS = CH / 4, ROW_B = CH * 4, STAGE_B = 128 * ROW_B;
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *q_s = reinterpret_cast<float *>(smem);                    // [IVF_QB][ld]
+    uint8_t *stage = smem + (size_t)IVF_QB * ld * 4;                 // [2][128 rows][128 B]
+    __shared__ uint32_t pos_s[128];
+    __shared__ int s_cnt[IVF_QB];
+    __shared__ int s_pair[IVF_QB];
+    const int tid = threadIdx.x;
+    // block of pairs -> list: largest l with blk_off[l] <= blockIdx.y
+    const int y = blockIdx.x;                                         // x: blocks of pairs (the blocks of a list are neighbours)
+    if (y >= blk_off[nlist]) return;
+    int lo = 0, hi = nlist;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blk_off[mid] <= y) lo = mid; else hi = mid;
+    }
+    const int l = lo;
+    const long long len = list_off[l + 1] - list_off[l];
+    const int tile = blockIdx.y;
+    const long long t0 = (long long)tile * 128;
+    if (t0 >= len) return;
+    const int first = pair_off[l] + (y - blk_off[l]) * IVF_QB;
+    const int nb = min(IVF_QB, pair_off[l + 1] - first);             // pairs of this block
+    const long long j = t0 + tid;
+    const bool live = j < len;
+    const uint32_t pos = members[list_off[l] + (live ? j : t0)];
+    pos_s[tid] = pos;
+    if (tid < IVF_QB) {
+        s_cnt[tid] = 0;
+        s_pair[tid] = tid < nb ? pairs_sorted[first + tid] : -1;
+    }
+    __syncthreads();
+    for (int qi = 0; qi < IVF_QB; qi++) {
+        const int pair = s_pair[qi];
+        const float *src = pair >= 0 ? queries + (size_t)(pair / nprobes) * ld : nullptr;
+        for (int e = tid; e < ld; e += 128) q_s[(size_t)qi * ld + e] = src ? src[e] : 0.0f;
+    }
+    const int n_ch = ld / CH;
+    auto issue = [&](int c) {
+        uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
+#pragma unroll
+        for (int p = 0; p < PCS; p++) {
+            const int idx = p * 128 + tid;
+            const int r = idx / PCS, piece = idx % PCS;
+            const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
+            const uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    float acc[IVF_QB];
+#pragma unroll
+    for (int qi = 0; qi < IVF_QB; qi++) acc[qi] = 0.0f;
+    for (int c = 0; c < n_ch; c++) {
+        if (c + 1 < n_ch) {
+            issue(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                              // also orders the q_s fill before its first use
+        const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
+        const float *qc = q_s + c * CH;
+#pragma unroll
+        for (int jj = 0; jj < PCS; jj++) {
+            const float4 xv = *reinterpret_cast<const float4 *>(sp + ((jj ^ (tid & 7)) << 4));
+#pragma unroll
+            for (int qi = 0; qi < IVF_QB; qi++) {
+                const float4 qv = *reinterpret_cast<const float4 *>(qc + (size_t)qi * ld + jj * 4);
+                float a = acc[qi];
+                if (FMA) {
+                    a = metric_step<METRIC, FMA>(a, qv.x, xv.x);
+                    a = metric_step<METRIC, FMA>(a, qv.y, xv.y);
+                    a = metric_step<METRIC, FMA>(a, qv.z, xv.z);
+                    a = metric_step<METRIC, FMA>(a, qv.w, xv.w);
+                } else {
+                    a = metric_step4_unfused<METRIC>(a, qv, xv);
+                }
+                acc[qi] = a;
+            }
+        }
+        __syncthreads();
+    }
+    const bool keep = live && !(skip != nullptr && skip[pos]);
+#pragma unroll
+    for (int qi = 0; qi < IVF_QB; qi++) {
+        const int pair = s_pair[qi];
+        if (pair < 0) continue;                                       // uniform
+        const int q = pair / nprobes, pr = pair - q * nprobes;
+        const float dist = metric_finish<METRIC>(acc[qi]);
+        const size_t part = (size_t)q * parts_per_q + (size_t)tile_off[(size_t)q * (nprobes + 1) + pr] + tile;
+        if (keep && !(threshold > 0.0f && dist > threshold)) {
+            const int slot = atomicAdd(&s_cnt[qi], 1);
+            out_keys[part * 128 + slot] = make_key(dist, (uint32_t)(q_off[(size_t)q * (nprobes + 1) + pr] + j));
+        }
+    }
+    __syncthreads();
+    if (tid < nb) {
+        const int pair = s_pair[tid];
+        const int q = pair / nprobes, pr = pair - q * nprobes;
+        out_cnt[(size_t)q * parts_per_q + tile_off[(size_t)q * (nprobes + 1) + pr] + tile] = s_cnt[tid];
+    }
+}
+
 // candidate numbers of the final lists -> store positions and ids.  List shards (cm_ivf_sharded_*): this index holds
 // only SOME lists, so its candidate numbers count its own vectors only; with the GLOBAL list lengths the same walk also
 // yields the number the candidate has in the reference's append loop over ALL probed lists (ivf_index_search.go:252-268)
@@ -352,26 +530,67 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
 
     // 5. list scans, in query groups so that the key workspace stays bounded (<= 1 GiB)
     const int n_chunks = (int)((bound_c + 127) / 128);
-    const long long cap_c = (long long)n_chunks * 128;
+    // batches take the list-major scan: a pair's keys go to whole 128-slot parts per tile of its list, so a query has up
+    // to nprobes more parts than candidates / 128
+    const int64_t max_len = ix.sizes_desc.empty() ? 0 : ix.sizes_desc[0];
+    const int64_t max_tiles = (max_len + 127) / 128;
+    bool list_major = nq >= 32 && max_tiles <= 65535;
+    if (const char *e = getenv("COMET_B200_IVF_LIST_MAJOR")) list_major = atoi(e) != 0 && max_tiles <= 65535 && max_tiles > 0;
+    const int n_parts = list_major ? n_chunks + nprobes : n_chunks;
+    const long long cap_c = (long long)n_parts * 128;
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (cap_c * 8)));
     uint64_t *keys = nullptr;
     int *kcnt = nullptr;
     CM_TRY(ws.get(&keys, (size_t)qgroup * cap_c * 8));
-    CM_TRY(ws.get(&kcnt, (size_t)qgroup * n_chunks * 4));
+    CM_TRY(ws.get(&kcnt, (size_t)qgroup * n_parts * 4));
+    long long *tile_off = nullptr;
+    int *grp = nullptr, *pairs_sorted = nullptr;                  // grp: list_cnt | pair_off | blk_off | cursor, nlist + 1 ints each
+    if (list_major) {
+        CM_TRY(ws.get(&tile_off, (size_t)qgroup * (nprobes + 1) * 8));
+        CM_TRY(ws.get(&grp, (size_t)4 * (ix.nlist + 1) * sizeof(int)));
+        CM_TRY(ws.get(&pairs_sorted, (size_t)qgroup * nprobes * sizeof(int)));
+    }
     size_t smem = (size_t)ld * 4 + 2 * 128 * 128;
     for (int64_t q0 = 0; q0 < nq; q0 += qgroup) {
         int64_t m = std::min(qgroup, nq - q0);
-        CM_CUDA(cudaMemsetAsync(kcnt, 0, (size_t)m * n_chunks * 4, st));
+        CM_CUDA(cudaMemsetAsync(kcnt, 0, (size_t)m * n_parts * 4, st));
         dim3 grid((unsigned)n_chunks, (unsigned)m);
         const float *qq = qp + (size_t)q0 * ld;
         const long long *pl = probe_list + (size_t)q0 * nprobes, *qo = q_off + (size_t)q0 * (nprobes + 1);
         ProfScope prof(CM_PROF_IVF_SCAN, st);
+        if (list_major) {
+            const int nl1 = ix.nlist + 1;
+            int *list_cnt = grp, *pair_off = grp + nl1, *blk_off = grp + 2 * nl1, *cursor = grp + 3 * nl1;
+            CM_CUDA(cudaMemsetAsync(list_cnt, 0, (size_t)nl1 * sizeof(int), st));
+            ivf_group_count_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(pl, ix.list_off, nprobes, (int)m, tile_off, list_cnt);
+            ivf_group_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, ix.nlist, pair_off, blk_off, cursor);
+            const long long n_pairs = (long long)m * nprobes;
+            ivf_group_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pl, n_pairs, cursor, pairs_sorted);
+            const long long blocks_max = n_pairs / IVF_QB + std::min<long long>(ix.nlist, n_pairs);
+            const size_t smem_l = (size_t)IVF_QB * ld * 4 + 2 * 128 * 128;
+            dim3 grid_l((unsigned)blocks_max, (unsigned)max_tiles);
+#define CM_IVF_LISTS(MM, F)                                                                                              \
+    do {                                                                                                                 \
+        CM_TRY(set_dyn_smem((const void *)ivf_scan_lists_kernel<MM, F>, smem_l));                                        \
+        ivf_scan_lists_kernel<MM, F><<<grid_l, 128, smem_l, st>>>(S.rows, ld, qq, qo, tile_off, ix.list_off, ix.members, nprobes, \
+                                                                 ix.nlist, pair_off, blk_off, pairs_sorted, skip, p->threshold, \
+                                                                 (long long)n_parts, keys, kcnt);                       \
+    } while (0)
+            switch (ix.metric) {
+            case CM_L2: if (fma) CM_IVF_LISTS(CM_L2, true); else CM_IVF_LISTS(CM_L2, false); break;
+            case CM_L2SQ: if (fma) CM_IVF_LISTS(CM_L2SQ, true); else CM_IVF_LISTS(CM_L2SQ, false); break;
+            default: if (fma) CM_IVF_LISTS(CM_COSINE, true); else CM_IVF_LISTS(CM_COSINE, false); break;
+            }
+#undef CM_IVF_LISTS
+            for (int i = 0; i < 4; i++) count_launch();
+            CM_CUDA(cudaGetLastError());
+        } else
         switch (ix.metric) {
         case CM_L2: CM_TRY(launch_ivf_scan_m<CM_L2>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
         case CM_L2SQ: CM_TRY(launch_ivf_scan_m<CM_L2SQ>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
         default: CM_TRY(launch_ivf_scan_m<CM_COSINE>(fma, grid, smem, st, S.rows, ld, qq, pl, qo, ix.list_off, ix.members, nprobes, skip, p->threshold, cap_c, n_chunks, keys, kcnt)); break;
         }
-        CM_TRY(launch_merge_topk(keys, kcnt, (int)m, n_chunks, 128, (int)k_eff, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
+        CM_TRY(launch_merge_topk(keys, kcnt, (int)m, n_parts, 128, (int)k_eff, nullptr, out_stride, out_ids + (size_t)q0 * out_stride,
                                  out_scores + (size_t)q0 * out_stride, nullptr, out_counts + q0, st));
         ivf_emit_kernel<<<(unsigned)m, 128, 0, st>>>(pl, qo, ix.list_off, ix.members, nprobes, S.ids, (long long)out_stride,
                                                      out_ids + (size_t)q0 * out_stride,

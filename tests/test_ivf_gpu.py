@@ -103,3 +103,37 @@ def test_ivf_k_all_beyond_the_shared_memory_merge():
     check(g, o, q, 0, 4)
     check(g, o, q, 20000, 3)
     check(g, o, q[:1], 0, 2, threshold=20.0)
+
+
+# Batches take the list-major scan (the (query, probe) pairs grouped by list, a 128-row tile of a list walked for up to 8
+# queries at once); candidate numbers -- the tie-break key -- and parts per query are laid out differently from the
+# query-major scan, the answers must not be.
+@pytest.mark.parametrize("metric,d", [(capi.L2, 48), (capi.COSINE, 100), (capi.L2SQ, 768)])
+def test_ivf_list_major_scan(metric, d, monkeypatch):
+    n = 7000 if d < 768 else 3000
+    g, o, rng, x, lists = build_pair(n, d, 23, metric, 500 + d)
+    x[100:140] = x[7]                           # ties inside and across lists are ordered by candidate number
+    q = rng.standard_normal((70, d)).astype(np.float32) + (0.3 if metric == capi.COSINE else 0.0)
+    q[3] = x[7] if metric != capi.COSINE else q[3]
+    for nprobes in (1, 5, 23):
+        check(g, o, q, 10, nprobes)
+    check(g, o, q[:40], 0, 2)                   # WithK(0)
+    check(g, o, q[:33], 200, 4, threshold=float(np.sqrt(2 * d)) if metric == capi.L2 else (2.0 * d if metric == capi.L2SQ else 0.9))
+    check(g, o, q[:33], 50, 6, filter_ids=np.arange(2, n, 3, dtype=np.uint32))
+    for i in range(5, n, 4):
+        g.remove(i)
+        o.remove(i)
+    check(g, o, q[:35], 20, 7)
+    g.flush()
+    o.flush()
+    check(g, o, q[:35], 20, 7)
+    # the same batch through both scans, and a small batch forced through the list-major one
+    lm = g.search(q, k=30, nprobes=9)
+    monkeypatch.setenv("COMET_B200_IVF_LIST_MAJOR", "0")
+    qm = g.search(q, k=30, nprobes=9)
+    monkeypatch.setenv("COMET_B200_IVF_LIST_MAJOR", "1")
+    check(g, o, q[:3], 10, 4)
+    check(g, o, q[:1], 0, 23)
+    monkeypatch.delenv("COMET_B200_IVF_LIST_MAJOR")
+    for a, b in zip(lm, qm):
+        assert np.array_equal(a, b)

@@ -153,11 +153,18 @@ def main():
         ivf = capi.IVFIndex(d, nlist, capi.L2)
         t0 = time.perf_counter(); ivf.train(x[: nlist * 16].copy()); t_train = time.perf_counter() - t0
         t0 = time.perf_counter(); ivf.add(ids, x.copy(), writeback=False); t_add = time.perf_counter() - t0
+        r_lm = ivf.search(q, k=100, nprobes=nprobe)
         dt = timed(lambda: ivf.search(q, k=100, nprobes=nprobe))
         scanned = capi.lib().cm_ivf_last_scanned(ivf.h) / nq       # measured: vectors of probed lists per query
+        os.environ["COMET_B200_IVF_LIST_MAJOR"] = "0"              # the query-major scan on the same index
+        r_qm = ivf.search(q, k=100, nprobes=nprobe)
+        dt_qm = timed(lambda: ivf.search(q, k=100, nprobes=nprobe), reps=3)
+        os.environ.pop("COMET_B200_IVF_LIST_MAJOR")
+        same = all(np.array_equal(a, b) for a, b in zip(r_lm, r_qm))
         out["ivf"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "k": 100, "train_s": t_train, "add_s": t_add,
                       "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
-                      "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9}
+                      "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9,
+                      "query_major_scan": {"ms_per_batch": dt_qm * 1e3, "qps_host_api": nq / dt_qm, "same_results": bool(same)}}
         del ivf
     if "pq" in only:
         pq = capi.PQIndex(d, capi.L2, M, 8)
