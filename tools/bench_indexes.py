@@ -156,6 +156,12 @@ def main():
         r_lm = ivf.search(q, k=100, nprobes=nprobe)
         dt = timed(lambda: ivf.search(q, k=100, nprobes=nprobe))
         scanned = capi.lib().cm_ivf_last_scanned(ivf.h) / nq       # measured: vectors of probed lists per query
+        L = capi.lib()
+        L.cm_profile_reset(); L.cm_profile_enable(1)
+        ivf.search(q, k=100, nprobes=nprobe)
+        L.cm_profile_enable(0)
+        phases = {"list_scan_ms": capi.profile_get(capi.PROF_IVF_SCAN)[0], "coarse_scan_ms": capi.profile_get(capi.PROF_FLAT_SCAN)[0],
+                  "merges_ms": capi.profile_get(capi.PROF_SELECT)[0]}
         os.environ["COMET_B200_IVF_LIST_MAJOR"] = "0"              # the query-major scan on the same index
         r_qm = ivf.search(q, k=100, nprobes=nprobe)
         dt_qm = timed(lambda: ivf.search(q, k=100, nprobes=nprobe), reps=3)
@@ -164,6 +170,7 @@ def main():
         out["ivf"] = {"n": n, "dim": d, "nlist": nlist, "nprobes": nprobe, "k": 100, "train_s": t_train, "add_s": t_add,
                       "qps_host_api": nq / dt, "ms_per_batch": dt * 1e3, "scanned_per_query": scanned,
                       "algorithmic_GBps": nq * (scanned * d * 4 + nlist * d * 4 / 8) / dt / 1e9,
+                      "phases_of_one_search": phases,
                       "query_major_scan": {"ms_per_batch": dt_qm * 1e3, "qps_host_api": nq / dt_qm, "same_results": bool(same)}}
         del ivf
     if "pq" in only:
