@@ -272,10 +272,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(
             compact_topk(buf, C, K, &cnt, &tau, tid, MERGE_THREADS, bar);
             continue;
         }
-        for (int pp = p; pp < p_end; pp++) {
-            int m = pc[pp];
-            for (int i = tid; i < m; i += MERGE_THREADS) {
-                uint64_t key = pk[(size_t)pp * Kp + i];
+        // the group's parts as one index space (part, slot): independent loads, not a latency chain per part (an IVF
+        // query has thousands of 128-slot parts)
+        const int span = p_end - p == 1 ? pc[p] : (p_end - p) * Kp;      // a single part: just its keys
+        for (int idx = tid; idx < span; idx += MERGE_THREADS) {
+            const int dp = idx / Kp, i = idx - dp * Kp;
+            if (i < pc[p + dp]) {
+                uint64_t key = pk[(size_t)(p + dp) * Kp + i];
                 if (key < t) buf[atomicAdd(&cnt, 1)] = key;
             }
         }

@@ -310,19 +310,10 @@ __global__ void __launch_bounds__(128) ivf_scan_lists_kernel(
     }
     const int l = lo;
     const long long len = list_off[l + 1] - list_off[l];
-    const int tile = blockIdx.y;
-    const long long t0 = (long long)tile * 128;
-    if (t0 >= len) return;
     const int first = pair_off[l] + (y - blk_off[l]) * IVF_QB;
     const int nb = min(IVF_QB, pair_off[l + 1] - first);             // pairs of this block
-    const long long j = t0 + tid;
-    const bool live = j < len;
-    const uint32_t pos = members[list_off[l] + (live ? j : t0)];
-    pos_s[tid] = pos;
-    if (tid < IVF_QB) {
-        s_cnt[tid] = 0;
-        s_pair[tid] = tid < nb ? pairs_sorted[first + tid] : -1;
-    }
+    if ((long long)blockIdx.y * 128 >= len) return;
+    if (tid < IVF_QB) s_pair[tid] = tid < nb ? pairs_sorted[first + tid] : -1;
     __syncthreads();
     for (int qi = 0; qi < IVF_QB; qi++) {
         const int pair = s_pair[qi];
@@ -330,70 +321,81 @@ __global__ void __launch_bounds__(128) ivf_scan_lists_kernel(
         for (int e = tid; e < ld; e += 128) q_s[(size_t)qi * ld + e] = src ? src[e] : 0.0f;
     }
     const int n_ch = ld / CH;
-    auto issue = [&](int c) {
-        uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
-#pragma unroll
-        for (int p = 0; p < PCS; p++) {
-            const int idx = p * 128 + tid;
-            const int r = idx / PCS, piece = idx % PCS;
-            const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
-            const uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    issue(0);
-    float acc[IVF_QB];
-#pragma unroll
-    for (int qi = 0; qi < IVF_QB; qi++) acc[qi] = 0.0f;
-    for (int c = 0; c < n_ch; c++) {
-        if (c + 1 < n_ch) {
-            issue(c + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();                                              // also orders the q_s fill before its first use
-        const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
-        const float *qc = q_s + c * CH;
-#pragma unroll
-        for (int jj = 0; jj < PCS; jj++) {
-            const float4 xv = *reinterpret_cast<const float4 *>(sp + ((jj ^ (tid & 7)) << 4));
-#pragma unroll
-            for (int qi = 0; qi < IVF_QB; qi++) {
-                const float4 qv = *reinterpret_cast<const float4 *>(qc + (size_t)qi * ld + jj * 4);
-                float a = acc[qi];
-                if (FMA) {
-                    a = metric_step<METRIC, FMA>(a, qv.x, xv.x);
-                    a = metric_step<METRIC, FMA>(a, qv.y, xv.y);
-                    a = metric_step<METRIC, FMA>(a, qv.z, xv.z);
-                    a = metric_step<METRIC, FMA>(a, qv.w, xv.w);
-                } else {
-                    a = metric_step4_unfused<METRIC>(a, qv, xv);
+    // the block's tiles of the list: gridDim.y CTAs share them (long lists: several tiles per CTA, the queries stay)
+    for (int tile = blockIdx.y; (long long)tile * 128 < len; tile += gridDim.y) {
+        const long long t0 = (long long)tile * 128;
+        const long long j = t0 + tid;
+        const bool live = j < len;
+        const uint32_t pos = members[list_off[l] + (live ? j : t0)];
+        __syncthreads();                                              // the previous tile is done with pos_s / s_cnt / stage
+        pos_s[tid] = pos;
+        if (tid < IVF_QB) s_cnt[tid] = 0;
+        __syncthreads();
+        auto issue = [&](int c) {
+            uint8_t *dst = stage + (size_t)(c & 1) * STAGE_B;
+    #pragma unroll
+            for (int p = 0; p < PCS; p++) {
+                const int idx = p * 128 + tid;
+                const int r = idx / PCS, piece = idx % PCS;
+                const float *src = rows + (size_t)pos_s[r] * ld + c * CH + piece * 4;
+                const uint32_t d = smem_u32(dst + r * ROW_B + ((piece ^ (r & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+        float acc[IVF_QB];
+    #pragma unroll
+        for (int qi = 0; qi < IVF_QB; qi++) acc[qi] = 0.0f;
+        for (int c = 0; c < n_ch; c++) {
+            if (c + 1 < n_ch) {
+                issue(c + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();                                              // also orders the q_s fill before its first use
+            const uint8_t *sp = stage + (size_t)(c & 1) * STAGE_B + tid * ROW_B;
+            const float *qc = q_s + c * CH;
+    #pragma unroll
+            for (int jj = 0; jj < PCS; jj++) {
+                const float4 xv = *reinterpret_cast<const float4 *>(sp + ((jj ^ (tid & 7)) << 4));
+    #pragma unroll
+                for (int qi = 0; qi < IVF_QB; qi++) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(qc + (size_t)qi * ld + jj * 4);
+                    float a = acc[qi];
+                    if (FMA) {
+                        a = metric_step<METRIC, FMA>(a, qv.x, xv.x);
+                        a = metric_step<METRIC, FMA>(a, qv.y, xv.y);
+                        a = metric_step<METRIC, FMA>(a, qv.z, xv.z);
+                        a = metric_step<METRIC, FMA>(a, qv.w, xv.w);
+                    } else {
+                        a = metric_step4_unfused<METRIC>(a, qv, xv);
+                    }
+                    acc[qi] = a;
                 }
-                acc[qi] = a;
+            }
+            __syncthreads();
+        }
+        const bool keep = live && !(skip != nullptr && skip[pos]);
+    #pragma unroll
+        for (int qi = 0; qi < IVF_QB; qi++) {
+            const int pair = s_pair[qi];
+            if (pair < 0) continue;                                       // uniform
+            const int q = pair / nprobes, pr = pair - q * nprobes;
+            const float dist = metric_finish<METRIC>(acc[qi]);
+            const size_t part = (size_t)q * parts_per_q + (size_t)tile_off[(size_t)q * (nprobes + 1) + pr] + tile;
+            if (keep && !(threshold > 0.0f && dist > threshold)) {
+                const int slot = atomicAdd(&s_cnt[qi], 1);
+                out_keys[part * 128 + slot] = make_key(dist, (uint32_t)(q_off[(size_t)q * (nprobes + 1) + pr] + j));
             }
         }
         __syncthreads();
-    }
-    const bool keep = live && !(skip != nullptr && skip[pos]);
-#pragma unroll
-    for (int qi = 0; qi < IVF_QB; qi++) {
-        const int pair = s_pair[qi];
-        if (pair < 0) continue;                                       // uniform
-        const int q = pair / nprobes, pr = pair - q * nprobes;
-        const float dist = metric_finish<METRIC>(acc[qi]);
-        const size_t part = (size_t)q * parts_per_q + (size_t)tile_off[(size_t)q * (nprobes + 1) + pr] + tile;
-        if (keep && !(threshold > 0.0f && dist > threshold)) {
-            const int slot = atomicAdd(&s_cnt[qi], 1);
-            out_keys[part * 128 + slot] = make_key(dist, (uint32_t)(q_off[(size_t)q * (nprobes + 1) + pr] + j));
+        if (tid < nb) {
+            const int pair = s_pair[tid];
+            const int q = pair / nprobes, pr = pair - q * nprobes;
+            out_cnt[(size_t)q * parts_per_q + tile_off[(size_t)q * (nprobes + 1) + pr] + tile] = s_cnt[tid];
         }
-    }
-    __syncthreads();
-    if (tid < nb) {
-        const int pair = s_pair[tid];
-        const int q = pair / nprobes, pr = pair - q * nprobes;
-        out_cnt[(size_t)q * parts_per_q + tile_off[(size_t)q * (nprobes + 1) + pr] + tile] = s_cnt[tid];
     }
 }
 
@@ -534,8 +536,8 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
     // to nprobes more parts than candidates / 128
     const int64_t max_len = ix.sizes_desc.empty() ? 0 : ix.sizes_desc[0];
     const int64_t max_tiles = (max_len + 127) / 128;
-    bool list_major = nq >= 32 && max_tiles <= 65535;
-    if (const char *e = getenv("COMET_B200_IVF_LIST_MAJOR")) list_major = atoi(e) != 0 && max_tiles <= 65535 && max_tiles > 0;
+    bool list_major = nq >= 32 && max_tiles > 0;
+    if (const char *e = getenv("COMET_B200_IVF_LIST_MAJOR")) list_major = atoi(e) != 0 && max_tiles > 0;
     const int n_parts = list_major ? n_chunks + nprobes : n_chunks;
     const long long cap_c = (long long)n_parts * 128;
     int64_t qgroup = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (cap_c * 8)));
@@ -568,7 +570,7 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
             ivf_group_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pl, n_pairs, cursor, pairs_sorted);
             const long long blocks_max = n_pairs / IVF_QB + std::min<long long>(ix.nlist, n_pairs);
             const size_t smem_l = (size_t)IVF_QB * ld * 4 + 2 * 128 * 128;
-            dim3 grid_l((unsigned)blocks_max, (unsigned)max_tiles);
+            dim3 grid_l((unsigned)blocks_max, (unsigned)std::min<int64_t>(max_tiles, 16));    // a hub list's tiles are looped over
 #define CM_IVF_LISTS(MM, F)                                                                                              \
     do {                                                                                                                 \
         CM_TRY(set_dyn_smem((const void *)ivf_scan_lists_kernel<MM, F>, smem_l));                                        \
