@@ -22,7 +22,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/la
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_tensor_path_l2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --metric-kind l2 > /dev/null 2>&1
 # full captures: one step of the tensor path, the ADC scan
 ncu --set full --clock-control none --import-source on -k regex:"flat_gemm_ts|ts_select|rescore|merge_topk|prep_queries" -s 24 -c 8 -o $O/prof_tensor python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_tensor.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"adc_scan" -s 2 -c 1 -o $O/prof_adc python tools/adc_sweep.py --n 2500000 --nlist 1024 --configs ";" > $O/ncu_adc.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"adc_ring|adc_scan" -s 2 -c 1 -o $O/prof_adc python tools/adc_sweep.py --n 2500000 --nlist 1024 --configs ";" > $O/ncu_adc.log 2>&1
 for r in tensor adc; do python tools/ncu_summary.py $O/prof_$r.ncu-rep > $O/summary_$r.md 2>/dev/null; done
 # sanitizers over every device path at small sizes
 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_smoke.py > $O/memcheck.log 2>&1; tail -3 $O/memcheck.log
