@@ -103,6 +103,12 @@ def test_ivf_k_all_beyond_the_shared_memory_merge():
     check(g, o, q, 0, 4)
     check(g, o, q, 20000, 3)
     check(g, o, q[:1], 0, 2, threshold=20.0)
+    # and a batch: the list-major scan's parts through the same sort
+    qb = rng.standard_normal((34, 16)).astype(np.float32)
+    ids, sc, cnt = g.search(qb, k=0, nprobes=3)
+    for i in (0, 17, 33):
+        oi, os_ = o.search(qb[i], k=0, nprobes=3)
+        assert_same_results(ids[i], sc[i], cnt[i], oi, os_, what=f"batch query {i}")
 
 
 # Batches take the list-major scan (the (query, probe) pairs grouped by list, a 128-row tile of a list walked for up to 8
