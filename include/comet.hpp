@@ -533,6 +533,136 @@ inline std::unique_ptr<IVFPQIndex> NewIVFPQIndex(int dim, DistanceKind kind, int
     return std::make_unique<IVFPQIndex>(dim, kind, nlist, m, nbits);
 }
 
+// ---- multi-GPU layouts of the trained indexes (one process drives every device) ---------------
+// Same VectorIndex surface as the single-device classes; WriteTo / ReadFrom are not offered on these (segments per shard
+// are the host's business, storage.go:545-626).
+class ShardedIVFIndex : public VectorIndex {             // lists spread over the devices, global candidate numbering
+public:
+    ShardedIVFIndex(int dim, int nlist, comet::DistanceKind kind, const std::vector<int> &devices) : VectorIndex(dim, kind) {
+        check(cm_ivf_sharded_create(dim, nlist, (int)kind, devices.data(), (int)devices.size(), &h_));
+    }
+    ~ShardedIVFIndex() override { cm_ivf_sharded_destroy(h_); }
+    void Train(const std::vector<VectorNode> &vectors) override {
+        std::vector<float> rows;
+        for (const auto &v : vectors) { checkDim(v); rows.insert(rows.end(), v.Vector().begin(), v.Vector().end()); }
+        check(cm_ivf_sharded_train(h_, rows.data(), (int64_t)vectors.size()));
+    }
+    void SetCentroids(const std::vector<float> &c) { check(cm_ivf_sharded_set_centroids(h_, c.data())); }
+    void Add(VectorNode v) override {
+        if (!Trained()) throw Error(CM_ERR_NOT_TRAINED, "index must be trained before adding vectors");
+        checkDim(v);
+        uint32_t id = v.ID();
+        check(cm_ivf_sharded_add(h_, &id, v.Vector().data(), 1, 1, nullptr));
+        remember(v);
+    }
+    void Remove(const VectorNode &v) override { check(cm_ivf_sharded_remove(h_, v.ID())); deleted_.insert(v.ID()); }
+    void Flush() override { check(cm_ivf_sharded_flush(h_)); forget(deleted_); deleted_.clear(); }
+    void Rebalance() { check(cm_ivf_sharded_rebalance(h_)); }
+    VectorIndexKind Kind() const override { return "ivf"; }
+    bool Trained() const override { return cm_ivf_sharded_trained(h_) != 0; }
+    int Shards() const { return cm_ivf_sharded_shards(h_); }
+
+protected:
+    int defaultNProbes() const override { return cm_ivf_sharded_default_nprobes(h_); }
+    void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
+                     std::vector<float> &scores, std::vector<int64_t> &counts) override {
+        check(cm_ivf_sharded_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), counts.data()));
+    }
+    int saveBytes(uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    int loadBytes(const uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    void rebuildMirror() override {}
+    cm_ivf_sharded *h_ = nullptr;
+};
+inline std::unique_ptr<ShardedIVFIndex> NewShardedIVFIndex(int dim, int nlist, DistanceKind kind, const std::vector<int> &devices) {
+    return std::make_unique<ShardedIVFIndex>(dim, nlist, kind, devices);
+}
+
+class ShardedPQIndex : public VectorIndex {              // rows spread over the devices like the flat row shards
+public:
+    ShardedPQIndex(int dim, comet::DistanceKind kind, int M, int Nbits, const std::vector<int> &devices, int64_t rowsPerShard)
+        : VectorIndex(dim, kind) {
+        check(cm_pq_sharded_create(dim, (int)kind, M, Nbits, devices.data(), (int)devices.size(), rowsPerShard, &h_));
+    }
+    ~ShardedPQIndex() override { cm_pq_sharded_destroy(h_); }
+    void Train(const std::vector<VectorNode> &vectors) override {
+        std::vector<float> rows;
+        for (const auto &v : vectors) { checkDim(v); rows.insert(rows.end(), v.Vector().begin(), v.Vector().end()); }
+        check(cm_pq_sharded_train(h_, rows.data(), (int64_t)vectors.size()));
+    }
+    void SetCodebooks(const std::vector<float> &cb) { check(cm_pq_sharded_set_codebooks(h_, cb.data())); }
+    void Add(VectorNode v) override {
+        if (!Trained()) throw Error(CM_ERR_NOT_TRAINED, "index must be trained before adding vectors");
+        checkDim(v);
+        uint32_t id = v.ID();
+        check(cm_pq_sharded_add(h_, &id, v.Vector().data(), 1, 1));
+        remember(v);
+    }
+    void Remove(const VectorNode &v) override { check(cm_pq_sharded_remove(h_, v.ID())); deleted_.insert(v.ID()); }
+    void Flush() override { check(cm_pq_sharded_flush(h_)); forget(deleted_); deleted_.clear(); }
+    VectorIndexKind Kind() const override { return "pq"; }
+    bool Trained() const override { return cm_pq_sharded_trained(h_) != 0; }
+    int Shards() const { return cm_pq_sharded_shards(h_); }
+
+protected:
+    void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
+                     std::vector<float> &scores, std::vector<int64_t> &counts) override {
+        check(cm_pq_sharded_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), counts.data()));
+    }
+    int saveBytes(uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    int loadBytes(const uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    void rebuildMirror() override {}
+    cm_pq_sharded *h_ = nullptr;
+};
+inline std::unique_ptr<ShardedPQIndex> NewShardedPQIndex(int dim, DistanceKind kind, int M, int Nbits, const std::vector<int> &devices,
+                                                         int64_t rowsPerShard) {
+    return std::make_unique<ShardedPQIndex>(dim, kind, M, Nbits, devices, rowsPerShard);
+}
+
+class ShardedIVFPQIndex : public VectorIndex {           // lists spread over the devices, codes travel with their list
+public:
+    ShardedIVFPQIndex(int dim, comet::DistanceKind kind, int nlist, int m, int nbits, const std::vector<int> &devices)
+        : VectorIndex(dim, kind) {
+        check(cm_ivfpq_sharded_create(dim, (int)kind, nlist, m, nbits, devices.data(), (int)devices.size(), &h_));
+    }
+    ~ShardedIVFPQIndex() override { cm_ivfpq_sharded_destroy(h_); }
+    void Train(const std::vector<VectorNode> &vectors) override {
+        std::vector<float> rows;
+        for (const auto &v : vectors) { checkDim(v); rows.insert(rows.end(), v.Vector().begin(), v.Vector().end()); }
+        check(cm_ivfpq_sharded_train(h_, rows.data(), (int64_t)vectors.size()));
+    }
+    void SetTrained(const std::vector<float> &centroids, const std::vector<float> &codebooks) {
+        check(cm_ivfpq_sharded_set_trained(h_, centroids.data(), codebooks.data()));
+    }
+    void Add(VectorNode v) override {
+        if (!Trained()) throw Error(CM_ERR_NOT_TRAINED, "index must be trained before adding");
+        checkDim(v);
+        uint32_t id = v.ID();
+        check(cm_ivfpq_sharded_add(h_, &id, v.Vector().data(), 1, 1, nullptr));
+        remember(v);
+    }
+    void Remove(const VectorNode &v) override { check(cm_ivfpq_sharded_remove(h_, v.ID())); deleted_.insert(v.ID()); }
+    void Flush() override { check(cm_ivfpq_sharded_flush(h_)); forget(deleted_); deleted_.clear(); }
+    void Rebalance() { check(cm_ivfpq_sharded_rebalance(h_)); }
+    VectorIndexKind Kind() const override { return "ivfpq"; }
+    bool Trained() const override { return cm_ivfpq_sharded_trained(h_) != 0; }
+    int Shards() const { return cm_ivfpq_sharded_shards(h_); }
+
+protected:
+    int defaultNProbes() const override { return cm_ivfpq_sharded_default_nprobes(h_); }
+    void searchBatch(const std::vector<float> &flat, int64_t nq, const cm_search_params &p, int64_t stride, std::vector<uint32_t> &ids,
+                     std::vector<float> &scores, std::vector<int64_t> &counts) override {
+        check(cm_ivfpq_sharded_search(h_, flat.data(), nq, dim_, &p, stride, ids.data(), scores.data(), counts.data()));
+    }
+    int saveBytes(uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    int loadBytes(const uint8_t *, int64_t, int64_t *) override { return CM_ERR_UNSUPPORTED; }
+    void rebuildMirror() override {}
+    cm_ivfpq_sharded *h_ = nullptr;
+};
+inline std::unique_ptr<ShardedIVFPQIndex> NewShardedIVFPQIndex(int dim, DistanceKind kind, int nlist, int m, int nbits,
+                                                               const std::vector<int> &devices) {
+    return std::make_unique<ShardedIVFPQIndex>(dim, kind, nlist, m, nbits, devices);
+}
+
 // ---- HNSWIndex (hnsw_index.go): insertion and search on the device; LoadGraph restores a serialised graph ----
 class HNSWIndex : public VectorIndex {
 public:

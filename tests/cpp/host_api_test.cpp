@@ -198,6 +198,37 @@ static void test_serialisation_flush_and_shards() {
         EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(25).Execute(), s->NewSearch()->WithQuery({q}).WithK(25).Execute()));
         EXPECT(throws([&] { s->Add(NewVectorNodeWithID(999, {1, 2, 3})); }, "vector dimension mismatch: expected 4, got 3"));
     }
+    {
+        // list shards (IVF, IVFPQ) and PQ row shards: same trained state, same answers as the single index, ties included
+        auto a = NewIVFIndex(4, 5, Euclidean);
+        a->Train(nodes);
+        auto s = NewShardedIVFIndex(4, 5, Euclidean, {0, 0});
+        EXPECT(throws([&] { s->Add(nodes[0]); }, "index must be trained before adding vectors"));
+        s->Train(nodes);
+        for (auto &n : nodes) { a->Add(n); s->Add(n); }
+        EXPECT(s->Shards() == 2 && s->Len() == 300 && s->Trained());
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(40).WithNProbes(3).Execute(), s->NewSearch()->WithQuery({q}).WithK(40).WithNProbes(3).Execute()));
+        s->Rebalance();
+        a->Remove(nodes[9]); s->Remove(nodes[9]);
+        a->Flush(); s->Flush();
+        EXPECT(same(a->NewSearch()->WithQuery({q}).WithK(40).Execute(), s->NewSearch()->WithQuery({q}).WithK(40).Execute()));
+
+        auto pa = NewPQIndex(4, Euclidean, 2, 4);
+        pa->Train(nodes);
+        auto ps = NewShardedPQIndex(4, Euclidean, 2, 4, {0, 0, 0}, 110);
+        ps->Train(nodes);
+        for (auto &n : nodes) { pa->Add(n); ps->Add(n); }
+        EXPECT(ps->Shards() == 3 && ps->Len() == 300);
+        EXPECT(same(pa->NewSearch()->WithQuery({q}).WithK(30).Execute(), ps->NewSearch()->WithQuery({q}).WithK(30).Execute()));
+
+        auto ia = NewIVFPQIndex(4, Euclidean, 3, 2, 4);
+        ia->Train(nodes);
+        auto is = NewShardedIVFPQIndex(4, Euclidean, 3, 2, 4, {0, 0});
+        is->Train(nodes);
+        for (auto &n : nodes) { ia->Add(n); is->Add(n); }
+        EXPECT(is->Shards() == 2 && is->Len() == 300);
+        EXPECT(same(ia->NewSearch()->WithQuery({q}).WithK(30).WithNProbes(2).Execute(), is->NewSearch()->WithQuery({q}).WithK(30).WithNProbes(2).Execute()));
+    }
 }
 
 int main(int argc, char **argv) {
