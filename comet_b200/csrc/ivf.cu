@@ -232,13 +232,16 @@ __global__ void __launch_bounds__(128) ivf_scan_kernel(const float *__restrict__
 static constexpr int IVF_QB = 8;
 
 // per query: tile_off[q][p] = number of 128-row tiles of probes 0..p-1; per list: pairs probing it
-__global__ void ivf_group_count_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ list_off,
-                                       int nprobes, int nq, long long *__restrict__ tile_off, int *__restrict__ list_cnt) {
+__global__ void ivf_group_count_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ probe_cnt,
+                                       const long long *__restrict__ list_off, int nprobes, int nq,
+                                       long long *__restrict__ tile_off, int *__restrict__ list_cnt) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    const int np = (int)min((long long)nprobes, probe_cnt[q]);       // probes the coarse step returned (ivf_offsets_kernel)
     long long acc = 0;
     for (int p = 0; p < nprobes; p++) {
         tile_off[(size_t)q * (nprobes + 1) + p] = acc;
+        if (p >= np) continue;
         const long long l = probe_list[(size_t)q * nprobes + p];
         acc += (list_off[l + 1] - list_off[l] + 127) >> 7;
         atomicAdd(&list_cnt[l], 1);
@@ -278,10 +281,12 @@ __global__ void ivf_group_scan_kernel(const int *__restrict__ list_cnt, int nlis
     }
 }
 
-__global__ void ivf_group_scatter_kernel(const long long *__restrict__ probe_list, long long n_pairs, int *__restrict__ cursor,
-                                         int *__restrict__ pairs_sorted) {
+__global__ void ivf_group_scatter_kernel(const long long *__restrict__ probe_list, const long long *__restrict__ probe_cnt,
+                                         int nprobes, long long n_pairs, int *__restrict__ cursor, int *__restrict__ pairs_sorted) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
+    const long long q = i / nprobes;
+    if (i - q * nprobes >= probe_cnt[q]) return;
     pairs_sorted[atomicAdd(&cursor[probe_list[i]], 1)] = (int)i;
 }
 
@@ -564,10 +569,10 @@ static int ivf_search_device(IVFIndex &ix, const float *q_dev, int64_t nq, const
             const int nl1 = ix.nlist + 1;
             int *list_cnt = grp, *pair_off = grp + nl1, *blk_off = grp + 2 * nl1, *cursor = grp + 3 * nl1;
             CM_CUDA(cudaMemsetAsync(list_cnt, 0, (size_t)nl1 * sizeof(int), st));
-            ivf_group_count_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(pl, ix.list_off, nprobes, (int)m, tile_off, list_cnt);
+            ivf_group_count_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(pl, probe_cnt + q0, ix.list_off, nprobes, (int)m, tile_off, list_cnt);
             ivf_group_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, ix.nlist, pair_off, blk_off, cursor);
             const long long n_pairs = (long long)m * nprobes;
-            ivf_group_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pl, n_pairs, cursor, pairs_sorted);
+            ivf_group_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pl, probe_cnt + q0, nprobes, n_pairs, cursor, pairs_sorted);
             const long long blocks_max = n_pairs / IVF_QB + std::min<long long>(ix.nlist, n_pairs);
             const size_t smem_l = (size_t)IVF_QB * ld * 4 + 2 * 128 * 128;
             dim3 grid_l((unsigned)blocks_max, (unsigned)std::min<int64_t>(max_tiles, 16));    // a hub list's tiles are looped over
