@@ -158,11 +158,29 @@ def cpu_reference_run(x_host, q_host, k, threads, nq_sample, metric=2):
     return nq_sample / dt, dt, ids, sc, t_add, o
 
 
+def workload_config(args, world, rows_mode):
+    """The `config` object of the line -- the workload, identical in both arms (`--impl ours` / `--impl reference`)."""
+    shard = N_ROWS // world if rows_mode else N_ROWS
+    name = ("flat_%s_%dx768_k100_b512" % (args.metric_kind, N_ROWS)
+            if (N_ROWS != 1_000_000 or args.metric_kind != "cosine") else "flat_cosine_1Mx768_k100_b512")
+    return {"workload": name, "rows": N_ROWS, "dim": DIM, "k": K, "batch_per_gpu": BATCH, "global_batch": BATCH * max(1, world),
+            "sharding": "single GPU" if world == 1 else (
+                f"rows/{world} per GPU, every rank searches the global batch, NCCL all-gather of per-shard top-K + device merge"
+                if rows_mode else
+                f"queries: {world} replicas of the corpus (it fits one GPU), {BATCH} queries per GPU, no data-path collective; "
+                "--sharding rows runs the row-sharded layout with the NCCL top-K merge"),
+            "l2_policy": "inputs (%.2f GB fp32 corpus + bf16 shadow per GPU) larger than the 126 MB L2; no flush needed" % (shard * DIM * 4 / 1e9)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    # which layout the other arm picks at this N (its rule: replicas when the corpus fits 60 % of a 178 GiB B200)
+    world = max(1, args.gpus)
+    ref_mode = args.sharding if args.sharding != "auto" else ("queries" if N_ROWS * DIM * 6 < 0.6 * 178 * 2 ** 30 else "rows")
+    ref_rows_mode = world == 1 or ref_mode == "rows"
     rng = np.random.default_rng(SEED)
     # bounded sample: a 1/8 row sample of the corpus, scaled (the reference's cost is linear in N:
     # one distance per row plus an N log N sort), so that steps x (cores queries) finish in minutes
@@ -187,9 +205,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "flat_cosine_1Mx768_k100_b512", "rows": N_ROWS, "dim": DIM, "k": K,
-                   "batch_per_gpu": BATCH, "global_batch": BATCH * max(1, args.gpus),
-                   "path": "reference CPU algorithm (C restatement of the Go loops), one query per host thread"},
+        # the same workload object as the other arm prints (sharding = the layout THAT arm runs at this N; this arm is
+        # one host process whatever N is)
+        "config": workload_config(args, max(1, args.gpus), ref_rows_mode),
+        "run_detail": {"path": "reference CPU algorithm (C restatement of the Go loops), one query per host thread"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -465,17 +484,9 @@ def run_ours(args):
             "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "flat_%s_%dx768_k100_b512" % (args.metric_kind, N_ROWS) if (N_ROWS != 1_000_000 or args.metric_kind != "cosine") else "flat_cosine_1Mx768_k100_b512",
-                       "rows": N_ROWS, "dim": DIM, "k": K,
-                       "batch_per_gpu": BATCH, "global_batch": nq_global,
-                       "sharding": "single GPU" if world == 1 else (
-                           f"rows/{world} per GPU, every rank searches the global batch, NCCL all-gather of per-shard top-K + device merge"
-                           if rows_mode else
-                           f"queries: {world} replicas of the corpus (it fits one GPU), {BATCH} queries per GPU, no data-path collective; "
-                           "--sharding rows runs the row-sharded layout with the NCCL top-K merge"),
-                       "path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
-                       "l2_policy": "inputs (%.2f GB fp32 corpus + bf16 shadow per GPU) larger than the 126 MB L2; no flush needed" % (shard * DIM * 4 / 1e9),
-                       "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
+            "config": workload_config(args, world, rows_mode),
+            "run_detail": {"path": {1: "exact fp32 scan", 2: "bf16 tcgen05 candidates + exact fp32 re-score"}.get(stats["path_used"], "?"),
+                           "scan_passes_per_step": stats["passes"], "rescored_candidates_per_step": stats["candidates"]},
             "step_vs_hbm_roofline": {
                 "note": "north-star target: the whole step at >= 0.70 of the time one fp32 corpus pass takes at the measured HBM peak",
                 "algorithmic_bytes_per_step": int(shard * DIM * 4 + nq * DIM * 4 + nq * K * 8),
